@@ -1,0 +1,62 @@
+"""ctypes binding of include/dapol_b200.h.  Fails loudly if the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdapol_b200.so")
+_lib = None
+
+u64 = C.c_uint64
+vp = C.c_void_p
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(f"{LIB_PATH} not built: run ./build.sh (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.dapol_strerror.restype = C.c_char_p
+    L.dapol_last_cuda_error.restype = C.c_char_p
+    L.dapol_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    L.dapol_ctx_destroy.argtypes = [vp]
+    L.dapol_tree_destroy.argtypes = [vp]
+    L.dapol_tree_build_from_nodes.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
+    L.dapol_tree_build_from_nodes_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
+    L.dapol_tree_build_from_liabilities.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, u64, vp, u64,
+                                                    C.POINTER(vp), C.POINTER(u64)]
+    L.dapol_tree_root.argtypes = [vp, vp, vp, C.POINTER(u64), vp]
+    L.dapol_tree_height.argtypes = [vp]
+    L.dapol_tree_num_nodes.argtypes = [vp]
+    L.dapol_tree_num_nodes.restype = u64
+    L.dapol_tree_num_padding.argtypes = [vp]
+    L.dapol_tree_num_padding.restype = u64
+    L.dapol_tree_level_size.argtypes = [vp, C.c_int]
+    L.dapol_tree_level_size.restype = u64
+    L.dapol_tree_level_copy.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    L.dapol_tree_leaf_index_of.argtypes = [vp, u64, C.POINTER(u64)]
+    L.dapol_tree_paths.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp]
+    L.dapol_commit_batch.argtypes = [vp, u64, vp, vp, vp]
+    L.dapol_imad_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.dapol_fe_bench.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.dapol_kernel_launches.argtypes = [vp]
+    L.dapol_kernel_launches.restype = u64
+    L.dapol_last_build_times.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def header_symbols():
+    """Function names declared in include/dapol_b200.h (used by the CPU-side export test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "dapol_b200.h")
+    txt = open(hdr).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dapol_[a-z0-9_]+)\s*\(", txt)))

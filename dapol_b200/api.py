@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference crate's public surface for the hot path (src/lib.rs:1-14),
+over the C ABI.  Names, argument meaning and error behaviour follow the reference:
+
+  Dapol::new / new_blank + build / root / root_raw / generate_proof*   src/dapol/mod.rs:100-208
+  DapolNode::{new, get_value, get_blinding}                              src/dapol/node.rs:29-56
+  DapolProofNode::{new, get_com, get_hash}                               src/proof/node.rs:30-49
+  DapolError                                                             src/errors.rs:5-17
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+
+HASH_BLAKE3, HASH_BLAKE2S = 0, 1
+POLICY_PADDING, POLICY_SPLITTING = 0, 1
+MAX_TREE_HEIGHT = 64
+
+_ERR_NAMES = {1: "TreeHeightTooBig", 2: "SparsityTooSmall", 3: "InvalidDigestSize", 4: "DuplicatedInternalId",
+              5: "FailedToMapIndex", 16: "BadArgument", 17: "NotFound", 18: "BufferTooSmall", 19: "Cuda", 20: "Decode"}
+
+
+class DapolError(Exception):
+    """src/errors.rs DapolError (codes 1-5) plus boundary errors (>= 16)."""
+
+    def __init__(self, code: int, detail=None):
+        L = _ffi.lib()
+        msg = L.dapol_strerror(code).decode()
+        if code == 19:
+            msg += ": " + L.dapol_last_cuda_error().decode()
+        super().__init__(f"{_ERR_NAMES.get(code, code)}: {msg}" + (f" (at input {detail})" if detail is not None else ""))
+        self.code, self.detail = code, detail
+
+
+def _check(rc, detail=None):
+    if rc != 0:
+        raise DapolError(rc, detail)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One CUDA device + precomputed generator tables (PedersenGens::default(), BulletproofGens)."""
+
+    def __init__(self, device: int = 0, comb_window: int = 0):
+        self._h = C.c_void_p()
+        _check(_ffi.lib().dapol_ctx_create(device, comb_window, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.lib().dapol_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def kernel_launches(self) -> int:
+        return _ffi.lib().dapol_kernel_launches(self._h)
+
+    def last_build_times(self):
+        ms = np.zeros(5, np.float32)
+        _check(_ffi.lib().dapol_last_build_times(self._h, _p(ms)))
+        return dict(zip(("structure", "leaves", "padding", "merges", "total"), ms.tolist()))
+
+    def commit_batch(self, values, blindings) -> np.ndarray:
+        """PedersenGens::default().commit(v, r).compress() for a batch (node.rs:31)."""
+        v = np.ascontiguousarray(values, np.uint64)
+        b = np.ascontiguousarray(blindings, np.uint8).reshape(-1, 32)
+        out = np.zeros((len(v), 32), np.uint8)
+        _check(_ffi.lib().dapol_commit_batch(self._h, len(v), _p(v), _p(b), _p(out)))
+        return out
+
+    def imad_peak(self, variant: int) -> float:
+        x = C.c_double()
+        _check(_ffi.lib().dapol_imad_peak(self._h, variant, C.byref(x)))
+        return x.value
+
+    def fe_bench(self, op: int) -> float:
+        x = C.c_double()
+        _check(_ffi.lib().dapol_fe_bench(self._h, op, C.byref(x)))
+        return x.value
+
+
+@dataclass
+class DapolNode:
+    """src/dapol/node.rs DapolNode {v, v_blinding, com, hash}; com is the compressed commitment."""
+    value: int
+    blinding: bytes
+    com: bytes
+    hash: bytes
+
+    def get_value(self):
+        return self.value
+
+    def get_blinding(self):
+        return self.blinding
+
+    def get_proof_node(self):
+        return DapolProofNode(self.com, self.hash)
+
+
+@dataclass
+class DapolProofNode:
+    """src/proof/node.rs DapolProofNode {com, hash}."""
+    com: bytes
+    hash: bytes
+
+    def get_com(self):
+        return self.com
+
+    def get_hash(self):
+        return self.hash
+
+    def serialize(self) -> bytes:  # proof/node.rs:74-79
+        return self.com + self.hash
+
+
+class Dapol:
+    """src/dapol/mod.rs Dapol<D, R>: D = hash_id, R = policy."""
+
+    def __init__(self, ctx: Context, hash_id: int, height: int, aggregation_factor: int, policy: int = POLICY_PADDING):
+        self.ctx, self.hash_id, self.height = ctx, hash_id, height
+        self.aggregation_factor, self.policy = aggregation_factor, policy
+        self._t = None
+
+    # -- constructors -------------------------------------------------------------------------
+    @classmethod
+    def new_blank(cls, ctx, hash_id, height, aggregation_factor, policy=POLICY_PADDING):
+        """Dapol::new_blank (mod.rs:196-204)."""
+        return cls(ctx, hash_id, height, aggregation_factor, policy)
+
+    def build(self, leaf_idx, values, blindings, pad_seed: bytes, pad_base: int = 0):
+        """Dapol::build(&items, &secret) (mod.rs:206-208) with items = DapolNode::new(values[i], blindings[i])
+        at TreeIndex::from_u64(height, leaf_idx[i]); padding randomness from the seeded stream."""
+        idx = np.ascontiguousarray(leaf_idx, np.uint64)
+        val = np.ascontiguousarray(values, np.uint64)
+        bl = np.ascontiguousarray(blindings, np.uint8).reshape(-1, 32)
+        if not (len(idx) == len(val) == len(bl)):
+            raise DapolError(16)
+        self._free()
+        h = C.c_void_p()
+        seed = (C.c_uint8 * 32).from_buffer_copy(pad_seed)
+        _check(_ffi.lib().dapol_tree_build_from_nodes(self.ctx._h, self.hash_id, self.height, len(idx), _p(idx), _p(val), _p(bl),
+                                                      seed, pad_base, C.byref(h)))
+        self._t = h
+        return self
+
+    def build_dev(self, n, d_leaf_idx: int, d_values: int, d_blindings: int, pad_seed: bytes, pad_base: int = 0):
+        """Same as build() with the inputs already in device memory (raw device pointers)."""
+        self._free()
+        h = C.c_void_p()
+        seed = (C.c_uint8 * 32).from_buffer_copy(pad_seed)
+        _check(_ffi.lib().dapol_tree_build_from_nodes_dev(self.ctx._h, self.hash_id, self.height, n, d_leaf_idx, d_values,
+                                                          d_blindings, seed, pad_base, C.byref(h)))
+        self._t = h
+        return self
+
+    def _free(self):
+        if getattr(self, "_t", None):
+            _ffi.lib().dapol_tree_destroy(self._t)
+            self._t = None
+
+    close = _free
+    __del__ = _free
+
+    # -- accessors ----------------------------------------------------------------------------
+    def root_raw(self) -> DapolNode:
+        """Dapol::root_raw (mod.rs:134-136)."""
+        com = np.zeros(32, np.uint8); hs = np.zeros(32, np.uint8); bl = np.zeros(32, np.uint8)
+        v = C.c_uint64()
+        _check(_ffi.lib().dapol_tree_root(self._t, _p(com), _p(hs), C.byref(v), _p(bl)))
+        return DapolNode(v.value, bl.tobytes(), com.tobytes(), hs.tobytes())
+
+    def root(self) -> DapolProofNode:
+        """Dapol::root (mod.rs:139-141)."""
+        return self.root_raw().get_proof_node()
+
+    @property
+    def num_nodes(self):
+        return _ffi.lib().dapol_tree_num_nodes(self._t)
+
+    @property
+    def num_padding(self):
+        return _ffi.lib().dapol_tree_num_padding(self._t)
+
+    def level(self, h: int):
+        n = _ffi.lib().dapol_tree_level_size(self._t, h)
+        idx = np.zeros(n, np.uint64); v = np.zeros(n, np.uint64)
+        r = np.zeros((n, 32), np.uint8); c = np.zeros((n, 32), np.uint8); hs = np.zeros((n, 32), np.uint8)
+        pad = np.zeros(n, np.uint8)
+        _check(_ffi.lib().dapol_tree_level_copy(self._t, h, _p(idx), _p(v), _p(r), _p(c), _p(hs), _p(pad)))
+        return dict(idx=idx, v=v, r=r, comc=c, hash=hs, is_pad=pad)
+
+    def paths(self, leaf_idx):
+        """Siblings (leaf level first) of each requested leaf + the leaf proof nodes; None if any is absent."""
+        li = np.ascontiguousarray(leaf_idx, np.uint64)
+        k, H = len(li), max(self.height, 1)
+        v = np.zeros((k, H), np.uint64)
+        r = np.zeros((k, H, 32), np.uint8); c = np.zeros((k, H, 32), np.uint8); hs = np.zeros((k, H, 32), np.uint8)
+        lc = np.zeros((k, 32), np.uint8); lh = np.zeros((k, 32), np.uint8)
+        rc = _ffi.lib().dapol_tree_paths(self._t, k, _p(li), _p(v), _p(r), _p(c), _p(hs), _p(lc), _p(lh))
+        if rc == 17:
+            return None
+        _check(rc)
+        return dict(v=v, r=r, comc=c, hash=hs, leaf_comc=lc, leaf_hash=lh)

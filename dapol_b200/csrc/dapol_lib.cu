@@ -1,0 +1,669 @@
+// dapol_b200 C-ABI library: CUDA kernels (sm_100a) + host orchestration for the DAPOL+ hot path.
+// Interface: include/dapol_b200.h.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dapol_b200.h"
+#include "tree_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_cuda_err;
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); \
+            return DAPOL_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+
+struct dapol_ctx {
+    int device = 0;
+    int W = 8;
+    cudaStream_t stream = nullptr;
+    ge_niels *tab_b = nullptr, *tab_bbl = nullptr;  // comb tables for B and B_blinding at window W
+    uint64_t launches = 0;
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[6] = {};
+};
+
+struct dapol_tree {
+    dapol_ctx *ctx = nullptr;
+    int hash_id = 0, height = 0;
+    uint64_t n_leaves = 0, T = 0, n_pads = 0;
+    std::vector<uint64_t> level_off, level_n, n_real;  // per level h = 0..H
+    NodeStore ns = {};
+    std::vector<uint32_t *> pos;  // pos[h]: slot of the k-th real node of level h (device), h = 1..H
+    uint32_t **d_pos = nullptr;   // device copy of the pointer table
+    uint64_t *d_level_off = nullptr;
+    uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
+};
+
+extern "C" const char *dapol_last_cuda_error(void) { return g_cuda_err.c_str(); }
+extern "C" const char *dapol_strerror(int code) {
+    switch (code) {
+        case DAPOL_OK: return "ok";
+        case DAPOL_ERR_TREE_HEIGHT_TOO_BIG: return "DAPOL tree height must not exceed 64";
+        case DAPOL_ERR_SPARSITY_TOO_SMALL: return "tree height too small for the liability set (2^height < 2*N)";
+        case DAPOL_ERR_INVALID_DIGEST_SIZE: return "expected digest size to be 32";
+        case DAPOL_ERR_DUPLICATED_INTERNAL_ID: return "liability set contains a duplicated internal ID";
+        case DAPOL_ERR_FAILED_TO_MAP_INDEX: return "failed to map audit ID to a tree index within 128 tries";
+        case DAPOL_ERR_BAD_ARG: return "bad argument";
+        case DAPOL_ERR_NOT_FOUND: return "not found";
+        case DAPOL_ERR_BUFFER: return "buffer too small";
+        case DAPOL_ERR_CUDA: return "CUDA error";
+        case DAPOL_ERR_DECODE: return "decoding error";
+    }
+    return "unknown";
+}
+
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <int W>
+__global__ void k_comb_table(ge_niels *table, int nw, int which, uint64_t total) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) comb_table_body<W>(t, table, nw, which);
+}
+__global__ void k_check_leaf_idx(const uint64_t *idx, uint64_t n, int height, int *bad) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n && leaf_idx_bad(k, idx, height)) *bad = 1;
+}
+__global__ void k_struct_flags(const uint64_t *idx, uint64_t c, uint64_t *flags) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < c) flags[k] = struct_flags_body(k, idx, c);
+}
+__global__ void k_struct_parent(const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *scan, uint64_t *parent_idx,
+                                uint64_t *totals) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < c) struct_parent_body(k, idx, c, flags, scan, parent_idx, totals);
+}
+__global__ void k_struct_emit(const uint64_t *idx, uint64_t c, const uint64_t *scan, uint32_t *pos, uint64_t level_off, NodeStore ns,
+                              uint64_t *pad_dest, uint64_t pad_ord_base) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < c) struct_emit_body(k, idx, c, scan, pos, level_off, ns, pad_dest, pad_ord_base);
+}
+
+// exclusive prefix sum of u64, three passes over tiles of SCAN_TILE items
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, uint64_t *total) {
+    __shared__ uint64_t warp_sums[SCAN_BLOCK / 32];
+    __shared__ uint64_t block_total;
+    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += y;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = lane < SCAN_BLOCK / 32 ? warp_sums[lane] : 0, wi = w;
+#pragma unroll
+        for (int d = 1; d < SCAN_BLOCK / 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (unsigned)d) wi += y;
+        }
+        if (lane < SCAN_BLOCK / 32) warp_sums[lane] = wi - w;
+        if (lane == SCAN_BLOCK / 32 - 1) block_total = wi;
+    }
+    __syncthreads();
+    if (total) *total = block_total;
+    uint64_t r = incl - x + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+__global__ void k_scan_tile_sums(const uint64_t *in, uint64_t n, uint64_t *tile_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
+    uint64_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void k_scan_tile_offsets(uint64_t *tile_sums, uint64_t ntiles) {  // one block; in place -> exclusive
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < ntiles; base += SCAN_BLOCK) {
+        uint64_t i = base + threadIdx.x;
+        uint64_t x = i < ntiles ? tile_sums[i] : 0, total;
+        uint64_t e = block_exclusive_scan(x, &total);
+        if (i < ntiles) tile_sums[i] = e + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+__global__ void k_scan_tile_apply(const uint64_t *in, uint64_t n, const uint64_t *tile_offsets, uint64_t *out) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t x[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { x[i] = base + i < n ? in[base + i] : 0; s += x[i]; }
+    uint64_t e = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = e; e += x[i]; }
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) k_leaf(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
+                                              const uint64_t *values, const uint32_t *blind, const ge_niels *tab_b,
+                                              const ge_niels *tab_bbl) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) leaf_body<W>(i, ns, level_off, pos, hash_id, values, blind, tab_b, tab_bbl);
+}
+struct Seed8 {
+    uint32_t w[8];
+};
+template <int W>
+__global__ void __launch_bounds__(128) k_pad(uint64_t n, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
+                                             uint64_t pad_base, const ge_niels *tab_bbl) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) pad_body<W>(g, ns, pad_dest, hash_id, seed.w, pad_base, tab_bbl);
+}
+__global__ void __launch_bounds__(128) k_merge(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos,
+                                               int hash_id) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) merge_body(j, ns, child_off, parent_pos ? parent_off + parent_pos[j] : parent_off, hash_id);
+}
+// leaves only (no tree): commitments for dapol_commit_batch
+template <int W>
+__global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *values, const uint32_t *blind, uint32_t *out,
+                                                const ge_niels *tab_b, const ge_niels *tab_bbl) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    sc rs, rr;
+    load8(rs.v, blind + 8 * i);
+    sc_reduce256(rr, rs);
+    uint64_t v = values[i];
+    uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
+    int32_t dr[NWR], dv[NWV];
+    sc_signed_digits<W, NWR>(dr, rr.v, 8);
+    sc_signed_digits<W, NWV>(dv, vw, 2);
+    ge acc;
+    ge_identity(acc);
+    ge_comb_accumulate<W, NWV>(acc, tab_b, dv);
+    ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
+    uint32_t cc[8];
+    ge_compress(cc, acc);
+    store8(out + 8 * i, cc);
+}
+__global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, NodeStore ns, const uint64_t *level_off, uint64_t n_leaf_level,
+                        uint32_t *const *pos, int height, uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h,
+                        uint32_t *o_lc, uint32_t *o_lh, int *not_found) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= k) return;
+    uint64_t off = level_off[height];
+    int64_t slot = find_leaf_slot(ns.idx + off, n_leaf_level, leaf_idx[q]);
+    if (slot < 0 || ns.is_pad[off + slot]) { *not_found = 1; return; }
+    uint32_t w[8];
+    if (o_lc) { load8(w, ns.comc + 8 * (off + slot)); store8(o_lc + 8 * q, w); }
+    if (o_lh) { load8(w, ns.hash + 8 * (off + slot)); store8(o_lh + 8 * q, w); }
+    uint64_t p = (uint64_t)slot;
+    for (int h = height, lvl = 0; h >= 1; h--, lvl++) {
+        uint64_t g = level_off[h] + (p ^ 1), o = q * (uint64_t)height + lvl;
+        o_v[o] = ns.v[g];
+        load8(w, ns.r + 8 * g); store8(o_r + 8 * o, w);
+        load8(w, ns.comc + 8 * g); store8(o_c + 8 * o, w);
+        load8(w, ns.hash + 8 * g); store8(o_h + 8 * o, w);
+        if (h > 1) p = pos[h - 1][p >> 1];
+    }
+}
+
+// ---- microbenchmarks: integer-multiply pipe peak and field-op throughput
+template <int VARIANT>
+__global__ void k_imad_peak(uint32_t *out, uint32_t a, uint32_t b, int iters) {
+    uint32_t x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    uint64_t y0 = x0, y1 = x1, y2 = x2, y3 = x3, y4 = x4, y5 = x5, y6 = x6, y7 = x7;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (VARIANT == 0) {  // 8 independent mad.lo chains: 8 IMAD
+                asm volatile("mad.lo.u32 %0, %0, %8, %9; mad.lo.u32 %1, %1, %8, %9; mad.lo.u32 %2, %2, %8, %9; mad.lo.u32 %3, %3, %8, %9;"
+                             "mad.lo.u32 %4, %4, %8, %9; mad.lo.u32 %5, %5, %8, %9; mad.lo.u32 %6, %6, %8, %9; mad.lo.u32 %7, %7, %8, %9;"
+                             : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(a), "r"(b));
+            } else if (VARIANT == 1) {  // 8 independent mad.wide chains: 8 IMAD.WIDE = 8 MAC32
+                asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %10, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %10, %3;"
+                             "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %10, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %10, %7;"
+                             : "+l"(y0), "+l"(y1), "+l"(y2), "+l"(y3), "+l"(y4), "+l"(y5), "+l"(y6), "+l"(y7) : "r"(a), "r"(b), "r"(x0));
+            } else {  // the carry-chain shape fe_mul uses: (mad.lo.cc, madc.hi.cc) x4 = 4 MAC32 in 8 instructions
+                asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;"
+                             "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5; madc.lo.cc.u32 %6, %8, %8, %6; madc.hi.u32 %7, %8, %8, %7;"
+                             : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(a), "r"(b), "r"(x0 | 1u));
+            }
+        }
+    }
+    uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)(y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7) ^ (uint32_t)((y0 ^ y3 ^ y5) >> 32);
+    if (r == 0x12345u) out[0] = r;  // practically never; keeps the chains live
+}
+template <int OP>
+__global__ void __launch_bounds__(256) k_fe_bench(uint32_t *out, int iters) {
+    fe a, b;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a.v[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x; b.v[i] = a.v[i] ^ 0x9e3779b9u; }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        if (OP == 0) { fe_mul(a, a, b); fe_mul(b, b, a); }
+        else { fe_sq(a, a); fe_sq(b, b); }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r ^= a.v[i] ^ b.v[i];
+    if (r == 0x12345u) out[0] = r;
+}
+
+// ------------------------------------------------------------------------------------------------ ctx
+template <int W>
+static int build_tables(dapol_ctx *ctx) {
+    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    uint64_t half = 1ull << (W - 1);
+    uint64_t nb = (uint64_t)NWV * half, nbl = (uint64_t)NWR * half;
+    CUDA_TRY(cudaMalloc(&ctx->tab_b, nb * sizeof(ge_niels)));
+    CUDA_TRY(cudaMalloc(&ctx->tab_bbl, nbl * sizeof(ge_niels)));
+    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWV, 0, nb);
+    k_comb_table<W><<<grid_for(nbl, 64), 64, 0, ctx->stream>>>(ctx->tab_bbl, NWR, 1, nbl);
+    ctx->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DAPOL_OK;
+}
+
+extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
+    if (!out) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { g_cuda_err = "no such CUDA device"; return DAPOL_ERR_CUDA; }
+    CUDA_TRY(cudaSetDevice(device));
+    dapol_ctx *ctx = new dapol_ctx();
+    ctx->device = device;
+    ctx->W = comb_window ? comb_window : 8;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &e : ctx->ev) CUDA_TRY(cudaEventCreate(&e));
+    int rc;
+    switch (ctx->W) {
+        case 4: rc = build_tables<4>(ctx); break;
+        case 8: rc = build_tables<8>(ctx); break;
+        case 10: rc = build_tables<10>(ctx); break;
+        case 12: rc = build_tables<12>(ctx); break;
+        default: rc = DAPOL_ERR_BAD_ARG;
+    }
+    if (rc) { dapol_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return DAPOL_OK;
+}
+extern "C" void dapol_ctx_destroy(dapol_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" uint64_t dapol_kernel_launches(const dapol_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]) {
+    if (!ctx) return DAPOL_ERR_BAD_ARG;
+    memcpy(ms, ctx->last_ms, sizeof(float) * 5);
+    return DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scan helper
+struct ScanScratch {
+    uint64_t *tile_sums = nullptr;
+    uint64_t cap = 0;
+};
+static int exclusive_scan(dapol_ctx *ctx, ScanScratch &ss, const uint64_t *in, uint64_t n, uint64_t *out) {
+    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles > ss.cap) {
+        if (ss.tile_sums) CUDA_TRY(cudaFree(ss.tile_sums));
+        CUDA_TRY(cudaMalloc(&ss.tile_sums, ntiles * 8));
+        ss.cap = ntiles;
+    }
+    k_scan_tile_sums<<<(unsigned)ntiles, SCAN_BLOCK, 0, ctx->stream>>>(in, n, ss.tile_sums);
+    k_scan_tile_offsets<<<1, SCAN_BLOCK, 0, ctx->stream>>>(ss.tile_sums, ntiles);
+    k_scan_tile_apply<<<(unsigned)ntiles, SCAN_BLOCK, 0, ctx->stream>>>(in, n, ss.tile_sums, out);
+    ctx->launches += 3;
+    return DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tree build
+extern "C" void dapol_tree_destroy(dapol_tree *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->ns.idx); cudaFree(t->ns.v); cudaFree(t->ns.r); cudaFree(t->ns.comc); cudaFree(t->ns.hash);
+    cudaFree(t->ns.ext); cudaFree(t->ns.is_pad);
+    for (auto p : t->pos) cudaFree(p);
+    cudaFree(t->d_pos); cudaFree(t->d_level_off); cudaFree(t->leaf_index_of);
+    delete t;
+}
+
+template <int W>
+static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
+                            const Seed8 &seed, uint64_t pad_base, int phase) {
+    int H = t->height;
+    if (phase == 0) {
+        if (H == 0) {
+            // single-node tree: the leaf is the root
+            static uint32_t *zero_pos = nullptr;
+            if (!zero_pos) { cudaMalloc(&zero_pos, 4); cudaMemset(zero_pos, 0, 4); }
+            k_leaf<W><<<1, 128, 0, ctx->stream>>>(1, t->ns, 0, zero_pos, t->hash_id, d_values, d_blind, ctx->tab_b, ctx->tab_bbl);
+        } else {
+            k_leaf<W><<<grid_for(t->n_leaves, 128), 128, 0, ctx->stream>>>(t->n_leaves, t->ns, t->level_off[H], t->pos[H], t->hash_id,
+                                                                           d_values, d_blind, ctx->tab_b, ctx->tab_bbl);
+        }
+        ctx->launches++;
+    } else if (t->n_pads) {
+        k_pad<W><<<grid_for(t->n_pads, 128), 128, 0, ctx->stream>>>(t->n_pads, t->ns, d_pad_dest, t->hash_id, seed, pad_base, ctx->tab_bbl);
+        ctx->launches++;
+    }
+}
+
+static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
+                          const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
+    if (!ctx || !out || !d_leaf_idx || !d_values || !d_blindings || !pad_seed) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
+    if (height < 0 || n == 0 || (height == 0 && n != 1) || n >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int H = height;
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
+
+    // leaf index validation
+    int *d_flag = nullptr;
+    CUDA_TRY(cudaMalloc(&d_flag, 4));
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, st));
+    k_check_leaf_idx<<<grid_for(n, 256), 256, 0, st>>>(d_leaf_idx, n, H, d_flag);
+    ctx->launches++;
+    int h_flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_flag);
+    if (h_flag) return DAPOL_ERR_BAD_ARG;
+
+    dapol_tree *t = new dapol_tree();
+    t->ctx = ctx; t->hash_id = hash_id; t->height = H; t->n_leaves = n;
+    t->level_off.assign(H + 1, 0); t->level_n.assign(H + 1, 0); t->n_real.assign(H + 1, 0);
+    t->pos.assign(H + 1, nullptr);
+    int rc = DAPOL_OK;
+    // ---- structure phase 1: per level flags -> scan -> parent indexes (= next level's real nodes)
+    std::vector<uint64_t *> real(H + 1, nullptr), scan(H + 1, nullptr);
+    std::vector<uint64_t> npads(H + 1, 0);
+    uint64_t *d_flags = nullptr, *d_totals = nullptr, *d_pad_dest = nullptr;
+    ScanScratch ss;
+    auto cleanup = [&]() {
+        for (int h = 0; h <= H; h++) { if (h != H) cudaFree(real[h]); cudaFree(scan[h]); }
+        cudaFree(d_flags); cudaFree(d_totals); cudaFree(ss.tile_sums); cudaFree(d_pad_dest);
+    };
+#define TRY_T(expr)                                                         \
+    do {                                                                    \
+        cudaError_t e_ = (expr);                                            \
+        if (e_ != cudaSuccess) {                                            \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            cleanup(); dapol_tree_destroy(t); return DAPOL_ERR_CUDA;        \
+        }                                                                   \
+    } while (0)
+    real[H] = const_cast<uint64_t *>(d_leaf_idx);
+    t->n_real[H] = n;
+    TRY_T(cudaMalloc(&d_flags, n * 8));
+    TRY_T(cudaMalloc(&d_totals, 16));
+    for (int h = H; h >= 1; h--) {
+        uint64_t c = t->n_real[h];
+        TRY_T(cudaMalloc(&scan[h], c * 8));
+        TRY_T(cudaMalloc(&real[h - 1], c * 8));  // upper bound; trimmed logically by n_real
+        k_struct_flags<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, d_flags);
+        ctx->launches++;
+        rc = exclusive_scan(ctx, ss, d_flags, c, scan[h]);
+        if (rc) { cleanup(); dapol_tree_destroy(t); return rc; }
+        k_struct_parent<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, d_flags, scan[h], real[h - 1], d_totals);
+        ctx->launches++;
+        uint64_t totals[2];
+        TRY_T(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, st));
+        TRY_T(cudaStreamSynchronize(st));
+        t->n_real[h - 1] = totals[0];
+        npads[h] = totals[1];
+        t->level_n[h] = 2 * totals[0];
+    }
+    t->level_n[0] = 1;
+    // levels are numbered root-first in the node store
+    uint64_t T = 1;
+    for (int h = 1; h <= H; h++) { t->level_off[h] = T; T += t->level_n[h]; }
+    t->T = T;
+    uint64_t total_pads = 0;
+    for (int h = 1; h <= H; h++) total_pads += npads[h];
+    t->n_pads = total_pads;
+    TRY_T(cudaMalloc(&t->ns.idx, T * 8));
+    TRY_T(cudaMalloc(&t->ns.v, T * 8));
+    TRY_T(cudaMalloc(&t->ns.r, T * 32));
+    TRY_T(cudaMalloc(&t->ns.comc, T * 32));
+    TRY_T(cudaMalloc(&t->ns.hash, T * 32));
+    TRY_T(cudaMalloc(&t->ns.ext, T * 128));
+    TRY_T(cudaMalloc(&t->ns.is_pad, T));
+    TRY_T(cudaMemsetAsync(t->ns.idx, 0, 8, st));
+    TRY_T(cudaMemsetAsync(t->ns.is_pad, 0, 1, st));
+    TRY_T(cudaMalloc(&d_pad_dest, (total_pads + 1) * 8));
+    // ---- structure phase 2: slots, padding destinations (RNG ordinal = creation order: level H..1, left to right)
+    uint64_t ord = 0;
+    for (int h = H; h >= 1; h--) {
+        uint64_t c = t->n_real[h];
+        TRY_T(cudaMalloc(&t->pos[h], c * 4));
+        k_struct_emit<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, scan[h], t->pos[h], t->level_off[h], t->ns, d_pad_dest, ord);
+        ctx->launches++;
+        ord += npads[h];
+    }
+    if (H == 0) TRY_T(cudaMemcpyAsync(t->ns.idx, d_leaf_idx, 8, cudaMemcpyDeviceToDevice, st));
+    TRY_T(cudaEventRecord(ctx->ev[1], st));
+    // ---- leaves, padding nodes
+    Seed8 seed;
+    memcpy(seed.w, pad_seed, 32);
+    const uint32_t *d_blind = reinterpret_cast<const uint32_t *>(d_blindings);
+    for (int phase = 0; phase < 2; phase++) {
+        switch (ctx->W) {
+            case 4: launch_leaf_pad<4>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
+            case 8: launch_leaf_pad<8>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
+            case 10: launch_leaf_pad<10>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
+            case 12: launch_leaf_pad<12>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
+        }
+        TRY_T(cudaEventRecord(ctx->ev[2 + phase], st));
+    }
+    // ---- merges, level by level
+    for (int h = H; h >= 1; h--) {
+        uint64_t np = t->n_real[h - 1];
+        k_merge<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
+        ctx->launches++;
+    }
+    TRY_T(cudaEventRecord(ctx->ev[4], st));
+    // pointer tables for path extraction
+    TRY_T(cudaMalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *)));
+    TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
+    TRY_T(cudaMalloc(&t->d_level_off, (H + 1) * 8));
+    TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
+    TRY_T(cudaGetLastError());
+    TRY_T(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ctx->last_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    cudaEventElapsedTime(&ctx->last_ms[4], ctx->ev[0], ctx->ev[4]);
+    // the extended points are only needed while merging
+    cudaFree(t->ns.ext);
+    t->ns.ext = nullptr;
+    cleanup();
+#undef TRY_T
+    *out = t;
+    return DAPOL_OK;
+}
+
+extern "C" int dapol_tree_build_from_nodes_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx,
+                                               const uint64_t *d_values, const uint8_t *d_blindings, const uint8_t pad_seed[32],
+                                               uint64_t pad_base, dapol_tree **out) {
+    return tree_build_dev(ctx, hash_id, height, n, d_leaf_idx, d_values, d_blindings, pad_seed, pad_base, out);
+}
+extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *leaf_idx,
+                                           const uint64_t *values, const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base,
+                                           dapol_tree **out) {
+    if (!ctx || !leaf_idx || !values || !blindings || n == 0) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t *d_idx = nullptr, *d_val = nullptr;
+    uint8_t *d_bl = nullptr;
+    CUDA_TRY(cudaMalloc(&d_idx, n * 8));
+    CUDA_TRY(cudaMalloc(&d_val, n * 8));
+    CUDA_TRY(cudaMalloc(&d_bl, n * 32));
+    CUDA_TRY(cudaMemcpyAsync(d_idx, leaf_idx, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_val, values, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_bl, blindings, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tree_build_dev(ctx, hash_id, height, n, d_idx, d_val, d_bl, pad_seed, pad_base, out);
+    cudaFree(d_idx); cudaFree(d_val); cudaFree(d_bl);
+    return rc;
+}
+extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *, int, int, uint64_t, const uint8_t *, const uint64_t *, const uint8_t *,
+                                                 const uint64_t *, const uint64_t *, const uint8_t *, uint64_t, const uint8_t *, uint64_t,
+                                                 dapol_tree **, uint64_t *) {
+    g_cuda_err = "dapol_tree_build_from_liabilities: not built yet";
+    return DAPOL_ERR_BAD_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------ accessors
+extern "C" int dapol_tree_height(const dapol_tree *t) { return t ? t->height : -1; }
+extern "C" uint64_t dapol_tree_num_nodes(const dapol_tree *t) { return t ? t->T : 0; }
+extern "C" uint64_t dapol_tree_num_padding(const dapol_tree *t) { return t ? t->n_pads : 0; }
+extern "C" uint64_t dapol_tree_level_size(const dapol_tree *t, int level) {
+    return (t && level >= 0 && level <= t->height) ? t->level_n[level] : 0;
+}
+extern "C" int dapol_tree_level_copy(const dapol_tree *t, int level, uint64_t *idx, uint64_t *values, uint8_t *blindings, uint8_t *coms,
+                                     uint8_t *hashes, uint8_t *is_padding) {
+    if (!t || level < 0 || level > t->height) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(t->ctx->device));
+    uint64_t o = t->level_off[level], n = t->level_n[level];
+    if (idx) CUDA_TRY(cudaMemcpy(idx, t->ns.idx + o, n * 8, cudaMemcpyDeviceToHost));
+    if (values) CUDA_TRY(cudaMemcpy(values, t->ns.v + o, n * 8, cudaMemcpyDeviceToHost));
+    if (blindings) CUDA_TRY(cudaMemcpy(blindings, t->ns.r + 8 * o, n * 32, cudaMemcpyDeviceToHost));
+    if (coms) CUDA_TRY(cudaMemcpy(coms, t->ns.comc + 8 * o, n * 32, cudaMemcpyDeviceToHost));
+    if (hashes) CUDA_TRY(cudaMemcpy(hashes, t->ns.hash + 8 * o, n * 32, cudaMemcpyDeviceToHost));
+    if (is_padding) CUDA_TRY(cudaMemcpy(is_padding, t->ns.is_pad + o, n, cudaMemcpyDeviceToHost));
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_root(const dapol_tree *t, uint8_t com[32], uint8_t hash[32], uint64_t *value, uint8_t blinding[32]) {
+    return dapol_tree_level_copy(t, 0, nullptr, value, blinding, com, hash, nullptr);
+}
+extern "C" int dapol_tree_leaf_index_of(const dapol_tree *t, uint64_t input_pos, uint64_t *leaf_idx) {
+    if (!t || !leaf_idx) return DAPOL_ERR_BAD_ARG;
+    if (!t->leaf_index_of || input_pos >= t->n_leaves) return DAPOL_ERR_NOT_FOUND;
+    CUDA_TRY(cudaMemcpy(leaf_idx, t->leaf_index_of + input_pos, 8, cudaMemcpyDeviceToHost));
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t *values, uint8_t *blindings,
+                                uint8_t *coms, uint8_t *hashes, uint8_t *leaf_coms, uint8_t *leaf_hashes) {
+    if (!t || !leaf_idx || !values || !blindings || !coms || !hashes || k == 0) return DAPOL_ERR_BAD_ARG;
+    dapol_ctx *ctx = t->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint64_t H = (uint64_t)t->height, kh = k * (H ? H : 1);
+    uint64_t *d_li = nullptr, *d_v = nullptr;
+    uint32_t *d_r = nullptr, *d_c = nullptr, *d_h = nullptr, *d_lc = nullptr, *d_lh = nullptr;
+    int *d_nf = nullptr, nf = 0;
+    CUDA_TRY(cudaMalloc(&d_li, k * 8)); CUDA_TRY(cudaMalloc(&d_v, kh * 8));
+    CUDA_TRY(cudaMalloc(&d_r, kh * 32)); CUDA_TRY(cudaMalloc(&d_c, kh * 32)); CUDA_TRY(cudaMalloc(&d_h, kh * 32));
+    CUDA_TRY(cudaMalloc(&d_lc, k * 32)); CUDA_TRY(cudaMalloc(&d_lh, k * 32)); CUDA_TRY(cudaMalloc(&d_nf, 4));
+    CUDA_TRY(cudaMemsetAsync(d_nf, 0, 4, st));
+    CUDA_TRY(cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st));
+    k_paths<<<grid_for(k, 128), 128, 0, st>>>(k, d_li, t->ns, t->d_level_off, t->level_n[t->height], t->d_pos, t->height, d_v, d_r, d_c, d_h,
+                                              d_lc, d_lh, d_nf);
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st));
+    if (H) {
+        CUDA_TRY(cudaMemcpyAsync(values, d_v, kh * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(blindings, d_r, kh * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(coms, d_c, kh * 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hashes, d_h, kh * 32, cudaMemcpyDeviceToHost, st));
+    }
+    if (leaf_coms) CUDA_TRY(cudaMemcpyAsync(leaf_coms, d_lc, k * 32, cudaMemcpyDeviceToHost, st));
+    if (leaf_hashes) CUDA_TRY(cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_li); cudaFree(d_v); cudaFree(d_r); cudaFree(d_c); cudaFree(d_h); cudaFree(d_lc); cudaFree(d_lh); cudaFree(d_nf);
+    return nf ? DAPOL_ERR_NOT_FOUND : DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ micro entry points
+extern "C" int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *values, const uint8_t *blindings, uint8_t *coms) {
+    if (!ctx || !values || !blindings || !coms || n == 0) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint64_t *d_v = nullptr; uint32_t *d_b = nullptr, *d_o = nullptr;
+    CUDA_TRY(cudaMalloc(&d_v, n * 8)); CUDA_TRY(cudaMalloc(&d_b, n * 32)); CUDA_TRY(cudaMalloc(&d_o, n * 32));
+    CUDA_TRY(cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_b, blindings, n * 32, cudaMemcpyHostToDevice, st));
+    unsigned g = grid_for(n, 128);
+    switch (ctx->W) {
+        case 4: k_commit<4><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+        case 8: k_commit<8><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+        case 10: k_commit<10><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+        case 12: k_commit<12><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(coms, d_o, n * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_v); cudaFree(d_b); cudaFree(d_o);
+    return DAPOL_OK;
+}
+
+template <typename F>
+static int time_kernel(dapol_ctx *ctx, F launch, float *ms_best) {
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(a, ctx->stream));
+        launch();
+        ctx->launches++;
+        CUDA_TRY(cudaEventRecord(b, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms; CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *ms_best = best;
+    return DAPOL_OK;
+}
+extern "C" int dapol_imad_peak(dapol_ctx *ctx, int variant, double *gmac_per_s) {
+    if (!ctx || !gmac_per_s || variant < 0 || variant > 2) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    uint32_t *d_out; CUDA_TRY(cudaMalloc(&d_out, 4));
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8, threads = 256;
+    float ms; int rc;
+    if (variant == 0) rc = time_kernel(ctx, [&]() { k_imad_peak<0><<<blocks, threads, 0, ctx->stream>>>(d_out, 0x9e3779b1u, 0x7f4a7c15u, iters); }, &ms);
+    else if (variant == 1) rc = time_kernel(ctx, [&]() { k_imad_peak<1><<<blocks, threads, 0, ctx->stream>>>(d_out, 0x9e3779b1u, 0x7f4a7c15u, iters); }, &ms);
+    else rc = time_kernel(ctx, [&]() { k_imad_peak<2><<<blocks, threads, 0, ctx->stream>>>(d_out, 0x9e3779b1u, 0x7f4a7c15u, iters); }, &ms);
+    cudaFree(d_out);
+    if (rc) return rc;
+    // instructions per thread: iters * 8 * 8; MAC32 per instruction: variant 0: 1 (32-bit low product only), 1: 1, 2: 0.5
+    double instr = (double)blocks * threads * iters * 64.0;
+    double macs = variant == 2 ? instr * 0.5 : instr;
+    *gmac_per_s = macs / (ms * 1e-3) / 1e9;
+    return DAPOL_OK;
+}
+extern "C" int dapol_fe_bench(dapol_ctx *ctx, int op, double *gop_per_s) {
+    if (!ctx || !gop_per_s || op < 0 || op > 1) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, ctx->device));
+    uint32_t *d_out; CUDA_TRY(cudaMalloc(&d_out, 4));
+    const int iters = 2048, blocks = prop.multiProcessorCount * 8, threads = 256;
+    float ms; int rc;
+    if (op == 0) rc = time_kernel(ctx, [&]() { k_fe_bench<0><<<blocks, threads, 0, ctx->stream>>>(d_out, iters); }, &ms);
+    else rc = time_kernel(ctx, [&]() { k_fe_bench<1><<<blocks, threads, 0, ctx->stream>>>(d_out, iters); }, &ms);
+    cudaFree(d_out);
+    if (rc) return rc;
+    *gop_per_s = (double)blocks * threads * iters * 2.0 / (ms * 1e-3) / 1e9;
+    return DAPOL_OK;
+}

@@ -1,0 +1,202 @@
+// Per-thread bodies of the level-synchronous padded sparse-Merkle-sum-tree build.
+//
+// What the reference does one node at a time on one CPU thread
+//   (/root/reference/src/dapol/mod.rs:118-121 -> smtree SparseMerkleTree::build, calling back into
+//    DapolNode::new / ::padding / ::merge, src/dapol/node.rs:29-45,64-80,86-88)
+// is split here into data-parallel passes over flat per-level arrays in HBM:
+//   structure pass  (integer/HBM-bound): pair detection, parent ranks, padding-node slots + RNG ordinals
+//   leaf pass       (IMAD-bound): v*B + r*B_blinding by fixed-base comb, compress, D(com)
+//   padding pass    (IMAD-bound): ChaCha20 draw -> r*B_blinding, compress, D(com)     [dominant, SURVEY F7]
+//   merge pass/level(IMAD-bound): point add, compress, D(C_L||C_R||H_L||H_R), v and r sums
+//
+// Node store (struct of arrays, one global numbering): level h (0 = root .. H = leaves) occupies
+// [level_off[h], level_off[h] + n_h); inside a level the two children of parent j sit at 2j, 2j+1,
+// so a node's sibling is position ^ 1 and no child pointers are stored.
+#pragma once
+#include "ge25519.cuh"
+#include "hash_dev.cuh"
+
+struct NodeStore {
+    uint64_t *idx;     // [T] tree index (path bits) of the node inside its level
+    uint64_t *v;       // [T] liability sum
+    uint32_t *r;       // [T][8] blinding factor words (leaves: as given, possibly unreduced; else canonical)
+    uint32_t *comc;    // [T][8] compress(com)
+    uint32_t *hash;    // [T][8] node hash
+    uint32_t *ext;     // [T][32] com in extended coordinates X,Y,Z,T (build-time only)
+    uint8_t *is_pad;   // [T]
+};
+
+DAPOL_HD_INLINE void store_ge(uint32_t *dst, const ge &p) {
+    store8(dst, p.X.v); store8(dst + 8, p.Y.v); store8(dst + 16, p.Z.v); store8(dst + 24, p.T.v);
+}
+DAPOL_HD_INLINE void load_ge(ge &p, const uint32_t *src) {
+    load8(p.X.v, src); load8(p.Y.v, src + 8); load8(p.Z.v, src + 16); load8(p.T.v, src + 24);
+}
+// ------------------------------------------------------------------------------------------------
+// structure pass, level h: idx[0..c) = sorted tree indexes of the real (non-padding) nodes
+// flags[k] = (starts_new_parent << 32) | is_lone
+DAPOL_HD_INLINE uint64_t struct_flags_body(uint64_t k, const uint64_t *idx, uint64_t c) {
+    uint64_t x = idx[k];
+    int newp = (k == 0) || ((idx[k - 1] >> 1) != (x >> 1));
+    int has_sib = (k > 0 && idx[k - 1] == (x ^ 1)) || (k + 1 < c && idx[k + 1] == (x ^ 1));
+    return ((uint64_t)newp << 32) | (uint64_t)(!has_sib);
+}
+// scan[k] = exclusive prefix sum of flags.  Phase 1 (before the node store exists): compact the parents'
+// tree indexes (= the next level's real nodes) and report the level's totals.
+DAPOL_HD_INLINE void struct_parent_body(uint64_t k, const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *scan,
+                                        uint64_t *parent_idx, uint64_t *totals /*[2]: parents, pads*/) {
+    uint64_t f = flags[k], s = scan[k];
+    uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
+    if (newp) parent_idx[s >> 32] = idx[k] >> 1;
+    if (k == c - 1) {
+        totals[0] = (s >> 32) + newp;
+        totals[1] = (s & 0xffffffffull) + lone;
+    }
+}
+// Phase 2: for real node k: its slot in the level's node array; for a lone node also its padding
+// sibling's slot + idx and the pad's destination (global node number) at its RNG ordinal.
+DAPOL_HD_INLINE void struct_emit_body(uint64_t k, const uint64_t *idx, uint64_t c, const uint64_t *scan, uint32_t *pos,
+                                      uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
+    uint64_t x = idx[k], f = struct_flags_body(k, idx, c), s = scan[k];
+    uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
+    uint64_t j = (s >> 32) - (newp ? 0 : 1);
+    uint64_t q = s & 0xffffffffull;
+    uint32_t slot = (uint32_t)(x & 1);
+    uint64_t p = 2 * j + slot;
+    pos[k] = (uint32_t)p;
+    ns.idx[level_off + p] = x;
+    ns.is_pad[level_off + p] = 0;
+    if (lone) {
+        uint64_t pp = 2 * j + (1 - slot);
+        ns.idx[level_off + pp] = x ^ 1;
+        ns.is_pad[level_off + pp] = 1;
+        pad_dest[pad_ord_base + q] = level_off + pp;
+    }
+}
+// leaf input validation: strictly increasing and inside the tree
+DAPOL_HD_INLINE int leaf_idx_bad(uint64_t k, const uint64_t *idx, int height) {
+    uint64_t x = idx[k];
+    if (height < 64 && (x >> height)) return 1;
+    return k > 0 && idx[k - 1] >= x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// node finalisation shared by leaves and padding nodes: hash = D(compress(com))  (node.rs:33-36)
+DAPOL_HD_INLINE void node_finish(const NodeStore &ns, uint64_t g, int hash_id, const ge &com, uint64_t v, const uint32_t r[8]) {
+    uint32_t cc[8], hh[8];
+    ge_compress(cc, com);
+    dapol_hash32(hash_id, hh, cc);
+    ns.v[g] = v;
+    store8(ns.r + 8 * g, r);
+    store8(ns.comc + 8 * g, cc);
+    store8(ns.hash + 8 * g, hh);
+    store_ge(ns.ext + 32 * g, com);
+}
+
+// DapolNode::new(value, blinding) (node.rs:29-45): com = v*B + r*B_blinding by signed-window comb.
+template <int W>
+DAPOL_HD_INLINE void leaf_body(uint64_t i, const NodeStore &ns, uint64_t level_off, const uint32_t *pos, int hash_id,
+                               const uint64_t *values, const uint32_t *blind /*[n][8]*/, const ge_niels *tab_b,
+                               const ge_niels *tab_bbl) {
+    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    uint32_t rw[8];
+    load8(rw, blind + 8 * i);
+    sc rs, rr;
+#pragma unroll
+    for (int k = 0; k < 8; k++) rs.v[k] = rw[k];
+    sc_reduce256(rr, rs);
+    uint64_t v = values[i];
+    uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
+    int32_t dr[NWR], dv[NWV];
+    sc_signed_digits<W, NWR>(dr, rr.v, 8);
+    sc_signed_digits<W, NWV>(dv, vw, 2);
+    ge acc;
+    ge_identity(acc);
+    ge_comb_accumulate<W, NWV>(acc, tab_b, dv);
+    ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
+    node_finish(ns, level_off + pos[i], hash_id, acc, v, rw);
+}
+
+// DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng)); rng draw #g of the seeded stream =
+// from_bytes_mod_order_wide(ChaCha20(pad_seed) block pad_base + g)   (RNG contract)
+template <int W>
+DAPOL_HD_INLINE void pad_body(uint64_t g, const NodeStore &ns, const uint64_t *pad_dest, int hash_id, const uint32_t seed[8],
+                              uint64_t pad_base, const ge_niels *tab_bbl) {
+    constexpr int NWR = 253 / W + 1;
+    uint32_t ks[16];
+    chacha20_block(ks, seed, pad_base + g, 0);
+    sc r;
+    sc_from_wide(r, ks);
+    int32_t dr[NWR];
+    sc_signed_digits<W, NWR>(dr, r.v, 8);
+    ge acc;
+    ge_identity(acc);
+    ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
+    node_finish(ns, pad_dest[g], hash_id, acc, 0, r.v);
+}
+
+// Mergeable::merge (node.rs:64-80) for parent j of the level whose children start at child_off:
+// hash = D(C(L)||C(R)||H(L)||H(R)); v, r, com = sums.  dest = global slot of the parent.
+DAPOL_HD_INLINE void merge_body(uint64_t j, const NodeStore &ns, uint64_t child_off, uint64_t dest, int hash_id) {
+    uint64_t l = child_off + 2 * j, r = l + 1;
+    uint32_t cl[8], cr[8], hl[8], hr[8], hh[8];
+    load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
+    load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
+    dapol_hash128(hash_id, hh, cl, cr, hl, hr);
+    store8(ns.hash + 8 * dest, hh);
+    ns.v[dest] = ns.v[l] + ns.v[r];  // u64 wrapping add, as release-mode Rust
+    sc a, b, s;
+    load8(a.v, ns.r + 8 * l); load8(b.v, ns.r + 8 * r);
+    sc_reduce256(a, a); sc_reduce256(b, b);  // leaf blindings may be unreduced (Scalar::from_bits)
+    sc_add(s, a, b);
+    store8(ns.r + 8 * dest, s.v);
+    ge p, q, sum;
+    load_ge(p, ns.ext + 32 * l); load_ge(q, ns.ext + 32 * r);
+    ge_add(sum, p, q);
+    store_ge(ns.ext + 32 * dest, sum);
+    uint32_t cc[8];
+    ge_compress(cc, sum);
+    store8(ns.comc + 8 * dest, cc);
+}
+
+// comb table entry (k, e): (e+1) * 2^(W k) * P in affine Niels form
+template <int W>
+DAPOL_HD_INLINE void comb_table_body(uint64_t t, ge_niels *table, int nw, int which /*0 = B, 1 = B_blinding*/) {
+    uint32_t half = 1u << (W - 1);
+    uint32_t k = (uint32_t)(t / half), e = (uint32_t)(t % half);
+    if ((int)k >= nw) return;
+    ge base;
+    if (which == 0) ge_basepoint(base); else ge_bblinding(base);
+#pragma unroll 1
+    for (uint32_t i = 0; i < k * W; i++) ge_dbl(base, base);
+    // (e+1) * base by left-to-right double-and-add
+    uint32_t m = e + 1;
+    ge acc = base;
+    int top = 31;
+    while (!((m >> top) & 1u)) top--;
+#pragma unroll 1
+    for (int b = top - 1; b >= 0; b--) {
+        ge_dbl(acc, acc);
+        if ((m >> b) & 1u) ge_add(acc, acc, base);
+    }
+    ge_niels n;
+    ge_to_niels(n, acc);
+    table[t] = n;
+}
+
+// path extraction (Dapol::generate_proof's get_merkle_path_ref_batch, mod.rs:173): siblings leaf level
+// first.  leaf_pos = slot of the leaf inside level H.  pos_maps[h] = slot map of level h's real nodes.
+struct PathOut {
+    uint64_t *v;      // [K][H]
+    uint32_t *r;      // [K][H][8]
+    uint32_t *comc;   // [K][H][8]
+    uint32_t *hash;   // [K][H][8]
+};
+DAPOL_HD_INLINE int64_t find_leaf_slot(const uint64_t *lvl_idx, uint64_t n, uint64_t leaf_idx) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (lvl_idx[mid] < leaf_idx) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && lvl_idx[lo] == leaf_idx) ? (int64_t)lo : -1;
+}

@@ -1,0 +1,122 @@
+/* dapol_b200 -- C ABI of the B200-native DAPOL+ hot path (tree build, inclusion proofs, range proofs).
+ *
+ * Drop-in boundary for the reference crate MystenLabs/dapol (/root/reference): each entry point
+ * names the reference interface it replaces.  The reference is generic Rust over a digest D and a
+ * range-proof policy R; here D is `hash_id` (BLAKE3 or BLAKE2s-256, 32-byte digests only --
+ * src/dapol/mod.rs:101-103) and R is `policy`.
+ *
+ * Conventions: plain pointers and sizes, caller-allocated little-endian flat buffers, `int` return
+ * (0 = ok; 1..5 mirror src/errors.rs DapolError variants; >= 16 are boundary errors), never unwinds.
+ * Handles are opaque and owned by the library.  A tree handle is immutable after build.
+ * There is NO CPU fallback: every compute entry point fails with DAPOL_ERR_CUDA when no sm_100
+ * device is usable.
+ *
+ * Randomness contract (the reference draws from thread_rng(), src/dapol/node.rs:87 and
+ * bulletproofs' prove_*; bit-exactness is defined against an injected stream):
+ *   ChaCha20 (rand_chacha::ChaCha20Rng layout: 64-bit block counter, 64-bit stream id);
+ *   k-th Scalar::random = from_bytes_mod_order_wide(keystream block k).
+ *   Padding nodes: stream 0, block pad_base + creation ordinal (level H..1, left to right).
+ *   Range proof #q of the inclusion proof for leaf x: stream x, blocks (q << 32) + draw#.
+ */
+#ifndef DAPOL_B200_H
+#define DAPOL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DAPOL_API __attribute__((visibility("default")))
+#else
+#define DAPOL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: 1..5 = src/errors.rs:5-17 in declaration order */
+#define DAPOL_OK 0
+#define DAPOL_ERR_TREE_HEIGHT_TOO_BIG 1
+#define DAPOL_ERR_SPARSITY_TOO_SMALL 2
+#define DAPOL_ERR_INVALID_DIGEST_SIZE 3
+#define DAPOL_ERR_DUPLICATED_INTERNAL_ID 4
+#define DAPOL_ERR_FAILED_TO_MAP_INDEX 5
+#define DAPOL_ERR_BAD_ARG 16     /* reference: panic (slice OOB, unsorted input, ...) */
+#define DAPOL_ERR_NOT_FOUND 17   /* reference: Option::None from generate_proof* */
+#define DAPOL_ERR_BUFFER 18      /* caller buffer too small; required size is reported */
+#define DAPOL_ERR_CUDA 19        /* no device / CUDA runtime failure (see dapol_last_cuda_error) */
+#define DAPOL_ERR_DECODE 20      /* smtree DecodingError / bulletproofs ProofError::FormatError */
+
+#define DAPOL_HASH_BLAKE3 0   /* blake3::Hasher     (benches/dapol.rs:38, src/tests.rs:102-103) */
+#define DAPOL_HASH_BLAKE2S 1  /* blake2::Blake2s    (src/dapol/tests.rs:13,21) */
+
+#define DAPOL_POLICY_PADDING 0    /* RangeProofPadding   (src/range/padding.rs) */
+#define DAPOL_POLICY_SPLITTING 1  /* RangeProofSplitting (src/range/splitting.rs) */
+
+#define DAPOL_MAX_TREE_HEIGHT 64  /* src/dapol/mod.rs:26 */
+
+typedef struct dapol_ctx dapol_ctx;
+typedef struct dapol_tree dapol_tree;
+
+/* Context = one CUDA device + its stream + the precomputed generator tables
+ * (PedersenGens::default(), src/dapol/node.rs:31; BulletproofGens::new, src/range/mod.rs:50,66 --
+ * the reference re-derives them on every call, here once).  comb_window = 0 picks the default. */
+DAPOL_API int dapol_ctx_create(int device, int comb_window, dapol_ctx **out);
+DAPOL_API void dapol_ctx_destroy(dapol_ctx *ctx);
+DAPOL_API const char *dapol_strerror(int code);
+DAPOL_API const char *dapol_last_cuda_error(void);
+
+/* Dapol::new_blank(height, _) + Dapol::build(&items, &secret)   (src/dapol/mod.rs:196-208; the path
+ * benches/dapol.rs:149-158 times).  Items = DapolNode::new(values[i], blindings[i]) at
+ * TreeIndex::from_u64(height, leaf_idx[i]); leaf_idx strictly increasing.  Host buffers. */
+DAPOL_API int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *leaf_idx,
+                                const uint64_t *values, const uint8_t *blindings /* n*32 */, const uint8_t pad_seed[32],
+                                uint64_t pad_base, dapol_tree **out);
+/* Same with the three input arrays already resident in device memory (HBM). */
+DAPOL_API int dapol_tree_build_from_nodes_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx,
+                                    const uint64_t *d_values, const uint8_t *d_blindings, const uint8_t pad_seed[32],
+                                    uint64_t pad_base, dapol_tree **out);
+
+/* Dapol::new(liabilities, options)   (src/dapol/mod.rs:100-128): argument checks, build_leaf_nodes
+ * (mod.rs:323-399: audit_id / index_seed / shuffle_index / blind_seed), sort, build.
+ * Ids are concatenated in a blob with n+1 offsets.  On DUPLICATED_INTERNAL_ID / FAILED_TO_MAP_INDEX
+ * *err_pos receives the input position of the offending liability. */
+DAPOL_API int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *iid_blob,
+                                      const uint64_t *iid_off, const uint8_t *eid_blob, const uint64_t *eid_off,
+                                      const uint64_t *values, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                      const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos);
+
+DAPOL_API void dapol_tree_destroy(dapol_tree *tree);
+
+/* Dapol::root_raw / root   (src/dapol/mod.rs:134-141): commitment (compressed), hash, value, blinding. */
+DAPOL_API int dapol_tree_root(const dapol_tree *tree, uint8_t com[32], uint8_t hash[32], uint64_t *value, uint8_t blinding[32]);
+
+/* Tree introspection for parity dumps: level 0 = root .. height = leaves; nodes of a level are in tree
+ * order with the two children of a parent adjacent. */
+DAPOL_API int dapol_tree_height(const dapol_tree *tree);
+DAPOL_API uint64_t dapol_tree_num_nodes(const dapol_tree *tree);
+DAPOL_API uint64_t dapol_tree_num_padding(const dapol_tree *tree);
+DAPOL_API uint64_t dapol_tree_level_size(const dapol_tree *tree, int level);
+DAPOL_API int dapol_tree_level_copy(const dapol_tree *tree, int level, uint64_t *idx, uint64_t *values, uint8_t *blindings,
+                          uint8_t *coms, uint8_t *hashes, uint8_t *is_padding); /* any pointer may be NULL */
+/* id -> TreeIndex map of Dapol::new (id_to_idx_map, mod.rs:80,389): leaf index of the i-th input liability */
+DAPOL_API int dapol_tree_leaf_index_of(const dapol_tree *tree, uint64_t input_pos, uint64_t *leaf_idx);
+
+/* smtree get_merkle_path_ref_batch for one leaf (src/dapol/mod.rs:173-184): the K x height siblings,
+ * leaf level first, with their secret (value, blinding) and public (com, hash) parts. */
+DAPOL_API int dapol_tree_paths(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t *values /* k*h */,
+                     uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*32 */,
+                     uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*32 or NULL */);
+
+/* Micro-entry points used by the parity tests and the roofline microbenchmark. */
+DAPOL_API int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *values, const uint8_t *blindings, uint8_t *coms /* n*32 */);
+DAPOL_API int dapol_imad_peak(dapol_ctx *ctx, int variant, double *gmac_per_s); /* measured 32x32->64 MAC/s, variant 0..3 */
+DAPOL_API int dapol_fe_bench(dapol_ctx *ctx, int op, double *gop_per_s);        /* field mul(0)/sq(1) throughput, Gop/s */
+DAPOL_API uint64_t dapol_kernel_launches(const dapol_ctx *ctx);                 /* kernels launched so far on this ctx */
+/* device-time of the last tree build on this ctx, split per phase (ms, CUDA events on the ctx stream):
+ * [0] structure, [1] leaves, [2] padding, [3] merges, [4] total */
+DAPOL_API int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+"""GPU parity tests (run on the B200 box): the CUDA tree build, called through the C ABI, against the
+CPU oracle (oracle/c via ctypes) on the same seeded inputs -- bit-exact for every node of every level."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PAD_SEED = hashlib.sha256(b"dapol-b200").digest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from dapol_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _inputs(H, n, seed, stride=False):
+    rnd = random.Random(seed)
+    if stride:  # benches/dapol.rs:160-175 layout: leaf i at i * 2^H / n
+        idx = np.arange(n, dtype=np.uint64) * np.uint64((1 << H) // n)
+    else:
+        idx = np.array(sorted(rnd.sample(range(1 << H), n)) if H < 40 else sorted({rnd.randrange(1 << H) for _ in range(n)}), np.uint64)
+    n = len(idx)
+    vals = np.array([rnd.randrange(1 << 32) for _ in range(n)], np.uint64)
+    bl = np.frombuffer(rnd.randbytes(32 * n), np.uint8).copy().reshape(n, 32)
+    bl[:, 31] &= 0x7F  # Scalar::from_bits domain (possibly unreduced)
+    return idx, vals, bl
+
+
+def _assert_same_tree(gpu, oracle_tree, H):
+    assert gpu.num_padding == oracle_tree.num_pads
+    for h in range(H + 1):
+        g, o = gpu.level(h), oracle_tree.level(h)
+        assert len(g["idx"]) == len(o["idx"]), h
+        for key in ("idx", "v", "comc", "hash", "is_pad"):
+            assert (g[key] == o[key]).all(), (h, key)
+        L = 2 ** 252 + 27742317777372353535851937790883648493
+        gr = [int.from_bytes(x.tobytes(), "little") % L for x in g["r"]]
+        orr = [int.from_bytes(x.tobytes(), "little") % L for x in o["r"]]
+        assert gr == orr, h
+
+
+def test_commit_batch_vs_oracle(ctx, cref):
+    rnd = random.Random(11)
+    vals = [0, 1, 5, 2 ** 64 - 1] + [rnd.randrange(1 << 64) for _ in range(300)]
+    bls = [(1).to_bytes(32, "little"), (7).to_bytes(32, "little"), bytes(32), ((1 << 255) - 1).to_bytes(32, "little")]
+    bls += [(rnd.randrange(1 << 255)).to_bytes(32, "little") for _ in range(300)]
+    out = ctx.commit_batch(vals, np.frombuffer(b"".join(bls), np.uint8))
+    for v, b, c in zip(vals, bls, out):
+        assert c.tobytes() == cref.commit(v, b)
+    assert out[1].tobytes().hex() != "" and ctx.commit_batch([5], np.frombuffer((7).to_bytes(32, "little"), np.uint8))[0].tobytes().hex() == \
+        "84dcc85db7eef17103ea879c4900162127debe4b41a8f06012a25911292aff18"
+
+
+@pytest.mark.parametrize("hash_id,H,n,stride", [
+    (0, 6, 9, False), (1, 4, 4, False), (0, 10, 200, False), (0, 16, 1024, True), (0, 16, 1024, False),
+    (1, 12, 300, False), (0, 3, 4, False), (0, 1, 1, False), (0, 1, 2, False), (0, 5, 1, False),
+    (0, 32, 2048, True), (0, 40, 500, False), (0, 64, 100, False), (0, 0, 1, False)])
+def test_tree_every_node_vs_oracle(ctx, cref, hash_id, H, n, stride):
+    from dapol_b200 import Dapol
+    idx, vals, bl = _inputs(H, n, 1000 + H * 7 + n, stride)
+    if H == 0:
+        idx = np.zeros(1, np.uint64)
+    gpu = Dapol.new_blank(ctx, hash_id, H, H).build(idx, vals, bl, PAD_SEED, 5)
+    ora = cref.Tree(hash_id, H, idx, vals, bl, PAD_SEED, 5)
+    _assert_same_tree(gpu, ora, H)
+    r, o = gpu.root_raw(), ora.root()
+    assert (r.value, r.com, r.hash) == (o["v"], o["comc"], o["hash"])
+    assert r.value == int(vals.sum()) % (1 << 64)  # liability-sum homomorphism (src/dapol/tests.rs:24)
+    gpu.close()
+
+
+def test_reference_kat_tree(ctx, cref):
+    """src/dapol/tests.rs:17-25: leaves at 7,12,2,4 (Blake2s, H=4), root value 26."""
+    from dapol_b200 import Dapol
+    ib, io = cref.pack_ids([b"a", b"b", b"c", b"d"]); eb, eo = cref.pack_ids([b"w", b"x", b"y", b"z"])
+    rc, idx, bl, _ = cref.derive_leaves(1, ib, io, eb, eo, b"test", 4)
+    order = np.argsort(idx)
+    gpu = Dapol.new_blank(ctx, 1, 4, 2).build(idx[order], np.array([3, 5, 7, 11], np.uint64)[order], bl[order], PAD_SEED)
+    assert gpu.root_raw().value == 26
+    lv = gpu.level(4)
+    k = list(lv["idx"]).index(7)
+    assert lv["comc"][k].tobytes().hex() == "bc9f755eff46224952e6c00e1ad0cef3d8e3393254af927c593ea1702e64e93a"
+    assert lv["hash"][k].tobytes().hex() == "b1a1242d5ad2d09503b05d312f13b5c88440fb30a5db0b6aa62881bae94a44fb"
+
+
+def test_paths_vs_oracle(ctx, cref):
+    from dapol_b200 import Dapol
+    H, n = 12, 300
+    idx, vals, bl = _inputs(H, n, 77)
+    gpu = Dapol.new_blank(ctx, 0, H, H).build(idx, vals, bl, PAD_SEED)
+    ora = cref.Tree(0, H, idx, vals, bl, PAD_SEED)
+    pick = idx[[0, 5, 17, 150, 299]]
+    p = gpu.paths(pick)
+    for q, leaf in enumerate(pick):
+        o = ora.path(int(leaf))
+        assert (p["v"][q] == o["v"]).all() and (p["comc"][q] == o["comc"]).all() and (p["hash"][q] == o["hash"]).all()
+        nd = ora.get_node(H, int(leaf))
+        assert p["leaf_comc"][q].tobytes() == nd["comc"] and p["leaf_hash"][q].tobytes() == nd["hash"]
+    absent = next(x for x in range(1 << H) if x not in set(idx.tolist()))
+    assert gpu.paths([absent]) is None  # reference: None for an unknown index (mod.rs:173)
+
+
+def test_bad_inputs(ctx):
+    from dapol_b200 import Dapol, DapolError
+    idx, vals, bl = _inputs(8, 10, 3)
+    with pytest.raises(DapolError) as e:
+        Dapol.new_blank(ctx, 0, 8, 8).build(idx[::-1].copy(), vals, bl, PAD_SEED)  # unsorted (smtree rejects)
+    assert e.value.code == 16
+    with pytest.raises(DapolError) as e:
+        Dapol.new_blank(ctx, 0, 65, 8).build(idx, vals, bl, PAD_SEED)
+    assert e.value.code == 1
+    with pytest.raises(DapolError) as e:
+        Dapol.new_blank(ctx, 0, 3, 3).build(idx, vals, bl, PAD_SEED)  # index outside the tree
+    assert e.value.code == 16
+
+
+def test_large_tree_properties(ctx, cref):
+    """2^16 leaves at H=32: full parity with the oracle at a size it finishes in seconds (8 threads),
+    plus size-independent properties: root value = sum, padding count formula, sibling adjacency."""
+    from dapol_b200 import Dapol
+    H, n = 32, 1 << 14
+    idx, vals, bl = _inputs(H, n, 5)
+    gpu = Dapol.new_blank(ctx, 0, H, H).build(idx, vals, bl, PAD_SEED)
+    ora = cref.Tree(0, H, idx, vals, bl, PAD_SEED)
+    r, o = gpu.root_raw(), ora.root()
+    assert (r.value, r.com, r.hash) == (o["v"], o["comc"], o["hash"])
+    assert gpu.num_padding == ora.num_pads
+    for h in (H, H - 1, 20, 8, 1):
+        g, oo = gpu.level(h), ora.level(h)
+        assert (g["comc"] == oo["comc"]).all() and (g["hash"] == oo["hash"]).all()
+        assert ((g["idx"][0::2] ^ 1) == g["idx"][1::2]).all()
