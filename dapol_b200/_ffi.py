@@ -27,6 +27,9 @@ def lib():
     L.dapol_last_cuda_error.restype = C.c_char_p
     L.dapol_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     L.dapol_ctx_destroy.argtypes = [vp]
+    L.dapol_ctx_set_stream.argtypes = [vp, vp]
+    L.dapol_tree_build_from_liabilities_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, u64, vp, u64,
+                                                        C.POINTER(vp), C.POINTER(u64)]
     L.dapol_tree_destroy.argtypes = [vp]
     L.dapol_tree_build_from_nodes.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
     L.dapol_tree_build_from_nodes_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]

@@ -59,6 +59,10 @@ class Context:
 
     __del__ = close
 
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _check(_ffi.lib().dapol_ctx_set_stream(self._h, cuda_stream))
+
     @property
     def kernel_launches(self) -> int:
         return _ffi.lib().dapol_kernel_launches(self._h)
@@ -160,6 +164,51 @@ class Dapol:
                                                           d_blindings, seed, pad_base, C.byref(h)))
         self._t = h
         return self
+
+    @staticmethod
+    def pack_ids(ids):
+        """list of bytes -> (blob u8[], offsets u64[n+1]) as the C ABI takes them."""
+        off = np.zeros(len(ids) + 1, dtype=np.uint64)
+        if len(ids):
+            off[1:] = np.cumsum([len(x) for x in ids], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(ids) or b"\0", dtype=np.uint8).copy()
+        return blob, off
+
+    @classmethod
+    def new(cls, ctx, hash_id, liabilities, audit_seed: bytes, tree_height: int, aggregation_factor: int, pad_seed: bytes,
+            policy=POLICY_PADDING, pad_base: int = 0):
+        """Dapol::new(liabilities, options) (mod.rs:100-128).  liabilities = [(internal_id, external_id, value)] or the
+        packed form (iid_blob, iid_off, eid_blob, eid_off, values).  `secret` of DapolOptions is ignored by the
+        reference's padding (node.rs:86); pad_seed seeds the padding RNG stream instead."""
+        self = cls(ctx, hash_id, tree_height, aggregation_factor, policy)
+        if isinstance(liabilities, tuple) and len(liabilities) == 5 and isinstance(liabilities[0], np.ndarray):
+            ib, io, eb, eo, vals = liabilities
+        else:
+            ib, io = cls.pack_ids([x[0] for x in liabilities])
+            eb, eo = cls.pack_ids([x[1] for x in liabilities])
+            vals = np.array([x[2] for x in liabilities], np.uint64)
+        ib = np.ascontiguousarray(ib, np.uint8); eb = np.ascontiguousarray(eb, np.uint8)
+        io = np.ascontiguousarray(io, np.uint64); eo = np.ascontiguousarray(eo, np.uint64)
+        vals = np.ascontiguousarray(vals, np.uint64)
+        n = len(io) - 1
+        h = C.c_void_p(); err = C.c_uint64(0)
+        seed = (C.c_uint8 * 32).from_buffer_copy(pad_seed)
+        aseed = (C.c_uint8 * max(len(audit_seed), 1)).from_buffer_copy(audit_seed or b"\0")
+        rc = _ffi.lib().dapol_tree_build_from_liabilities(ctx._h, hash_id, tree_height, n, _p(ib), _p(io), _p(eb), _p(eo), _p(vals),
+                                                          aseed, len(audit_seed), seed, pad_base, C.byref(h), C.byref(err))
+        _check(rc, err.value if rc in (4, 5) else None)
+        self._t = h
+        self._n = n
+        return self
+
+    def leaf_index_of(self, input_pos: int):
+        """id_to_idx_map lookup (mod.rs:148-151) by input position; None if the tree was not built from liabilities."""
+        x = C.c_uint64()
+        rc = _ffi.lib().dapol_tree_leaf_index_of(self._t, input_pos, C.byref(x))
+        if rc == 17:
+            return None
+        _check(rc)
+        return x.value
 
     def _free(self):
         if getattr(self, "_t", None):

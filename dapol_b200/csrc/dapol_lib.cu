@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/dapol_b200.h"
 #include "tree_kernels.cuh"
@@ -25,10 +26,12 @@ struct dapol_ctx {
     int device = 0;
     int W = 8;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     ge_niels *tab_b = nullptr, *tab_bbl = nullptr;  // comb tables for B and B_blinding at window W
     uint64_t launches = 0;
     float last_ms[5] = {0, 0, 0, 0, 0};
     cudaEvent_t ev[6] = {};
+    unsigned long long *scratch = nullptr;  // 1 KB of device scratch (histograms, counters)
 };
 
 struct dapol_tree {
@@ -38,6 +41,7 @@ struct dapol_tree {
     std::vector<uint64_t> level_off, level_n, n_real;  // per level h = 0..H
     NodeStore ns = {};
     std::vector<uint32_t *> pos;  // pos[h]: slot of the k-th real node of level h (device), h = 1..H
+    uint32_t *pos_all = nullptr;  // backing allocation of pos[]
     uint32_t **d_pos = nullptr;   // device copy of the pointer table
     uint64_t *d_level_off = nullptr;
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
@@ -69,25 +73,21 @@ __global__ void k_comb_table(ge_niels *table, int nw, int which, uint64_t total)
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < total) comb_table_body<W>(t, table, nw, which);
 }
-__global__ void k_check_leaf_idx(const uint64_t *idx, uint64_t n, int height, int *bad) {
+// adjacent-leaf msb histogram (hist[0..63]) + input validation (hist[64] = bad flag)
+__global__ void k_leaf_msb_hist(const uint64_t *idx, uint64_t n, int height, unsigned long long *hist) {
+    __shared__ unsigned int sh[65];
+    for (int i = threadIdx.x; i < 65; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n && leaf_idx_bad(k, idx, height)) *bad = 1;
+    if (k < n) {
+        int bad = 0;
+        int m = leaf_pair_msb(k, idx, height, &bad);
+        if (bad) atomicAdd(&sh[64], 1u);
+        if (m >= 0) atomicAdd(&sh[m], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 65; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
-__global__ void k_struct_flags(const uint64_t *idx, uint64_t c, uint64_t *flags) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < c) flags[k] = struct_flags_body(k, idx, c);
-}
-__global__ void k_struct_parent(const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *scan, uint64_t *parent_idx,
-                                uint64_t *totals) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < c) struct_parent_body(k, idx, c, flags, scan, parent_idx, totals);
-}
-__global__ void k_struct_emit(const uint64_t *idx, uint64_t c, const uint64_t *scan, uint32_t *pos, uint64_t level_off, NodeStore ns,
-                              uint64_t *pad_dest, uint64_t pad_ord_base) {
-    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < c) struct_emit_body(k, idx, c, scan, pos, level_off, ns, pad_dest, pad_ord_base);
-}
-
 // exclusive prefix sum of u64, three passes over tiles of SCAN_TILE items
 #define SCAN_BLOCK 256
 #define SCAN_ITEMS 8
@@ -120,11 +120,13 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, uint64_t *t
     __syncthreads();
     return r;
 }
-__global__ void k_scan_tile_sums(const uint64_t *in, uint64_t n, uint64_t *tile_sums) {
+// pass 1: flags of a level + per-tile sums
+__global__ void k_struct_flags_tiles(const uint64_t *idx, uint64_t c, uint64_t *flags, uint64_t *tile_sums) {
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) if (base + i < n) s += in[base + i];
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < c) { uint64_t f = struct_flags_body(base + i, idx, c); flags[base + i] = f; s += f; }
     uint64_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -143,14 +145,67 @@ __global__ void k_scan_tile_offsets(uint64_t *tile_sums, uint64_t ntiles) {  // 
         __syncthreads();
     }
 }
-__global__ void k_scan_tile_apply(const uint64_t *in, uint64_t n, const uint64_t *tile_offsets, uint64_t *out) {
+// pass 3: exclusive scan inside the tile + slots / parents / padding destinations
+__global__ void k_struct_apply(const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *tile_offsets, uint32_t *pos,
+                               uint64_t *parent_idx, uint64_t level_off, NodeStore ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t x[SCAN_ITEMS], s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { x[i] = base + i < n ? in[base + i] : 0; s += x[i]; }
+    for (int i = 0; i < SCAN_ITEMS; i++) { x[i] = base + i < c ? flags[base + i] : 0; s += x[i]; }
     uint64_t e = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) { if (base + i < n) out[base + i] = e; e += x[i]; }
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < c) struct_apply_body(base + i, idx, x[i], e, pos, parent_idx, level_off, ns, pad_dest, pad_ord_base);
+        e += x[i];
+    }
+}
+
+// ---- leaf derivation (K1)
+__global__ void k_derive(uint64_t n, int hash_id, const uint8_t *iid_blob, const uint64_t *iid_off, const uint8_t *eid_blob,
+                         const uint64_t *eid_off, const uint8_t *audit_seed, uint32_t seed_len, int height, uint32_t *audit,
+                         uint32_t *cur_seed, uint64_t *cand, uint32_t *blind, uint32_t *tries, uint64_t *audit_key, uint32_t *iota,
+                         int *too_long) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (derive_body(i, hash_id, iid_blob, iid_off, eid_blob, eid_off, audit_seed, seed_len, height, audit, cur_seed, cand, blind)) *too_long = 1;
+    tries[i] = 1;
+    audit_key[i] = (uint64_t)audit[8 * i] | ((uint64_t)audit[8 * i + 1] << 32);
+    iota[i] = (uint32_t)i;
+}
+// sorted by 64-bit audit-id prefix (stable, so ties are in input order): exact duplicate detection inside runs
+__global__ void k_find_dups(uint64_t n, const uint64_t *keys, const uint32_t *who, const uint32_t *audit, unsigned long long *first_dup) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 || j >= n || keys[j] != keys[j - 1]) return;
+    uint32_t a[8], b[8];
+    load8(a, audit + 8 * (uint64_t)who[j]);
+    for (uint64_t t = j; t-- > 0 && keys[t] == keys[j];) {
+        load8(b, audit + 8 * (uint64_t)who[t]);
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= a[i] ^ b[i];
+        if (d == 0) { atomicMin(first_dup, (unsigned long long)who[j]); return; }
+    }
+}
+// sorted by candidate index (stable => inside a group the earliest input position is first and keeps the slot):
+// every later member of a group lost and re-hashes.  counters[0] = losers this round, counters[1] = min failed position
+__global__ void k_resolve_collisions(uint64_t n, const uint64_t *sorted_cand, const uint32_t *who, int hash_id, int height,
+                                     uint32_t *cur_seed, uint64_t *cand, uint32_t *tries, unsigned long long *counters) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0 || j >= n || sorted_cand[j] != sorted_cand[j - 1]) return;
+    uint64_t u = who[j];
+    if (tries[u] > 128) return;  // already failed
+    if (rehash_body(u, hash_id, height, cur_seed, cand, tries)) atomicAdd(&counters[0], 1ull);
+    else { tries[u] = 129; atomicMin(&counters[1], (unsigned long long)u); }
+}
+__global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t *values, const uint32_t *blind, uint64_t *values_sorted,
+                                uint32_t *blind_sorted) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t u = who[j];
+    values_sorted[j] = values[u];
+    uint32_t w[8];
+    load8(w, blind + 8 * u);
+    store8(blind_sorted + 8 * j, w);
 }
 
 template <int W>
@@ -290,6 +345,7 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     ctx->W = comb_window ? comb_window : 8;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaMalloc(&ctx->scratch, 1024));
     int rc;
     switch (ctx->W) {
         case 4: rc = build_tables<4>(ctx); break;
@@ -305,34 +361,23 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
 extern "C" void dapol_ctx_destroy(dapol_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl);
+    cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl); cudaFree(ctx->scratch);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+extern "C" int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    return DAPOL_OK;
 }
 extern "C" uint64_t dapol_kernel_launches(const dapol_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]) {
     if (!ctx) return DAPOL_ERR_BAD_ARG;
     memcpy(ms, ctx->last_ms, sizeof(float) * 5);
-    return DAPOL_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ scan helper
-struct ScanScratch {
-    uint64_t *tile_sums = nullptr;
-    uint64_t cap = 0;
-};
-static int exclusive_scan(dapol_ctx *ctx, ScanScratch &ss, const uint64_t *in, uint64_t n, uint64_t *out) {
-    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    if (ntiles > ss.cap) {
-        if (ss.tile_sums) CUDA_TRY(cudaFree(ss.tile_sums));
-        CUDA_TRY(cudaMalloc(&ss.tile_sums, ntiles * 8));
-        ss.cap = ntiles;
-    }
-    k_scan_tile_sums<<<(unsigned)ntiles, SCAN_BLOCK, 0, ctx->stream>>>(in, n, ss.tile_sums);
-    k_scan_tile_offsets<<<1, SCAN_BLOCK, 0, ctx->stream>>>(ss.tile_sums, ntiles);
-    k_scan_tile_apply<<<(unsigned)ntiles, SCAN_BLOCK, 0, ctx->stream>>>(in, n, ss.tile_sums, out);
-    ctx->launches += 3;
     return DAPOL_OK;
 }
 
@@ -342,7 +387,7 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     cudaSetDevice(t->ctx->device);
     cudaFree(t->ns.idx); cudaFree(t->ns.v); cudaFree(t->ns.r); cudaFree(t->ns.comc); cudaFree(t->ns.hash);
     cudaFree(t->ns.ext); cudaFree(t->ns.is_pad);
-    for (auto p : t->pos) cudaFree(p);
+    cudaFree(t->pos_all);
     cudaFree(t->d_pos); cudaFree(t->d_level_off); cudaFree(t->leaf_index_of);
     delete t;
 }
@@ -352,21 +397,28 @@ static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_val
                             const Seed8 &seed, uint64_t pad_base, int phase) {
     int H = t->height;
     if (phase == 0) {
-        if (H == 0) {
-            // single-node tree: the leaf is the root
-            static uint32_t *zero_pos = nullptr;
-            if (!zero_pos) { cudaMalloc(&zero_pos, 4); cudaMemset(zero_pos, 0, 4); }
-            k_leaf<W><<<1, 128, 0, ctx->stream>>>(1, t->ns, 0, zero_pos, t->hash_id, d_values, d_blind, ctx->tab_b, ctx->tab_bbl);
-        } else {
-            k_leaf<W><<<grid_for(t->n_leaves, 128), 128, 0, ctx->stream>>>(t->n_leaves, t->ns, t->level_off[H], t->pos[H], t->hash_id,
-                                                                           d_values, d_blind, ctx->tab_b, ctx->tab_bbl);
-        }
+        k_leaf<W><<<grid_for(t->n_leaves, 128), 128, 0, ctx->stream>>>(t->n_leaves, t->ns, t->level_off[H], t->pos[H], t->hash_id, d_values,
+                                                                       d_blind, ctx->tab_b, ctx->tab_bbl);
         ctx->launches++;
     } else if (t->n_pads) {
         k_pad<W><<<grid_for(t->n_pads, 128), 128, 0, ctx->stream>>>(t->n_pads, t->ns, d_pad_dest, t->hash_id, seed, pad_base, ctx->tab_bbl);
         ctx->launches++;
     }
 }
+
+// bump allocator over one cudaMalloc'ed arena (256-byte aligned pieces)
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t size = 0, used = 0;
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
+};
 
 static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
                           const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
@@ -380,69 +432,48 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     const int H = height;
     CUDA_TRY(cudaEventRecord(ctx->ev[0], st));
 
-    // leaf index validation
-    int *d_flag = nullptr;
-    CUDA_TRY(cudaMalloc(&d_flag, 4));
-    CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, st));
-    k_check_leaf_idx<<<grid_for(n, 256), 256, 0, st>>>(d_leaf_idx, n, H, d_flag);
+    // ---- sizes of every level from one pass over adjacent leaves (+ validation)
+    unsigned long long h_hist[65];
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 65 * 8, st));
+    k_leaf_msb_hist<<<grid_for(n, 256), 256, 0, st>>>(d_leaf_idx, n, H, ctx->scratch);
     ctx->launches++;
-    int h_flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_hist, ctx->scratch, 65 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_flag);
-    if (h_flag) return DAPOL_ERR_BAD_ARG;
+    if (h_hist[64]) return DAPOL_ERR_BAD_ARG;  // unsorted / duplicate / out-of-tree leaf index
 
     dapol_tree *t = new dapol_tree();
     t->ctx = ctx; t->hash_id = hash_id; t->height = H; t->n_leaves = n;
     t->level_off.assign(H + 1, 0); t->level_n.assign(H + 1, 0); t->n_real.assign(H + 1, 0);
     t->pos.assign(H + 1, nullptr);
-    int rc = DAPOL_OK;
-    // ---- structure phase 1: per level flags -> scan -> parent indexes (= next level's real nodes)
-    std::vector<uint64_t *> real(H + 1, nullptr), scan(H + 1, nullptr);
-    std::vector<uint64_t> npads(H + 1, 0);
-    uint64_t *d_flags = nullptr, *d_totals = nullptr, *d_pad_dest = nullptr;
-    ScanScratch ss;
-    auto cleanup = [&]() {
-        for (int h = 0; h <= H; h++) { if (h != H) cudaFree(real[h]); cudaFree(scan[h]); }
-        cudaFree(d_flags); cudaFree(d_totals); cudaFree(ss.tile_sums); cudaFree(d_pad_dest);
-    };
-#define TRY_T(expr)                                                         \
-    do {                                                                    \
-        cudaError_t e_ = (expr);                                            \
-        if (e_ != cudaSuccess) {                                            \
-            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
-            cleanup(); dapol_tree_destroy(t); return DAPOL_ERR_CUDA;        \
-        }                                                                   \
-    } while (0)
-    real[H] = const_cast<uint64_t *>(d_leaf_idx);
-    t->n_real[H] = n;
-    TRY_T(cudaMalloc(&d_flags, n * 8));
-    TRY_T(cudaMalloc(&d_totals, 16));
-    for (int h = H; h >= 1; h--) {
-        uint64_t c = t->n_real[h];
-        TRY_T(cudaMalloc(&scan[h], c * 8));
-        TRY_T(cudaMalloc(&real[h - 1], c * 8));  // upper bound; trimmed logically by n_real
-        k_struct_flags<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, d_flags);
-        ctx->launches++;
-        rc = exclusive_scan(ctx, ss, d_flags, c, scan[h]);
-        if (rc) { cleanup(); dapol_tree_destroy(t); return rc; }
-        k_struct_parent<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, d_flags, scan[h], real[h - 1], d_totals);
-        ctx->launches++;
-        uint64_t totals[2];
-        TRY_T(cudaMemcpyAsync(totals, d_totals, 16, cudaMemcpyDeviceToHost, st));
-        TRY_T(cudaStreamSynchronize(st));
-        t->n_real[h - 1] = totals[0];
-        npads[h] = totals[1];
-        t->level_n[h] = 2 * totals[0];
+    std::vector<uint64_t> npads(H + 1, 0), pos_off(H + 2, 0);
+    {   // real nodes at level h = 1 + #{adjacent pairs whose highest differing bit >= H - h}
+        uint64_t acc = 0;
+        for (int h = 0; h <= H; h++) {
+            if (h >= 1) acc += h_hist[H - h];
+            t->n_real[h] = 1 + acc;
+        }
     }
+    uint64_t T = 1, total_pads = 0;
     t->level_n[0] = 1;
-    // levels are numbered root-first in the node store
-    uint64_t T = 1;
-    for (int h = 1; h <= H; h++) { t->level_off[h] = T; T += t->level_n[h]; }
-    t->T = T;
-    uint64_t total_pads = 0;
-    for (int h = 1; h <= H; h++) total_pads += npads[h];
-    t->n_pads = total_pads;
+    for (int h = 1; h <= H; h++) {
+        t->level_n[h] = 2 * t->n_real[h - 1];
+        npads[h] = t->level_n[h] - t->n_real[h];
+        t->level_off[h] = T;
+        T += t->level_n[h];
+        total_pads += npads[h];
+        pos_off[h + 1] = pos_off[h] + ((t->n_real[h] + 63) & ~63ull);
+    }
+    t->T = T; t->n_pads = total_pads;
+
+    uint8_t *arena_mem = nullptr;
+#define TRY_T(expr)                                                          \
+    do {                                                                     \
+        cudaError_t e_ = (expr);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            cudaFree(arena_mem); dapol_tree_destroy(t); return DAPOL_ERR_CUDA; \
+        }                                                                    \
+    } while (0)
     TRY_T(cudaMalloc(&t->ns.idx, T * 8));
     TRY_T(cudaMalloc(&t->ns.v, T * 8));
     TRY_T(cudaMalloc(&t->ns.r, T * 32));
@@ -450,19 +481,39 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     TRY_T(cudaMalloc(&t->ns.hash, T * 32));
     TRY_T(cudaMalloc(&t->ns.ext, T * 128));
     TRY_T(cudaMalloc(&t->ns.is_pad, T));
-    TRY_T(cudaMemsetAsync(t->ns.idx, 0, 8, st));
-    TRY_T(cudaMemsetAsync(t->ns.is_pad, 0, 1, st));
-    TRY_T(cudaMalloc(&d_pad_dest, (total_pads + 1) * 8));
-    // ---- structure phase 2: slots, padding destinations (RNG ordinal = creation order: level H..1, left to right)
+    TRY_T(cudaMalloc(&t->pos_all, (pos_off[H + 1] + 64) * 4));
+    for (int h = 1; h <= H; h++) t->pos[h] = t->pos_all + pos_off[h];
+    uint64_t ntiles_max = (n + SCAN_TILE - 1) / SCAN_TILE;
+    Arena ar;
+    ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 8) + Arena::need(ntiles_max, 8) + Arena::need(total_pads + 1, 8);
+    TRY_T(cudaMalloc(&arena_mem, ar.size));
+    ar.base = arena_mem;
+    uint64_t *realA = ar.take<uint64_t>(n), *realB = ar.take<uint64_t>(n), *d_flags = ar.take<uint64_t>(n);
+    uint64_t *d_tiles = ar.take<uint64_t>(ntiles_max), *d_pad_dest = ar.take<uint64_t>(total_pads + 1);
+    if (H == 0) {
+        TRY_T(cudaMemcpyAsync(t->ns.idx, d_leaf_idx, 8, cudaMemcpyDeviceToDevice, st));
+        TRY_T(cudaMemsetAsync(t->ns.is_pad, 0, 1, st));
+        TRY_T(cudaMemsetAsync(t->pos_all, 0, 4, st));
+        t->pos[0] = t->pos_all;
+    } else {
+        TRY_T(cudaMemsetAsync(t->ns.idx, 0, 8, st));  // root: TreeIndex::zero(0)
+        TRY_T(cudaMemsetAsync(t->ns.is_pad, 0, 1, st));
+    }
+    // ---- structure: per level flags -> scan -> slots, parents, padding destinations.  Padding RNG ordinal =
+    // creation order of smtree's build: level H..1, left to right.
+    const uint64_t *cur = d_leaf_idx;
     uint64_t ord = 0;
     for (int h = H; h >= 1; h--) {
         uint64_t c = t->n_real[h];
-        TRY_T(cudaMalloc(&t->pos[h], c * 4));
-        k_struct_emit<<<grid_for(c, 256), 256, 0, st>>>(real[h], c, scan[h], t->pos[h], t->level_off[h], t->ns, d_pad_dest, ord);
-        ctx->launches++;
+        uint64_t *next = (cur == realA) ? realB : realA;
+        unsigned ntiles = (unsigned)((c + SCAN_TILE - 1) / SCAN_TILE);
+        k_struct_flags_tiles<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles);
+        k_scan_tile_offsets<<<1, SCAN_BLOCK, 0, st>>>(d_tiles, ntiles);
+        k_struct_apply<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles, t->pos[h], next, t->level_off[h], t->ns, d_pad_dest, ord);
+        ctx->launches += 3;
         ord += npads[h];
+        cur = next;
     }
-    if (H == 0) TRY_T(cudaMemcpyAsync(t->ns.idx, d_leaf_idx, 8, cudaMemcpyDeviceToDevice, st));
     TRY_T(cudaEventRecord(ctx->ev[1], st));
     // ---- leaves, padding nodes
     Seed8 seed;
@@ -496,7 +547,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     // the extended points are only needed while merging
     cudaFree(t->ns.ext);
     t->ns.ext = nullptr;
-    cleanup();
+    cudaFree(arena_mem);
 #undef TRY_T
     *out = t;
     return DAPOL_OK;
@@ -512,23 +563,133 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
                                            dapol_tree **out) {
     if (!ctx || !leaf_idx || !values || !blindings || n == 0) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    uint64_t *d_idx = nullptr, *d_val = nullptr;
-    uint8_t *d_bl = nullptr;
-    CUDA_TRY(cudaMalloc(&d_idx, n * 8));
-    CUDA_TRY(cudaMalloc(&d_val, n * 8));
-    CUDA_TRY(cudaMalloc(&d_bl, n * 32));
-    CUDA_TRY(cudaMemcpyAsync(d_idx, leaf_idx, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_val, values, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(d_bl, blindings, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 32);
+    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    ar.base = mem;
+    uint64_t *d_idx = ar.take<uint64_t>(n), *d_val = ar.take<uint64_t>(n);
+    uint8_t *d_bl = ar.take<uint8_t>(n * 32);
+    cudaMemcpyAsync(d_idx, leaf_idx, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_val, values, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_bl, blindings, n * 32, cudaMemcpyHostToDevice, ctx->stream);
     int rc = tree_build_dev(ctx, hash_id, height, n, d_idx, d_val, d_bl, pad_seed, pad_base, out);
-    cudaFree(d_idx); cudaFree(d_val); cudaFree(d_bl);
+    cudaFree(mem);
     return rc;
 }
-extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *, int, int, uint64_t, const uint8_t *, const uint64_t *, const uint8_t *,
-                                                 const uint64_t *, const uint64_t *, const uint8_t *, uint64_t, const uint8_t *, uint64_t,
-                                                 dapol_tree **, uint64_t *) {
-    g_cuda_err = "dapol_tree_build_from_liabilities: not built yet";
-    return DAPOL_ERR_BAD_ARG;
+
+// Dapol::new: checks (mod.rs:101-116), build_leaf_nodes on the device (mod.rs:323-399), sort, build.
+static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob, const uint64_t *d_iid_off,
+                                 const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint64_t *d_values, const uint8_t *audit_seed,
+                                 uint64_t seed_len, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos) {
+    if (!ctx || !out) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
+    if (height < 0) return DAPOL_ERR_BAD_ARG;
+    if (height < 64 && (1ull << height) < n * 2) return DAPOL_ERR_SPARSITY_TOO_SMALL;  // MIN_SPARSITY = 2 (mod.rs:27,110)
+    if (n == 0 || height == 0 || n >= (1ull << 31) || seed_len > 512) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (int)n, 0, 64, st);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = 3 * Arena::need(n, 32) + 4 * Arena::need(n, 8) + 3 * Arena::need(n, 4) + Arena::need(n, 32) + Arena::need(cub_bytes, 1) +
+              Arena::need(seed_len + 1, 1) + 1024;
+    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    ar.base = mem;
+    uint32_t *audit = ar.take<uint32_t>(8 * n), *cur_seed = ar.take<uint32_t>(8 * n), *blind = ar.take<uint32_t>(8 * n);
+    uint64_t *akey = ar.take<uint64_t>(n), *keys_sorted = ar.take<uint64_t>(n), *values_sorted = ar.take<uint64_t>(n);
+    uint64_t *cand = nullptr;
+    uint32_t *tries = ar.take<uint32_t>(n), *iota = ar.take<uint32_t>(n), *who = ar.take<uint32_t>(n);
+    uint32_t *blind_sorted = ar.take<uint32_t>(8 * n);
+    uint8_t *cub_tmp = ar.take<uint8_t>(cub_bytes), *d_seed = ar.take<uint8_t>(seed_len + 1);
+    unsigned long long *counters = ar.take<unsigned long long>(8);
+    int rc = DAPOL_OK;
+#define TRY_L(expr)                                                          \
+    do {                                                                     \
+        cudaError_t e_ = (expr);                                             \
+        if (e_ != cudaSuccess) {                                             \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
+            cudaFree(mem); cudaFree(cand); return DAPOL_ERR_CUDA;            \
+        }                                                                    \
+    } while (0)
+    TRY_L(cudaMalloc(&cand, n * 8));  // survives as the id -> leaf index map of the tree
+    if (seed_len) TRY_L(cudaMemcpyAsync(d_seed, audit_seed, seed_len, cudaMemcpyHostToDevice, st));
+    // counters: [0] losers, [1] min failed pos, [2] first dup pos, [3] too-long flag (int)
+    unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
+    TRY_L(cudaMemcpyAsync(counters, h_cnt, 32, cudaMemcpyHostToDevice, st));
+    k_derive<<<grid_for(n, 128), 128, 0, st>>>(n, hash_id, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, (uint32_t)seed_len, height, audit,
+                                               cur_seed, cand, blind, tries, akey, iota, reinterpret_cast<int *>(counters + 3));
+    // duplicate internal ids <=> identical audit ids
+    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, akey, keys_sorted, iota, who, (int)n, 0, 64, st);
+    k_find_dups<<<grid_for(n, 256), 256, 0, st>>>(n, keys_sorted, who, audit, counters + 2);
+    ctx->launches += 3;
+    // collision fix-point: serial dictatorship by input position (mod.rs:408-441 processed in input order)
+    int end_bit = height < 1 ? 1 : height;
+    for (int round = 0;; round++) {
+        cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, cand, keys_sorted, iota, who, (int)n, 0, end_bit, st);
+        TRY_L(cudaMemsetAsync(counters, 0, 8, st));
+        k_resolve_collisions<<<grid_for(n, 256), 256, 0, st>>>(n, keys_sorted, who, hash_id, height, cur_seed, cand, tries, counters);
+        ctx->launches += 2;
+        TRY_L(cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, st));
+        TRY_L(cudaStreamSynchronize(st));
+        if (h_cnt[0] == 0) break;
+        if (round > 4096) { rc = DAPOL_ERR_BAD_ARG; break; }
+    }
+    if (rc == DAPOL_OK && (int)h_cnt[3]) rc = DAPOL_ERR_BAD_ARG;  // id too long for single-chunk hashing (> 1024 B)
+    if (rc == DAPOL_OK) {
+        unsigned long long f = h_cnt[1], d = h_cnt[2];
+        if (d != ~0ull && d <= f) { rc = DAPOL_ERR_DUPLICATED_INTERNAL_ID; if (err_pos) *err_pos = d; }
+        else if (f != ~0ull) { rc = DAPOL_ERR_FAILED_TO_MAP_INDEX; if (err_pos) *err_pos = f; }
+    }
+    if (rc != DAPOL_OK) { cudaFree(mem); cudaFree(cand); return rc; }
+    // the last sort (no losers) is the final sorted order: result.sort_by_key(index) (mod.rs:396)
+    k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, who, d_values, blind, values_sorted, blind_sorted);
+    ctx->launches++;
+    rc = tree_build_dev(ctx, hash_id, height, n, keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
+    cudaFree(mem);
+    if (rc != DAPOL_OK) { cudaFree(cand); return rc; }
+    (*out)->leaf_index_of = cand;
+#undef TRY_L
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_build_from_liabilities_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob,
+                                                     const uint64_t *d_iid_off, const uint8_t *d_eid_blob, const uint64_t *d_eid_off,
+                                                     const uint64_t *d_values, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                                     const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos) {
+    return liabilities_build_dev(ctx, hash_id, height, n, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_values, audit_seed, audit_seed_len,
+                                 pad_seed, pad_base, out, err_pos);
+}
+extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *iid_blob,
+                                                 const uint64_t *iid_off, const uint8_t *eid_blob, const uint64_t *eid_off,
+                                                 const uint64_t *values, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                                 const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos) {
+    if (!ctx || !iid_off || !eid_off || !values || !out) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
+    if (height >= 0 && height < 64 && (1ull << height) < n * 2) return DAPOL_ERR_SPARSITY_TOO_SMALL;
+    if (n == 0) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t ib = iid_off[n], eb = eid_off[n];
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(ib + 1, 1) + Arena::need(eb + 1, 1) + 3 * Arena::need(n + 1, 8);
+    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    ar.base = mem;
+    uint8_t *d_ib = ar.take<uint8_t>(ib + 1), *d_eb = ar.take<uint8_t>(eb + 1);
+    uint64_t *d_io = ar.take<uint64_t>(n + 1), *d_eo = ar.take<uint64_t>(n + 1), *d_v = ar.take<uint64_t>(n + 1);
+    cudaStream_t st = ctx->stream;
+    if (ib) cudaMemcpyAsync(d_ib, iid_blob, ib, cudaMemcpyHostToDevice, st);
+    if (eb) cudaMemcpyAsync(d_eb, eid_blob, eb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_io, iid_off, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_eo, eid_off, (n + 1) * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, st);
+    int rc = liabilities_build_dev(ctx, hash_id, height, n, d_ib, d_io, d_eb, d_eo, d_v, audit_seed, audit_seed_len, pad_seed, pad_base, out, err_pos);
+    cudaFree(mem);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ accessors

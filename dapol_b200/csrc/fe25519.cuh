@@ -15,7 +15,7 @@
 #define DAPOL_HD_INLINE __host__ __device__ __forceinline__
 #else
 #define DAPOL_HD
-#define DAPOL_HD_INLINE static inline __attribute__((always_inline))
+#define DAPOL_HD_INLINE static inline
 #endif
 
 #ifndef __CUDA_ARCH__

@@ -41,23 +41,12 @@ DAPOL_HD_INLINE uint64_t struct_flags_body(uint64_t k, const uint64_t *idx, uint
     int has_sib = (k > 0 && idx[k - 1] == (x ^ 1)) || (k + 1 < c && idx[k + 1] == (x ^ 1));
     return ((uint64_t)newp << 32) | (uint64_t)(!has_sib);
 }
-// scan[k] = exclusive prefix sum of flags.  Phase 1 (before the node store exists): compact the parents'
-// tree indexes (= the next level's real nodes) and report the level's totals.
-DAPOL_HD_INLINE void struct_parent_body(uint64_t k, const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *scan,
-                                        uint64_t *parent_idx, uint64_t *totals /*[2]: parents, pads*/) {
-    uint64_t f = flags[k], s = scan[k];
-    uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
-    if (newp) parent_idx[s >> 32] = idx[k] >> 1;
-    if (k == c - 1) {
-        totals[0] = (s >> 32) + newp;
-        totals[1] = (s & 0xffffffffull) + lone;
-    }
-}
-// Phase 2: for real node k: its slot in the level's node array; for a lone node also its padding
+// s = exclusive prefix sum of flags at k.  For real node k of the level: its slot in the level's node array
+// and its parent's tree index (compaction = next level's real nodes); for a lone node also its padding
 // sibling's slot + idx and the pad's destination (global node number) at its RNG ordinal.
-DAPOL_HD_INLINE void struct_emit_body(uint64_t k, const uint64_t *idx, uint64_t c, const uint64_t *scan, uint32_t *pos,
-                                      uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
-    uint64_t x = idx[k], f = struct_flags_body(k, idx, c), s = scan[k];
+DAPOL_HD_INLINE void struct_apply_body(uint64_t k, const uint64_t *idx, uint64_t f, uint64_t s, uint32_t *pos, uint64_t *parent_idx,
+                                       uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
+    uint64_t x = idx[k];
     uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
     uint64_t j = (s >> 32) - (newp ? 0 : 1);
     uint64_t q = s & 0xffffffffull;
@@ -66,6 +55,7 @@ DAPOL_HD_INLINE void struct_emit_body(uint64_t k, const uint64_t *idx, uint64_t 
     pos[k] = (uint32_t)p;
     ns.idx[level_off + p] = x;
     ns.is_pad[level_off + p] = 0;
+    if (newp) parent_idx[j] = x >> 1;
     if (lone) {
         uint64_t pp = 2 * j + (1 - slot);
         ns.idx[level_off + pp] = x ^ 1;
@@ -73,11 +63,77 @@ DAPOL_HD_INLINE void struct_emit_body(uint64_t k, const uint64_t *idx, uint64_t 
         pad_dest[pad_ord_base + q] = level_off + pp;
     }
 }
-// leaf input validation: strictly increasing and inside the tree
-DAPOL_HD_INLINE int leaf_idx_bad(uint64_t k, const uint64_t *idx, int height) {
+// Sizes of every level from one pass over adjacent leaves: msb of idx[k] ^ idx[k-1] (k >= 1).  The number
+// of real nodes at level h is 1 + #{k : msb >= H - h}.  Returns -1 for k = 0; sets *bad on unsorted /
+// out-of-tree input (smtree rejects those).
+DAPOL_HD_INLINE int leaf_pair_msb(uint64_t k, const uint64_t *idx, int height, int *bad) {
     uint64_t x = idx[k];
-    if (height < 64 && (x >> height)) return 1;
-    return k > 0 && idx[k - 1] >= x;
+    if (height < 64 && (x >> height)) *bad = 1;
+    if (k == 0) return -1;
+    uint64_t y = idx[k - 1];
+    if (y >= x) { *bad = 1; return -1; }
+    uint64_t d = x ^ y;
+    int msb = 0;
+    while (d >>= 1) msb++;
+    return msb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf derivation (build_leaf_nodes + shuffle_index, /root/reference/src/dapol/mod.rs:323-441)
+DAPOL_HD_INLINE uint64_t seed_to_index(const uint32_t seed[8], int height) {
+    // u64::from_be_bytes(seed[..8]) >> (64 - height)   (mod.rs:427-431)
+    uint32_t w0 = seed[0], w1 = seed[1];
+    uint64_t hi = ((uint64_t)(w0 & 0xff) << 24) | ((uint64_t)((w0 >> 8) & 0xff) << 16) | ((uint64_t)((w0 >> 16) & 0xff) << 8) | (w0 >> 24);
+    uint64_t lo = ((uint64_t)(w1 & 0xff) << 24) | ((uint64_t)((w1 >> 8) & 0xff) << 16) | ((uint64_t)((w1 >> 16) & 0xff) << 8) | (w1 >> 24);
+    uint64_t be = (hi << 32) | lo;
+    return height >= 64 ? be : (be >> (64 - height));
+}
+// per user: audit_id = D(audit_seed || internal_id); index_seed = D(audit_id || "index_seed" || external_id);
+// first candidate = D(index_seed); blinding = from_bits(D(audit_id || "blind_seed" || external_id)).
+// Returns 0, or -1 if an input exceeds the single-chunk hashing limit.
+DAPOL_HD_INLINE int derive_body(uint64_t i, int hash_id, const uint8_t *iid_blob, const uint64_t *iid_off, const uint8_t *eid_blob,
+                                const uint64_t *eid_off, const uint8_t *audit_seed, uint32_t seed_len, int height, uint32_t *audit_out,
+                                uint32_t *cur_seed, uint64_t *cand, uint32_t *blind_out) {
+    dapol_hasher hs;
+    uint32_t audit[8], iseed[8], bs[8];
+    int rc = 0;
+    hasher_init(hs, hash_id);
+    hasher_update(hs, audit_seed, seed_len);
+    hasher_update(hs, iid_blob + iid_off[i], (uint32_t)(iid_off[i + 1] - iid_off[i]));
+    rc |= hasher_final(hs, audit);
+    const uint8_t *eid = eid_blob + eid_off[i];
+    uint32_t elen = (uint32_t)(eid_off[i + 1] - eid_off[i]);
+    const uint8_t tag_i[10] = {'i', 'n', 'd', 'e', 'x', '_', 's', 'e', 'e', 'd'};
+    const uint8_t tag_b[10] = {'b', 'l', 'i', 'n', 'd', '_', 's', 'e', 'e', 'd'};
+    hasher_init(hs, hash_id);
+    hasher_update_words(hs, audit, 8);
+    hasher_update(hs, tag_i, 10);
+    hasher_update(hs, eid, elen);
+    rc |= hasher_final(hs, iseed);
+    dapol_hash32(hash_id, iseed, iseed);  // first shuffle_index iteration (mod.rs:419-424)
+    hasher_init(hs, hash_id);
+    hasher_update_words(hs, audit, 8);
+    hasher_update(hs, tag_b, 10);
+    hasher_update(hs, eid, elen);
+    rc |= hasher_final(hs, bs);
+    bs[7] &= 0x7fffffffu;  // Scalar::from_bits (mod.rs:385)
+    store8(audit_out + 8 * i, audit);
+    store8(cur_seed + 8 * i, iseed);
+    store8(blind_out + 8 * i, bs);
+    cand[i] = seed_to_index(iseed, height);
+    return rc;
+}
+// a user that lost its candidate slot to an earlier user re-hashes its seed (mod.rs:416-437); tries counts
+// the candidates consumed so far (1 after derive_body); returns 0 if the 128 tries are exhausted.
+DAPOL_HD_INLINE int rehash_body(uint64_t u, int hash_id, int height, uint32_t *cur_seed, uint64_t *cand, uint32_t *tries) {
+    if (tries[u] >= 128) return 0;
+    uint32_t s[8];
+    load8(s, cur_seed + 8 * u);
+    dapol_hash32(hash_id, s, s);
+    store8(cur_seed + 8 * u, s);
+    cand[u] = seed_to_index(s, height);
+    tries[u] += 1;
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -62,6 +62,9 @@ typedef struct dapol_tree dapol_tree;
  * the reference re-derives them on every call, here once).  comb_window = 0 picks the default. */
 DAPOL_API int dapol_ctx_create(int device, int comb_window, dapol_ctx **out);
 DAPOL_API void dapol_ctx_destroy(dapol_ctx *ctx);
+/* Run this context's kernels and copies on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's
+ * current stream, so the caller's events bracket the work.  The stream must outlive the context. */
+DAPOL_API int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream);
 DAPOL_API const char *dapol_strerror(int code);
 DAPOL_API const char *dapol_last_cuda_error(void);
 
@@ -84,6 +87,12 @@ DAPOL_API int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, int
                                       const uint64_t *iid_off, const uint8_t *eid_blob, const uint64_t *eid_off,
                                       const uint64_t *values, const uint8_t *audit_seed, uint64_t audit_seed_len,
                                       const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos);
+
+/* Same with ids, offsets and values already resident in device memory (audit_seed stays a host pointer). */
+DAPOL_API int dapol_tree_build_from_liabilities_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob,
+                                          const uint64_t *d_iid_off, const uint8_t *d_eid_blob, const uint64_t *d_eid_off,
+                                          const uint64_t *d_values, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                          const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos);
 
 DAPOL_API void dapol_tree_destroy(dapol_tree *tree);
 

@@ -131,41 +131,38 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
         for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWV, 0);
         for (uint64_t t = 0; t < tbbl.size(); t++) comb_table_body<W>(t, tbbl.data(), NWR, 1);
     }
-    for (uint64_t k = 0; k < n; k++) if (leaf_idx_bad(k, leaf_idx, height)) return nullptr;
-    // structure phase on index arrays only
-    std::vector<std::vector<uint64_t>> real(height + 1), flags(height + 1), scan(height + 1);
-    std::vector<std::vector<uint32_t>> pos(height + 1);
-    std::vector<uint64_t> npads(height + 1, 0), nparents(height + 1, 0);
-    real[height].assign(leaf_idx, leaf_idx + n);
-    for (int h = height; h >= 1; h--) {
-        uint64_t c = real[h].size();
-        flags[h].resize(c); scan[h].resize(c);
-        for (uint64_t k = 0; k < c; k++) flags[h][k] = struct_flags_body(k, real[h].data(), c);
-        uint64_t s = 0;
-        for (uint64_t k = 0; k < c; k++) { scan[h][k] = s; s += flags[h][k]; }
-        nparents[h] = s >> 32; npads[h] = s & 0xffffffffull;
-        real[h - 1].resize(nparents[h]);
-        uint64_t totals[2];
-        for (uint64_t k = 0; k < c; k++) struct_parent_body(k, real[h].data(), c, flags[h].data(), scan[h].data(), real[h - 1].data(), totals);
-        if (totals[0] != nparents[h] || totals[1] != npads[h]) abort();
-    }
+    // level sizes from the adjacent-leaf msb histogram (as the CUDA host code does)
+    uint64_t hist[65] = {0};
+    for (uint64_t k = 0; k < n; k++) { int bad = 0; int m = leaf_pair_msb(k, leaf_idx, height, &bad); if (bad) return nullptr; if (m >= 0) hist[m]++; }
+    std::vector<uint64_t> n_real(height + 1), npads(height + 1, 0), nparents(height + 1, 0);
+    { uint64_t acc = 0; for (int h = 0; h <= height; h++) { if (h >= 1) acc += hist[height - h]; n_real[h] = 1 + acc; } }
+    if (n_real[height] != n) abort();
     auto *t = new EmuTree();
     t->height = height; t->level_off.resize(height + 1); t->level_n.resize(height + 1);
-    uint64_t T = 1; t->level_off[0] = 0; t->level_n[0] = 1;
-    for (int h = 1; h <= height; h++) { t->level_off[h] = T; t->level_n[h] = 2 * nparents[h]; T += t->level_n[h]; }
-    if (height == 0) { T = 1; }
+    uint64_t T = 1, total_pads = 0; t->level_off[0] = 0; t->level_n[0] = 1;
+    for (int h = 1; h <= height; h++) {
+        nparents[h] = n_real[h - 1]; t->level_n[h] = 2 * n_real[h - 1]; npads[h] = t->level_n[h] - n_real[h];
+        t->level_off[h] = T; T += t->level_n[h]; total_pads += npads[h];
+    }
     t->idx.assign(T, 0); t->v.assign(T, 0); t->r.assign(8 * T, 0); t->comc.assign(8 * T, 0); t->hash.assign(8 * T, 0);
     t->ext.assign(32 * T, 0); t->is_pad.assign(T, 0);
     NodeStore ns{t->idx.data(), t->v.data(), t->r.data(), t->comc.data(), t->hash.data(), t->ext.data(), t->is_pad.data()};
-    uint64_t total_pads = 0;
-    for (int h = height; h >= 1; h--) total_pads += npads[h];
     std::vector<uint64_t> pad_dest(total_pads + 1);
+    std::vector<std::vector<uint64_t>> real(height + 1);
+    std::vector<std::vector<uint32_t>> pos(height + 1);
+    real[height].assign(leaf_idx, leaf_idx + n);
     uint64_t ord = 0;
     for (int h = height; h >= 1; h--) {
         uint64_t c = real[h].size();
-        pos[h].resize(c);
-        for (uint64_t k = 0; k < c; k++)
-            struct_emit_body(k, real[h].data(), c, scan[h].data(), pos[h].data(), t->level_off[h], ns, pad_dest.data(), ord);
+        if (c != n_real[h]) abort();
+        pos[h].resize(c); real[h - 1].assign(n_real[h - 1], ~0ull);
+        uint64_t s = 0;
+        for (uint64_t k = 0; k < c; k++) {
+            uint64_t f = struct_flags_body(k, real[h].data(), c);
+            struct_apply_body(k, real[h].data(), f, s, pos[h].data(), real[h - 1].data(), t->level_off[h], ns, pad_dest.data(), ord);
+            s += f;
+        }
+        if ((s >> 32) != nparents[h] || (s & 0xffffffffull) != npads[h]) abort();
         ord += npads[h];
     }
     t->n_pads = total_pads;
@@ -178,6 +175,39 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
         for (uint64_t j = 0; j < nparents[h]; j++)
             merge_body(j, ns, t->level_off[h], h - 1 == 0 ? 0 : t->level_off[h - 1] + pos[h - 1][j], hash_id);
     return t;
+}
+// leaf derivation through the kernel bodies, with the sort/fix-point orchestration mirrored serially
+#include <algorithm>
+#include <numeric>
+EX int emu_derive_leaves(int hash_id, uint64_t n, const uint8_t *iid_blob, const uint64_t *iid_off, const uint8_t *eid_blob,
+                         const uint64_t *eid_off, const uint8_t *seed, uint32_t seed_len, int height, uint64_t *out_idx, uint8_t *out_blind,
+                         uint64_t *err_pos) {
+    std::vector<uint32_t> audit(8 * n), cur(8 * n), blind(8 * n), tries(n, 1);
+    std::vector<uint64_t> cand(n);
+    for (uint64_t i = 0; i < n; i++)
+        if (derive_body(i, hash_id, iid_blob, iid_off, eid_blob, eid_off, seed, seed_len, height, audit.data(), cur.data(), cand.data(), blind.data())) return 16;
+    uint64_t first_dup = ~0ull, first_fail = ~0ull;
+    for (uint64_t i = 0; i < n; i++) for (uint64_t j = 0; j < i; j++) if (!memcmp(&audit[8 * i], &audit[8 * j], 32)) { first_dup = std::min(first_dup, i); break; }
+    std::vector<uint32_t> who(n);
+    for (;;) {
+        std::iota(who.begin(), who.end(), 0u);
+        std::stable_sort(who.begin(), who.end(), [&](uint32_t a, uint32_t b) { return cand[a] < cand[b]; });
+        std::vector<uint64_t> sorted(n);
+        for (uint64_t j = 0; j < n; j++) sorted[j] = cand[who[j]];
+        uint64_t losers = 0;
+        for (uint64_t j = 1; j < n; j++) {
+            if (sorted[j] != sorted[j - 1]) continue;
+            uint64_t u = who[j];
+            if (tries[u] > 128) continue;
+            if (rehash_body(u, hash_id, height, cur.data(), cand.data(), tries.data())) losers++;
+            else { tries[u] = 129; first_fail = std::min(first_fail, u); }
+        }
+        if (!losers) break;
+    }
+    if (first_dup != ~0ull && first_dup <= first_fail) { *err_pos = first_dup; return 4; }
+    if (first_fail != ~0ull) { *err_pos = first_fail; return 5; }
+    memcpy(out_idx, cand.data(), 8 * n); memcpy(out_blind, blind.data(), 32 * n);
+    return 0;
 }
 EX uint64_t emu_tree_level_size(EmuTree *t, int h) { return t->level_n[h]; }
 EX uint64_t emu_tree_num_pads(EmuTree *t) { return t->n_pads; }

@@ -135,3 +135,56 @@ def test_large_tree_properties(ctx, cref):
         g, oo = gpu.level(h), ora.level(h)
         assert (g["comc"] == oo["comc"]).all() and (g["hash"] == oo["hash"]).all()
         assert ((g["idx"][0::2] ^ 1) == g["idx"][1::2]).all()
+
+
+def _liabs(n, seed, dense=False):
+    rnd = random.Random(seed)
+    ids = [rnd.randbytes(rnd.randrange(0, 40)) + i.to_bytes(3, "little") for i in range(n)]
+    eids = [rnd.randbytes(rnd.randrange(0, 70)) for _ in range(n)]
+    vals = [rnd.randrange(1 << 32) for _ in range(n)]
+    return ids, eids, vals
+
+
+@pytest.mark.parametrize("hash_id,H,n", [(1, 4, 4), (0, 7, 64), (0, 10, 300), (1, 9, 256), (0, 16, 5000), (0, 32, 3000), (0, 64, 50)])
+def test_from_liabilities_vs_oracle(ctx, cref, hash_id, H, n):
+    """Dapol::new end to end (leaf derivation incl. collisions, sort, build) == oracle derive + oracle build."""
+    from dapol_b200 import Dapol
+    ids, eids, vals = _liabs(n, 31 + n)
+    seed = b"audit-seed"
+    if H == 4:
+        ids, eids, vals, seed = [b"a", b"b", b"c", b"d"], [b"w", b"x", b"y", b"z"], [3, 5, 7, 11], b"test"
+    gpu = Dapol.new(ctx, hash_id, list(zip(ids, eids, vals)), seed, H, H, PAD_SEED)
+    ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+    rc, idx, bl, _ = cref.derive_leaves(hash_id, ib, io, eb, eo, seed, H)
+    assert rc == 0
+    for i in (0, 1, n // 2, n - 1):
+        assert gpu.leaf_index_of(i) == int(idx[i])
+    if H == 4:
+        assert [gpu.leaf_index_of(i) for i in range(4)] == [7, 12, 2, 4] and gpu.root_raw().value == 26
+    order = np.argsort(idx)
+    ora = cref.Tree(hash_id, H, idx[order], np.array(vals, np.uint64)[order], bl[order], PAD_SEED)
+    _assert_same_tree(gpu, ora, H)
+    # leaf blindings are kept as Scalar::from_bits gives them (unreduced), like the reference node
+    assert (gpu.level(H)["r"][gpu.level(H)["is_pad"] == 0] == bl[order]).all()
+
+
+def test_from_liabilities_errors(ctx, cref):
+    from dapol_b200 import Dapol, DapolError
+    ids, eids, vals = _liabs(100, 5)
+    ids[57] = ids[13]
+    with pytest.raises(DapolError) as e:
+        Dapol.new(ctx, 0, list(zip(ids, eids, vals)), b"s", 10, 10, PAD_SEED)
+    assert e.value.code == 4 and e.value.detail == 57          # DuplicatedInternalId (mod.rs:341-343)
+    ids, eids, vals = _liabs(100, 6)
+    with pytest.raises(DapolError) as e:
+        Dapol.new(ctx, 0, list(zip(ids, eids, vals)), b"s", 7, 7, PAD_SEED)
+    assert e.value.code == 2                                   # SparsityTooSmall: 2^7 < 2*100 (mod.rs:110-116)
+    with pytest.raises(DapolError) as e:
+        Dapol.new(ctx, 0, list(zip(ids, eids, vals)), b"s", 65, 7, PAD_SEED)
+    assert e.value.code == 1                                   # TreeHeightTooBig (mod.rs:104-109)
+    # densest legal tree (N = 2^H / 2): many collisions, result must still match the serial rule
+    ids, eids, vals = _liabs(128, 8)
+    gpu = Dapol.new(ctx, 0, list(zip(ids, eids, vals)), b"s", 8, 8, PAD_SEED)
+    ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+    rc, idx, _, _ = cref.derive_leaves(0, ib, io, eb, eo, b"s", 8)
+    assert rc == 0 and [gpu.leaf_index_of(i) for i in range(128)] == idx.tolist()
