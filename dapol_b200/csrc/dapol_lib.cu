@@ -22,6 +22,13 @@ static thread_local std::string g_cuda_err;
         }                                                                                                \
     } while (0)
 
+// Device memory on the hot path comes from the stream-ordered pool (cudaMallocAsync) with the release
+// threshold lifted, so repeated builds reuse the same HBM without paying cudaMalloc/cudaFree each time.
+static inline cudaError_t dmalloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
+template <typename T>
+static inline cudaError_t dmalloc(T **p, size_t bytes, cudaStream_t st) { return dmalloc(reinterpret_cast<void **>(p), bytes, st); }
+static inline void dfree(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+
 struct dapol_ctx {
     int device = 0;
     int W = 8;
@@ -346,6 +353,12 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaMalloc(&ctx->scratch, 1024));
+    {
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     int rc;
     switch (ctx->W) {
         case 4: rc = build_tables<4>(ctx); break;
@@ -385,10 +398,11 @@ extern "C" int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]) {
 extern "C" void dapol_tree_destroy(dapol_tree *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
-    cudaFree(t->ns.idx); cudaFree(t->ns.v); cudaFree(t->ns.r); cudaFree(t->ns.comc); cudaFree(t->ns.hash);
-    cudaFree(t->ns.ext); cudaFree(t->ns.is_pad);
-    cudaFree(t->pos_all);
-    cudaFree(t->d_pos); cudaFree(t->d_level_off); cudaFree(t->leaf_index_of);
+    cudaStream_t st = t->ctx->stream;
+    dfree(t->ns.idx, st); dfree(t->ns.v, st); dfree(t->ns.r, st); dfree(t->ns.comc, st); dfree(t->ns.hash, st);
+    dfree(t->ns.ext, st); dfree(t->ns.is_pad, st);
+    dfree(t->pos_all, st);
+    dfree(t->d_pos, st); dfree(t->d_level_off, st); dfree(t->leaf_index_of, st);
     delete t;
 }
 
@@ -471,22 +485,22 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
         cudaError_t e_ = (expr);                                             \
         if (e_ != cudaSuccess) {                                             \
             g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
-            cudaFree(arena_mem); dapol_tree_destroy(t); return DAPOL_ERR_CUDA; \
+            dfree(arena_mem, st); dapol_tree_destroy(t); return DAPOL_ERR_CUDA; \
         }                                                                    \
     } while (0)
-    TRY_T(cudaMalloc(&t->ns.idx, T * 8));
-    TRY_T(cudaMalloc(&t->ns.v, T * 8));
-    TRY_T(cudaMalloc(&t->ns.r, T * 32));
-    TRY_T(cudaMalloc(&t->ns.comc, T * 32));
-    TRY_T(cudaMalloc(&t->ns.hash, T * 32));
-    TRY_T(cudaMalloc(&t->ns.ext, T * 128));
-    TRY_T(cudaMalloc(&t->ns.is_pad, T));
-    TRY_T(cudaMalloc(&t->pos_all, (pos_off[H + 1] + 64) * 4));
+    TRY_T(dmalloc(&t->ns.idx, T * 8, st));
+    TRY_T(dmalloc(&t->ns.v, T * 8, st));
+    TRY_T(dmalloc(&t->ns.r, T * 32, st));
+    TRY_T(dmalloc(&t->ns.comc, T * 32, st));
+    TRY_T(dmalloc(&t->ns.hash, T * 32, st));
+    TRY_T(dmalloc(&t->ns.ext, T * 128, st));
+    TRY_T(dmalloc(&t->ns.is_pad, T, st));
+    TRY_T(dmalloc(&t->pos_all, (pos_off[H + 1] + 64) * 4, st));
     for (int h = 1; h <= H; h++) t->pos[h] = t->pos_all + pos_off[h];
     uint64_t ntiles_max = (n + SCAN_TILE - 1) / SCAN_TILE;
     Arena ar;
     ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 8) + Arena::need(ntiles_max, 8) + Arena::need(total_pads + 1, 8);
-    TRY_T(cudaMalloc(&arena_mem, ar.size));
+    TRY_T(dmalloc(&arena_mem, ar.size, st));
     ar.base = arena_mem;
     uint64_t *realA = ar.take<uint64_t>(n), *realB = ar.take<uint64_t>(n), *d_flags = ar.take<uint64_t>(n);
     uint64_t *d_tiles = ar.take<uint64_t>(ntiles_max), *d_pad_dest = ar.take<uint64_t>(total_pads + 1);
@@ -536,18 +550,18 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     }
     TRY_T(cudaEventRecord(ctx->ev[4], st));
     // pointer tables for path extraction
-    TRY_T(cudaMalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *)));
+    TRY_T(dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *, st)));
     TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
-    TRY_T(cudaMalloc(&t->d_level_off, (H + 1) * 8));
+    TRY_T(dmalloc(&t->d_level_off, (H + 1) * 8, st));
     TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
     TRY_T(cudaGetLastError());
     TRY_T(cudaStreamSynchronize(st));
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ctx->last_ms[i], ctx->ev[i], ctx->ev[i + 1]);
     cudaEventElapsedTime(&ctx->last_ms[4], ctx->ev[0], ctx->ev[4]);
     // the extended points are only needed while merging
-    cudaFree(t->ns.ext);
+    dfree(t->ns.ext, st);
     t->ns.ext = nullptr;
-    cudaFree(arena_mem);
+    dfree(arena_mem, st);
 #undef TRY_T
     *out = t;
     return DAPOL_OK;
@@ -566,7 +580,7 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 32);
-    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint64_t *d_idx = ar.take<uint64_t>(n), *d_val = ar.take<uint64_t>(n);
     uint8_t *d_bl = ar.take<uint8_t>(n * 32);
@@ -574,7 +588,7 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
     cudaMemcpyAsync(d_val, values, n * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_bl, blindings, n * 32, cudaMemcpyHostToDevice, ctx->stream);
     int rc = tree_build_dev(ctx, hash_id, height, n, d_idx, d_val, d_bl, pad_seed, pad_base, out);
-    cudaFree(mem);
+    dfree(mem, ctx->stream);
     return rc;
 }
 
@@ -598,7 +612,7 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
     Arena ar;
     ar.size = 3 * Arena::need(n, 32) + 4 * Arena::need(n, 8) + 3 * Arena::need(n, 4) + Arena::need(n, 32) + Arena::need(cub_bytes, 1) +
               Arena::need(seed_len + 1, 1) + 1024;
-    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint32_t *audit = ar.take<uint32_t>(8 * n), *cur_seed = ar.take<uint32_t>(8 * n), *blind = ar.take<uint32_t>(8 * n);
     uint64_t *akey = ar.take<uint64_t>(n), *keys_sorted = ar.take<uint64_t>(n), *values_sorted = ar.take<uint64_t>(n);
@@ -613,10 +627,10 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
         cudaError_t e_ = (expr);                                             \
         if (e_ != cudaSuccess) {                                             \
             g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
-            cudaFree(mem); cudaFree(cand); return DAPOL_ERR_CUDA;            \
+            dfree(mem, st); dfree(cand, st); return DAPOL_ERR_CUDA;            \
         }                                                                    \
     } while (0)
-    TRY_L(cudaMalloc(&cand, n * 8));  // survives as the id -> leaf index map of the tree
+    TRY_L(dmalloc(&cand, n * 8, st));  // survives as the id -> leaf index map of the tree
     if (seed_len) TRY_L(cudaMemcpyAsync(d_seed, audit_seed, seed_len, cudaMemcpyHostToDevice, st));
     // counters: [0] losers, [1] min failed pos, [2] first dup pos, [3] too-long flag (int)
     unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
@@ -645,13 +659,13 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
         if (d != ~0ull && d <= f) { rc = DAPOL_ERR_DUPLICATED_INTERNAL_ID; if (err_pos) *err_pos = d; }
         else if (f != ~0ull) { rc = DAPOL_ERR_FAILED_TO_MAP_INDEX; if (err_pos) *err_pos = f; }
     }
-    if (rc != DAPOL_OK) { cudaFree(mem); cudaFree(cand); return rc; }
+    if (rc != DAPOL_OK) { dfree(mem, st); dfree(cand, st); return rc; }
     // the last sort (no losers) is the final sorted order: result.sort_by_key(index) (mod.rs:396)
     k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, who, d_values, blind, values_sorted, blind_sorted);
     ctx->launches++;
     rc = tree_build_dev(ctx, hash_id, height, n, keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
-    cudaFree(mem);
-    if (rc != DAPOL_OK) { cudaFree(cand); return rc; }
+    dfree(mem, st);
+    if (rc != DAPOL_OK) { dfree(cand, st); return rc; }
     (*out)->leaf_index_of = cand;
 #undef TRY_L
     return DAPOL_OK;
@@ -677,7 +691,7 @@ extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, in
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = Arena::need(ib + 1, 1) + Arena::need(eb + 1, 1) + 3 * Arena::need(n + 1, 8);
-    CUDA_TRY(cudaMalloc(&mem, ar.size));
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint8_t *d_ib = ar.take<uint8_t>(ib + 1), *d_eb = ar.take<uint8_t>(eb + 1);
     uint64_t *d_io = ar.take<uint64_t>(n + 1), *d_eo = ar.take<uint64_t>(n + 1), *d_v = ar.take<uint64_t>(n + 1);
@@ -688,7 +702,7 @@ extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, in
     cudaMemcpyAsync(d_eo, eid_off, (n + 1) * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, st);
     int rc = liabilities_build_dev(ctx, hash_id, height, n, d_ib, d_io, d_eb, d_eo, d_v, audit_seed, audit_seed_len, pad_seed, pad_base, out, err_pos);
-    cudaFree(mem);
+    dfree(mem, st);
     return rc;
 }
 

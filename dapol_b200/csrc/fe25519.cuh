@@ -38,7 +38,11 @@
 #define EMU_ADD(d, x, y) EMU_SETNC_(d, (uint64_t)(x) + (uint64_t)(y))
 #endif
 
+#ifdef DAPOL_FE_GEN_INC
+#include DAPOL_FE_GEN_INC
+#else
 #include "fe_mulsqr_gen.inc"
+#endif
 
 struct fe {
     uint32_t v[8];

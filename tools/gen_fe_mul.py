@@ -14,7 +14,23 @@ One instruction list is emitted twice: as an inline-asm block per chain for the 
 import os
 import sys
 
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "dapol_b200", "csrc", "fe_mulsqr_gen.inc")
+# Tuning knobs (defaults = the variant measured fastest on B200, see profiles/fe_variants_r01.txt):
+#   DAPOL_FE_PLAIN_MUL  : comma list of "row:parity" half-rows of the 8x8 product computed as plain (carry-free,
+#                         full-rate) IMAD.WIDE products and merged with ALU-pipe add chains instead of the
+#                         half-rate carry-predicated IMAD.WIDE.X chain
+#   DAPOL_FE_PLAIN_SQR  : same for the off-diagonal rows of the squaring
+#   DAPOL_FE_SQR_DIAG   : "chain" (mad chain) or "plain" (plain products + add chain)
+#   DAPOL_FE_FOLD       : "chain" (original) or "plain"
+def _pairs(env, default):
+    v = os.environ.get(env, default)
+    return set(tuple(int(x) for x in t.split(":")) for t in v.split(",") if t)
+
+
+PLAIN_MUL = _pairs("DAPOL_FE_PLAIN_MUL", "")
+PLAIN_SQR = _pairs("DAPOL_FE_PLAIN_SQR", "")
+SQR_DIAG = os.environ.get("DAPOL_FE_SQR_DIAG", "chain")
+FOLD = os.environ.get("DAPOL_FE_FOLD", "plain")
+OUT = os.environ.get("DAPOL_FE_OUT") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "dapol_b200", "csrc", "fe_mulsqr_gen.inc")
 
 
 class Chain:
@@ -117,6 +133,57 @@ def product_chain(acc: Acc, start: int, prods):
     return ch.emit(fresh)
 
 
+_tmp_counter = [0]
+
+
+def plain_product_chain(acc: Acc, start: int, prods):
+    """Same contract as product_chain, but the products are carry-free 64-bit multiplies (full-rate IMAD.WIDE)
+    and only the accumulation is a carry chain (ALU pipe)."""
+    _tmp_counter[0] += 1
+    t = "pt%d_" % _tmp_counter[0]
+    n = len(prods)
+    s = "    uint32_t %s[%d];\n" % (t, 2 * n)
+    for k, (x, y) in enumerate(prods):
+        s += "    { uint64_t p_ = (uint64_t)%s * (uint64_t)%s; %s[%d] = (uint32_t)p_; %s[%d] = (uint32_t)(p_ >> 32); }\n" % (x, y, t, 2 * k, t, 2 * k + 1)
+    ch = Chain()
+    carry = False
+    fresh = set()
+    last_was_live = False
+    for k in range(2 * n):
+        word = start + k
+        assert word < acc.limit
+        dst, src = acc.w(word), "%s[%d]" % (t, k)
+        live = word in acc.live
+        if live:
+            ch.add("addc.cc" if carry else "add.cc", dst, dst, src)
+            carry = True
+        else:
+            if carry:
+                ch.add("addc.cc", dst, src, "0")
+            else:
+                s += "    %s = %s;\n" % (dst, src)
+            fresh.add(dst)
+            acc.live.add(word)
+        last_was_live = live
+    if carry and last_was_live:
+        word = start + 2 * n
+        while word < acc.limit:
+            dst = acc.w(word)
+            if word in acc.live:
+                ch.add("addc.cc", dst, dst, "0")
+                word += 1
+            else:
+                ch.add("addc", dst, "0", "0")
+                fresh.add(dst)
+                acc.live.add(word)
+                break
+    if ch.ins:
+        op, dst, srcs = ch.ins[-1]
+        if op.endswith(".cc") and op.startswith("addc"):
+            ch.ins[-1] = (op[:-3], dst, srcs)
+    return s + ch.emit(fresh)
+
+
 def merge_EO(R, E: Acc, O: Acc, n):
     """R = E + (O << 32), n words."""
     out = "    %s[0] = %s;\n" % (R, E.w(0))
@@ -148,7 +215,8 @@ def gen_mul():
             js = [j for j in range(8) if j % 2 == parity]
             p0 = i + js[0]
             acc, start = (E, p0) if p0 % 2 == 0 else (O, p0 - 1)
-            s += product_chain(acc, start, [("a[%d]" % j, "b[%d]" % i) for j in js])
+            fn = plain_product_chain if (i, parity) in PLAIN_MUL else product_chain
+            s += fn(acc, start, [("a[%d]" % j, "b[%d]" % i) for j in js])
     assert E.live == set(range(16)) and O.live == set(range(15)), (E.live, O.live)
     s += merge_EO("R", E, O, 16)
     s += "}\n\n"
@@ -166,7 +234,8 @@ def gen_sqr():
                 continue
             p0 = i + js[0]
             acc, start = (E, p0) if p0 % 2 == 0 else (O, p0 - 1)
-            s += product_chain(acc, start, [("a[%d]" % i, "a[%d]" % j) for j in js])
+            fn = plain_product_chain if (i, parity) in PLAIN_SQR else product_chain
+            s += fn(acc, start, [("a[%d]" % i, "a[%d]" % j) for j in js])
     # off-diagonal sum U = E + (O<<32); words never written are zero
     for k in range(16):
         if k not in E.live:
@@ -183,6 +252,16 @@ def gen_sqr():
         ch.add("add.cc" if k == 0 else ("addc.cc" if k < 15 else "addc"), "U[%d]" % k, "U[%d]" % k, "U[%d]" % k)
     s += ch.emit(set())
     # add diagonal squares
+    if SQR_DIAG == "plain":
+        s += "    uint32_t dg_[16];\n"
+        for i in range(8):
+            s += "    { uint64_t p_ = (uint64_t)a[%d] * (uint64_t)a[%d]; dg_[%d] = (uint32_t)p_; dg_[%d] = (uint32_t)(p_ >> 32); }\n" % (i, i, 2 * i, 2 * i + 1)
+        ch = Chain()
+        for k in range(16):
+            ch.add("add.cc" if k == 0 else ("addc.cc" if k < 15 else "addc"), "R[%d]" % k, "U[%d]" % k, "dg_[%d]" % k)
+        s += ch.emit(set())
+        s += "}\n\n"
+        return s
     ch = Chain()
     for i in range(8):
         ch.add("mad.lo.cc" if i == 0 else "madc.lo.cc", "R[%d]" % (2 * i), "a[%d]" % i, "a[%d]" % i, "U[%d]" % (2 * i))
@@ -195,6 +274,30 @@ def gen_sqr():
 def gen_fold():
     """r = R[0..8) + 38 * R[8..16)  mod 2^256-38 (i.e. a representative < 2^256 of the value mod p)."""
     s = "DAPOL_HD_INLINE void fold38(uint32_t r[8], const uint32_t R[16]) {\n"
+    if FOLD == "plain":
+        s += "    uint32_t t8, fl_[8], fh_[8];\n"
+        for k in range(8):
+            s += "    { uint64_t p_ = (uint64_t)R[%d] * 38ull; fl_[%d] = (uint32_t)p_; fh_[%d] = (uint32_t)(p_ >> 32); }\n" % (8 + k, k, k)
+        ch = Chain()
+        for k in range(8):
+            ch.add("add.cc" if k == 0 else "addc.cc", "r[%d]" % k, "R[%d]" % k, "fl_[%d]" % k)
+        ch.add("addc", "t8", "0", "0")
+        s += ch.emit(set())
+        ch = Chain()
+        for k in range(7):
+            ch.add("add.cc" if k == 0 else "addc.cc", "r[%d]" % (k + 1), "r[%d]" % (k + 1), "fh_[%d]" % k)
+        ch.add("addc", "t8", "t8", "fh_[7]")
+        s += ch.emit(set())
+        s += "    uint32_t m_ = t8 * 38u;\n"
+        ch = Chain()
+        ch.add("add.cc", "r[0]", "r[0]", "m_")
+        for k in range(1, 8):
+            ch.add("addc.cc", "r[%d]" % k, "r[%d]" % k, "0")
+        ch.add("addc", "t8", "0", "0")
+        s += ch.emit(set())
+        s += "    r[0] += t8 * 38u;\n"
+        s += "}\n\n"
+        return s
     s += "    uint32_t t8, c38 = 38u;\n"
     ch = Chain()
     for k in range(8):
