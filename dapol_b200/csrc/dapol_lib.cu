@@ -550,7 +550,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     }
     TRY_T(cudaEventRecord(ctx->ev[4], st));
     // pointer tables for path extraction
-    TRY_T(dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *, st)));
+    TRY_T(dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *), st));
     TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
     TRY_T(dmalloc(&t->d_level_off, (H + 1) * 8, st));
     TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -577,6 +577,7 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
                                            dapol_tree **out) {
     if (!ctx || !leaf_idx || !values || !blindings || n == 0) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 32);
@@ -688,6 +689,7 @@ extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, in
     if (n == 0) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     uint64_t ib = iid_off[n], eb = eid_off[n];
+    cudaStream_t st = ctx->stream;
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = Arena::need(ib + 1, 1) + Arena::need(eb + 1, 1) + 3 * Arena::need(n + 1, 8);
@@ -695,7 +697,6 @@ extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, in
     ar.base = mem;
     uint8_t *d_ib = ar.take<uint8_t>(ib + 1), *d_eb = ar.take<uint8_t>(eb + 1);
     uint64_t *d_io = ar.take<uint64_t>(n + 1), *d_eo = ar.take<uint64_t>(n + 1), *d_v = ar.take<uint64_t>(n + 1);
-    cudaStream_t st = ctx->stream;
     if (ib) cudaMemcpyAsync(d_ib, iid_blob, ib, cudaMemcpyHostToDevice, st);
     if (eb) cudaMemcpyAsync(d_eb, eid_blob, eb, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_io, iid_off, (n + 1) * 8, cudaMemcpyHostToDevice, st);
