@@ -215,26 +215,29 @@ __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t 
     store8(blind_sorted + 8 * j, w);
 }
 
+// units per thread of the node passes = batch size of the shared inversion (ge_dc_batch)
+#define NODE_BATCH 8
 template <int W>
-__global__ void __launch_bounds__(128) k_leaf(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
+__global__ void __launch_bounds__(128) k_leaf(uint64_t n, uint64_t stride, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
                                               const uint64_t *values, const uint32_t *blind, const ge_niels *tab_b,
                                               const ge_niels *tab_bbl) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) leaf_body<W>(i, ns, level_off, pos, hash_id, values, blind, tab_b, tab_bbl);
+    if (i < stride) leaf_batch_body<W, NODE_BATCH>(i, stride, n, ns, level_off, pos, hash_id, values, blind, tab_b, tab_bbl);
 }
 struct Seed8 {
     uint32_t w[8];
 };
 template <int W>
-__global__ void __launch_bounds__(128) k_pad(uint64_t n, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
+__global__ void __launch_bounds__(128) k_pad(uint64_t n, uint64_t stride, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
                                              uint64_t pad_base, const ge_niels *tab_bbl) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < n) pad_body<W>(g, ns, pad_dest, hash_id, seed.w, pad_base, tab_bbl);
+    if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_base, tab_bbl);
 }
-__global__ void __launch_bounds__(128) k_merge(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos,
-                                               int hash_id) {
+template <int B>
+__global__ void __launch_bounds__(128) k_merge(uint64_t n, uint64_t stride, NodeStore ns, uint64_t child_off, uint64_t parent_off,
+                                               const uint32_t *parent_pos, int hash_id) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) merge_body(j, ns, child_off, parent_pos ? parent_off + parent_pos[j] : parent_off, hash_id);
+    if (j < stride) merge_batch_body<B>(j, stride, n, ns, child_off, parent_off, parent_pos, hash_id);
 }
 // leaves only (no tree): commitments for dapol_commit_batch
 template <int W>
@@ -327,12 +330,12 @@ __global__ void __launch_bounds__(256) k_fe_bench(uint32_t *out, int iters) {
 // ------------------------------------------------------------------------------------------------ ctx
 template <int W>
 static int build_tables(dapol_ctx *ctx) {
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    constexpr int NWR = 253 / W + 1;  // both bases carry full-width windows: leaf values are halved mod l too
     uint64_t half = 1ull << (W - 1);
-    uint64_t nb = (uint64_t)NWV * half, nbl = (uint64_t)NWR * half;
+    uint64_t nb = (uint64_t)NWR * half, nbl = (uint64_t)NWR * half;
     CUDA_TRY(cudaMalloc(&ctx->tab_b, nb * sizeof(ge_niels)));
     CUDA_TRY(cudaMalloc(&ctx->tab_bbl, nbl * sizeof(ge_niels)));
-    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWV, 0, nb);
+    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWR, 0, nb);
     k_comb_table<W><<<grid_for(nbl, 64), 64, 0, ctx->stream>>>(ctx->tab_bbl, NWR, 1, nbl);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -406,16 +409,27 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     delete t;
 }
 
+// threads for n units at up to NODE_BATCH units each; small launches keep one unit per thread so the
+// upper tree levels still spread over the SMs
+static inline uint64_t batch_stride(uint64_t n) {
+    const uint64_t full = 148ull * 4 * 128;  // one resident wave of 128-thread CTAs
+    uint64_t per = (n + full - 1) / full;
+    if (per < 1) per = 1;
+    if (per > NODE_BATCH) per = NODE_BATCH;
+    return (n + per - 1) / per;
+}
 template <int W>
 static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
                             const Seed8 &seed, uint64_t pad_base, int phase) {
     int H = t->height;
     if (phase == 0) {
-        k_leaf<W><<<grid_for(t->n_leaves, 128), 128, 0, ctx->stream>>>(t->n_leaves, t->ns, t->level_off[H], t->pos[H], t->hash_id, d_values,
-                                                                       d_blind, ctx->tab_b, ctx->tab_bbl);
+        uint64_t stride = batch_stride(t->n_leaves);
+        k_leaf<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_leaves, stride, t->ns, t->level_off[H], t->pos[H], t->hash_id, d_values,
+                                                                  d_blind, ctx->tab_b, ctx->tab_bbl);
         ctx->launches++;
     } else if (t->n_pads) {
-        k_pad<W><<<grid_for(t->n_pads, 128), 128, 0, ctx->stream>>>(t->n_pads, t->ns, d_pad_dest, t->hash_id, seed, pad_base, ctx->tab_bbl);
+        uint64_t stride = batch_stride(t->n_pads);
+        k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, pad_base, ctx->tab_bbl);
         ctx->launches++;
     }
 }
@@ -545,7 +559,9 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     // ---- merges, level by level
     for (int h = H; h >= 1; h--) {
         uint64_t np = t->n_real[h - 1];
-        k_merge<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
+        uint64_t stride = batch_stride(np);
+        k_merge<NODE_BATCH><<<grid_for(stride, 128), 128, 0, st>>>(np, stride, t->ns, t->level_off[h], t->level_off[h - 1],
+                                                                   h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
         ctx->launches++;
     }
     TRY_T(cudaEventRecord(ctx->ev[4], st));

@@ -13,9 +13,11 @@
 #if defined(__CUDACC__)
 #define DAPOL_HD __host__ __device__
 #define DAPOL_HD_INLINE __host__ __device__ __forceinline__
+#define DAPOL_HD_MEMBER __host__ __device__ __forceinline__
 #else
 #define DAPOL_HD
 #define DAPOL_HD_INLINE static inline
+#define DAPOL_HD_MEMBER inline
 #endif
 
 #ifndef __CUDA_ARCH__
@@ -222,6 +224,15 @@ DAPOL_HD_INLINE void fe_fromwords(fe &r, const uint32_t w[8]) {
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = w[i];
     r.v[7] &= 0x7fffffffu;
+}
+// raw 8-word storage inside an fe (used to park already-canonical byte strings in fe-typed scratch)
+DAPOL_HD_INLINE void fe_setwords_raw(fe &r, const uint32_t w[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = w[i];
+}
+DAPOL_HD_INLINE void fe_getwords_raw(uint32_t w[8], const fe &a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = a.v[i];
 }
 DAPOL_HD_INLINE int fe_isneg(const fe &a) {
     uint32_t o[8];

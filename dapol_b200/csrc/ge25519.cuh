@@ -168,6 +168,83 @@ DAPOL_HD_INLINE void ge_compress(uint32_t s[8], const ge &p) {
     fe_abs(t0);
     fe_canon(s, t0);
 }
+// ---- batched compress(2Q): dalek RistrettoPoint::double_and_compress_batch ------------------------------
+// compress() spends ~252 squarings on an inverse square root per point.  For a point known as 2Q the root is
+// explicit, so one field INVERSION shared by a whole batch (Montgomery's trick) replaces the per-point chain.
+// The tree keeps every commitment as its half point Q (com = 2Q: scalars are halved mod l before the comb,
+// parents are Q_L + Q_R), so every node is compressed this way.  Same group element => same canonical bytes.
+struct ge_dc_state {
+    fe e, f, g, h, x;  // x = e*g*f*h, the value to invert
+};
+DAPOL_HD_INLINE void ge_dc_prepare(ge_dc_state &st, const ge &p) {
+    fe XX, YY, ZZ, dTT, t;
+    fe_sq(XX, p.X); fe_sq(YY, p.Y); fe_sq(ZZ, p.Z);
+    fe_sq(dTT, p.T); fe_mul(dTT, dTT, fe_const_d());
+    fe_dbl(t, p.Y); fe_mul(st.e, p.X, t);   // 2XY
+    fe_add(st.f, ZZ, dTT);                  // Z^2 + dT^2
+    fe_add(st.g, YY, XX);                   // Y^2 - aX^2
+    fe_sub(st.h, ZZ, dTT);                  // Z^2 - dT^2
+    fe eg, fh;
+    fe_mul(eg, st.e, st.g); fe_mul(fh, st.f, st.h);
+    fe_mul(st.x, eg, fh);
+}
+// xinv = 1/st.x (or 0 when st.x == 0, which only happens for the identity coset: result is then 0 = identity)
+DAPOL_HD_INLINE void ge_dc_finish(uint32_t s[8], const ge_dc_state &st, const fe &xinv) {
+    fe eg, fh, Zinv, Tinv, t, e, g, h, magic, minus_e, fsq;
+    fe_mul(eg, st.e, st.g); fe_mul(fh, st.f, st.h);
+    fe_mul(Zinv, eg, xinv); fe_mul(Tinv, fh, xinv);
+    fe_mul(t, eg, Zinv);
+    int nc1 = fe_isneg(t);
+    fe_neg(minus_e, st.e);
+    fe_mul(fsq, st.f, fe_const_sqrtm1());
+    e = st.e; g = st.g; h = st.h; magic = fe_const_invsqrt_a_minus_d();
+    fe_cmov(e, st.g, nc1); fe_cmov(g, minus_e, nc1); fe_cmov(h, fsq, nc1); fe_cmov(magic, fe_const_sqrtm1(), nc1);
+    fe_mul(t, h, e); fe_mul(t, t, Zinv);
+    fe_cneg(g, fe_isneg(t));
+    fe_mul(t, g, Tinv); fe_mul(t, magic, t);
+    fe_sub(h, h, g); fe_mul(t, h, t);
+    fe_abs(t);
+    fe_canon(s, t);
+}
+// Up to B points per thread; arrays live in local memory (loops are kept rolled).
+template <int B>
+struct ge_dc_batch {
+    ge_dc_state st[B];
+    fe pre[B];  // prefix products; after solve(): the compressed words
+    fe acc;
+    int n;
+    DAPOL_HD_MEMBER void init() { fe_set1(acc); n = 0; }
+    DAPOL_HD_MEMBER void push(const ge &q) {
+        ge_dc_prepare(st[n], q);
+        fe x = st[n].x, one;
+        fe_set1(one);
+        fe_cmov(x, one, fe_iszero(x));
+        pre[n] = acc;
+        fe_mul(acc, acc, x);
+        n++;
+    }
+    DAPOL_HD_MEMBER void solve() {
+        fe inv;
+        fe_invert(inv, acc);
+#pragma unroll 1
+        for (int b = n - 1; b >= 0; b--) {
+            fe x = st[b].x, one, xinv;
+            fe_set1(one);
+            int z = fe_iszero(x);
+            fe_cmov(x, one, z);
+            fe_mul(xinv, inv, pre[b]);
+            fe_mul(inv, inv, x);
+            fe zero;
+            fe_set0(zero);
+            fe_cmov(xinv, zero, z);
+            uint32_t s[8];
+            ge_dc_finish(s, st[b], xinv);
+            fe_setwords_raw(pre[b], s);
+        }
+    }
+    DAPOL_HD_MEMBER void get(int b, uint32_t s[8]) const { fe_getwords_raw(s, pre[b]); }
+};
+
 // RFC 9496 4.3.1 Decode from 8 LE words; returns 1 on success
 DAPOL_HD_INLINE int ge_decompress(ge &p, const uint32_t s[8]) {
     fe sf, ss, u1, u2, u2s, v, t0, isq, den_x, den_y, one;

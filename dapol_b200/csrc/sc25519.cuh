@@ -75,6 +75,11 @@ DAPOL_HD_INLINE void sc_mul(sc &r, const sc &a, const sc &b) {  // a any 256-bit
     sc_montmul(r, t, sc_const_rr());
 }
 DAPOL_HD_INLINE void sc_reduce256(sc &r, const sc &a) { sc_montmul(r, a, sc_const_r1()); }
+// r = a / 2 mod l for any 256-bit a (canonical result): one Montgomery product with 2^-1 * R
+DAPOL_HD_INLINE void sc_half256(sc &r, const sc &a) {
+    sc h = {{SC_INV2R_WORDS}};
+    sc_montmul(r, a, h);
+}
 // Scalar::from_bytes_mod_order_wide on 16 LE words
 DAPOL_HD_INLINE void sc_from_wide(sc &r, const uint32_t w[16]) {
     sc lo, hi;

@@ -137,82 +137,137 @@ DAPOL_HD_INLINE int rehash_body(uint64_t u, int hash_id, int height, uint32_t *c
 }
 
 // ------------------------------------------------------------------------------------------------
-// node finalisation shared by leaves and padding nodes: hash = D(compress(com))  (node.rs:33-36)
-DAPOL_HD_INLINE void node_finish(const NodeStore &ns, uint64_t g, int hash_id, const ge &com, uint64_t v, const uint32_t r[8]) {
-    uint32_t cc[8], hh[8];
-    ge_compress(cc, com);
-    dapol_hash32(hash_id, hh, cc);
-    ns.v[g] = v;
-    store8(ns.r + 8 * g, r);
-    store8(ns.comc + 8 * g, cc);
-    store8(ns.hash + 8 * g, hh);
-    store_ge(ns.ext + 32 * g, com);
-}
+// Node passes.  Every commitment is carried as its HALF point Q (com = 2Q) in ns.ext: scalars are halved mod l
+// before the comb and parents are Q_L + Q_R, so that compress(com) is the batched double-and-compress of
+// ge25519.cuh (one shared inversion per thread batch instead of a 252-squaring chain per node).
+// A thread handles up to B units t, t + stride, t + 2 stride, ... (coalesced across the warp).
 
-// DapolNode::new(value, blinding) (node.rs:29-45): com = v*B + r*B_blinding by signed-window comb.
-template <int W>
-DAPOL_HD_INLINE void leaf_body(uint64_t i, const NodeStore &ns, uint64_t level_off, const uint32_t *pos, int hash_id,
-                               const uint64_t *values, const uint32_t *blind /*[n][8]*/, const ge_niels *tab_b,
-                               const ge_niels *tab_bbl) {
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
-    uint32_t rw[8];
-    load8(rw, blind + 8 * i);
-    sc rs, rr;
+// DapolNode::new(value, blinding) (node.rs:29-45): com = v*B + r*B_blinding by signed-window comb;
+// hash = D(compress(com)) (node.rs:33-36).
+template <int W, int B>
+DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, uint64_t level_off, const uint32_t *pos,
+                                     int hash_id, const uint64_t *values, const uint32_t *blind /*[n][8]*/, const ge_niels *tab_b,
+                                     const ge_niels *tab_bbl) {
+    constexpr int NWR = 253 / W + 1;
+    ge_dc_batch<B> dc;
+    dc.init();
+#pragma unroll 1
+    for (int b = 0; b < B; b++) {
+        uint64_t i = t + (uint64_t)b * stride;
+        if (i >= n) break;
+        uint32_t rw[8];
+        load8(rw, blind + 8 * i);
+        sc rs, rh, vs, vh;
 #pragma unroll
-    for (int k = 0; k < 8; k++) rs.v[k] = rw[k];
-    sc_reduce256(rr, rs);
-    uint64_t v = values[i];
-    uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
-    int32_t dr[NWR], dv[NWV];
-    sc_signed_digits<W, NWR>(dr, rr.v, 8);
-    sc_signed_digits<W, NWV>(dv, vw, 2);
-    ge acc;
-    ge_identity(acc);
-    ge_comb_accumulate<W, NWV>(acc, tab_b, dv);
-    ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
-    node_finish(ns, level_off + pos[i], hash_id, acc, v, rw);
+        for (int k = 0; k < 8; k++) rs.v[k] = rw[k];
+        sc_half256(rh, rs);  // blinding may be unreduced (Scalar::from_bits, mod.rs:385)
+        uint64_t v = values[i];
+        sc_set_u64(vs, v);
+        sc_half256(vh, vs);
+        int32_t d[NWR];
+        ge acc;
+        ge_identity(acc);
+        sc_signed_digits<W, NWR>(d, vh.v, 8);
+        ge_comb_accumulate<W, NWR>(acc, tab_b, d);
+        sc_signed_digits<W, NWR>(d, rh.v, 8);
+        ge_comb_accumulate<W, NWR>(acc, tab_bbl, d);
+        uint64_t g = level_off + pos[i];
+        ns.v[g] = v;
+        store8(ns.r + 8 * g, rw);
+        store_ge(ns.ext + 32 * g, acc);
+        dc.push(acc);
+    }
+    dc.solve();
+#pragma unroll 1
+    for (int b = 0; b < dc.n; b++) {
+        uint64_t g = level_off + pos[t + (uint64_t)b * stride];
+        uint32_t cc[8], hh[8];
+        dc.get(b, cc);
+        dapol_hash32(hash_id, hh, cc);
+        store8(ns.comc + 8 * g, cc);
+        store8(ns.hash + 8 * g, hh);
+    }
 }
 
 // DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng)); rng draw #g of the seeded stream =
 // from_bytes_mod_order_wide(ChaCha20(pad_seed) block pad_base + g)   (RNG contract)
-template <int W>
-DAPOL_HD_INLINE void pad_body(uint64_t g, const NodeStore &ns, const uint64_t *pad_dest, int hash_id, const uint32_t seed[8],
-                              uint64_t pad_base, const ge_niels *tab_bbl) {
+template <int W, int B>
+DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, const uint64_t *pad_dest, int hash_id,
+                                    const uint32_t seed[8], uint64_t pad_base, const ge_niels *tab_bbl) {
     constexpr int NWR = 253 / W + 1;
-    uint32_t ks[16];
-    chacha20_block(ks, seed, pad_base + g, 0);
-    sc r;
-    sc_from_wide(r, ks);
-    int32_t dr[NWR];
-    sc_signed_digits<W, NWR>(dr, r.v, 8);
-    ge acc;
-    ge_identity(acc);
-    ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
-    node_finish(ns, pad_dest[g], hash_id, acc, 0, r.v);
+    ge_dc_batch<B> dc;
+    dc.init();
+#pragma unroll 1
+    for (int b = 0; b < B; b++) {
+        uint64_t g = t + (uint64_t)b * stride;
+        if (g >= n) break;
+        uint32_t ks[16];
+        chacha20_block(ks, seed, pad_base + g, 0);
+        sc r, rh;
+        sc_from_wide(r, ks);
+        sc_half256(rh, r);
+        int32_t d[NWR];
+        sc_signed_digits<W, NWR>(d, rh.v, 8);
+        ge acc;
+        ge_identity(acc);
+        ge_comb_accumulate<W, NWR>(acc, tab_bbl, d);
+        uint64_t dest = pad_dest[g];
+        ns.v[dest] = 0;
+        store8(ns.r + 8 * dest, r.v);
+        store_ge(ns.ext + 32 * dest, acc);
+        dc.push(acc);
+    }
+    dc.solve();
+#pragma unroll 1
+    for (int b = 0; b < dc.n; b++) {
+        uint64_t dest = pad_dest[t + (uint64_t)b * stride];
+        uint32_t cc[8], hh[8];
+        dc.get(b, cc);
+        dapol_hash32(hash_id, hh, cc);
+        store8(ns.comc + 8 * dest, cc);
+        store8(ns.hash + 8 * dest, hh);
+    }
 }
 
-// Mergeable::merge (node.rs:64-80) for parent j of the level whose children start at child_off:
-// hash = D(C(L)||C(R)||H(L)||H(R)); v, r, com = sums.  dest = global slot of the parent.
-DAPOL_HD_INLINE void merge_body(uint64_t j, const NodeStore &ns, uint64_t child_off, uint64_t dest, int hash_id) {
-    uint64_t l = child_off + 2 * j, r = l + 1;
-    uint32_t cl[8], cr[8], hl[8], hr[8], hh[8];
-    load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
-    load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
-    dapol_hash128(hash_id, hh, cl, cr, hl, hr);
-    store8(ns.hash + 8 * dest, hh);
-    ns.v[dest] = ns.v[l] + ns.v[r];  // u64 wrapping add, as release-mode Rust
-    sc a, b, s;
-    load8(a.v, ns.r + 8 * l); load8(b.v, ns.r + 8 * r);
-    sc_reduce256(a, a); sc_reduce256(b, b);  // leaf blindings may be unreduced (Scalar::from_bits)
-    sc_add(s, a, b);
-    store8(ns.r + 8 * dest, s.v);
-    ge p, q, sum;
-    load_ge(p, ns.ext + 32 * l); load_ge(q, ns.ext + 32 * r);
-    ge_add(sum, p, q);
-    store_ge(ns.ext + 32 * dest, sum);
-    uint32_t cc[8];
-    ge_compress(cc, sum);
-    store8(ns.comc + 8 * dest, cc);
+// Mergeable::merge (node.rs:64-80) for the parents j of the level whose children start at child_off:
+// hash = D(C(L)||C(R)||H(L)||H(R)); v, r, com = sums.  parent_pos == nullptr: the single root at slot parent_off.
+template <int B>
+DAPOL_HD_INLINE void merge_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, uint64_t child_off, uint64_t parent_off,
+                                      const uint32_t *parent_pos, int hash_id) {
+    ge_dc_batch<B> dc;
+    dc.init();
+#pragma unroll 1
+    for (int b = 0; b < B; b++) {
+        uint64_t j = t + (uint64_t)b * stride;
+        if (j >= n) break;
+        uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
+        uint64_t l = child_off + 2 * j, r = l + 1;
+        uint32_t cl[8], cr[8], hl[8], hr[8], hh[8];
+        load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
+        load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
+        dapol_hash128(hash_id, hh, cl, cr, hl, hr);
+        store8(ns.hash + 8 * dest, hh);
+        ns.v[dest] = ns.v[l] + ns.v[r];  // u64 wrapping add, as release-mode Rust
+        sc a, c, s;
+        load8(a.v, ns.r + 8 * l); load8(c.v, ns.r + 8 * r);
+        sc_reduce256(a, a); sc_reduce256(c, c);  // leaf blindings may be unreduced (Scalar::from_bits)
+        sc_add(s, a, c);
+        store8(ns.r + 8 * dest, s.v);
+        ge p, q, sum;
+        load_ge(p, ns.ext + 32 * l); load_ge(q, ns.ext + 32 * r);
+        ge_add(sum, p, q);
+        store_ge(ns.ext + 32 * dest, sum);
+        dc.push(sum);
+    }
+    dc.solve();
+#pragma unroll 1
+    for (int b = 0; b < dc.n; b++) {
+        uint64_t j = t + (uint64_t)b * stride;
+        uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
+        uint32_t cc[8];
+        dc.get(b, cc);
+        store8(ns.comc + 8 * dest, cc);
+    }
 }
 
 // comb table entry (k, e): (e+1) * 2^(W k) * P in affine Niels form

@@ -95,19 +95,19 @@ EX void emu_keccak(uint8_t st[200]) { uint64_t s[25]; memcpy(s, st, 200); keccak
 // ---- comb commit with tables built by the same body the init kernel uses
 template <int W>
 static void commit_w(uint64_t v, const uint8_t r[32], uint8_t out[32]) {
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    constexpr int NWR = 253 / W + 1;
     const uint32_t half = 1u << (W - 1);
     static std::vector<ge_niels> tb, tbbl;
     if (tb.empty()) {
-        tb.resize((size_t)NWV * half); tbbl.resize((size_t)NWR * half);
-        for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWV, 0);
+        tb.resize((size_t)NWR * half); tbbl.resize((size_t)NWR * half);
+        for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWR, 0);
         for (uint64_t t = 0; t < tbbl.size(); t++) comb_table_body<W>(t, tbbl.data(), NWR, 1);
     }
     // one-node store
     uint64_t idx = 0, vv = 0; uint32_t rr[8], cc[8], hh[8], ext[32], blind[8]; uint8_t pad = 0; uint32_t pos = 0;
     NodeStore ns{&idx, &vv, rr, cc, hh, ext, &pad};
     b2w(blind, r, 8);
-    leaf_body<W>(0, ns, 0, &pos, 0, &v, blind, tb.data(), tbbl.data());
+    leaf_batch_body<W, 1>(0, 1, 1, ns, 0, &pos, 0, &v, blind, tb.data(), tbbl.data());
     w2b(out, cc, 8);
 }
 EX void emu_commit(int w, uint64_t v, const uint8_t r[32], uint8_t out[32]) {
@@ -123,12 +123,12 @@ struct EmuTree {
 EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *leaf_idx, const uint64_t *values,
                            const uint8_t *blind, const uint8_t pad_seed[32], uint64_t pad_base) {
     constexpr int W = 4;
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    constexpr int NWR = 253 / W + 1;
     const uint32_t half = 1u << (W - 1);
     static std::vector<ge_niels> tb, tbbl;
     if (tb.empty()) {
-        tb.resize((size_t)NWV * half); tbbl.resize((size_t)NWR * half);
-        for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWV, 0);
+        tb.resize((size_t)NWR * half); tbbl.resize((size_t)NWR * half);
+        for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWR, 0);
         for (uint64_t t = 0; t < tbbl.size(); t++) comb_table_body<W>(t, tbbl.data(), NWR, 1);
     }
     // level sizes from the adjacent-leaf msb histogram (as the CUDA host code does)
@@ -168,12 +168,15 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     t->n_pads = total_pads;
     uint32_t seed[8]; b2w(seed, pad_seed, 8);
     std::vector<uint32_t> bw(8 * n); b2w(bw.data(), blind, 8 * n);
-    if (height == 0) { uint32_t p0 = 0; leaf_body<W>(0, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0]; return t; }
-    for (uint64_t i = 0; i < n; i++) leaf_body<W>(i, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
-    for (uint64_t g = 0; g < total_pads; g++) pad_body<W>(g, ns, pad_dest.data(), hash_id, seed, pad_base, tbbl.data());
+    constexpr int BT = 3;  // units per emulated thread (exercises full and partial batches)
+    auto threads = [](uint64_t units) { return (units + BT - 1) / BT; };
+    if (height == 0) { uint32_t p0 = 0; leaf_batch_body<W, BT>(0, 1, 1, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0]; return t; }
+    for (uint64_t i = 0, st = threads(n); i < st; i++)
+        leaf_batch_body<W, BT>(i, st, n, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
+    for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_base, tbbl.data());
     for (int h = height; h >= 1; h--)
-        for (uint64_t j = 0; j < nparents[h]; j++)
-            merge_body(j, ns, t->level_off[h], h - 1 == 0 ? 0 : t->level_off[h - 1] + pos[h - 1][j], hash_id);
+        for (uint64_t j = 0, st = threads(nparents[h]); j < st; j++)
+            merge_batch_body<BT>(j, st, nparents[h], ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);
     return t;
 }
 // leaf derivation through the kernel bodies, with the sort/fix-point orchestration mirrored serially

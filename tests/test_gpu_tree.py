@@ -75,6 +75,24 @@ def test_tree_every_node_vs_oracle(ctx, cref, hash_id, H, n, stride):
     gpu.close()
 
 
+def test_identity_commitments_in_batch(ctx, cref):
+    """Identity commitments (v = 0, r = 0 mod l) zero the batched inversion's input; the kernels mask them out."""
+    from dapol_b200 import Dapol
+    L = 2 ** 252 + 27742317777372353535851937790883648493
+    H, n = 5, 7
+    idx = np.array([1, 2, 3, 9, 17, 18, 30], np.uint64)
+    vals = np.array([0, 0, 5, 0, 7, 0, 0], np.uint64)
+    bl = np.zeros((n, 32), np.uint8)
+    bl[1] = np.frombuffer(L.to_bytes(32, "little"), np.uint8)
+    bl[2] = 9; bl[4] = 1
+    bl[6] = np.frombuffer((2 * L).to_bytes(32, "little"), np.uint8)
+    gpu = Dapol.new_blank(ctx, 0, H, H).build(idx, vals, bl, PAD_SEED)
+    ora = cref.Tree(0, H, idx, vals, bl, PAD_SEED)
+    _assert_same_tree(gpu, ora, H)
+    lv = gpu.level(H)
+    assert lv["comc"][list(lv["idx"]).index(1)].tobytes() == bytes(32)
+
+
 def test_reference_kat_tree(ctx, cref):
     """src/dapol/tests.rs:17-25: leaves at 7,12,2,4 (Blake2s, H=4), root value 26."""
     from dapol_b200 import Dapol

@@ -155,6 +155,38 @@ def test_tree_bodies_vs_oracle(E, cref, hid, H, n):
     E.emu_tree_free(C.c_void_p(t))
 
 
+def _emu_tree_levels(E, t, H):
+    out = []
+    for h in range(H + 1):
+        m = E.emu_tree_level_size(t, h)
+        i2 = np.zeros(m, np.uint64); v2 = np.zeros(m, np.uint64); r2 = np.zeros((m, 32), np.uint8); c2 = np.zeros((m, 32), np.uint8)
+        h2 = np.zeros((m, 32), np.uint8); p2 = np.zeros(m, np.uint8)
+        E.emu_tree_level_copy(C.c_void_p(t), h, *[a.ctypes.data_as(C.c_void_p) for a in (i2, v2, r2, c2, h2, p2)])
+        out.append(dict(idx=i2, v=v2, r=r2, comc=c2, hash=h2, is_pad=p2))
+    return out
+
+
+def test_identity_commitments_in_batch(E, cref):
+    """Leaves whose commitment is the identity (v = 0 with r = 0 or r = l) make the batched inversion's input zero:
+    the batch must still give every node of the tree the oracle's bytes (the zero is masked out of the product)."""
+    H, n = 5, 7
+    idx = np.array([1, 2, 3, 9, 17, 18, 30], np.uint64)
+    vals_ = np.array([0, 0, 5, 0, 7, 0, 0], np.uint64)
+    bl = np.zeros((n, 32), np.uint8)
+    bl[1] = np.frombuffer(L.to_bytes(32, "little"), np.uint8)   # unreduced l == 0
+    bl[2] = 9; bl[4] = 1
+    bl[6] = np.frombuffer((2 * L).to_bytes(32, "little"), np.uint8)
+    T = cref.Tree(0, H, idx, vals_, bl, PAD_SEED, 0)
+    t = E.emu_tree_build(0, H, C.c_uint64(n), idx.ctypes.data_as(C.c_void_p), vals_.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), B(PAD_SEED), C.c_uint64(0))
+    assert t
+    lv = _emu_tree_levels(E, t, H)
+    assert bytes(lv[H]["comc"][list(lv[H]["idx"]).index(1)]) == bytes(32)
+    for h in range(H + 1):
+        Lc = T.level(h)
+        assert (lv[h]["comc"] == Lc["comc"]).all() and (lv[h]["hash"] == Lc["hash"]).all(), h
+    E.emu_tree_free(C.c_void_p(t))
+
+
 def test_unsorted_leaves_rejected(E):
     idx = np.array([5, 3], np.uint64); v = np.zeros(2, np.uint64); bl = np.zeros((2, 32), np.uint8)
     assert not E.emu_tree_build(0, 4, C.c_uint64(2), idx.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), B(PAD_SEED), C.c_uint64(0))
