@@ -52,6 +52,14 @@ def lib():
     L.dapol_kernel_launches.argtypes = [vp]
     L.dapol_kernel_launches.restype = u64
     L.dapol_last_build_times.argtypes = [vp, vp]
+    L.dapol_rangeproof_size.argtypes = [C.c_int, C.c_int]
+    L.dapol_rangeproof_size.restype = u64
+    L.dapol_rangeproof_prove_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp]
+    L.dapol_rangeproof_prove_batch_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp]
+    L.dapol_rangeproof_verify_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, u64, vp, vp]
+    L.dapol_rangeproof_verify_batch_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, u64, vp, vp]
+    L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
+    L.dapol_rangeproof_last_times.argtypes = [vp, vp]
     _lib = L
     return L
 

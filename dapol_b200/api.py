@@ -80,6 +80,39 @@ class Context:
         _check(_ffi.lib().dapol_commit_batch(self._h, len(v), _p(v), _p(b), _p(out)))
         return out
 
+    # -- range proofs (src/range/mod.rs:48-119), batched ----------------------------------------
+    def set_rangeproof_window(self, window: int):
+        _check(_ffi.lib().dapol_ctx_set_rangeproof_window(self._h, window))
+
+    def rangeproof_last_times(self):
+        ms = np.zeros(4, np.float32)
+        _check(_ffi.lib().dapol_rangeproof_last_times(self._h, _p(ms)))
+        return dict(zip(("total", "msm", "other", "table_build"), ms.tolist()))
+
+    def rangeproof_prove_batch(self, nbits: int, values, blindings, seed: bytes, streams, base_blocks) -> np.ndarray:
+        """k x generate_aggregated_range_proof (m = values.shape[1] parties; m = 1 is generate_single_range_proof).
+        values [k][m] u64, blindings [k][m][32] Scalar bytes; returns [k][proof_len] bytes."""
+        v = np.ascontiguousarray(values, np.uint64)
+        k, m = v.shape
+        b = np.ascontiguousarray(blindings, np.uint8).reshape(k, m, 32)
+        st = np.ascontiguousarray(streams, np.uint64); bb = np.ascontiguousarray(base_blocks, np.uint64)
+        size = _ffi.lib().dapol_rangeproof_size(nbits, m)
+        if size == 0 or len(st) != k or len(bb) != k:
+            raise DapolError(16)
+        out = np.zeros((k, size), np.uint8)
+        sd = (C.c_uint8 * 32).from_buffer_copy(seed)
+        _check(_ffi.lib().dapol_rangeproof_prove_batch(self._h, nbits, m, k, _p(v), _p(b), sd, _p(st), _p(bb), _p(out)))
+        return out
+
+    def rangeproof_verify_batch(self, nbits: int, m: int, proofs, commitments) -> np.ndarray:
+        """k x verify_aggregated_range_proof: proofs [k][proof_len], commitments [k][m][32]; returns bool[k]."""
+        pr = np.ascontiguousarray(proofs, np.uint8)
+        k = pr.shape[0]
+        cm = np.ascontiguousarray(commitments, np.uint8).reshape(k, m, 32)
+        ok = np.zeros(k, np.uint8)
+        _check(_ffi.lib().dapol_rangeproof_verify_batch(self._h, nbits, m, k, _p(pr), pr.shape[1], _p(cm), _p(ok)))
+        return ok.astype(bool)
+
     def imad_peak(self, variant: int) -> float:
         x = C.c_double()
         _check(_ffi.lib().dapol_imad_peak(self._h, variant, C.byref(x)))

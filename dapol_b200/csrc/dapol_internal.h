@@ -1,0 +1,61 @@
+// Internals shared by the translation units of libdapol_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include "../../include/dapol_b200.h"
+#include "ge25519.cuh"
+
+std::string &dapol_cuda_err();  // thread-local last CUDA error text (dapol_last_cuda_error)
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            dapol_cuda_err() = std::string(#expr) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); \
+            return DAPOL_ERR_CUDA;                                                                           \
+        }                                                                                                    \
+    } while (0)
+
+// Device memory on the hot path comes from the stream-ordered pool (cudaMallocAsync) with the release
+// threshold lifted, so repeated calls reuse the same HBM without paying cudaMalloc/cudaFree each time.
+static inline cudaError_t dmalloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
+template <typename T>
+static inline cudaError_t dmalloc(T **p, size_t bytes, cudaStream_t st) { return dmalloc(reinterpret_cast<void **>(p), bytes, st); }
+static inline void dfree(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+struct dapol_ctx {
+    int device = 0;
+    int W = 8;  // comb window of the tree tables
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    ge_niels *tab_b = nullptr, *tab_bbl = nullptr;  // comb tables for B and B_blinding at window W (253/W+1 windows each)
+    uint64_t launches = 0;
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t ev[6] = {};
+    unsigned long long *scratch = nullptr;  // 1 KB of device scratch (histograms, counters)
+    // range proofs: window tables of the Bulletproof generators G_j[i], H_j[i] (j < rp_mcap, i < 64) and of B, B_blinding
+    int rp_W = 12;
+    int rp_mcap = 0;
+    ge_niels *rp_tab = nullptr;  // [(128 mcap + 2)][NW][2^(W-1)]
+    float rp_last_ms[4] = {0, 0, 0, 0};  // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build
+};
+
+// bump allocator over one device allocation (256-byte aligned pieces)
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t size = 0, used = 0;
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        T *p = reinterpret_cast<T *>(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
+};
+
+// device-resident batch range proofs (dapol_rp.cu), shared with the inclusion-proof path
+int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint64_t *d_values, const uint8_t *d_blind, const uint8_t seed[32],
+                       const uint64_t *d_stream, const uint64_t *d_base, uint8_t *d_proofs);
+int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);

@@ -8,38 +8,12 @@
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
-#include "../../include/dapol_b200.h"
+#include "dapol_internal.h"
 #include "tree_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_cuda_err;
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess) {                                                                         \
-            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__); \
-            return DAPOL_ERR_CUDA;                                                                       \
-        }                                                                                                \
-    } while (0)
-
-// Device memory on the hot path comes from the stream-ordered pool (cudaMallocAsync) with the release
-// threshold lifted, so repeated builds reuse the same HBM without paying cudaMalloc/cudaFree each time.
-static inline cudaError_t dmalloc(void **p, size_t bytes, cudaStream_t st) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
-template <typename T>
-static inline cudaError_t dmalloc(T **p, size_t bytes, cudaStream_t st) { return dmalloc(reinterpret_cast<void **>(p), bytes, st); }
-static inline void dfree(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
-
-struct dapol_ctx {
-    int device = 0;
-    int W = 8;
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
-    ge_niels *tab_b = nullptr, *tab_bbl = nullptr;  // comb tables for B and B_blinding at window W
-    uint64_t launches = 0;
-    float last_ms[5] = {0, 0, 0, 0, 0};
-    cudaEvent_t ev[6] = {};
-    unsigned long long *scratch = nullptr;  // 1 KB of device scratch (histograms, counters)
-};
+std::string &dapol_cuda_err() { return g_cuda_err; }
 
 struct dapol_tree {
     dapol_ctx *ctx = nullptr;
@@ -72,7 +46,6 @@ extern "C" const char *dapol_strerror(int code) {
     return "unknown";
 }
 
-static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------------ kernels
 template <int W>
@@ -377,7 +350,7 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
 extern "C" void dapol_ctx_destroy(dapol_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl); cudaFree(ctx->scratch);
+    cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl); cudaFree(ctx->scratch); cudaFree(ctx->rp_tab);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -433,20 +406,6 @@ static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_val
         ctx->launches++;
     }
 }
-
-// bump allocator over one cudaMalloc'ed arena (256-byte aligned pieces)
-struct Arena {
-    uint8_t *base = nullptr;
-    size_t size = 0, used = 0;
-    template <typename T>
-    T *take(size_t count) {
-        size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
-        T *p = reinterpret_cast<T *>(base + used);
-        used += bytes;
-        return p;
-    }
-    static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~(size_t)255; }
-};
 
 static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
                           const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {

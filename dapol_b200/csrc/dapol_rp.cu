@@ -1,0 +1,521 @@
+// Range proofs of the DAPOL+ hot path on the GPU: batched Bulletproofs prover and verifier (sm_100a), the generator
+// window tables they run on, and the C-ABI entry points (include/dapol_b200.h).  Per-thread bodies: rp_kernels.cuh.
+// Replaces /root/reference/src/range/mod.rs:48-119 (generate_/verify_{single,aggregated}_range_proof).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "dapol_internal.h"
+#include "rp_kernels.cuh"
+
+#define RP_MSM_MAX_T 128
+
+// ------------------------------------------------------------------------------------------------ CTA reductions
+__device__ __forceinline__ void block_reduce_ge(ge &acc, uint32_t *sh /*[blockDim.x][32]*/) {
+    uint32_t tid = threadIdx.x;
+    rp_store_ext(sh + 32 * tid, acc);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            ge o;
+            rp_load_ext(o, sh + 32 * (tid + s));
+            ge_add(acc, acc, o);
+            rp_store_ext(sh + 32 * tid, acc);
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void block_reduce_sc(sc &acc, uint32_t *sh /*[blockDim.x][8]*/) {
+    uint32_t tid = threadIdx.x;
+    store8(sh + 8 * tid, acc.v);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            sc o;
+            load8(o.v, sh + 8 * (tid + s));
+            sc_add(acc, acc, o);
+            store8(sh + 8 * tid, acc.v);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------ table kernels
+__global__ void k_rp_gen_chain(int mcap, uint32_t *uniform) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * mcap) rp_gen_chain_body((uint32_t)(t % mcap), t / mcap, uniform + (uint64_t)t * 64 * 16);
+}
+__global__ void __launch_bounds__(64) k_rp_gen_point(uint64_t n, const uint32_t *uniform, uint32_t *ext) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) rp_gen_point_body(g, uniform, ext);
+    if (g == n) { ge p; ge_basepoint(p); rp_store_ext(ext + 32 * n, p); }
+    if (g == n + 1) { ge p; ge_bblinding(p); rp_store_ext(ext + 32 * (n + 1), p); }
+}
+template <int W>
+__global__ void __launch_bounds__(64) k_rp_tab_windows(uint64_t n, const uint32_t *ext, uint32_t *wb) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) rp_tab_windows_body<W>(g, ext, wb);
+}
+template <int W>
+__global__ void __launch_bounds__(128) k_rp_tab_chunk(uint64_t items, const uint32_t *wb, ge_niels *tab) {
+    uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it < items) rp_tab_chunk_body<W>(it, wb, tab);
+}
+
+template <int W>
+static int rp_build_tables(dapol_ctx *ctx, int mcap) {
+    constexpr int NW = 253 / W + 1;
+    constexpr uint64_t HALF = 1ull << (W - 1);
+    constexpr uint64_t C = HALF < RP_TAB_CHUNK ? HALF : RP_TAB_CHUNK;
+    cudaStream_t st = ctx->stream;
+    uint64_t ngen = 128ull * mcap, nb = ngen + 2;
+    uint32_t *uniform = nullptr, *ext = nullptr, *wb = nullptr;
+    ge_niels *tab = nullptr;
+    CUDA_TRY(cudaMalloc(&tab, nb * NW * HALF * sizeof(ge_niels)));
+    CUDA_TRY(cudaMalloc(&uniform, 2ull * mcap * 64 * 64));
+    CUDA_TRY(cudaMalloc(&ext, nb * 128));
+    CUDA_TRY(cudaMalloc(&wb, nb * NW * 128));
+    k_rp_gen_chain<<<grid_for(2 * mcap, 32), 32, 0, st>>>(mcap, uniform);
+    k_rp_gen_point<<<grid_for(nb, 64), 64, 0, st>>>(ngen, uniform, ext);
+    k_rp_tab_windows<W><<<grid_for(nb, 64), 64, 0, st>>>(nb, ext, wb);
+    uint64_t items = nb * NW * (HALF / C);
+    k_rp_tab_chunk<W><<<grid_for(items, 128), 128, 0, st>>>(items, wb, tab);
+    ctx->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(uniform); cudaFree(ext); cudaFree(wb);
+    if (ctx->rp_tab) cudaFree(ctx->rp_tab);
+    ctx->rp_tab = tab;
+    ctx->rp_mcap = mcap;
+    return DAPOL_OK;
+}
+static int rp_ensure_tables(dapol_ctx *ctx, int m) {
+    if (ctx->rp_mcap >= m) return DAPOL_OK;
+    int mc = 1;
+    while (mc < m) mc <<= 1;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, ctx->stream);
+    int rc = ctx->rp_W == 8 ? rp_build_tables<8>(ctx, mc) : rp_build_tables<12>(ctx, mc);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&ctx->rp_last_ms[3], a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ prover kernels
+__global__ void __launch_bounds__(64) k_rp_p0(RpBatch b) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rp_p0_body(b, p);
+}
+template <int WT>
+__global__ void __launch_bounds__(64) k_rp_p1(RpBatch b, const ge_niels *tab_b, const ge_niels *tab_bbl) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * b.m) rp_p1_body<WT>(b, t / b.m, (int)(t % b.m), tab_b, tab_bbl);
+}
+__global__ void __launch_bounds__(128) k_rp_p2(RpBatch b) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * b.N) rp_p2_body(b, t / b.N, (uint32_t)(t % b.N));
+}
+template <int W>
+__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p3(RpBatch b) {
+    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    ge acc;
+    rp_p3_partial<W>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    block_reduce_ge(acc, sh);
+    if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
+}
+__global__ void __launch_bounds__(64) k_rp_p4(RpBatch b) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rp_p4_body(b, p);
+}
+// doubling expansion of one vector per proof (CTA per proof): vec[i + 2^s] = vec[i] * mult[s]
+__global__ void __launch_bounds__(256) k_rp_expand(RpBatch b, uint32_t *vec, int slot) {
+    uint64_t p = blockIdx.x;
+    for (int s = 0; s < b.lg; s++) {
+        for (uint32_t i = threadIdx.x; i < (1u << s); i += blockDim.x) rp_expand_step(vec + p * b.N * 8, b.mult + (p * 3 + slot) * 32 * 8, s, i);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p5(RpBatch b) {
+    __shared__ uint32_t sh[RP_MSM_MAX_T * 8];
+    sc t0, t1, t2;
+    uint64_t p = blockIdx.x;
+    rp_p5_partial(t0, t1, t2, b, p, threadIdx.x, blockDim.x);
+    block_reduce_sc(t0, sh); block_reduce_sc(t1, sh); block_reduce_sc(t2, sh);
+    if (threadIdx.x == 0) { rp_st(rp_ch(b, p, CH_T0), t0); rp_st(rp_ch(b, p, CH_T1), t1); rp_st(rp_ch(b, p, CH_T2), t2); }
+}
+template <int W>
+__global__ void __launch_bounds__(64) k_rp_p6(RpBatch b) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * b.K) rp_p6_body<W>(b, t >> 1, (int)(t & 1));
+}
+__global__ void __launch_bounds__(64) k_rp_p7(RpBatch b) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rp_p7_body(b, p);
+}
+__global__ void __launch_bounds__(128) k_rp_p8(RpBatch b) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * b.N) rp_p8_body(b, t / b.N, (uint32_t)(t % b.N));
+}
+__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p9(RpBatch b, int rnd) {
+    __shared__ uint32_t sh[RP_MSM_MAX_T * 8];
+    sc cl, cr;
+    uint64_t p = blockIdx.x;
+    rp_p9_partial(cl, cr, b, p, rnd, threadIdx.x, blockDim.x);
+    block_reduce_sc(cl, sh); block_reduce_sc(cr, sh);
+    if (threadIdx.x == 0) { rp_st(rp_ch(b, p, CH_CL), cl); rp_st(rp_ch(b, p, CH_CR), cr); }
+}
+template <int W>
+__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p10(RpBatch b, int rnd) {
+    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    ge acc;
+    rp_p10_partial<W>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
+    block_reduce_ge(acc, sh);
+    if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
+}
+__global__ void __launch_bounds__(64) k_rp_p11(RpBatch b, int rnd) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rp_p11_body(b, p, rnd);
+}
+__global__ void __launch_bounds__(128) k_rp_p12(RpBatch b, int rnd, uint32_t cnt) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * cnt) rp_p12_body(b, t / cnt, rnd, (uint32_t)(t % cnt));
+}
+// ------------------------------------------------------------------------------------------------ verifier kernels
+__global__ void __launch_bounds__(64) k_rp_v0(RpBatch b) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rp_v0_body(b, p);
+}
+__global__ void __launch_bounds__(64) k_rp_v1(RpBatch b, int nv) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * nv) rp_v1_body(b, t / nv, (int)(t % nv));
+}
+template <int W>
+__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_v2(RpBatch b) {
+    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    ge acc;
+    uint64_t p = blockIdx.x;
+    rp_v2_partial<W>(acc, b, p, threadIdx.x, blockDim.x);
+    block_reduce_ge(acc, sh);
+    if (threadIdx.x == 0) b.status[p] = b.status[p] && ge_is_identity(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ host orchestration
+static inline int ilog2(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return l; }
+static inline unsigned msm_threads(uint64_t terms) {  // a few terms per thread, 32..RP_MSM_MAX_T threads
+    unsigned t = 32;
+    while (t < RP_MSM_MAX_T && (uint64_t)t * 4 < terms) t <<= 1;
+    return t;
+}
+static bool rp_shape_ok(int nbits, int m) {
+    return (nbits == 8 || nbits == 16 || nbits == 32 || nbits == 64) && m >= 1 && m <= 64 && (m & (m - 1)) == 0;
+}
+extern "C" uint64_t dapol_rangeproof_size(int nbits, int m) {
+    if (!rp_shape_ok(nbits, m)) return 0;
+    return 32ull * (9 + 2 * ilog2((uint64_t)nbits * m));
+}
+// scratch bytes per proof of a batch
+static size_t rp_per_proof_bytes(int N, int m, int lg, bool verify) {
+    size_t s = sizeof(merlin) + 2 * (size_t)m * 32 + CH_COUNT * 32 + (size_t)m * 32 + 3 * 32 * 32 + 256 + 4 + 4 * 256;
+    s += (size_t)N * 32 * (verify ? 2 : 3);          // ypow, svec | vecA, vecB, ypow
+    if (!verify) s += 4 * (size_t)(N / 2) * 32;      // cu, cui ping-pong
+    if (verify) s += (size_t)rp_nvar(lg, m) * (128 + 32);
+    return s;
+}
+struct RpPlan {
+    RpBatch b;
+    uint8_t *mem = nullptr;
+};
+// carve the scratch of a batch of K proofs out of one pool allocation
+static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, bool verify) {
+    RpBatch &b = pl.b;
+    memset(&b, 0, sizeof b);
+    b.nbits = nbits; b.m = m; b.N = nbits * m; b.lg = ilog2((uint64_t)b.N); b.K = K;
+    b.plen = 32 * (9 + 2 * b.lg);
+    const int nv = rp_nvar(b.lg, m);
+    const uint64_t N = b.N;
+    Arena ar;
+    ar.size = Arena::need(K, sizeof(merlin)) + 3 * Arena::need(K * m, 32) + Arena::need(K * CH_COUNT, 32) + Arena::need(K * 3 * 32, 32) +
+              4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * nv, 128) +
+              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4);
+    CUDA_TRY(dmalloc(&pl.mem, ar.size, ctx->stream));
+    ar.base = pl.mem;
+    b.tr = ar.take<merlin>(K);
+    b.Vc = ar.take<uint32_t>(K * m * 8); b.blr = ar.take<uint32_t>(K * m * 8); b.zpow = ar.take<uint32_t>(K * m * 8);
+    b.chal = ar.take<uint32_t>(K * CH_COUNT * 8);
+    b.mult = ar.take<uint32_t>(K * 3 * 32 * 8);
+    b.ypow = ar.take<uint32_t>(K * N * 8);
+    if (verify) {
+        b.svec = ar.take<uint32_t>(K * N * 8);
+        b.varpts = ar.take<uint32_t>(K * nv * 32);
+        b.varsc = ar.take<uint32_t>(K * nv * 8);
+    } else {
+        b.vecA = ar.take<uint32_t>(K * N * 8); b.vecB = ar.take<uint32_t>(K * N * 8);
+        for (int i = 0; i < 2; i++) { b.cu[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); b.cui[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); }
+        b.pts = ar.take<uint32_t>(K * 2 * 32);
+        b.proof = ar.take<uint32_t>(K * b.plen / 4);
+    }
+    b.status = ar.take<int>(K);
+    const int W = ctx->rp_W;
+    uint64_t per = (uint64_t)(253 / W + 1) * (1ull << (W - 1));
+    b.tabG = ctx->rp_tab;
+    b.tabH = b.tabG + 64ull * ctx->rp_mcap * per;
+    b.tabB = b.tabG + 128ull * ctx->rp_mcap * per;
+    b.tabBbl = b.tabB + per;
+    return DAPOL_OK;
+}
+// proofs per chunk so that the scratch stays within a fixed HBM budget
+static uint64_t rp_chunk(int N, int m, int lg, bool verify, uint64_t K) {
+    const size_t budget = 6ull << 30;
+    uint64_t c = budget / rp_per_proof_bytes(N, m, lg, verify);
+    if (c < 1) c = 1;
+    return std::min<uint64_t>(K, c);
+}
+
+struct PhaseTimer {  // device time of the MSM passes vs the rest, on the ctx stream
+    cudaStream_t st;
+    cudaEvent_t e[2];
+    float ms[2] = {0, 0};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[2];
+    explicit PhaseTimer(cudaStream_t s) : st(s) {}
+    void begin(int which) { cudaEventCreate(&e[0]); cudaEventCreate(&e[1]); cudaEventRecord(e[0], st); cur = which; }
+    void end() { cudaEventRecord(e[1], st); spans[cur].push_back({e[0], e[1]}); }
+    void collect() {
+        for (int w = 0; w < 2; w++)
+            for (auto &s : spans[w]) { float t = 0; cudaEventElapsedTime(&t, s.first, s.second); ms[w] += t; cudaEventDestroy(s.first); cudaEventDestroy(s.second); }
+    }
+    int cur = 0;
+};
+
+template <int W>
+static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t K = b.K, N = b.N;
+    const unsigned T = msm_threads(N + 1), TS = msm_threads(2 * N + 1);
+    tm.begin(1);
+    k_rp_p0<<<grid_for(K, 64), 64, 0, st>>>(b);
+    switch (ctx->W) {
+        case 4: k_rp_p1<4><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+        case 8: k_rp_p1<8><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+        case 10: k_rp_p1<10><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+        default: k_rp_p1<12><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+    }
+    k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
+    tm.end();
+    tm.begin(0);
+    k_rp_p3<W><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
+    tm.end();
+    tm.begin(1);
+    k_rp_p4<<<grid_for(K, 64), 64, 0, st>>>(b);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 0);
+    k_rp_p5<<<(unsigned)K, T, 0, st>>>(b);
+    k_rp_p6<W><<<grid_for(2 * K, 64), 64, 0, st>>>(b);
+    k_rp_p7<<<grid_for(K, 64), 64, 0, st>>>(b);
+    k_rp_p8<<<grid_for(K * N, 128), 128, 0, st>>>(b);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
+    tm.end();
+    ctx->launches += 10;
+    for (int rnd = 1; rnd <= b.lg; rnd++) {
+        uint32_t h = (uint32_t)(N >> rnd), cnt = std::max<uint32_t>(h, 1u << (rnd - 1));
+        tm.begin(1);
+        k_rp_p9<<<(unsigned)K, msm_threads(h), 0, st>>>(b, rnd);
+        tm.end();
+        tm.begin(0);
+        k_rp_p10<W><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
+        tm.end();
+        tm.begin(1);
+        k_rp_p11<<<grid_for(K, 64), 64, 0, st>>>(b, rnd);
+        k_rp_p12<<<grid_for(K * cnt, 128), 128, 0, st>>>(b, rnd, cnt);
+        tm.end();
+        ctx->launches += 4;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
+template <int W>
+static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t K = b.K, N = b.N;
+    const int nv = rp_nvar(b.lg, b.m);
+    tm.begin(1);
+    k_rp_v0<<<grid_for(K, 64), 64, 0, st>>>(b);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.svec, 2);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
+    tm.end();
+    tm.begin(0);
+    k_rp_v1<<<grid_for(K * nv, 64), 64, 0, st>>>(b, nv);
+    k_rp_v2<W><<<(unsigned)K, msm_threads(2 * N + 2 + nv), 0, st>>>(b);
+    tm.end();
+    ctx->launches += 5;
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
+
+// Device-resident batch prove.  d_values [K][m], d_blind [K][m][32], d_stream / d_base [K], d_proofs [K][plen] out.
+int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint64_t *d_values, const uint8_t *d_blind, const uint8_t seed[32],
+                       const uint64_t *d_stream, const uint64_t *d_base, uint8_t *d_proofs) {
+    if (!ctx || !rp_shape_ok(nbits, m) || !K) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = rp_ensure_tables(ctx, m);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int N = nbits * m, lg = ilog2((uint64_t)N);
+    const uint64_t plen = 32ull * (9 + 2 * lg), chunk = rp_chunk(N, m, lg, false, K);
+    PhaseTimer tm(st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    int bad = 0;
+    for (uint64_t first = 0; first < K; first += chunk) {
+        uint64_t kc = std::min(chunk, K - first);
+        RpPlan pl;
+        rc = rp_plan(ctx, pl, nbits, m, kc, false);
+        if (rc) return rc;
+        RpBatch &b = pl.b;
+        b.values = d_values + first * m;
+        b.blind = reinterpret_cast<const uint32_t *>(d_blind) + first * m * 8;
+        b.stream = d_stream + first; b.base_block = d_base + first;
+        memcpy(b.seed, seed, 32);
+        rc = ctx->rp_W == 8 ? rp_prove_chunk<8>(ctx, b, tm) : rp_prove_chunk<12>(ctx, b, tm);
+        if (rc) { dfree(pl.mem, st); return rc; }
+        CUDA_TRY(cudaMemcpyAsync(d_proofs + first * plen, b.proof, kc * plen, cudaMemcpyDeviceToDevice, st));
+        std::vector<int> status(kc);
+        CUDA_TRY(cudaMemcpyAsync(status.data(), b.status, kc * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int s : status) bad |= s;
+        dfree(pl.mem, st);
+    }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tm.collect();
+    ctx->rp_last_ms[1] = tm.ms[0]; ctx->rp_last_ms[2] = tm.ms[1];
+    return bad ? DAPOL_ERR_BAD_ARG : DAPOL_OK;
+}
+// Device-resident batch verify.  d_proofs [K][plen], d_coms [K][m][32], d_ok [K] out (1 accept, 0 reject).
+int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);
+__global__ void k_status_to_ok(uint64_t K, const int *status, uint8_t *ok) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < K) ok[p] = status[p] ? 1 : 0;
+}
+int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok) {
+    if (!ctx || !rp_shape_ok(nbits, m) || !K) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = rp_ensure_tables(ctx, m);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const int N = nbits * m, lg = ilog2((uint64_t)N);
+    const uint64_t plen = 32ull * (9 + 2 * lg), chunk = rp_chunk(N, m, lg, true, K);
+    PhaseTimer tm(st);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (uint64_t first = 0; first < K; first += chunk) {
+        uint64_t kc = std::min(chunk, K - first);
+        RpPlan pl;
+        rc = rp_plan(ctx, pl, nbits, m, kc, true);
+        if (rc) return rc;
+        RpBatch &b = pl.b;
+        b.proof_in = reinterpret_cast<const uint32_t *>(d_proofs + first * plen);
+        b.coms = reinterpret_cast<const uint32_t *>(d_coms) + first * m * 8;
+        rc = ctx->rp_W == 8 ? rp_verify_chunk<8>(ctx, b, tm) : rp_verify_chunk<12>(ctx, b, tm);
+        if (rc) { dfree(pl.mem, st); return rc; }
+        k_status_to_ok<<<grid_for(kc, 128), 128, 0, st>>>(kc, b.status, d_ok + first);
+        ctx->launches++;
+        dfree(pl.mem, st);
+    }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    tm.collect();
+    ctx->rp_last_ms[1] = tm.ms[0]; ctx->rp_last_ms[2] = tm.ms[1];
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int dapol_rangeproof_prove_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint64_t *d_values, const uint8_t *d_blindings,
+                                                const uint8_t seed[32], const uint64_t *d_streams, const uint64_t *d_base_blocks,
+                                                uint8_t *d_proofs) {
+    if (!d_values || !d_blindings || !seed || !d_streams || !d_base_blocks || !d_proofs) return DAPOL_ERR_BAD_ARG;
+    return dapol_rp_prove_dev(ctx, nbits, m, k, d_values, d_blindings, seed, d_streams, d_base_blocks, d_proofs);
+}
+extern "C" int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *d_proofs, uint64_t proof_len,
+                                                 const uint8_t *d_commitments, uint8_t *d_ok) {
+    if (!ctx || !d_proofs || !d_commitments || !d_ok || !rp_shape_ok(nbits, m)) return DAPOL_ERR_BAD_ARG;
+    if (proof_len != dapol_rangeproof_size(nbits, m)) {  // RangeProof::from_bytes / verify: wrong size for (n, m) is a reject, not an error
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaMemsetAsync(d_ok, 0, k, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return DAPOL_OK;
+    }
+    return dapol_rp_verify_dev(ctx, nbits, m, k, d_proofs, d_commitments, d_ok);
+}
+extern "C" int dapol_rangeproof_prove_batch(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint64_t *values, const uint8_t *blindings,
+                                            const uint8_t seed[32], const uint64_t *streams, const uint64_t *base_blocks, uint8_t *proofs) {
+    if (!ctx || !values || !blindings || !seed || !streams || !base_blocks || !proofs || !rp_shape_ok(nbits, m) || !k) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t plen = dapol_rangeproof_size(nbits, m);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(k * m, 8) + Arena::need(k * m, 32) + 2 * Arena::need(k, 8) + Arena::need(k, plen);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *d_v = ar.take<uint64_t>(k * m);
+    uint8_t *d_b = ar.take<uint8_t>(k * m * 32);
+    uint64_t *d_s = ar.take<uint64_t>(k), *d_bb = ar.take<uint64_t>(k);
+    uint8_t *d_p = ar.take<uint8_t>(k * plen);
+    cudaMemcpyAsync(d_v, values, k * m * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_b, blindings, k * m * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_s, streams, k * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_bb, base_blocks, k * 8, cudaMemcpyHostToDevice, st);
+    int rc = dapol_rp_prove_dev(ctx, nbits, m, k, d_v, d_b, seed, d_s, d_bb, d_p);
+    if (rc == DAPOL_OK) {
+        cudaMemcpyAsync(proofs, d_p, k * plen, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = DAPOL_ERR_CUDA;
+    }
+    dfree(mem, st);
+    return rc;
+}
+extern "C" int dapol_rangeproof_verify_batch(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *proofs, uint64_t proof_len,
+                                             const uint8_t *commitments, uint8_t *ok) {
+    if (!ctx || !proofs || !commitments || !ok || !rp_shape_ok(nbits, m) || !k) return DAPOL_ERR_BAD_ARG;
+    if (proof_len != dapol_rangeproof_size(nbits, m)) { memset(ok, 0, k); return DAPOL_OK; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(k, proof_len) + Arena::need(k * m, 32) + Arena::need(k, 1);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint8_t *d_p = ar.take<uint8_t>(k * proof_len), *d_c = ar.take<uint8_t>(k * m * 32), *d_ok = ar.take<uint8_t>(k);
+    cudaMemcpyAsync(d_p, proofs, k * proof_len, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_c, commitments, k * m * 32, cudaMemcpyHostToDevice, st);
+    int rc = dapol_rp_verify_dev(ctx, nbits, m, k, d_p, d_c, d_ok);
+    if (rc == DAPOL_OK) {
+        cudaMemcpyAsync(ok, d_ok, k, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = DAPOL_ERR_CUDA;
+    }
+    dfree(mem, st);
+    return rc;
+}
+extern "C" int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]) {
+    if (!ctx || !ms) return DAPOL_ERR_BAD_ARG;
+    memcpy(ms, ctx->rp_last_ms, sizeof(float) * 4);
+    return DAPOL_OK;
+}
+extern "C" int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window) {
+    if (!ctx || (window != 8 && window != 12)) return DAPOL_ERR_BAD_ARG;
+    if (ctx->rp_W != window) {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->rp_tab) cudaFree(ctx->rp_tab);
+        ctx->rp_tab = nullptr; ctx->rp_mcap = 0; ctx->rp_W = window;
+    }
+    return DAPOL_OK;
+}

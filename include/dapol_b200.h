@@ -116,6 +116,31 @@ DAPOL_API int dapol_tree_paths(const dapol_tree *tree, uint64_t k, const uint64_
                      uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*32 */,
                      uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*32 or NULL */);
 
+/* ---- range proofs: src/range/mod.rs:48-119 generate_/verify_{single,aggregated}_range_proof in batches.
+ * One call = k independent Bulletproofs of one shape: nbits in {8,16,32,64} (the reference fixes BIT_SIZE = 64,
+ * range/mod.rs:16), m parties (power of two <= 64; m = 1 is prove_single / verify_single), each over a fresh
+ * Transcript::new(&[]).  Proof bytes = RangeProof::to_bytes(): 32 * (9 + 2 log2(nbits m)) (672 for 64 x 1 =
+ * SINGLE_PROOF_BYTE_NUM, range/mod.rs:18).  Randomness of proof i: ChaCha20(seed) stream streams[i], draw j at
+ * block base_blocks[i] + j, in bulletproofs' draw order (see the contract at the top of this header).
+ * The generator tables (BulletproofGens::new(64, m), range/mod.rs:50,66,85,104) are built on first use per context. */
+DAPOL_API uint64_t dapol_rangeproof_size(int nbits, int m); /* 0 for an unsupported shape */
+DAPOL_API int dapol_rangeproof_prove_batch(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint64_t *values /* k*m */,
+                                           const uint8_t *blindings /* k*m*32, Scalar bytes, may be unreduced */, const uint8_t seed[32],
+                                           const uint64_t *streams /* k */, const uint64_t *base_blocks /* k */, uint8_t *proofs /* k*size */);
+/* ok[i] = 1 iff RangeProof::from_bytes + verify_multiple accept proof i for its m commitments; malformed input is a
+ * reject (0), never an error. */
+DAPOL_API int dapol_rangeproof_verify_batch(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *proofs /* k*proof_len */,
+                                            uint64_t proof_len, const uint8_t *commitments /* k*m*32 */, uint8_t *ok /* k */);
+/* Same with every array already resident in device memory (HBM). */
+DAPOL_API int dapol_rangeproof_prove_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint64_t *d_values, const uint8_t *d_blindings,
+                                               const uint8_t seed[32], const uint64_t *d_streams, const uint64_t *d_base_blocks, uint8_t *d_proofs);
+DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *d_proofs, uint64_t proof_len,
+                                                const uint8_t *d_commitments, uint8_t *d_ok);
+/* window (8 or 12 bits) of the generator tables; drops tables already built.  Default 12. */
+DAPOL_API int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window);
+/* device time of the last range-proof batch on this ctx (ms): [0] total, [1] MSM passes, [2] other passes, [3] last table build */
+DAPOL_API int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]);
+
 /* Micro-entry points used by the parity tests and the roofline microbenchmark. */
 DAPOL_API int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *values, const uint8_t *blindings, uint8_t *coms /* n*32 */);
 DAPOL_API int dapol_imad_peak(dapol_ctx *ctx, int variant, double *gmac_per_s); /* measured 32x32->64 MAC/s, variant 0..3 */
