@@ -158,6 +158,39 @@ class DapolProofNode:
         return self.com + self.hash
 
 
+class DapolProof:
+    """src/proof/mod.rs DapolProof<D, R> in its serialised form (DapolProof::serialize, proof/mod.rs:68-73)."""
+
+    def __init__(self, data: bytes, hash_id: int, policy: int):
+        self.data, self.hash_id, self.policy = bytes(data), hash_id, policy
+
+    def serialize(self) -> bytes:
+        return self.data
+
+    @classmethod
+    def deserialize(cls, data: bytes, hash_id: int, policy: int):
+        return cls(data, hash_id, policy)
+
+    def verify(self, ctx: "Context", root: "DapolProofNode", leaf: "DapolProofNode") -> bool:
+        """DapolProof::verify(&root, &leaf) (proof/mod.rs:41-47)."""
+        return bool(self.verify_many(ctx, root, [leaf], [self])[0])
+
+    @staticmethod
+    def verify_many(ctx: "Context", root: "DapolProofNode", leaves, proofs) -> np.ndarray:
+        """k independent DapolProof::verify calls against one root, as one GPU batch."""
+        k = len(proofs)
+        blob = np.frombuffer(b"".join(p.data for p in proofs) or b"\0", np.uint8).copy()
+        off = np.zeros(k + 1, np.uint64)
+        off[1:] = np.cumsum([len(p.data) for p in proofs], dtype=np.uint64)
+        lc = np.frombuffer(b"".join(l.com for l in leaves), np.uint8).copy()
+        lh = np.frombuffer(b"".join(l.hash for l in leaves), np.uint8).copy()
+        ok = np.zeros(k, np.uint8)
+        rc = _ffi.lib().dapol_verify_batch(ctx._h, proofs[0].hash_id, proofs[0].policy, k, _p(np.frombuffer(root.com, np.uint8).copy()),
+                                           _p(np.frombuffer(root.hash, np.uint8).copy()), _p(lc), _p(lh), _p(blob), _p(off), _p(ok))
+        _check(rc)
+        return ok.astype(bool)
+
+
 class Dapol:
     """src/dapol/mod.rs Dapol<D, R>: D = hash_id, R = policy."""
 
@@ -291,3 +324,27 @@ class Dapol:
             return None
         _check(rc)
         return dict(v=v, r=r, comc=c, hash=hs, leaf_comc=lc, leaf_hash=lh)
+
+    # -- inclusion proofs -----------------------------------------------------------------------
+    def generate_proofs(self, leaf_idx, seed: bytes):
+        """[Dapol::generate_proof(idx) for idx in leaf_idx] (mod.rs:167-190) as one GPU batch; None if any index is not a
+        leaf (the reference returns None).  Prover randomness comes from the seeded stream (include/dapol_b200.h)."""
+        li = np.ascontiguousarray(leaf_idx, np.uint64)
+        k = len(li)
+        L = _ffi.lib()
+        size = L.dapol_inclusion_proof_size(self.height, self.aggregation_factor, self.policy)
+        if size == 0:
+            raise DapolError(16)
+        out = np.zeros(k * size, np.uint8)
+        got = C.c_uint64()
+        sd = (C.c_uint8 * 32).from_buffer_copy(seed)
+        rc = L.dapol_prove_batch(self._t, k, _p(li), self.aggregation_factor, self.policy, sd, _p(out), out.nbytes, C.byref(got))
+        if rc == 17:
+            return None
+        _check(rc)
+        return [DapolProof(out[i * size:(i + 1) * size].tobytes(), self.hash_id, self.policy) for i in range(k)]
+
+    def generate_proof(self, leaf_idx: int, seed: bytes):
+        """Dapol::generate_proof (mod.rs:167-169)."""
+        r = self.generate_proofs([leaf_idx], seed)
+        return None if r is None else r[0]

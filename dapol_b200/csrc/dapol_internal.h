@@ -4,7 +4,8 @@
 #include <cstdint>
 #include <string>
 #include "../../include/dapol_b200.h"
-#include "ge25519.cuh"
+#include <vector>
+#include "tree_kernels.cuh"
 
 std::string &dapol_cuda_err();  // thread-local last CUDA error text (dapol_last_cuda_error)
 #define CUDA_TRY(expr)                                                                                       \
@@ -41,6 +42,19 @@ struct dapol_ctx {
     float rp_last_ms[4] = {0, 0, 0, 0};  // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build
 };
 
+struct dapol_tree {
+    dapol_ctx *ctx = nullptr;
+    int hash_id = 0, height = 0;
+    uint64_t n_leaves = 0, T = 0, n_pads = 0;
+    std::vector<uint64_t> level_off, level_n, n_real;  // per level h = 0..H
+    NodeStore ns = {};
+    std::vector<uint32_t *> pos;  // pos[h]: slot of the k-th real node of level h (device), h = 1..H
+    uint32_t *pos_all = nullptr;  // backing allocation of pos[]
+    uint32_t **d_pos = nullptr;   // device copy of the pointer table
+    uint64_t *d_level_off = nullptr;
+    uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
+};
+
 // bump allocator over one device allocation (256-byte aligned pieces)
 struct Arena {
     uint8_t *base = nullptr;
@@ -59,3 +73,7 @@ struct Arena {
 int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint64_t *d_values, const uint8_t *d_blind, const uint8_t seed[32],
                        const uint64_t *d_stream, const uint64_t *d_base, uint8_t *d_proofs);
 int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);
+
+// device-resident Merkle paths of k leaves (dapol_lib.cu): siblings leaf level first, [k][height] each
+int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
+                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found);

@@ -15,19 +15,6 @@
 static thread_local std::string g_cuda_err;
 std::string &dapol_cuda_err() { return g_cuda_err; }
 
-struct dapol_tree {
-    dapol_ctx *ctx = nullptr;
-    int hash_id = 0, height = 0;
-    uint64_t n_leaves = 0, T = 0, n_pads = 0;
-    std::vector<uint64_t> level_off, level_n, n_real;  // per level h = 0..H
-    NodeStore ns = {};
-    std::vector<uint32_t *> pos;  // pos[h]: slot of the k-th real node of level h (device), h = 1..H
-    uint32_t *pos_all = nullptr;  // backing allocation of pos[]
-    uint32_t **d_pos = nullptr;   // device copy of the pointer table
-    uint64_t *d_level_off = nullptr;
-    uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
-};
-
 extern "C" const char *dapol_last_cuda_error(void) { return g_cuda_err.c_str(); }
 extern "C" const char *dapol_strerror(int code) {
     switch (code) {
@@ -711,6 +698,16 @@ extern "C" int dapol_tree_leaf_index_of(const dapol_tree *t, uint64_t input_pos,
     CUDA_TRY(cudaMemcpy(leaf_idx, t->leaf_index_of + input_pos, 8, cudaMemcpyDeviceToHost));
     return DAPOL_OK;
 }
+// device-resident path extraction (shared with the inclusion-proof path): all outputs are device pointers
+int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
+                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found) {
+    dapol_ctx *ctx = t->ctx;
+    k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, d_leaf_idx, t->ns, t->d_level_off, t->level_n[t->height], t->d_pos, t->height, d_v, d_r,
+                                                       d_c, d_h, d_lc, d_lh, d_not_found);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
 extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t *values, uint8_t *blindings,
                                 uint8_t *coms, uint8_t *hashes, uint8_t *leaf_coms, uint8_t *leaf_hashes) {
     if (!t || !leaf_idx || !values || !blindings || !coms || !hashes || k == 0) return DAPOL_ERR_BAD_ARG;
@@ -718,28 +715,30 @@ extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t 
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     uint64_t H = (uint64_t)t->height, kh = k * (H ? H : 1);
-    uint64_t *d_li = nullptr, *d_v = nullptr;
-    uint32_t *d_r = nullptr, *d_c = nullptr, *d_h = nullptr, *d_lc = nullptr, *d_lh = nullptr;
-    int *d_nf = nullptr, nf = 0;
-    CUDA_TRY(cudaMalloc(&d_li, k * 8)); CUDA_TRY(cudaMalloc(&d_v, kh * 8));
-    CUDA_TRY(cudaMalloc(&d_r, kh * 32)); CUDA_TRY(cudaMalloc(&d_c, kh * 32)); CUDA_TRY(cudaMalloc(&d_h, kh * 32));
-    CUDA_TRY(cudaMalloc(&d_lc, k * 32)); CUDA_TRY(cudaMalloc(&d_lh, k * 32)); CUDA_TRY(cudaMalloc(&d_nf, 4));
-    CUDA_TRY(cudaMemsetAsync(d_nf, 0, 4, st));
-    CUDA_TRY(cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st));
-    k_paths<<<grid_for(k, 128), 128, 0, st>>>(k, d_li, t->ns, t->d_level_off, t->level_n[t->height], t->d_pos, t->height, d_v, d_r, d_c, d_h,
-                                              d_lc, d_lh, d_nf);
-    ctx->launches++;
-    CUDA_TRY(cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st));
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 3 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256;
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *d_li = ar.take<uint64_t>(k), *d_v = ar.take<uint64_t>(kh);
+    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8);
+    uint32_t *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8);
+    int *d_nf = ar.take<int>(1), nf = 0;
+    cudaMemsetAsync(d_nf, 0, 4, st);
+    cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st);
+    int rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf);
+    if (rc) { dfree(mem, st); return rc; }
+    cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st);
     if (H) {
-        CUDA_TRY(cudaMemcpyAsync(values, d_v, kh * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(blindings, d_r, kh * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(coms, d_c, kh * 32, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(hashes, d_h, kh * 32, cudaMemcpyDeviceToHost, st));
+        cudaMemcpyAsync(values, d_v, kh * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(blindings, d_r, kh * 32, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(coms, d_c, kh * 32, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(hashes, d_h, kh * 32, cudaMemcpyDeviceToHost, st);
     }
-    if (leaf_coms) CUDA_TRY(cudaMemcpyAsync(leaf_coms, d_lc, k * 32, cudaMemcpyDeviceToHost, st));
-    if (leaf_hashes) CUDA_TRY(cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st));
+    if (leaf_coms) cudaMemcpyAsync(leaf_coms, d_lc, k * 32, cudaMemcpyDeviceToHost, st);
+    if (leaf_hashes) cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st);
     CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_li); cudaFree(d_v); cudaFree(d_r); cudaFree(d_c); cudaFree(d_h); cudaFree(d_lc); cudaFree(d_lh); cudaFree(d_nf);
+    dfree(mem, st);
     return nf ? DAPOL_ERR_NOT_FOUND : DAPOL_OK;
 }
 

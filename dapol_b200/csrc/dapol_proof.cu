@@ -1,0 +1,330 @@
+// Inclusion proofs of the DAPOL+ hot path: Dapol::generate_proof_batch (src/dapol/mod.rs:172-190) with the two
+// aggregation policies (src/range/padding.rs:88-118, src/range/splitting.rs:100-129), DapolProof::serialize /
+// deserialize (src/proof/mod.rs:68-84) and DapolProof::verify (src/proof/mod.rs:41-47,89-95: Merkle fold with
+// DapolProofNode::merge, src/proof/node.rs:56-69, then R::verify, padding.rs:168-197 / splitting.rs:180-211).
+// The range proofs of a batch of leaves run as a few LARGE batches on the GPU (one per aggregate size + one of singles).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+#include "dapol_internal.h"
+#include "rp_kernels.cuh"
+
+#define SINGLE_PROOF_BYTE_NUM 672  // src/range/mod.rs:18
+
+static inline uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+static inline void put_be(uint8_t *o, uint64_t x, int k) { for (int i = 0; i < k; i++) o[i] = (uint8_t)(x >> (8 * (k - 1 - i))); }
+static inline uint64_t get_be(const uint8_t *o, int k) { uint64_t x = 0; for (int i = 0; i < k; i++) x = (x << 8) | o[i]; return x; }
+
+// which siblings go into which aggregated proof; the rest are single proofs (padding.rs:88-118, splitting.rs:100-129)
+struct AggGroup {
+    uint64_t start, count, m;
+};
+static int policy_plan(uint64_t nsib, uint64_t agg, int policy, std::vector<AggGroup> &g, uint64_t &single_from) {
+    g.clear();
+    if (agg > nsib) return DAPOL_ERR_BAD_ARG;  // reference: slice out of bounds panic (padding.rs:95-97, splitting.rs:110-113)
+    if (policy == DAPOL_POLICY_PADDING) {
+        g.push_back({0, agg, next_pow2(agg)});  // agg = 0: next_power_of_two(0) = 1 -> one proof of a single dummy party
+        single_from = agg;
+    } else if (policy == DAPOL_POLICY_SPLITTING) {
+        uint64_t base = next_pow2(agg), pos = 0;
+        while (pos < agg) {
+            if (agg & base) { g.push_back({pos, base, base}); pos += base; }
+            base >>= 1;
+        }
+        single_from = pos;
+    } else return DAPOL_ERR_BAD_ARG;
+    for (auto &x : g) if (x.m > 64) return DAPOL_ERR_BAD_ARG;
+    return DAPOL_OK;
+}
+static uint64_t merkle_bytes(uint64_t H) { return 2 + 8 + (H + 7) / 8 + 8 + 64 * H; }
+extern "C" uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy) {
+    std::vector<AggGroup> g;
+    uint64_t sf;
+    if (height < 0 || height > 64 || policy_plan((uint64_t)height, aggregation_factor, policy, g, sf)) return 0;
+    uint64_t sz = policy == DAPOL_POLICY_SPLITTING ? 2 : 0;
+    for (auto &x : g) sz += 8 + dapol_rangeproof_size(64, (int)x.m);
+    sz += 8 + SINGLE_PROOF_BYTE_NUM * ((uint64_t)height - sf);
+    return sz + merkle_bytes((uint64_t)height);
+}
+
+// ------------------------------------------------------------------------------------------------ prove
+// values / blindings of one aggregated group for every leaf: party j < count is sibling start + j, the rest are the
+// (0, Scalar::one()) dummy parties of the Padding policy (padding.rs:98-101)
+__global__ void k_gather_group(uint64_t k, int H, uint64_t start, uint64_t count, uint64_t m, const uint64_t *pv, const uint32_t *pr,
+                               uint64_t *ov, uint32_t *orr) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * m) return;
+    uint64_t p = t / m, j = t % m;
+    uint32_t w[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t v = 0;
+    if (j < count) { v = pv[p * H + start + j]; load8(w, pr + (p * H + start + j) * 8); }
+    ov[t] = v;
+    store8(orr + t * 8, w);
+}
+// RNG contract: range proof #q of the inclusion proof of leaf x draws from ChaCha20(seed) stream x from block q << 32
+__global__ void k_proof_streams(uint64_t k, uint64_t per, uint64_t q0, const uint64_t *leaf_idx, uint64_t *stream, uint64_t *base) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * per) return;
+    stream[t] = leaf_idx[t / per];
+    base[t] = (q0 + t % per) << 32;
+}
+
+extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                 const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size) {
+    if (!t || !leaf_idx || !seed || !k) return DAPOL_ERR_BAD_ARG;
+    dapol_ctx *ctx = t->ctx;
+    const uint64_t H = (uint64_t)t->height;
+    std::vector<AggGroup> groups;
+    uint64_t sf;
+    int rc = policy_plan(H, aggregation_factor, policy, groups, sf);
+    if (rc) return rc;
+    const uint64_t size = dapol_inclusion_proof_size(t->height, aggregation_factor, policy);
+    if (proof_size) *proof_size = size;
+    if (!out || cap < k * size) return DAPOL_ERR_BUFFER;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t kh = k * (H ? H : 1), nsingle = H - sf;
+    uint64_t max_m = 1;
+    for (auto &g : groups) max_m = std::max(max_m, g.m);
+    const uint64_t rows = std::max(k * max_m, k * std::max<uint64_t>(nsingle, 1));  // proofs x parties of the largest range-proof batch
+    uint64_t agg_bytes = 0;
+    for (auto &g : groups) agg_bytes += dapol_rangeproof_size(64, (int)g.m);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 3 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256 + Arena::need(rows, 8) +
+              Arena::need(rows, 32) + 2 * Arena::need(rows, 8) + Arena::need(k * agg_bytes, 1) + Arena::need(k * nsingle + 1, SINGLE_PROOF_BYTE_NUM);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *d_li = ar.take<uint64_t>(k), *d_v = ar.take<uint64_t>(kh);
+    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8);
+    uint32_t *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8);
+    int *d_nf = ar.take<int>(1), nf = 0;
+    uint64_t *g_v = ar.take<uint64_t>(rows);
+    uint32_t *g_r = ar.take<uint32_t>(rows * 8);
+    uint64_t *g_s = ar.take<uint64_t>(rows), *g_b = ar.take<uint64_t>(rows);
+    uint8_t *d_agg = ar.take<uint8_t>(k * agg_bytes), *d_single = ar.take<uint8_t>((k * nsingle + 1) * SINGLE_PROOF_BYTE_NUM);
+#define FAIL(code) do { dfree(mem, st); return (code); } while (0)
+    cudaMemsetAsync(d_nf, 0, 4, st);
+    cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st);
+    rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf);
+    if (rc) FAIL(rc);
+    cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) FAIL(DAPOL_ERR_CUDA);
+    if (nf) FAIL(DAPOL_ERR_NOT_FOUND);  // reference: None for an index that is not a leaf (mod.rs:173)
+    // aggregated proofs, one GPU batch of k proofs per group
+    uint64_t q = 0, off = 0;
+    std::vector<uint64_t> agg_off;
+    for (auto &g : groups) {
+        k_gather_group<<<grid_for(k * g.m, 128), 128, 0, st>>>(k, (int)H, g.start, g.count, g.m, d_v, d_r, g_v, g_r);
+        k_proof_streams<<<grid_for(k, 128), 128, 0, st>>>(k, 1, q, d_li, g_s, g_b);
+        ctx->launches += 2;
+        rc = dapol_rp_prove_dev(ctx, 64, (int)g.m, k, g_v, reinterpret_cast<const uint8_t *>(g_r), seed, g_s, g_b, d_agg + k * off);
+        if (rc) FAIL(rc);
+        agg_off.push_back(off);
+        off += dapol_rangeproof_size(64, (int)g.m);
+        q++;
+    }
+    // single proofs of the remaining siblings: one batch of k * nsingle proofs (sibling-major per leaf)
+    if (nsingle) {
+        k_gather_group<<<grid_for(k * nsingle, 128), 128, 0, st>>>(k, (int)H, sf, nsingle, nsingle, d_v, d_r, g_v, g_r);
+        k_proof_streams<<<grid_for(k * nsingle, 128), 128, 0, st>>>(k, nsingle, q, d_li, g_s, g_b);
+        ctx->launches += 2;
+        rc = dapol_rp_prove_dev(ctx, 64, 1, k * nsingle, g_v, reinterpret_cast<const uint8_t *>(g_r), seed, g_s, g_b, d_single);
+        if (rc) FAIL(rc);
+    }
+    // host assembly of DapolProof::serialize = R::serialize || MerkleProof::serialize
+    std::vector<uint8_t> h_agg(k * agg_bytes), h_single(k * nsingle * SINGLE_PROOF_BYTE_NUM), h_c(kh * 32), h_h(kh * 32);
+    if (agg_bytes) cudaMemcpyAsync(h_agg.data(), d_agg, h_agg.size(), cudaMemcpyDeviceToHost, st);
+    if (nsingle) cudaMemcpyAsync(h_single.data(), d_single, h_single.size(), cudaMemcpyDeviceToHost, st);
+    if (H) { cudaMemcpyAsync(h_c.data(), d_c, kh * 32, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h_h.data(), d_h, kh * 32, cudaMemcpyDeviceToHost, st); }
+    if (cudaStreamSynchronize(st) != cudaSuccess) FAIL(DAPOL_ERR_CUDA);
+    dfree(mem, st);
+#undef FAIL
+    for (uint64_t p = 0; p < k; p++) {
+        uint8_t *o = out + p * size;
+        if (policy == DAPOL_POLICY_SPLITTING) { put_be(o, groups.size(), 2); o += 2; }         // splitting.rs:38-59
+        for (size_t gi = 0; gi < groups.size(); gi++) {                                        // padding.rs:40-53
+            uint64_t plen = dapol_rangeproof_size(64, (int)groups[gi].m);
+            put_be(o, plen, 8); o += 8;
+            memcpy(o, h_agg.data() + k * agg_off[gi] + p * plen, plen); o += plen;
+        }
+        put_be(o, nsingle, 8); o += 8;
+        memcpy(o, h_single.data() + p * nsingle * SINGLE_PROOF_BYTE_NUM, nsingle * SINGLE_PROOF_BYTE_NUM);
+        o += nsingle * SINGLE_PROOF_BYTE_NUM;
+        // MerkleProof::serialize (smtree ^0.1.2; prefix widths are UPSTREAM-RECALL): height, #indexes,
+        // path bits MSB-first, #siblings, siblings (com || hash, src/proof/node.rs:74-79) leaf level first
+        put_be(o, H, 2); o += 2;
+        put_be(o, 1, 8); o += 8;
+        uint64_t nb = (H + 7) / 8;
+        if (nb) { put_be(o, H == 64 ? leaf_idx[p] : leaf_idx[p] << (8 * nb - H), (int)nb); o += nb; }
+        put_be(o, H, 8); o += 8;
+        for (uint64_t s = 0; s < H; s++) {
+            memcpy(o, h_c.data() + (p * H + s) * 32, 32);
+            memcpy(o + 32, h_h.data() + (p * H + s) * 32, 32);
+            o += 64;
+        }
+    }
+    return DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ verify
+// MerkleProof::verify: fold upward from the leaf with DapolProofNode::merge (src/proof/node.rs:56-69):
+// hash = D(C_l || C_r || H_l || H_r), com = com_l + com_r.  One thread per proof; sibs = [H][com 32 || hash 32].
+__global__ void __launch_bounds__(64) k_merkle_fold(uint64_t k, int hash_id, const uint8_t *blob, const uint64_t *sib_off, const uint32_t *heights,
+                                                    const uint64_t *idx, const uint32_t *leaf_c, const uint32_t *leaf_h, const uint32_t *root,
+                                                    uint8_t *ok) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= k || !ok[p]) return;
+    uint32_t curc[8], curh[8], sc_[8], sh[8];
+    load8(curc, leaf_c + 8 * p); load8(curh, leaf_h + 8 * p);
+    ge cur, s;
+    int good = ge_decompress(cur, curc);
+    const uint8_t *sib = blob + sib_off[p];
+    const uint32_t H = heights[p];
+    const uint64_t x = idx[p];
+#pragma unroll 1
+    for (uint32_t lv = 0; lv < H && good; lv++) {
+        for (int i = 0; i < 8; i++) {  // the blob is byte-aligned only
+            const uint8_t *a = sib + 64 * lv + 4 * i;
+            sc_[i] = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);
+            sh[i] = (uint32_t)a[32] | ((uint32_t)a[33] << 8) | ((uint32_t)a[34] << 16) | ((uint32_t)a[35] << 24);
+        }
+        good &= ge_decompress(s, sc_);
+        uint32_t hh[8];
+        if ((x >> lv) & 1) dapol_hash128(hash_id, hh, sc_, curc, sh, curh);
+        else dapol_hash128(hash_id, hh, curc, sc_, curh, sh);
+#pragma unroll
+        for (int i = 0; i < 8; i++) curh[i] = hh[i];
+        ge_add(cur, cur, s);
+        ge_compress(curc, cur);
+    }
+    uint32_t d = 0;
+    for (int i = 0; i < 8; i++) d |= (curc[i] ^ root[i]) | (curh[i] ^ root[8 + i]);
+    ok[p] = (uint8_t)(good && d == 0);
+}
+
+struct ParsedProof {
+    bool ok = false;
+    std::vector<std::pair<uint64_t, uint64_t>> agg;  // (offset, length) inside the blob
+    uint64_t nind = 0, ind_off = 0, H = 0, idx = 0, sib_off = 0;
+};
+// DapolProof::deserialize (src/proof/mod.rs:76-84): R::deserialize then MerkleProof::deserialize; any framing error rejects
+static ParsedProof parse_proof(const uint8_t *p, uint64_t base, uint64_t len, int policy) {
+    ParsedProof r;
+    uint64_t pos = 0, nagg = 1;
+#define NEED(n) do { if (len - pos < (uint64_t)(n)) return r; } while (0)
+    if (policy == DAPOL_POLICY_SPLITTING) { NEED(2); nagg = get_be(p, 2); pos += 2; if (nagg > 64) return r; }
+    for (uint64_t i = 0; i < nagg; i++) {
+        NEED(8);
+        uint64_t sz = get_be(p + pos, 8); pos += 8;
+        if (sz > len - pos) return r;
+        r.agg.push_back({base + pos, sz}); pos += sz;
+    }
+    NEED(8);
+    r.nind = get_be(p + pos, 8); pos += 8;
+    if (r.nind > 64 || (len - pos) / SINGLE_PROOF_BYTE_NUM < r.nind) return r;
+    r.ind_off = base + pos; pos += SINGLE_PROOF_BYTE_NUM * r.nind;
+    NEED(10);
+    r.H = get_be(p + pos, 2); pos += 2;
+    if (get_be(p + pos, 8) != 1 || r.H > 64) return r;
+    pos += 8;
+    uint64_t nb = (r.H + 7) / 8;
+    NEED(nb + 8);
+    r.idx = nb ? get_be(p + pos, (int)nb) : 0;
+    if (nb && r.H != 64) r.idx >>= (8 * nb - r.H);
+    pos += nb;
+    uint64_t nsib = get_be(p + pos, 8); pos += 8;
+    if (nsib != r.H || (len - pos) / 64 < nsib) return r;
+    r.sib_off = base + pos;
+    if (r.nind > nsib) return r;  // reference: usize underflow panic (padding.rs:171, splitting.rs:182)
+#undef NEED
+    r.ok = true;
+    return r;
+}
+
+extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
+                                  const uint8_t *leaf_coms, const uint8_t *leaf_hashes, const uint8_t *proofs, const uint64_t *offsets,
+                                  uint8_t *ok) {
+    if (!ctx || !root_com || !root_hash || !leaf_coms || !leaf_hashes || !proofs || !offsets || !ok || !k) return DAPOL_ERR_BAD_ARG;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (policy != DAPOL_POLICY_PADDING && policy != DAPOL_POLICY_SPLITTING) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t total = offsets[k];
+    std::vector<ParsedProof> pp(k);
+    std::vector<uint64_t> h_sib(k), h_idx(k);
+    std::vector<uint32_t> h_H(k);
+    for (uint64_t p = 0; p < k; p++) {
+        if (offsets[p + 1] < offsets[p] || offsets[p + 1] > total) return DAPOL_ERR_BAD_ARG;
+        pp[p] = parse_proof(proofs + offsets[p], offsets[p], offsets[p + 1] - offsets[p], policy);
+        ok[p] = pp[p].ok ? 1 : 0;
+        h_sib[p] = pp[p].sib_off; h_idx[p] = pp[p].idx; h_H[p] = (uint32_t)pp[p].H;
+    }
+    // range-proof work items grouped by aggregate size m: (proof, blob offset of the range proof, first sibling, real parties)
+    struct Item { uint64_t p, off, first, count; };
+    std::map<uint64_t, std::vector<Item>> by_m;
+    for (uint64_t p = 0; p < k; p++) {
+        if (!pp[p].ok) continue;
+        const ParsedProof &r = pp[p];
+        uint64_t nagg_coms = r.H - r.nind;
+        std::vector<AggGroup> groups;
+        uint64_t sf;
+        if (policy_plan(r.H, nagg_coms, policy, groups, sf) || groups.size() > r.agg.size() ||
+            (policy == DAPOL_POLICY_PADDING && r.agg.size() != 1)) { ok[p] = 0; continue; }
+        bool good = true;
+        for (size_t gi = 0; gi < groups.size() && good; gi++)
+            if (r.agg[gi].second != dapol_rangeproof_size(64, (int)groups[gi].m)) good = false;  // RangeProof::from_bytes / size mismatch
+        if (!good) { ok[p] = 0; continue; }
+        for (size_t gi = 0; gi < groups.size(); gi++) by_m[groups[gi].m].push_back({p, r.agg[gi].first, groups[gi].start, groups[gi].count});
+        for (uint64_t s = 0; s < r.nind; s++) by_m[1].push_back({p, r.ind_off + s * SINGLE_PROOF_BYTE_NUM, nagg_coms + s, 1});
+    }
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(total + 1, 1) + 2 * Arena::need(k, 8) + Arena::need(k, 4) + 2 * Arena::need(k, 32) + 256 + Arena::need(k, 1);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint8_t *d_blob = ar.take<uint8_t>(total + 1);
+    uint64_t *d_sib = ar.take<uint64_t>(k), *d_idx = ar.take<uint64_t>(k);
+    uint32_t *d_H = ar.take<uint32_t>(k), *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8), *d_root = ar.take<uint32_t>(16);
+    uint8_t *d_ok = ar.take<uint8_t>(k);
+    cudaMemcpyAsync(d_blob, proofs, total, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_sib, h_sib.data(), k * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_idx, h_idx.data(), k * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_H, h_H.data(), k * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_lc, leaf_coms, k * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_lh, leaf_hashes, k * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_root, root_com, 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_root + 8, root_hash, 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_ok, ok, k, cudaMemcpyHostToDevice, st);
+    k_merkle_fold<<<grid_for(k, 64), 64, 0, st>>>(k, hash_id, d_blob, d_sib, d_H, d_idx, d_lc, d_lh, d_root, d_ok);
+    ctx->launches++;
+    cudaMemcpyAsync(ok, d_ok, k, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { dfree(mem, st); CUDA_TRY(cudaGetLastError()); return DAPOL_ERR_CUDA; }
+    dfree(mem, st);
+    // R::verify: one GPU batch per aggregate size.  The Padding policy fills the missing parties with
+    // commit(0, 1) = B_blinding (padding.rs:176-180).
+    uint8_t com_padding[32];
+    {
+        ge bb;
+        uint32_t w[8];
+        ge_bblinding(bb);
+        ge_compress(w, bb);
+        memcpy(com_padding, w, 32);
+    }
+    for (auto &kv : by_m) {
+        const uint64_t m = kv.first, plen = dapol_rangeproof_size(64, (int)m);
+        const std::vector<Item> &items = kv.second;
+        std::vector<uint8_t> hp(items.size() * plen), hc(items.size() * m * 32), hok(items.size());
+        for (size_t i = 0; i < items.size(); i++) {
+            const Item &it = items[i];
+            memcpy(hp.data() + i * plen, proofs + it.off, plen);
+            const uint8_t *sib = proofs + pp[it.p].sib_off;
+            for (uint64_t j = 0; j < m; j++) memcpy(hc.data() + (i * m + j) * 32, j < it.count ? sib + 64 * (it.first + j) : com_padding, 32);
+        }
+        int rc = dapol_rangeproof_verify_batch(ctx, 64, (int)m, items.size(), hp.data(), plen, hc.data(), hok.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < items.size(); i++) if (!hok[i]) ok[items[i].p] = 0;
+    }
+    return DAPOL_OK;
+}

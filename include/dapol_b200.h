@@ -116,6 +116,24 @@ DAPOL_API int dapol_tree_paths(const dapol_tree *tree, uint64_t k, const uint64_
                      uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*32 */,
                      uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*32 or NULL */);
 
+/* ---- inclusion proofs.
+ * Dapol::generate_proof_batch-per-leaf (src/dapol/mod.rs:167-190) for k leaves, each serialised as DapolProof::serialize
+ * (src/proof/mod.rs:68-73) = R::serialize (padding.rs:40-53 / splitting.rs:38-59) || MerkleProof::serialize.  All k
+ * proofs have the same size (dapol_inclusion_proof_size); proof i is written at out + i * size.  The range proofs of all
+ * k leaves run as a few large GPU batches (one per aggregate size, one of singles).  DAPOL_ERR_NOT_FOUND if a leaf index
+ * is not a leaf of the tree (reference: None), DAPOL_ERR_BAD_ARG if aggregation_factor > height (reference: panic),
+ * DAPOL_ERR_BUFFER (with *proof_size set) if cap < k * size. */
+DAPOL_API uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy);
+DAPOL_API int dapol_prove_batch(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size);
+/* DapolProof::deserialize + verify (src/proof/mod.rs:41-47,76-95) for k proofs against one root: proof i is
+ * proofs[offsets[i] .. offsets[i+1]), leaf i = DapolProofNode{leaf_coms[i], leaf_hashes[i]}.  ok[i] = 1 iff the Merkle
+ * path folds to the root (DapolProofNode::merge, src/proof/node.rs:56-69) and R::verify accepts the siblings'
+ * commitments (padding.rs:168-197 / splitting.rs:180-211).  Malformed bytes are a reject, never an error. */
+DAPOL_API int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
+                                 const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*32 */, const uint8_t *proofs,
+                                 const uint64_t *offsets /* k+1 */, uint8_t *ok /* k */);
+
 /* ---- range proofs: src/range/mod.rs:48-119 generate_/verify_{single,aggregated}_range_proof in batches.
  * One call = k independent Bulletproofs of one shape: nbits in {8,16,32,64} (the reference fixes BIT_SIZE = 64,
  * range/mod.rs:16), m parties (power of two <= 64; m = 1 is prove_single / verify_single), each over a fresh
