@@ -32,6 +32,9 @@ AUDIT_SEED = b"dapol-b200-bench"
 PAD_SEED = hashlib.sha256(b"dapol-b200").digest()
 # algorithmic work per unit, MAC32 = one 32x32->64 multiply-accumulate (SURVEY.md 8(d) / BASELINE.md / DESIGN.md)
 MAC32_LEAF, MAC32_PAD, MAC32_MERGE = 53.6e3, 45.5e3, 13.9e3
+# what the kernels here actually execute per unit (window-12 comb on half points, batched
+# double-and-compress with one inversion per 8 nodes); roofline.frac uses these, survey_unit_frac the figures above
+MAC32_LEAF_EXEC, MAC32_PAD_EXEC, MAC32_MERGE_EXEC = 25.6e3, 14.5e3, 4.0e3
 NODE_BYTES = 104  # com 32 + hash 32 + v 8 + r 32
 
 
@@ -141,36 +144,99 @@ def cpu_baseline_leg(args):
     H = args.height - (args.users_log2 - sample_log2)
     n = 1 << sample_log2
     iid, io, eid, eo, vals = synth_liabilities(n)
-    t0 = time.perf_counter()
-    rc, idx, bl, _ = cref.derive_leaves(0, iid, io, eid, eo, AUDIT_SEED, H)
-    order = np.argsort(idx, kind="stable")
-    t = cref.Tree(0, H, idx[order], vals[order], bl[order], PAD_SEED, 0, cores)
-    dt = time.perf_counter() - t0
-    root = t.root()["comc"]
-    del t
-    return {"value": n / dt, "unit": "leaves/s", "cores": cores, "kind": "port",
-            "sample": f"2^{sample_log2} users at height {H} (same sparsity as the workload), 1 build, {dt:.1f} s"}, (n, H, root)
+    reps, dt = 2, 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc, idx, bl, _ = cref.derive_leaves(0, iid, io, eid, eo, AUDIT_SEED, H)
+        order = np.argsort(idx, kind="stable")
+        t = cref.Tree(0, H, idx[order], vals[order], bl[order], PAD_SEED, 0, cores)
+        dt += time.perf_counter() - t0
+        root = t.root()["comc"]
+        del t
+    return {"value": reps * n / dt, "unit": "leaves/s", "cores": cores, "kind": "port",
+            "sample": f"2^{sample_log2} users at height {H} (same sparsity as the workload), {reps} builds, {dt:.1f} s, OpenMP over {cores} threads"}, (n, H, root)
+
+
+def rangeproof_leg(ctx, L, dev, world, dist, args):
+    """Range proofs/s (BASELINE.json's second metric): K independent 64-bit Bulletproofs per GPU, prove then verify,
+    device-resident (CUDA events) and end to end through the host-buffer C ABI.  Shapes: m = 1 (single proofs, C5) and
+    m = 32 (the aggregated proof of one height-32 inclusion proof under the Padding policy, C3)."""
+    import ctypes as C
+    import torch
+    out = {}
+    seed = (C.c_uint8 * 32).from_buffer_copy(PAD_SEED)
+    for m, K in ((1, args.rp_singles), (32, args.rp_aggregates)):
+        if K <= 0:
+            continue
+        rng = np.random.default_rng(1234 + m)
+        vals = rng.integers(0, 1 << 63, size=(K, m), dtype=np.uint64)
+        bl = rng.integers(0, 256, size=(K, m, 32), dtype=np.uint8); bl[:, :, 31] &= 0x0F
+        streams = np.arange(K, dtype=np.uint64); bases = np.zeros(K, np.uint64)
+        size = L.dapol_rangeproof_size(64, m)
+        coms = np.stack([ctx.commit_batch(vals[:, j], bl[:, j]) for j in range(m)], axis=1)
+        tv, tb, ts, tbs, tc = (torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (vals, bl, streams, bases, coms))
+        d_proofs = torch.empty(K * size, dtype=torch.uint8, device=dev)
+        d_ok = torch.empty(K, dtype=torch.uint8, device=dev)
+
+        def prove_dev():
+            rc = L.dapol_rangeproof_prove_batch_dev(ctx._h, 64, m, K, tv.data_ptr(), tb.data_ptr(), seed, ts.data_ptr(), tbs.data_ptr(), d_proofs.data_ptr())
+            assert rc == 0, rc
+
+        def verify_dev():
+            rc = L.dapol_rangeproof_verify_batch_dev(ctx._h, 64, m, K, d_proofs.data_ptr(), size, tc.data_ptr(), d_ok.data_ptr())
+            assert rc == 0, rc
+        prove_dev(); verify_dev()  # builds the generator tables, warms up
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev[0].record(); prove_dev(); ev[1].record(); verify_dev(); ev[2].record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev)
+        all_ok = bool(d_ok.all().item())
+        # end to end: host buffers in, proofs / verdicts out
+        h_proofs = np.zeros((K, size), np.uint8); h_ok = np.zeros(K, np.uint8)
+        t0 = time.perf_counter()
+        rc = L.dapol_rangeproof_prove_batch(ctx._h, 64, m, K, vals.ctypes.data, bl.ctypes.data, seed, streams.ctypes.data, bases.ctypes.data,
+                                            h_proofs.ctypes.data)
+        t1 = time.perf_counter()
+        rc |= L.dapol_rangeproof_verify_batch(ctx._h, 64, m, K, h_proofs.ctypes.data, size, coms.ctypes.data, h_ok.ctypes.data)
+        t2 = time.perf_counter()
+        assert rc == 0
+        te = torch.tensor([(t1 - t0) * 1e3, (t2 - t1) * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        pm, vm = t.tolist(); pe, ve = te.tolist()
+        out[f"n64_m{m}"] = {"proofs_per_gpu": K, "prove_per_s": world * K / pm * 1e3, "verify_per_s": world * K / vm * 1e3,
+                            "prove_plus_verify_per_s": world * K / (pm + vm) * 1e3,
+                            "e2e_prove_per_s": world * K / pe * 1e3, "e2e_verify_per_s": world * K / ve * 1e3,
+                            "e2e_prove_plus_verify_per_s": world * K / (pe + ve) * 1e3,
+                            "all_verified": all_ok and bool(h_ok.all()), "proof_bytes": int(size)}
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--users-log2", type=int, default=20)
-    ap.add_argument("--height", type=int, default=32)
-    ap.add_argument("--comb-window", type=int, default=12)
-    ap.add_argument("--cpu-sample-log2", type=int, default=14)
+    ap.add_argument("--users-log2", type=int, default=20, help="users per GPU (weak scaling)")
+    ap.add_argument("--height", type=int, default=32, help="tree height at 1 GPU; N GPUs build ONE tree of height + log2(N)")
+    ap.add_argument("--comb-window", type=int, default=0)
+    ap.add_argument("--cpu-sample-log2", type=int, default=17)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rp-singles", type=int, default=16384, help="single range proofs per GPU in the range-proof leg (0 = skip)")
+    ap.add_argument("--rp-aggregates", type=int, default=512, help="m = 32 aggregated range proofs per GPU (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from dapol_b200 import Context, Dapol, _ffi
+    from dapol_b200 import Comm, Context, CudaEngine, Dapol, ShardedDapol, _ffi
     import ctypes as C
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,78 +252,96 @@ def main():
     ctx = Context(local, args.comb_window)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     L = _ffi.lib()
+    comm = Comm()
+    engine = CudaEngine(ctx)
+    k = (world - 1).bit_length()
+    assert (1 << k) == world, "--gpus must be a power of two"
 
-    # weak scaling: every rank builds an independent 2^users_log2-user tree over its own user range (per-GPU work fixed);
-    # the sharded single-tree build with an NVLink root gather is exercised by tests/ + DESIGN.md section "multi-GPU".
-    n, H = 1 << args.users_log2, args.height
+    # Weak scaling: every rank holds 2^users_log2 users.  N GPUs build ONE tree over all N * 2^users_log2 users, of height
+    # height + log2 N (same sparsity, so per-GPU work is fixed): per-user hashing on the owner of the slice, one all-gather
+    # of the 112-byte user records, independent subtrees per leaf-index prefix, one all-gather of the N subtree roots.
+    n, H = 1 << args.users_log2, args.height + k
     iid, io, eid, eo, vals = synth_liabilities(n, first=rank * n)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     h_iid, h_io, h_eid, h_eo, h_vals = map(pin, (iid, io.view(np.int64), eid, eo.view(np.int64), vals.view(np.int64)))
     d_iid, d_io, d_eid, d_eo, d_vals = (t.to(dev) for t in (h_iid, h_io, h_eid, h_eo, h_vals))
     seed = (C.c_uint8 * 32).from_buffer_copy(PAD_SEED)
     aseed = (C.c_uint8 * len(AUDIT_SEED)).from_buffer_copy(AUDIT_SEED)
+    phase_keys = ("structure", "leaves", "padding", "merges", "total")
 
     def step_dev():
-        h = C.c_void_p(); err = C.c_uint64()
-        rc = L.dapol_tree_build_from_liabilities_dev(ctx._h, 0, H, n, d_iid.data_ptr(), d_io.data_ptr(), d_eid.data_ptr(), d_eo.data_ptr(),
-                                                     d_vals.data_ptr(), aseed, len(AUDIT_SEED), seed, 0, C.byref(h), C.byref(err))
-        assert rc == 0, (rc, L.dapol_last_cuda_error())
-        return h
+        """one build with the liabilities already resident in HBM; returns (nodes, pads, phase times of the rank's tree build)"""
+        if world == 1:
+            h = C.c_void_p(); err = C.c_uint64()
+            rc = L.dapol_tree_build_from_liabilities_dev(ctx._h, 0, H, n, d_iid.data_ptr(), d_io.data_ptr(), d_eid.data_ptr(), d_eo.data_ptr(),
+                                                         d_vals.data_ptr(), aseed, len(AUDIT_SEED), seed, 0, C.byref(h), C.byref(err))
+            assert rc == 0, (rc, L.dapol_last_cuda_error())
+            res = (L.dapol_tree_num_nodes(h), L.dapol_tree_num_padding(h), ctx.last_build_times())
+            L.dapol_tree_destroy(h)
+            return res
+        t = ShardedDapol.new(engine, comm, 0, (d_iid, d_io, d_eid, d_eo, d_vals), AUDIT_SEED, H, H, PAD_SEED)
+        res = (L.dapol_tree_num_nodes(t.subtree) if t.subtree else 0, L.dapol_tree_num_padding(t.subtree) if t.subtree else 0,
+               engine.last_shard_times or dict.fromkeys(phase_keys, 0.0))
+        t.close()
+        return res
 
     def step_host():
-        h = C.c_void_p(); err = C.c_uint64()
-        rc = L.dapol_tree_build_from_liabilities(ctx._h, 0, H, n, h_iid.data_ptr(), h_io.data_ptr(), h_eid.data_ptr(), h_eo.data_ptr(),
-                                                 h_vals.data_ptr(), aseed, len(AUDIT_SEED), seed, 0, C.byref(h), C.byref(err))
-        assert rc == 0, (rc, L.dapol_last_cuda_error())
-        com = np.zeros(32, np.uint8); hs = np.zeros(32, np.uint8); bl = np.zeros(32, np.uint8); v = C.c_uint64()
-        L.dapol_tree_root(h, com.ctypes.data, hs.ctypes.data, C.byref(v), bl.ctypes.data)  # D2H of the step's result
-        return h, com.tobytes(), v.value
+        """the same through the public call on pinned HOST buffers: H2D of the liabilities + D2H of the root inside"""
+        if world == 1:
+            h = C.c_void_p(); err = C.c_uint64()
+            rc = L.dapol_tree_build_from_liabilities(ctx._h, 0, H, n, h_iid.data_ptr(), h_io.data_ptr(), h_eid.data_ptr(), h_eo.data_ptr(),
+                                                     h_vals.data_ptr(), aseed, len(AUDIT_SEED), seed, 0, C.byref(h), C.byref(err))
+            assert rc == 0, (rc, L.dapol_last_cuda_error())
+            com = np.zeros(32, np.uint8); hs = np.zeros(32, np.uint8); bl = np.zeros(32, np.uint8); v = C.c_uint64()
+            L.dapol_tree_root(h, com.ctypes.data, hs.ctypes.data, C.byref(v), bl.ctypes.data)  # D2H of the step's result
+            L.dapol_tree_destroy(h)
+            return com.tobytes(), v.value
+        t = ShardedDapol.new(engine, comm, 0, (h_iid, h_io, h_eid, h_eo, h_vals), AUDIT_SEED, H, H, PAD_SEED)
+        r = t.root_raw()
+        t.close()
+        return r.com, r.value
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    imad_peak = ctx.imad_peak(1)  # GMAC32/s, IMAD.WIDE.U32, measured live
-    launches0 = ctx.kernel_launches
+    imad_peak = ctx.imad_peak(1)  # GMAC32/s: IMAD.WIDE.U32 with a 64-bit addend, measured live
+    fe_rate = (ctx.fe_bench(0), ctx.fe_bench(1))
 
     # ---- device-resident arm
-    for _ in range(args.warmup):
-        L.dapol_tree_destroy(step_dev())
-    phase_ms = {"structure": [], "leaves": [], "padding": [], "merges": [], "total": []}
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_dev()
+    phase_ms = {kk: [] for kk in phase_keys}
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches1 = ctx.kernel_launches
     e0.record()
-    trees = []
     for _ in range(args.steps):
-        h = step_dev()
-        for k, v in ctx.last_build_times().items():
-            phase_ms[k].append(v)
-        stats = (L.dapol_tree_num_nodes(h), L.dapol_tree_num_padding(h))
-        L.dapol_tree_destroy(h)
+        nodes, pads, times = step_dev()
+        for kk in phase_keys:
+            phase_ms[kk].append(times[kk])
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
     gpu_launches = ctx.kernel_launches - launches1
-    clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
     value = world * n * args.steps / (ms_max * 1e-3)
 
-    # ---- end-to-end arm: public API call on pinned host buffers, H2D + D2H inside the timed region
+    # ---- end-to-end arm: public call on pinned host buffers, H2D + D2H inside the timed region
     for _ in range(2):
-        L.dapol_tree_destroy(step_host()[0])
+        step_host()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        h, root_com, root_v = step_host()
-        L.dapol_tree_destroy(h)
+        root_com, root_v = step_host()
     e1.record()
     barrier()
+    clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -265,13 +349,15 @@ def main():
     h2d = int(iid.nbytes + io.nbytes + eid.nbytes + eo.nbytes + vals.nbytes)
     d2h = 104 + 65 * 8 + 32 * 4  # root record + level histogram + collision-round counters (approx. 4 rounds)
 
+    rp = rangeproof_leg(ctx, L, dev, world, dist, args) if (args.rp_singles or args.rp_aggregates) else None
+
     if rank == 0:
-        nodes, pads = stats
-        internal = nodes - n - pads
-        med = {k: statistics.median(v) for k, v in phase_ms.items()}
-        pad_macs = pads * MAC32_PAD
-        achieved = pad_macs / (med["padding"] * 1e-3) / 1e9  # GMAC32/s
-        build_macs = n * MAC32_LEAF + pads * MAC32_PAD + internal * MAC32_MERGE
+        internal = (nodes - 1) // 2  # every internal node has exactly two children
+        leaves_here = nodes - pads - internal
+        med = {kk: statistics.median(v) for kk, v in phase_ms.items()}
+        achieved = pads * MAC32_PAD_EXEC / (med["padding"] * 1e-3) / 1e9  # GMAC32/s
+        build_exec = leaves_here * MAC32_LEAF_EXEC + pads * MAC32_PAD_EXEC + internal * MAC32_MERGE_EXEC
+        build_survey = leaves_here * MAC32_LEAF + pads * MAC32_PAD + internal * MAC32_MERGE
         prof = {}
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "k_pad_traffic.json")))
@@ -281,24 +367,34 @@ def main():
             "metric": "leaves/sec tree build", "value": value, "unit": "leaves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (8x32-bit GF(2^255-19), integer)", "data": "synthetic",
-            "config": {"workload": f"DAPOL+ tree build from liabilities, 2^{args.users_log2} users/GPU, height {H}, D=blake3 "
-                                   f"(leaf derivation + commit + hash + merge + padding)",
-                       "users_per_gpu": n, "height": H, "nodes": nodes, "padding_nodes": pads, "comb_window": args.comb_window,
-                       "parallelism": f"independent trees x{world}" if world > 1 else "single GPU",
-                       "l2": "per-step working set (node store + extended points ~%.1f GB) >> 126 MB L2; no reuse across steps" % (nodes * 232 / 1e9)},
+            "config": {"workload": f"DAPOL+ tree build from liabilities, 2^{args.users_log2} users/GPU, one tree of height {H} over "
+                                   f"{world * n} users, D=blake3 (leaf derivation + commit + hash + merge + padding)",
+                       "users_per_gpu": n, "height": H, "nodes_rank0": nodes, "padding_nodes_rank0": pads,
+                       "comb_window": args.comb_window or "default",
+                       "parallelism": (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs: all-gather of user records "
+                                       f"(112 B/user) + all-gather of {world} subtree roots (232 B)") if world > 1 else "single GPU",
+                       "l2": "per-step working set (node store + half points ~%.1f GB) >> 126 MB L2; no reuse across steps" % (nodes * 232 / 1e9)},
             "phase_ms": med,
             "roofline": {"bound": "imad", "kernel": "k_pad (padding-node pass)", "achieved": achieved, "peak": imad_peak,
                          "unit": "GMAC32/s", "frac": achieved / imad_peak,
-                         "peak_source": "measured live: IMAD.WIDE.U32 microbenchmark (dapol_imad_peak variant 1); MEASURED_PEAKS.json has no integer peak",
-                         "algorithmic_mac32_per_launch": pad_macs, "launch_ms": med["padding"],
+                         "peak_source": "measured live: IMAD.WIDE.U32 (64-bit addend) microbenchmark, dapol_imad_peak variant 1; "
+                                        "MEASURED_PEAKS.json has no integer peak",
+                         "algorithmic_mac32_per_launch": pads * MAC32_PAD_EXEC, "mac32_per_pad_executed": MAC32_PAD_EXEC,
+                         "launch_ms": med["padding"],
+                         "survey_unit_frac": pads * MAC32_PAD / (med["padding"] * 1e-3) / 1e9 / imad_peak,
                          "traffic": prof.get("dram_bytes_per_launch"),
-                         "whole_build_frac": build_macs / (med["total"] * 1e-3) / 1e9 / imad_peak,
+                         "whole_build_frac": build_exec / (med["total"] * 1e-3) / 1e9 / imad_peak,
+                         "whole_build_survey_unit_frac": build_survey / (med["total"] * 1e-3) / 1e9 / imad_peak,
+                         "fe_mul_Gop_s": fe_rate[0], "fe_sq_Gop_s": fe_rate[1],
+                         "fe_mul_frac_of_peak": fe_rate[0] * 72 / imad_peak,
                          "hbm_GBs_algorithmic": (NODE_BYTES * nodes + 2 * NODE_BYTES * internal) / (med["total"] * 1e-3) / 1e9},
             "e2e": {"value": e2e_value, "unit": "leaves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "root": root_com.hex()[:16],
         }
+        if rp is not None:
+            line["range_proofs"] = rp
         if not args.no_cpu_baseline and world == 1:
             cb, (sn, sH, sroot) = cpu_baseline_leg(args)
             line["cpu_baseline"] = cb

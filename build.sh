@@ -1,18 +1,23 @@
 #!/bin/bash
 # Builds the in-tree CUDA library for sm_100a (B200).  The .so is git-ignored but travels with gpurun.
+# A translation unit is recompiled only when it, a header, or this script is newer than its object (FORCE=1: all).
 set -e
 cd "$(dirname "$0")"
 mkdir -p dapol_b200/lib build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden ${DAPOL_PTXAS_V:+-Xptxas -v}"
-pids=()
+newest_hdr=$(ls -t dapol_b200/csrc/*.cuh dapol_b200/csrc/*.h dapol_b200/csrc/*.inc include/*.h build.sh | head -1)
+pids=(); tus=()
 for tu in dapol_lib dapol_rp dapol_proof; do
-  $NVCC $FLAGS -c -o build/$tu.o dapol_b200/csrc/$tu.cu "$@" > build/$tu.log 2>&1 &
-  pids+=($!)
+  o=build/$tu.o
+  if [ -n "$FORCE" ] || [ -n "$*" ] || [ ! -f $o ] || [ dapol_b200/csrc/$tu.cu -nt $o ] || [ "$newest_hdr" -nt $o ]; then
+    $NVCC $FLAGS -c -o $o.tmp dapol_b200/csrc/$tu.cu "$@" > build/$tu.log 2>&1 && mv $o.tmp $o &
+    pids+=($!); tus+=($tu)
+  fi
 done
 rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
-cat build/dapol_lib.log build/dapol_rp.log build/dapol_proof.log
+for tu in "${tus[@]}"; do cat build/$tu.log; done
 [ $rc -eq 0 ] || { echo "build failed"; exit 1; }
 $NVCC -gencode arch=compute_100a,code=sm_100a --shared -o dapol_b200/lib/libdapol_b200.so build/dapol_lib.o build/dapol_rp.o build/dapol_proof.o
-echo "built dapol_b200/lib/libdapol_b200.so"
+echo "built dapol_b200/lib/libdapol_b200.so (recompiled: ${tus[*]:-nothing})"

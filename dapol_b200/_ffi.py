@@ -35,6 +35,14 @@ def lib():
     L.dapol_tree_build_from_nodes_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
     L.dapol_tree_build_from_liabilities.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, u64, vp, u64,
                                                     C.POINTER(vp), C.POINTER(u64)]
+    L.dapol_leaves_derive_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]
+    L.dapol_leaves_assign_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, C.c_int, u64, vp, vp, vp, u64,
+                                          C.POINTER(u64), C.POINTER(u64)]
+    L.dapol_tree_level_pad_counts_dev.argtypes = [vp, C.c_int, u64, vp, vp]
+    L.dapol_tree_build_shard_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.dapol_tree_root_record.argtypes = [vp, vp]
+    L.dapol_tree_build_from_records.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, u64, C.POINTER(vp)]
+    L.dapol_tree_attach_top.argtypes = [vp, vp, u64]
     L.dapol_tree_root.argtypes = [vp, vp, vp, C.POINTER(u64), vp]
     L.dapol_tree_height.argtypes = [vp]
     L.dapol_tree_num_nodes.argtypes = [vp]

@@ -53,7 +53,13 @@ struct dapol_tree {
     uint32_t **d_pos = nullptr;   // device copy of the pointer table
     uint64_t *d_level_off = nullptr;
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
+    std::vector<uint64_t> npads;        // padding nodes per level
+    uint32_t root_ext[32] = {};         // half point of the root commitment (kept for the shard root record)
+    // sharded trees: this tree is the subtree under node `prefix` of level top->height of `top`
+    const dapol_tree *top = nullptr;
+    uint64_t prefix = 0;
 };
+static inline int dapol_total_height(const dapol_tree *t) { return t->height + (t->top ? t->top->height : 0); }
 
 // bump allocator over one device allocation (256-byte aligned pieces)
 struct Arena {
@@ -74,6 +80,7 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
                        const uint64_t *d_stream, const uint64_t *d_base, uint8_t *d_proofs);
 int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);
 
-// device-resident Merkle paths of k leaves (dapol_lib.cu): siblings leaf level first, [k][height] each
+// device-resident Merkle paths of k leaves (dapol_lib.cu): siblings leaf level first, [k][total height] each; leaf
+// indexes are those of the whole tree (prefix included when the tree is a shard with its top tree attached)
 int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
                          uint32_t *d_lc, uint32_t *d_lh, int *d_not_found);

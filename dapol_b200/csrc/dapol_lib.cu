@@ -34,6 +34,10 @@ extern "C" const char *dapol_strerror(int code) {
 }
 
 
+// comb windows of the tree tables that are instantiated (dapol_ctx_create's comb_window)
+#define DAPOL_DEFAULT_COMB_WINDOW 12
+#define DAPOL_W_CASES(X) X(4) X(8) X(10) X(12) X(13) X(14) X(15) X(16)
+
 // ------------------------------------------------------------------------------------------------ kernels
 template <int W>
 __global__ void k_comb_table(ge_niels *table, int nw, int which, uint64_t total) {
@@ -114,7 +118,8 @@ __global__ void k_scan_tile_offsets(uint64_t *tile_sums, uint64_t ntiles) {  // 
 }
 // pass 3: exclusive scan inside the tile + slots / parents / padding destinations
 __global__ void k_struct_apply(const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *tile_offsets, uint32_t *pos,
-                               uint64_t *parent_idx, uint64_t level_off, NodeStore ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
+                               uint64_t *parent_idx, uint64_t level_off, NodeStore ns, uint64_t *pad_dest, uint64_t pad_ord_base,
+                               uint64_t *pad_rng, uint64_t pad_rng_base) {
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t x[SCAN_ITEMS], s = 0;
 #pragma unroll
@@ -122,7 +127,7 @@ __global__ void k_struct_apply(const uint64_t *idx, uint64_t c, const uint64_t *
     uint64_t e = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < c) struct_apply_body(base + i, idx, x[i], e, pos, parent_idx, level_off, ns, pad_dest, pad_ord_base);
+        if (base + i < c) struct_apply_body(base + i, idx, x[i], e, pos, parent_idx, level_off, ns, pad_dest, pad_ord_base, pad_rng, pad_rng_base);
         e += x[i];
     }
 }
@@ -135,9 +140,43 @@ __global__ void k_derive(uint64_t n, int hash_id, const uint8_t *iid_blob, const
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (derive_body(i, hash_id, iid_blob, iid_off, eid_blob, eid_off, audit_seed, seed_len, height, audit, cur_seed, cand, blind)) *too_long = 1;
+    if (tries) {
+        tries[i] = 1;
+        audit_key[i] = (uint64_t)audit[8 * i] | ((uint64_t)audit[8 * i + 1] << 32);
+        iota[i] = (uint32_t)i;
+    }
+}
+// stage-2 state for records that were derived elsewhere (sharded build)
+__global__ void k_assign_init(uint64_t n, const uint32_t *audit, uint32_t *tries, uint64_t *audit_key, uint32_t *iota) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     tries[i] = 1;
     audit_key[i] = (uint64_t)audit[8 * i] | ((uint64_t)audit[8 * i + 1] << 32);
     iota[i] = (uint32_t)i;
+}
+// [lo, hi) = positions of the sorted leaf indexes that start with `prefix` (top prefix_bits of height bits)
+__global__ void k_prefix_bounds(uint64_t n, const uint64_t *sorted_idx, int shift, uint64_t prefix, uint64_t *out) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int side = 0; side < 2; side++) {
+        uint64_t want = prefix + side, lo = 0, hi = n;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if ((shift >= 64 ? 0 : sorted_idx[mid] >> shift) < want) lo = mid + 1; else hi = mid;
+        }
+        out[side] = lo;
+    }
+}
+// leaves of one shard out of the global sorted order: local index (prefix stripped), value, blinding
+__global__ void k_gather_shard(uint64_t lo, uint64_t cnt, uint64_t mask, const uint64_t *sorted_idx, const uint32_t *who, const uint64_t *values,
+                               const uint32_t *blind, uint64_t *o_idx, uint64_t *o_values, uint32_t *o_blind) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    uint64_t u = who[lo + j];
+    o_idx[j] = sorted_idx[lo + j] & mask;
+    o_values[j] = values[u];
+    uint32_t w[8];
+    load8(w, blind + 8 * u);
+    store8(o_blind + 8 * j, w);
 }
 // sorted by 64-bit audit-id prefix (stable, so ties are in input order): exact duplicate detection inside runs
 __global__ void k_find_dups(uint64_t n, const uint64_t *keys, const uint32_t *who, const uint32_t *audit, unsigned long long *first_dup) {
@@ -189,9 +228,14 @@ struct Seed8 {
 };
 template <int W>
 __global__ void __launch_bounds__(128) k_pad(uint64_t n, uint64_t stride, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
-                                             uint64_t pad_base, const ge_niels *tab_bbl) {
+                                             const uint64_t *pad_rng, const ge_niels *tab_bbl) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_base, tab_bbl);
+    if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_rng, tab_bbl);
+}
+// leaves of a top tree: subtree-root records gathered from the shards
+__global__ void k_leaf_records(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, const uint32_t *recs) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) record_leaf_body(i, ns, level_off, pos, recs);
 }
 template <int B>
 __global__ void __launch_bounds__(128) k_merge(uint64_t n, uint64_t stride, NodeStore ns, uint64_t child_off, uint64_t parent_off,
@@ -222,20 +266,28 @@ __global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *valu
     ge_compress(cc, acc);
     store8(out + 8 * i, cc);
 }
-__global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, NodeStore ns, const uint64_t *level_off, uint64_t n_leaf_level,
-                        uint32_t *const *pos, int height, uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h,
-                        uint32_t *o_lc, uint32_t *o_lh, int *not_found) {
+// Siblings of leaf_idx[q] (or of the fixed leaf `fixed_idx` when leaf_idx == nullptr: the shard's own root inside the
+// top tree), leaf level first, written at [q][lvl0 ..] of arrays with out_stride levels per proof.  Leaf indexes carry
+// the shard prefix above `height` bits when prefix_check is set.
+__global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, uint64_t fixed_idx, int prefix_check, uint64_t prefix, NodeStore ns,
+                        const uint64_t *level_off, uint64_t n_leaf_level, uint32_t *const *pos, int height, int out_stride, int lvl0,
+                        uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint32_t *o_lc, uint32_t *o_lh, int *not_found) {
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= k) return;
+    uint64_t want = leaf_idx ? leaf_idx[q] : fixed_idx;
+    if (prefix_check) {
+        if (height < 64 && (want >> height) != prefix) { *not_found = 1; return; }
+        if (height < 64) want &= (1ull << height) - 1;
+    }
     uint64_t off = level_off[height];
-    int64_t slot = find_leaf_slot(ns.idx + off, n_leaf_level, leaf_idx[q]);
+    int64_t slot = find_leaf_slot(ns.idx + off, n_leaf_level, want);
     if (slot < 0 || ns.is_pad[off + slot]) { *not_found = 1; return; }
     uint32_t w[8];
     if (o_lc) { load8(w, ns.comc + 8 * (off + slot)); store8(o_lc + 8 * q, w); }
     if (o_lh) { load8(w, ns.hash + 8 * (off + slot)); store8(o_lh + 8 * q, w); }
     uint64_t p = (uint64_t)slot;
-    for (int h = height, lvl = 0; h >= 1; h--, lvl++) {
-        uint64_t g = level_off[h] + (p ^ 1), o = q * (uint64_t)height + lvl;
+    for (int h = height, lvl = lvl0; h >= 1; h--, lvl++) {
+        uint64_t g = level_off[h] + (p ^ 1), o = q * (uint64_t)out_stride + lvl;
         o_v[o] = ns.v[g];
         load8(w, ns.r + 8 * g); store8(o_r + 8 * o, w);
         load8(w, ns.comc + 8 * g); store8(o_c + 8 * o, w);
@@ -248,7 +300,7 @@ __global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, NodeStore ns, cons
 template <int VARIANT>
 __global__ void k_imad_peak(uint32_t *out, uint32_t a, uint32_t b, int iters) {
     uint32_t x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    uint64_t y0 = x0, y1 = x1, y2 = x2, y3 = x3, y4 = x4, y5 = x5, y6 = x6, y7 = x7;
+    uint32_t z0 = 0, z1 = 1, z2 = 2, z3 = 3, z4 = 4, z5 = 5, z6 = 6, z7 = 7;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
@@ -257,10 +309,12 @@ __global__ void k_imad_peak(uint32_t *out, uint32_t a, uint32_t b, int iters) {
                 asm volatile("mad.lo.u32 %0, %0, %8, %9; mad.lo.u32 %1, %1, %8, %9; mad.lo.u32 %2, %2, %8, %9; mad.lo.u32 %3, %3, %8, %9;"
                              "mad.lo.u32 %4, %4, %8, %9; mad.lo.u32 %5, %5, %8, %9; mad.lo.u32 %6, %6, %8, %9; mad.lo.u32 %7, %7, %8, %9;"
                              : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(a), "r"(b));
-            } else if (VARIANT == 1) {  // 8 independent mad.wide chains: 8 IMAD.WIDE = 8 MAC32
-                asm volatile("mad.wide.u32 %0, %8, %9, %0; mad.wide.u32 %1, %8, %10, %1; mad.wide.u32 %2, %8, %9, %2; mad.wide.u32 %3, %8, %10, %3;"
-                             "mad.wide.u32 %4, %8, %9, %4; mad.wide.u32 %5, %8, %10, %5; mad.wide.u32 %6, %8, %9, %6; mad.wide.u32 %7, %8, %10, %7;"
-                             : "+l"(y0), "+l"(y1), "+l"(y2), "+l"(y3), "+l"(y4), "+l"(y5), "+l"(y6), "+l"(y7) : "r"(a), "r"(b), "r"(x0));
+            } else if (VARIANT == 1) {  // 8 IMAD.WIDE.U32 with a 64-bit addend each = 8 MAC32 (ptxas fuses each mad.lo.cc / madc.hi pair);
+                                        // the multiplicand is the neighbour chain's low word, so nothing is loop-invariant
+#define DAPOL_WIDE_MAC(lo, hi, m, c) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(m), "r"(c))
+                DAPOL_WIDE_MAC(x0, z0, x1, b); DAPOL_WIDE_MAC(x1, z1, x2, b); DAPOL_WIDE_MAC(x2, z2, x3, a); DAPOL_WIDE_MAC(x3, z3, x4, a);
+                DAPOL_WIDE_MAC(x4, z4, x5, b); DAPOL_WIDE_MAC(x5, z5, x6, b); DAPOL_WIDE_MAC(x6, z6, x7, a); DAPOL_WIDE_MAC(x7, z7, x0, a);
+#undef DAPOL_WIDE_MAC
             } else {  // the carry-chain shape fe_mul uses: (mad.lo.cc, madc.hi.cc) x4 = 4 MAC32 in 8 instructions
                 asm volatile("mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;"
                              "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5; madc.lo.cc.u32 %6, %8, %8, %6; madc.hi.u32 %7, %8, %8, %7;"
@@ -268,7 +322,7 @@ __global__ void k_imad_peak(uint32_t *out, uint32_t a, uint32_t b, int iters) {
             }
         }
     }
-    uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (uint32_t)(y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7) ^ (uint32_t)((y0 ^ y3 ^ y5) >> 32);
+    uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ z0 ^ z1 ^ z2 ^ z3 ^ z4 ^ z5 ^ z6 ^ z7;
     if (r == 0x12345u) out[0] = r;  // practically never; keeps the chains live
 }
 template <int OP>
@@ -312,7 +366,7 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     CUDA_TRY(cudaSetDevice(device));
     dapol_ctx *ctx = new dapol_ctx();
     ctx->device = device;
-    ctx->W = comb_window ? comb_window : 8;
+    ctx->W = comb_window ? comb_window : DAPOL_DEFAULT_COMB_WINDOW;
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaMalloc(&ctx->scratch, 1024));
@@ -324,10 +378,9 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     }
     int rc;
     switch (ctx->W) {
-        case 4: rc = build_tables<4>(ctx); break;
-        case 8: rc = build_tables<8>(ctx); break;
-        case 10: rc = build_tables<10>(ctx); break;
-        case 12: rc = build_tables<12>(ctx); break;
+#define W_CASE(w) case w: rc = build_tables<w>(ctx); break;
+        DAPOL_W_CASES(W_CASE)
+#undef W_CASE
         default: rc = DAPOL_ERR_BAD_ARG;
     }
     if (rc) { dapol_ctx_destroy(ctx); return rc; }
@@ -380,7 +433,7 @@ static inline uint64_t batch_stride(uint64_t n) {
 }
 template <int W>
 static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
-                            const Seed8 &seed, uint64_t pad_base, int phase) {
+                            const Seed8 &seed, const uint64_t *d_pad_rng, int phase) {
     int H = t->height;
     if (phase == 0) {
         uint64_t stride = batch_stride(t->n_leaves);
@@ -389,14 +442,19 @@ static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_val
         ctx->launches++;
     } else if (t->n_pads) {
         uint64_t stride = batch_stride(t->n_pads);
-        k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, pad_base, ctx->tab_bbl);
+        k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, d_pad_rng, ctx->tab_bbl);
         ctx->launches++;
     }
 }
 
+// d_records != nullptr: the leaves are subtree-root records (top tree of a sharded build) instead of (value, blinding).
+// pad_level_base != nullptr (host, [height + 1]): RNG block of the first padding node of each level (a shard's levels
+// interleave with the other shards' in the single-tree creation order); nullptr: pad_base + running creation ordinal.
 static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
-                          const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
-    if (!ctx || !out || !d_leaf_idx || !d_values || !d_blindings || !pad_seed) return DAPOL_ERR_BAD_ARG;
+                          const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out,
+                          const uint64_t *pad_level_base = nullptr, const uint32_t *d_records = nullptr) {
+    if (!ctx || !out || !d_leaf_idx || !pad_seed) return DAPOL_ERR_BAD_ARG;
+    if (!d_records && (!d_values || !d_blindings)) return DAPOL_ERR_BAD_ARG;
     *out = nullptr;
     if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
     if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
@@ -419,7 +477,9 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     t->ctx = ctx; t->hash_id = hash_id; t->height = H; t->n_leaves = n;
     t->level_off.assign(H + 1, 0); t->level_n.assign(H + 1, 0); t->n_real.assign(H + 1, 0);
     t->pos.assign(H + 1, nullptr);
-    std::vector<uint64_t> npads(H + 1, 0), pos_off(H + 2, 0);
+    std::vector<uint64_t> pos_off(H + 2, 0);
+    std::vector<uint64_t> &npads = t->npads;
+    npads.assign(H + 1, 0);
     {   // real nodes at level h = 1 + #{adjacent pairs whose highest differing bit >= H - h}
         uint64_t acc = 0;
         for (int h = 0; h <= H; h++) {
@@ -459,11 +519,12 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     for (int h = 1; h <= H; h++) t->pos[h] = t->pos_all + pos_off[h];
     uint64_t ntiles_max = (n + SCAN_TILE - 1) / SCAN_TILE;
     Arena ar;
-    ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 8) + Arena::need(ntiles_max, 8) + Arena::need(total_pads + 1, 8);
+    ar.size = 2 * Arena::need(n, 8) + Arena::need(n, 8) + Arena::need(ntiles_max, 8) + 2 * Arena::need(total_pads + 1, 8);
     TRY_T(dmalloc(&arena_mem, ar.size, st));
     ar.base = arena_mem;
     uint64_t *realA = ar.take<uint64_t>(n), *realB = ar.take<uint64_t>(n), *d_flags = ar.take<uint64_t>(n);
     uint64_t *d_tiles = ar.take<uint64_t>(ntiles_max), *d_pad_dest = ar.take<uint64_t>(total_pads + 1);
+    uint64_t *d_pad_rng = ar.take<uint64_t>(total_pads + 1);
     if (H == 0) {
         TRY_T(cudaMemcpyAsync(t->ns.idx, d_leaf_idx, 8, cudaMemcpyDeviceToDevice, st));
         TRY_T(cudaMemsetAsync(t->ns.is_pad, 0, 1, st));
@@ -483,7 +544,8 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
         unsigned ntiles = (unsigned)((c + SCAN_TILE - 1) / SCAN_TILE);
         k_struct_flags_tiles<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles);
         k_scan_tile_offsets<<<1, SCAN_BLOCK, 0, st>>>(d_tiles, ntiles);
-        k_struct_apply<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles, t->pos[h], next, t->level_off[h], t->ns, d_pad_dest, ord);
+        k_struct_apply<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles, t->pos[h], next, t->level_off[h], t->ns, d_pad_dest, ord,
+                                                      d_pad_rng, pad_level_base ? pad_level_base[h] : pad_base + ord);
         ctx->launches += 3;
         ord += npads[h];
         cur = next;
@@ -494,11 +556,13 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     memcpy(seed.w, pad_seed, 32);
     const uint32_t *d_blind = reinterpret_cast<const uint32_t *>(d_blindings);
     for (int phase = 0; phase < 2; phase++) {
-        switch (ctx->W) {
-            case 4: launch_leaf_pad<4>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
-            case 8: launch_leaf_pad<8>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
-            case 10: launch_leaf_pad<10>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
-            case 12: launch_leaf_pad<12>(ctx, t, d_values, d_blind, d_pad_dest, seed, pad_base, phase); break;
+        if (phase == 0 && d_records) {
+            k_leaf_records<<<grid_for(n, 128), 128, 0, st>>>(n, t->ns, t->level_off[H], t->pos[H], d_records);
+            ctx->launches++;
+        } else switch (ctx->W) {
+#define W_CASE(w) case w: launch_leaf_pad<w>(ctx, t, d_values, d_blind, d_pad_dest, seed, d_pad_rng, phase); break;
+            DAPOL_W_CASES(W_CASE)
+#undef W_CASE
         }
         TRY_T(cudaEventRecord(ctx->ev[2 + phase], st));
     }
@@ -516,6 +580,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
     TRY_T(dmalloc(&t->d_level_off, (H + 1) * 8, st));
     TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
+    TRY_T(cudaMemcpyAsync(t->root_ext, t->ns.ext, 128, cudaMemcpyDeviceToHost, st));  // root = global node 0
     TRY_T(cudaGetLastError());
     TRY_T(cudaStreamSynchronize(st));
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ctx->last_ms[i], ctx->ev[i], ctx->ev[i + 1]);
@@ -555,36 +620,99 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
     return rc;
 }
 
+// ---- build_leaf_nodes (mod.rs:323-399) in two device stages, so that a sharded build can hash its own slice of the
+// liabilities and run the (global) duplicate / collision rules over the gathered per-user records.
+// stage 1: per-user hashing of a slice (k_derive); tries / audit_key / iota are written only when given.
+static int derive_stage(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob, const uint64_t *d_iid_off,
+                        const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint8_t *d_seed, uint32_t seed_len, uint32_t *audit,
+                        uint32_t *cur_seed, uint64_t *cand, uint32_t *blind, uint32_t *tries, uint64_t *akey, uint32_t *iota, int *d_too_long) {
+    k_derive<<<grid_for(n, 128), 128, 0, ctx->stream>>>(n, hash_id, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, seed_len, height, audit,
+                                                        cur_seed, cand, blind, tries, akey, iota, d_too_long);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
+// scratch of stage 2 for n users
+struct AssignScratch {
+    uint64_t *akey, *keys_sorted;
+    uint32_t *tries, *iota, *who;
+    uint8_t *cub_tmp;
+    size_t cub_bytes;
+    unsigned long long *counters;  // [0] losers, [1] min failed pos, [2] first dup pos, [3] too-long flag (int)
+    static size_t cub_need(uint64_t n, cudaStream_t st) {
+        size_t b = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (int)n, 0, 64, st);
+        return b;
+    }
+    static size_t need(uint64_t n, size_t cub_bytes) { return 2 * Arena::need(n, 8) + 3 * Arena::need(n, 4) + Arena::need(cub_bytes, 1) + 1024; }
+    void take(Arena &ar, uint64_t n, size_t cb) {
+        akey = ar.take<uint64_t>(n); keys_sorted = ar.take<uint64_t>(n);
+        tries = ar.take<uint32_t>(n); iota = ar.take<uint32_t>(n); who = ar.take<uint32_t>(n);
+        cub_tmp = ar.take<uint8_t>(cb); cub_bytes = cb;
+        counters = ar.take<unsigned long long>(8);
+    }
+};
+// stage 2 over ALL users in input order: duplicate internal ids (mod.rs:345-349 <=> identical audit ids), shuffle_index's
+// first-come-first-served collision rule as a fix-point (mod.rs:408-441), final sort by index (mod.rs:396).
+// On return sc.keys_sorted = sorted leaf indexes, sc.who = input position of each, cand[i] = index of user i.
+// The caller initialised sc.counters = {0, ~0, ~0, too_long} and sc.tries / sc.akey / sc.iota (k_derive or k_assign_init).
+static int assign_stage(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint32_t *audit, uint32_t *cur_seed, uint64_t *cand,
+                        AssignScratch &sc, uint64_t *err_pos) {
+    cudaStream_t st = ctx->stream;
+    unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
+    cub::DeviceRadixSort::SortPairs(sc.cub_tmp, sc.cub_bytes, sc.akey, sc.keys_sorted, sc.iota, sc.who, (int)n, 0, 64, st);
+    k_find_dups<<<grid_for(n, 256), 256, 0, st>>>(n, sc.keys_sorted, sc.who, audit, sc.counters + 2);
+    ctx->launches += 2;
+    int end_bit = height < 1 ? 1 : height;
+    for (int round = 0;; round++) {
+        cub::DeviceRadixSort::SortPairs(sc.cub_tmp, sc.cub_bytes, cand, sc.keys_sorted, sc.iota, sc.who, (int)n, 0, end_bit, st);
+        CUDA_TRY(cudaMemsetAsync(sc.counters, 0, 8, st));
+        k_resolve_collisions<<<grid_for(n, 256), 256, 0, st>>>(n, sc.keys_sorted, sc.who, hash_id, height, cur_seed, cand, sc.tries, sc.counters);
+        ctx->launches += 2;
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, sc.counters, 32, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_cnt[0] == 0) break;
+        if (round > 4096) return DAPOL_ERR_BAD_ARG;
+    }
+    if ((int)h_cnt[3]) return DAPOL_ERR_BAD_ARG;  // id too long for single-chunk hashing (> 1024 B)
+    unsigned long long f = h_cnt[1], d = h_cnt[2];
+    if (d != ~0ull && d <= f) { if (err_pos) *err_pos = d; return DAPOL_ERR_DUPLICATED_INTERNAL_ID; }
+    if (f != ~0ull) { if (err_pos) *err_pos = f; return DAPOL_ERR_FAILED_TO_MAP_INDEX; }
+    return DAPOL_OK;
+}
+static int liabilities_check(int hash_id, int height, uint64_t n, uint64_t seed_len) {
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
+    if (height < 0) return DAPOL_ERR_BAD_ARG;
+    if (height < 64 && (1ull << height) < n * 2) return DAPOL_ERR_SPARSITY_TOO_SMALL;  // MIN_SPARSITY = 2 (mod.rs:27,110)
+    if (n == 0 || height == 0 || n >= (1ull << 31) || seed_len > 512) return DAPOL_ERR_BAD_ARG;
+    return DAPOL_OK;
+}
+
 // Dapol::new: checks (mod.rs:101-116), build_leaf_nodes on the device (mod.rs:323-399), sort, build.
 static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob, const uint64_t *d_iid_off,
                                  const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint64_t *d_values, const uint8_t *audit_seed,
                                  uint64_t seed_len, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos) {
     if (!ctx || !out) return DAPOL_ERR_BAD_ARG;
     *out = nullptr;
-    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
-    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
-    if (height < 0) return DAPOL_ERR_BAD_ARG;
-    if (height < 64 && (1ull << height) < n * 2) return DAPOL_ERR_SPARSITY_TOO_SMALL;  // MIN_SPARSITY = 2 (mod.rs:27,110)
-    if (n == 0 || height == 0 || n >= (1ull << 31) || seed_len > 512) return DAPOL_ERR_BAD_ARG;
+    int rc = liabilities_check(hash_id, height, n, seed_len);
+    if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int)n, 0, 64, st);
+    size_t cub_bytes = AssignScratch::cub_need(n, st);
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = 3 * Arena::need(n, 32) + 4 * Arena::need(n, 8) + 3 * Arena::need(n, 4) + Arena::need(n, 32) + Arena::need(cub_bytes, 1) +
-              Arena::need(seed_len + 1, 1) + 1024;
+    ar.size = 3 * Arena::need(n, 32) + Arena::need(n, 8) + Arena::need(n, 32) + AssignScratch::need(n, cub_bytes) + Arena::need(seed_len + 1, 1);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint32_t *audit = ar.take<uint32_t>(8 * n), *cur_seed = ar.take<uint32_t>(8 * n), *blind = ar.take<uint32_t>(8 * n);
-    uint64_t *akey = ar.take<uint64_t>(n), *keys_sorted = ar.take<uint64_t>(n), *values_sorted = ar.take<uint64_t>(n);
-    uint64_t *cand = nullptr;
-    uint32_t *tries = ar.take<uint32_t>(n), *iota = ar.take<uint32_t>(n), *who = ar.take<uint32_t>(n);
+    uint64_t *values_sorted = ar.take<uint64_t>(n);
     uint32_t *blind_sorted = ar.take<uint32_t>(8 * n);
-    uint8_t *cub_tmp = ar.take<uint8_t>(cub_bytes), *d_seed = ar.take<uint8_t>(seed_len + 1);
-    unsigned long long *counters = ar.take<unsigned long long>(8);
-    int rc = DAPOL_OK;
+    AssignScratch sc;
+    sc.take(ar, n, cub_bytes);
+    uint8_t *d_seed = ar.take<uint8_t>(seed_len + 1);
+    uint64_t *cand = nullptr;
 #define TRY_L(expr)                                                          \
     do {                                                                     \
         cudaError_t e_ = (expr);                                             \
@@ -595,38 +723,16 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
     } while (0)
     TRY_L(dmalloc(&cand, n * 8, st));  // survives as the id -> leaf index map of the tree
     if (seed_len) TRY_L(cudaMemcpyAsync(d_seed, audit_seed, seed_len, cudaMemcpyHostToDevice, st));
-    // counters: [0] losers, [1] min failed pos, [2] first dup pos, [3] too-long flag (int)
     unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
-    TRY_L(cudaMemcpyAsync(counters, h_cnt, 32, cudaMemcpyHostToDevice, st));
-    k_derive<<<grid_for(n, 128), 128, 0, st>>>(n, hash_id, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, (uint32_t)seed_len, height, audit,
-                                               cur_seed, cand, blind, tries, akey, iota, reinterpret_cast<int *>(counters + 3));
-    // duplicate internal ids <=> identical audit ids
-    cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, akey, keys_sorted, iota, who, (int)n, 0, 64, st);
-    k_find_dups<<<grid_for(n, 256), 256, 0, st>>>(n, keys_sorted, who, audit, counters + 2);
-    ctx->launches += 3;
-    // collision fix-point: serial dictatorship by input position (mod.rs:408-441 processed in input order)
-    int end_bit = height < 1 ? 1 : height;
-    for (int round = 0;; round++) {
-        cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, cand, keys_sorted, iota, who, (int)n, 0, end_bit, st);
-        TRY_L(cudaMemsetAsync(counters, 0, 8, st));
-        k_resolve_collisions<<<grid_for(n, 256), 256, 0, st>>>(n, keys_sorted, who, hash_id, height, cur_seed, cand, tries, counters);
-        ctx->launches += 2;
-        TRY_L(cudaMemcpyAsync(h_cnt, counters, 32, cudaMemcpyDeviceToHost, st));
-        TRY_L(cudaStreamSynchronize(st));
-        if (h_cnt[0] == 0) break;
-        if (round > 4096) { rc = DAPOL_ERR_BAD_ARG; break; }
-    }
-    if (rc == DAPOL_OK && (int)h_cnt[3]) rc = DAPOL_ERR_BAD_ARG;  // id too long for single-chunk hashing (> 1024 B)
-    if (rc == DAPOL_OK) {
-        unsigned long long f = h_cnt[1], d = h_cnt[2];
-        if (d != ~0ull && d <= f) { rc = DAPOL_ERR_DUPLICATED_INTERNAL_ID; if (err_pos) *err_pos = d; }
-        else if (f != ~0ull) { rc = DAPOL_ERR_FAILED_TO_MAP_INDEX; if (err_pos) *err_pos = f; }
-    }
+    TRY_L(cudaMemcpyAsync(sc.counters, h_cnt, 32, cudaMemcpyHostToDevice, st));
+    rc = derive_stage(ctx, hash_id, height, n, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, (uint32_t)seed_len, audit, cur_seed, cand, blind,
+                      sc.tries, sc.akey, sc.iota, reinterpret_cast<int *>(sc.counters + 3));
+    if (rc == DAPOL_OK) rc = assign_stage(ctx, hash_id, height, n, audit, cur_seed, cand, sc, err_pos);
     if (rc != DAPOL_OK) { dfree(mem, st); dfree(cand, st); return rc; }
     // the last sort (no losers) is the final sorted order: result.sort_by_key(index) (mod.rs:396)
-    k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, who, d_values, blind, values_sorted, blind_sorted);
+    k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, sc.who, d_values, blind, values_sorted, blind_sorted);
     ctx->launches++;
-    rc = tree_build_dev(ctx, hash_id, height, n, keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
+    rc = tree_build_dev(ctx, hash_id, height, n, sc.keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
     dfree(mem, st);
     if (rc != DAPOL_OK) { dfree(cand, st); return rc; }
     (*out)->leaf_index_of = cand;
@@ -669,6 +775,140 @@ extern "C" int dapol_tree_build_from_liabilities(dapol_ctx *ctx, int hash_id, in
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------------ sharded build
+extern "C" int dapol_leaves_derive_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob, const uint64_t *d_iid_off,
+                                       const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                       uint8_t *d_audit, uint8_t *d_seed_state, uint64_t *d_cand, uint8_t *d_blind) {
+    if (!ctx || !d_iid_off || !d_eid_off || !d_audit || !d_seed_state || !d_cand || !d_blind) return DAPOL_ERR_BAD_ARG;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
+    if (height < 1 || n == 0 || n >= (1ull << 31) || audit_seed_len > 512) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint8_t *d_seed = nullptr;
+    CUDA_TRY(dmalloc(&d_seed, audit_seed_len + 8, st));
+    int *d_flag = reinterpret_cast<int *>(d_seed + ((audit_seed_len + 3) & ~3ull)), flag = 0;
+    cudaMemsetAsync(d_flag, 0, 4, st);
+    if (audit_seed_len) cudaMemcpyAsync(d_seed, audit_seed, audit_seed_len, cudaMemcpyHostToDevice, st);
+    int rc = derive_stage(ctx, hash_id, height, n, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, (uint32_t)audit_seed_len,
+                          reinterpret_cast<uint32_t *>(d_audit), reinterpret_cast<uint32_t *>(d_seed_state), d_cand,
+                          reinterpret_cast<uint32_t *>(d_blind), nullptr, nullptr, nullptr, d_flag);
+    cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    dfree(d_seed, st);
+    if (rc) return rc;
+    CUDA_TRY(e);
+    return flag ? DAPOL_ERR_BAD_ARG : DAPOL_OK;
+}
+extern "C" int dapol_leaves_assign_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n_total, const uint8_t *d_audit, uint8_t *d_seed_state,
+                                       uint64_t *d_cand, const uint8_t *d_blind, const uint64_t *d_values, int prefix_bits, uint64_t prefix,
+                                       uint64_t *d_out_idx, uint64_t *d_out_values, uint8_t *d_out_blind, uint64_t cap, uint64_t *n_out,
+                                       uint64_t *err_pos) {
+    if (!ctx || !d_audit || !d_seed_state || !d_cand || !d_blind || !d_values || !n_out) return DAPOL_ERR_BAD_ARG;
+    int rc = liabilities_check(hash_id, height, n_total, 0);
+    if (rc) return rc;
+    if (prefix_bits < 0 || prefix_bits >= height || prefix_bits > 16 || (prefix >> prefix_bits)) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n = n_total;
+    size_t cub_bytes = AssignScratch::cub_need(n, st);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = AssignScratch::need(n, cub_bytes) + 256;
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    AssignScratch sc;
+    sc.take(ar, n, cub_bytes);
+    unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
+    cudaMemcpyAsync(sc.counters, h_cnt, 32, cudaMemcpyHostToDevice, st);
+    const uint32_t *audit = reinterpret_cast<const uint32_t *>(d_audit);
+    k_assign_init<<<grid_for(n, 256), 256, 0, st>>>(n, audit, sc.tries, sc.akey, sc.iota);
+    ctx->launches++;
+    rc = assign_stage(ctx, hash_id, height, n, audit, reinterpret_cast<uint32_t *>(d_seed_state), d_cand, sc, err_pos);
+    if (rc) { dfree(mem, st); return rc; }
+    uint64_t bounds[2] = {0, n};
+    const int shift = height - prefix_bits;
+    if (prefix_bits) {
+        k_prefix_bounds<<<1, 32, 0, st>>>(n, sc.keys_sorted, shift, prefix, reinterpret_cast<uint64_t *>(sc.counters + 4));
+        ctx->launches++;
+        cudaMemcpyAsync(bounds, sc.counters + 4, 16, cudaMemcpyDeviceToHost, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { dfree(mem, st); CUDA_TRY(cudaGetLastError()); return DAPOL_ERR_CUDA; }
+    }
+    const uint64_t cnt = bounds[1] - bounds[0];
+    *n_out = cnt;
+    if (cnt > cap || (cnt && (!d_out_idx || !d_out_values || !d_out_blind))) { dfree(mem, st); return DAPOL_ERR_BUFFER; }
+    if (cnt) {
+        k_gather_shard<<<grid_for(cnt, 256), 256, 0, st>>>(bounds[0], cnt, shift >= 64 ? ~0ull : (1ull << shift) - 1, sc.keys_sorted, sc.who, d_values,
+                                                           reinterpret_cast<const uint32_t *>(d_blind), d_out_idx, d_out_values,
+                                                           reinterpret_cast<uint32_t *>(d_out_blind));
+        ctx->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    dfree(mem, st);
+    CUDA_TRY(e);
+    CUDA_TRY(cudaGetLastError());
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_level_pad_counts_dev(dapol_ctx *ctx, int height, uint64_t n, const uint64_t *d_leaf_idx, uint64_t *counts) {
+    if (!ctx || !d_leaf_idx || !counts || height < 0 || height > DAPOL_MAX_TREE_HEIGHT || n == 0 || n >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    unsigned long long h_hist[65];
+    CUDA_TRY(cudaMemsetAsync(ctx->scratch, 0, 65 * 8, st));
+    k_leaf_msb_hist<<<grid_for(n, 256), 256, 0, st>>>(d_leaf_idx, n, height, ctx->scratch);
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h_hist, ctx->scratch, 65 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_hist[64]) return DAPOL_ERR_BAD_ARG;
+    uint64_t acc = 0, prev_real = 1;
+    counts[0] = 0;
+    for (int h = 1; h <= height; h++) {  // same level plan as tree_build_dev
+        acc += h_hist[height - h];
+        uint64_t real = 1 + acc;
+        counts[h] = 2 * prev_real - real;
+        prev_real = real;
+    }
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_build_shard_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
+                                          const uint8_t *d_blindings, const uint8_t pad_seed[32], const uint64_t *pad_level_base, dapol_tree **out) {
+    if (!pad_level_base) return DAPOL_ERR_BAD_ARG;
+    return tree_build_dev(ctx, hash_id, height, n, d_leaf_idx, d_values, d_blindings, pad_seed, 0, out, pad_level_base, nullptr);
+}
+extern "C" int dapol_tree_root_record(const dapol_tree *t, uint8_t *rec) {
+    if (!t || !rec) return DAPOL_ERR_BAD_ARG;
+    memcpy(rec, t->root_ext, 128);
+    uint64_t v = 0;
+    int rc = dapol_tree_level_copy(t, 0, nullptr, &v, rec + 192, rec + 128, rec + 160, nullptr);
+    memcpy(rec + 224, &v, 8);
+    return rc;
+}
+extern "C" int dapol_tree_build_from_records(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *leaf_idx, const uint8_t *records,
+                                             const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
+    if (!ctx || !leaf_idx || !records || n == 0 || n > (1ull << 20)) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(n, 8) + Arena::need(n, DAPOL_RECORD_BYTES);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *d_idx = ar.take<uint64_t>(n);
+    uint8_t *d_rec = ar.take<uint8_t>(n * DAPOL_RECORD_BYTES);
+    cudaMemcpyAsync(d_idx, leaf_idx, n * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_rec, records, n * DAPOL_RECORD_BYTES, cudaMemcpyHostToDevice, st);
+    int rc = tree_build_dev(ctx, hash_id, height, n, d_idx, nullptr, nullptr, pad_seed, pad_base, out, nullptr, reinterpret_cast<const uint32_t *>(d_rec));
+    dfree(mem, st);
+    return rc;
+}
+extern "C" int dapol_tree_attach_top(dapol_tree *t, const dapol_tree *top, uint64_t prefix) {
+    if (!t || !top || t->ctx != top->ctx || t->hash_id != top->hash_id || t->height + top->height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_BAD_ARG;
+    if (top->height < 64 && (prefix >> top->height)) return DAPOL_ERR_BAD_ARG;
+    t->top = top;
+    t->prefix = prefix;
+    return DAPOL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ accessors
 extern "C" int dapol_tree_height(const dapol_tree *t) { return t ? t->height : -1; }
 extern "C" uint64_t dapol_tree_num_nodes(const dapol_tree *t) { return t ? t->T : 0; }
@@ -702,9 +942,16 @@ extern "C" int dapol_tree_leaf_index_of(const dapol_tree *t, uint64_t input_pos,
 int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
                          uint32_t *d_lc, uint32_t *d_lh, int *d_not_found) {
     dapol_ctx *ctx = t->ctx;
-    k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, d_leaf_idx, t->ns, t->d_level_off, t->level_n[t->height], t->d_pos, t->height, d_v, d_r,
-                                                       d_c, d_h, d_lc, d_lh, d_not_found);
+    const int Ht = dapol_total_height(t);
+    k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, d_leaf_idx, 0, t->top != nullptr, t->prefix, t->ns, t->d_level_off, t->level_n[t->height],
+                                                       t->d_pos, t->height, Ht, 0, d_v, d_r, d_c, d_h, d_lc, d_lh, d_not_found);
     ctx->launches++;
+    if (t->top && t->top->height > 0) {  // the upper levels come from the (replicated) top tree: siblings of this shard's root
+        const dapol_tree *u = t->top;
+        k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, nullptr, t->prefix, 0, 0, u->ns, u->d_level_off, u->level_n[u->height], u->d_pos,
+                                                           u->height, Ht, t->height, d_v, d_r, d_c, d_h, nullptr, nullptr, d_not_found);
+        ctx->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     return DAPOL_OK;
 }
@@ -714,7 +961,7 @@ extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t 
     dapol_ctx *ctx = t->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    uint64_t H = (uint64_t)t->height, kh = k * (H ? H : 1);
+    uint64_t H = (uint64_t)dapol_total_height(t), kh = k * (H ? H : 1);
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 3 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256;
@@ -753,10 +1000,9 @@ extern "C" int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *va
     CUDA_TRY(cudaMemcpyAsync(d_b, blindings, n * 32, cudaMemcpyHostToDevice, st));
     unsigned g = grid_for(n, 128);
     switch (ctx->W) {
-        case 4: k_commit<4><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
-        case 8: k_commit<8><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
-        case 10: k_commit<10><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
-        case 12: k_commit<12><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+#define W_CASE(w) case w: k_commit<w><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
+        DAPOL_W_CASES(W_CASE)
+#undef W_CASE
     }
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());

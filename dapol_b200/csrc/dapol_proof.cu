@@ -74,12 +74,12 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
                                  const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size) {
     if (!t || !leaf_idx || !seed || !k) return DAPOL_ERR_BAD_ARG;
     dapol_ctx *ctx = t->ctx;
-    const uint64_t H = (uint64_t)t->height;
+    const uint64_t H = (uint64_t)dapol_total_height(t);  // a shard with its top tree attached proves against the whole tree
     std::vector<AggGroup> groups;
     uint64_t sf;
     int rc = policy_plan(H, aggregation_factor, policy, groups, sf);
     if (rc) return rc;
-    const uint64_t size = dapol_inclusion_proof_size(t->height, aggregation_factor, policy);
+    const uint64_t size = dapol_inclusion_proof_size((int)H, aggregation_factor, policy);
     if (proof_size) *proof_size = size;
     if (!out || cap < k * size) return DAPOL_ERR_BUFFER;
     CUDA_TRY(cudaSetDevice(ctx->device));

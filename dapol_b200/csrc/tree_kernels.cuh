@@ -43,9 +43,11 @@ DAPOL_HD_INLINE uint64_t struct_flags_body(uint64_t k, const uint64_t *idx, uint
 }
 // s = exclusive prefix sum of flags at k.  For real node k of the level: its slot in the level's node array
 // and its parent's tree index (compaction = next level's real nodes); for a lone node also its padding
-// sibling's slot + idx and the pad's destination (global node number) at its RNG ordinal.
+// sibling's slot + idx, the pad's destination (global node number) at its build ordinal and its RNG block
+// (pad_rng_base + rank inside the level: single tree = running creation ordinal; shard = the level's global base).
 DAPOL_HD_INLINE void struct_apply_body(uint64_t k, const uint64_t *idx, uint64_t f, uint64_t s, uint32_t *pos, uint64_t *parent_idx,
-                                       uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base) {
+                                       uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base,
+                                       uint64_t *pad_rng, uint64_t pad_rng_base) {
     uint64_t x = idx[k];
     uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
     uint64_t j = (s >> 32) - (newp ? 0 : 1);
@@ -61,6 +63,7 @@ DAPOL_HD_INLINE void struct_apply_body(uint64_t k, const uint64_t *idx, uint64_t
         ns.idx[level_off + pp] = x ^ 1;
         ns.is_pad[level_off + pp] = 1;
         pad_dest[pad_ord_base + q] = level_off + pp;
+        pad_rng[pad_ord_base + q] = pad_rng_base + q;  // block of the seeded stream this padding node draws (RNG contract)
     }
 }
 // Sizes of every level from one pass over adjacent leaves: msb of idx[k] ^ idx[k-1] (k >= 1).  The number
@@ -190,10 +193,10 @@ DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, co
 }
 
 // DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng)); rng draw #g of the seeded stream =
-// from_bytes_mod_order_wide(ChaCha20(pad_seed) block pad_base + g)   (RNG contract)
+// from_bytes_mod_order_wide(ChaCha20(pad_seed) block pad_rng[g])   (RNG contract)
 template <int W, int B>
 DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, const uint64_t *pad_dest, int hash_id,
-                                    const uint32_t seed[8], uint64_t pad_base, const ge_niels *tab_bbl) {
+                                    const uint32_t seed[8], const uint64_t *pad_rng, const ge_niels *tab_bbl) {
     constexpr int NWR = 253 / W + 1;
     ge_dc_batch<B> dc;
     dc.init();
@@ -202,7 +205,7 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         uint64_t g = t + (uint64_t)b * stride;
         if (g >= n) break;
         uint32_t ks[16];
-        chacha20_block(ks, seed, pad_base + g, 0);
+        chacha20_block(ks, seed, pad_rng[g], 0);
         sc r, rh;
         sc_from_wide(r, ks);
         sc_half256(rh, r);
@@ -227,6 +230,21 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         store8(ns.comc + 8 * dest, cc);
         store8(ns.hash + 8 * dest, hh);
     }
+}
+
+// Subtree-root record exchanged between shards: 58 LE words = half point X,Y,Z,T (32) | compress(com) (8) |
+// hash (8) | blinding (8) | value (2).  The leaves of the top tree are these records instead of fresh commitments.
+#define DAPOL_RECORD_WORDS 58
+DAPOL_HD_INLINE void record_leaf_body(uint64_t i, const NodeStore &ns, uint64_t level_off, const uint32_t *pos, const uint32_t *recs) {
+    const uint32_t *rec = recs + (uint64_t)DAPOL_RECORD_WORDS * i;
+    uint64_t g = level_off + pos[i];
+    for (int k = 0; k < 32; k++) ns.ext[32 * g + k] = rec[k];
+    for (int k = 0; k < 8; k++) {
+        ns.comc[8 * g + k] = rec[32 + k];
+        ns.hash[8 * g + k] = rec[40 + k];
+        ns.r[8 * g + k] = rec[48 + k];
+    }
+    ns.v[g] = (uint64_t)rec[56] | ((uint64_t)rec[57] << 32);
 }
 
 // Mergeable::merge (node.rs:64-80) for the parents j of the level whose children start at child_off:

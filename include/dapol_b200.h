@@ -94,6 +94,47 @@ DAPOL_API int dapol_tree_build_from_liabilities_dev(dapol_ctx *ctx, int hash_id,
                                           const uint64_t *d_values, const uint8_t *audit_seed, uint64_t audit_seed_len,
                                           const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out, uint64_t *err_pos);
 
+/* ---- sharded build (one process per GPU).  The tree of 2^k shards splits at level k: shard r owns the
+ * leaves whose index starts with the k-bit prefix r and builds the height-(H-k) subtree below node r of level k; the
+ * 2^k subtree roots are exchanged as 232-byte records and every shard builds the top k levels itself.  The reference
+ * has no counterpart (it is single-threaded); the result is bit-identical with the single-tree build
+ * (dapol_tree_build_from_liabilities) for the same pad_seed.
+ *
+ * build_leaf_nodes (src/dapol/mod.rs:323-399) in two stages.  Stage 1, per slice of the liabilities (per-user hashing,
+ * mod.rs:338-386): audit id, index-seed state after the first shuffle_index iteration, first candidate index, blinding.
+ * All outputs are device arrays of n elements (32 B, 32 B, u64, 32 B). */
+DAPOL_API int dapol_leaves_derive_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint8_t *d_iid_blob, const uint64_t *d_iid_off,
+                                      const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint8_t *audit_seed, uint64_t audit_seed_len,
+                                      uint8_t *d_audit, uint8_t *d_seed_state, uint64_t *d_cand, uint8_t *d_blind);
+/* Stage 2 over the records of ALL n_total users in input order (slices concatenated): duplicate-id check (mod.rs:345-349),
+ * shuffle_index collision rule (mod.rs:408-441), sort by index (mod.rs:396).  d_seed_state and d_cand are updated in
+ * place (d_cand[i] = final leaf index of user i = id_to_idx_map).  Outputs the sorted leaves whose index starts with the
+ * prefix_bits-bit `prefix`, indexes with the prefix stripped: *n_out leaves (DAPOL_ERR_BUFFER if > cap, *n_out is set). */
+DAPOL_API int dapol_leaves_assign_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n_total, const uint8_t *d_audit, uint8_t *d_seed_state,
+                                      uint64_t *d_cand, const uint8_t *d_blind, const uint64_t *d_values, int prefix_bits, uint64_t prefix,
+                                      uint64_t *d_out_idx, uint64_t *d_out_values, uint8_t *d_out_blind, uint64_t cap, uint64_t *n_out,
+                                      uint64_t *err_pos);
+/* Padding nodes per level (counts[0..height], counts[0] = 0) of the tree over the given sorted leaves: the shards
+ * all-gather these to place their padding draws in the single-tree creation order (level H..1, left to right). */
+DAPOL_API int dapol_tree_level_pad_counts_dev(dapol_ctx *ctx, int height, uint64_t n, const uint64_t *d_leaf_idx, uint64_t *counts);
+/* dapol_tree_build_from_nodes_dev for one shard: pad_level_base[h] (host, h = 0..height) = block of the seeded padding
+ * stream drawn by the first padding node of the shard's level h. */
+DAPOL_API int dapol_tree_build_shard_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx,
+                                         const uint64_t *d_values, const uint8_t *d_blindings, const uint8_t pad_seed[32],
+                                         const uint64_t *pad_level_base, dapol_tree **out);
+/* Root of a (sub)tree as the record the shards exchange: half point of the commitment X,Y,Z,T (128 B) | compressed
+ * commitment (32) | hash (32) | blinding (32) | value (8, LE). */
+#define DAPOL_RECORD_BYTES 232
+DAPOL_API int dapol_tree_root_record(const dapol_tree *tree, uint8_t *rec /* DAPOL_RECORD_BYTES */);
+/* Top tree: the leaves are n subtree-root records at (strictly increasing) indexes leaf_idx of level `height`; missing
+ * subtrees are padded like any missing sibling, drawing from the padding stream at pad_base + creation ordinal. */
+DAPOL_API int dapol_tree_build_from_records(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *leaf_idx,
+                                            const uint8_t *records /* n*DAPOL_RECORD_BYTES */, const uint8_t pad_seed[32], uint64_t pad_base,
+                                            dapol_tree **out);
+/* Make `tree` the subtree under node `prefix` of the leaf level of `top` (same context; `top` must outlive `tree`):
+ * dapol_tree_paths / dapol_prove_batch then take whole-tree leaf indexes and emit whole-tree paths and proofs. */
+DAPOL_API int dapol_tree_attach_top(dapol_tree *tree, const dapol_tree *top, uint64_t prefix);
+
 DAPOL_API void dapol_tree_destroy(dapol_tree *tree);
 
 /* Dapol::root_raw / root   (src/dapol/mod.rs:134-141): commitment (compressed), hash, value, blinding. */

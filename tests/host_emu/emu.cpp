@@ -147,7 +147,7 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     t->idx.assign(T, 0); t->v.assign(T, 0); t->r.assign(8 * T, 0); t->comc.assign(8 * T, 0); t->hash.assign(8 * T, 0);
     t->ext.assign(32 * T, 0); t->is_pad.assign(T, 0);
     NodeStore ns{t->idx.data(), t->v.data(), t->r.data(), t->comc.data(), t->hash.data(), t->ext.data(), t->is_pad.data()};
-    std::vector<uint64_t> pad_dest(total_pads + 1);
+    std::vector<uint64_t> pad_dest(total_pads + 1), pad_rng(total_pads + 1);
     std::vector<std::vector<uint64_t>> real(height + 1);
     std::vector<std::vector<uint32_t>> pos(height + 1);
     real[height].assign(leaf_idx, leaf_idx + n);
@@ -159,7 +159,7 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
         uint64_t s = 0;
         for (uint64_t k = 0; k < c; k++) {
             uint64_t f = struct_flags_body(k, real[h].data(), c);
-            struct_apply_body(k, real[h].data(), f, s, pos[h].data(), real[h - 1].data(), t->level_off[h], ns, pad_dest.data(), ord);
+            struct_apply_body(k, real[h].data(), f, s, pos[h].data(), real[h - 1].data(), t->level_off[h], ns, pad_dest.data(), ord, pad_rng.data(), pad_base + ord);
             s += f;
         }
         if ((s >> 32) != nparents[h] || (s & 0xffffffffull) != npads[h]) abort();
@@ -173,7 +173,7 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     if (height == 0) { uint32_t p0 = 0; leaf_batch_body<W, BT>(0, 1, 1, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0]; return t; }
     for (uint64_t i = 0, st = threads(n); i < st; i++)
         leaf_batch_body<W, BT>(i, st, n, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
-    for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_base, tbbl.data());
+    for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_rng.data(), tbbl.data());
     for (int h = height; h >= 1; h--)
         for (uint64_t j = 0, st = threads(nparents[h]); j < st; j++)
             merge_batch_body<BT>(j, st, nparents[h], ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);

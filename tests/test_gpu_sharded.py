@@ -1,0 +1,16 @@
+"""Sharded build on the GPU: 1, 2 and 4 ranks (processes) share the test box's one GPU, rendezvous over gloo,
+and go through the real C ABI (dapol_leaves_derive_dev / _assign_dev, dapol_tree_build_shard_dev, dapol_tree_build_from_records,
+dapol_tree_attach_top).  tests/sharded_worker.py checks, per rank: every node of the shard's subtree, the whole-tree root,
+the id -> index map, byte-identical inclusion proofs (both policies) and their verification -- all against the oracle's
+single-tree build of the same liabilities."""
+import pytest
+
+from test_sharded_cpu import run_world
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,n,H,hash_id,extra", [(1, 300, 12, 0, ()), (2, 500, 14, 0, ()), (4, 700, 16, 1, ()), (2, 65, 9, 0, ("uneven",)),
+                                                      (4, 5, 8, 0, ())])
+def test_sharded_build_matches_single_tree_oracle(world, n, H, hash_id, extra):
+    run_world(world, "cuda", n, H, hash_id, extra, timeout=900)

@@ -75,6 +75,23 @@ def test_tree_every_node_vs_oracle(ctx, cref, hash_id, H, n, stride):
     gpu.close()
 
 
+@pytest.mark.parametrize("W", [4, 8, 10, 13, 14, 15, 16])
+def test_every_comb_window_gives_the_same_tree(cref, W):
+    """The comb window of the fixed-base tables is a speed knob only: every instantiated width gives the oracle's tree."""
+    from dapol_b200 import Context, Dapol
+    c = Context(0, W)
+    H, n = 12, 200
+    idx, vals, bl = _inputs(H, n, 4242)
+    vals[:3] = [0, 2 ** 64 - 1, 1]
+    gpu = Dapol.new_blank(c, 0, H, H).build(idx, vals, bl, PAD_SEED, 1)
+    _assert_same_tree(gpu, cref.Tree(0, H, idx, vals, bl, PAD_SEED, 1), H)
+    out = c.commit_batch([0, 1, 2 ** 64 - 1], np.frombuffer(bytes(32) + (1).to_bytes(32, "little") + ((1 << 255) - 19).to_bytes(32, "little"), np.uint8))
+    assert [x.tobytes() for x in out] == [cref.commit(0, bytes(32)), cref.commit(1, (1).to_bytes(32, "little")),
+                                          cref.commit(2 ** 64 - 1, ((1 << 255) - 19).to_bytes(32, "little"))]
+    gpu.close()
+    c.close()
+
+
 def test_identity_commitments_in_batch(ctx, cref):
     """Identity commitments (v = 0, r = 0 mod l) zero the batched inversion's input; the kernels mask them out."""
     from dapol_b200 import Dapol

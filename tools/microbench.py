@@ -19,7 +19,7 @@ idx = np.unique(rng.integers(0, 1 << H, size=n, dtype=np.uint64))
 n = len(idx)
 vals = rng.integers(0, 1 << 32, size=n, dtype=np.uint64)
 bl = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); bl[:, 31] &= 0x7F
-for W in (4, 8, 10, 12):
+for W in (8, 12, 13, 14, 15, 16):
     ctx = Context(0, W)
     best = None
     for rep in range(3):
