@@ -25,6 +25,12 @@ static inline cudaError_t dmalloc(T **p, size_t bytes, cudaStream_t st) { return
 static inline void dfree(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
 static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+// comb windows of the tree tables that are instantiated (dapol_ctx_create's comb_window; 0 = default)
+#ifndef DAPOL_DEFAULT_COMB_WINDOW
+#define DAPOL_DEFAULT_COMB_WINDOW 15
+#endif
+#define DAPOL_W_CASES(X) X(4) X(8) X(10) X(12) X(13) X(14) X(15) X(16)
+
 struct dapol_ctx {
     int device = 0;
     int W = 8;  // comb window of the tree tables

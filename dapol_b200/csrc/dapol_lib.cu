@@ -1,6 +1,7 @@
 // dapol_b200 C-ABI library: CUDA kernels (sm_100a) + host orchestration for the DAPOL+ hot path.
 // Interface: include/dapol_b200.h.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,10 +34,6 @@ extern "C" const char *dapol_strerror(int code) {
     return "unknown";
 }
 
-
-// comb windows of the tree tables that are instantiated (dapol_ctx_create's comb_window)
-#define DAPOL_DEFAULT_COMB_WINDOW 12
-#define DAPOL_W_CASES(X) X(4) X(8) X(10) X(12) X(13) X(14) X(15) X(16)
 
 // ------------------------------------------------------------------------------------------------ kernels
 template <int W>
@@ -215,9 +212,21 @@ __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t 
 }
 
 // units per thread of the node passes = batch size of the shared inversion (ge_dc_batch)
+#ifndef NODE_BATCH
 #define NODE_BATCH 8
+#endif
+// minimum resident 128-thread CTAs per SM the node kernels are compiled for (register cap = 65536 / (128 * MINB))
+#ifndef DAPOL_LEAF_MINB
+#define DAPOL_LEAF_MINB 3
+#endif
+#ifndef DAPOL_PAD_MINB
+#define DAPOL_PAD_MINB 4
+#endif
+#ifndef DAPOL_MERGE_MINB
+#define DAPOL_MERGE_MINB 4
+#endif
 template <int W>
-__global__ void __launch_bounds__(128) k_leaf(uint64_t n, uint64_t stride, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
+__global__ void __launch_bounds__(128, DAPOL_LEAF_MINB) k_leaf(uint64_t n, uint64_t stride, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
                                               const uint64_t *values, const uint32_t *blind, const ge_niels *tab_b,
                                               const ge_niels *tab_bbl) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,7 +236,7 @@ struct Seed8 {
     uint32_t w[8];
 };
 template <int W>
-__global__ void __launch_bounds__(128) k_pad(uint64_t n, uint64_t stride, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
+__global__ void __launch_bounds__(128, DAPOL_PAD_MINB) k_pad(uint64_t n, uint64_t stride, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
                                              const uint64_t *pad_rng, const ge_niels *tab_bbl) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_rng, tab_bbl);
@@ -238,7 +247,7 @@ __global__ void k_leaf_records(uint64_t n, NodeStore ns, uint64_t level_off, con
     if (i < n) record_leaf_body(i, ns, level_off, pos, recs);
 }
 template <int B>
-__global__ void __launch_bounds__(128) k_merge(uint64_t n, uint64_t stride, NodeStore ns, uint64_t child_off, uint64_t parent_off,
+__global__ void __launch_bounds__(128, DAPOL_MERGE_MINB) k_merge(uint64_t n, uint64_t stride, NodeStore ns, uint64_t child_off, uint64_t parent_off,
                                                const uint32_t *parent_pos, int hash_id) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < stride) merge_batch_body<B>(j, stride, n, ns, child_off, parent_off, parent_pos, hash_id);
@@ -250,20 +259,24 @@ __global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *valu
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
-    sc rs, rr;
+    sc rs, rh;
     load8(rs.v, blind + 8 * i);
-    sc_reduce256(rr, rs);
+    sc_half256(rh, rs);
     uint64_t v = values[i];
     uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
     int32_t dr[NWR], dv[NWV];
-    sc_signed_digits<W, NWR>(dr, rr.v, 8);
+    sc_signed_digits<W, NWR>(dr, rh.v, 8);
     sc_signed_digits<W, NWV>(dv, vw, 2);
-    ge acc;
+    ge acc;  // half point of the commitment: v * (B/2) + (r/2) * B_blinding
     ge_identity(acc);
     ge_comb_accumulate<W, NWV>(acc, tab_b, dv);
     ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
+    ge_dc_batch<1> dc;
+    dc.init();
+    dc.push(acc);
+    dc.solve();
     uint32_t cc[8];
-    ge_compress(cc, acc);
+    dc.get(0, cc);
     store8(out + 8 * i, cc);
 }
 // Siblings of leaf_idx[q] (or of the fixed leaf `fixed_idx` when leaf_idx == nullptr: the shard's own root inside the
@@ -344,12 +357,12 @@ __global__ void __launch_bounds__(256) k_fe_bench(uint32_t *out, int iters) {
 // ------------------------------------------------------------------------------------------------ ctx
 template <int W>
 static int build_tables(dapol_ctx *ctx) {
-    constexpr int NWR = 253 / W + 1;  // both bases carry full-width windows: leaf values are halved mod l too
+    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;  // B/2 multiples for 64-bit values, B_blinding for halved 253-bit scalars
     uint64_t half = 1ull << (W - 1);
-    uint64_t nb = (uint64_t)NWR * half, nbl = (uint64_t)NWR * half;
+    uint64_t nb = (uint64_t)NWV * half, nbl = (uint64_t)NWR * half;
     CUDA_TRY(cudaMalloc(&ctx->tab_b, nb * sizeof(ge_niels)));
     CUDA_TRY(cudaMalloc(&ctx->tab_bbl, nbl * sizeof(ge_niels)));
-    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWR, 0, nb);
+    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWV, 0, nb);
     k_comb_table<W><<<grid_for(nbl, 64), 64, 0, ctx->stream>>>(ctx->tab_bbl, NWR, 1, nbl);
     ctx->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -422,26 +435,39 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     delete t;
 }
 
-// threads for n units at up to NODE_BATCH units each; small launches keep one unit per thread so the
-// upper tree levels still spread over the SMs
-static inline uint64_t batch_stride(uint64_t n) {
-    const uint64_t full = 148ull * 4 * 128;  // one resident wave of 128-thread CTAs
-    uint64_t per = (n + full - 1) / full;
-    if (per < 1) per = 1;
-    if (per > NODE_BATCH) per = NODE_BATCH;
-    return (n + per - 1) / per;
+// Threads for n units at 1..NODE_BATCH units each.  A thread's cost is per * unit_cost + inv_cost (the shared field
+// inversion of its batch; costs in thousands of MAC32); the grid runs in waves of 148 SMs x resident CTAs, so the batch
+// size is chosen to minimise waves x thread cost -- small levels keep one unit per thread and spread over the SMs, and a
+// level of a few waves does not end on a nearly empty one.
+template <typename K>
+static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, double inv_cost = 12.0) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 128, 0) != cudaSuccess || resident <= 0) resident = 3;
+    const double wave = (double)sms * resident;
+    double best = 1e300;
+    uint64_t best_threads = n;
+    for (int per = 1; per <= NODE_BATCH; per++) {
+        uint64_t threads = (n + per - 1) / per, ctas = (threads + 127) / 128;
+        double waves = ctas / wave;
+        if (waves < 6.0) waves = ceil(waves);  // few waves: the last one costs a full wave
+        double cost = waves * (per * unit_cost + inv_cost);
+        if (cost < best) { best = cost; best_threads = threads; }
+    }
+    return best_threads;
 }
 template <int W>
 static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
                             const Seed8 &seed, const uint64_t *d_pad_rng, int phase) {
     int H = t->height;
     if (phase == 0) {
-        uint64_t stride = batch_stride(t->n_leaves);
+        uint64_t stride = batch_stride(t->n_leaves, k_leaf<W>, 24.0);
         k_leaf<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_leaves, stride, t->ns, t->level_off[H], t->pos[H], t->hash_id, d_values,
                                                                   d_blind, ctx->tab_b, ctx->tab_bbl);
         ctx->launches++;
     } else if (t->n_pads) {
-        uint64_t stride = batch_stride(t->n_pads);
+        uint64_t stride = batch_stride(t->n_pads, k_pad<W>, 13.0);
         k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, d_pad_rng, ctx->tab_bbl);
         ctx->launches++;
     }
@@ -569,7 +595,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     // ---- merges, level by level
     for (int h = H; h >= 1; h--) {
         uint64_t np = t->n_real[h - 1];
-        uint64_t stride = batch_stride(np);
+        uint64_t stride = batch_stride(np, k_merge<NODE_BATCH>, 2.5);
         k_merge<NODE_BATCH><<<grid_for(stride, 128), 128, 0, st>>>(np, stride, t->ns, t->level_off[h], t->level_off[h - 1],
                                                                    h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
         ctx->launches++;

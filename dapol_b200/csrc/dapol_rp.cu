@@ -10,18 +10,36 @@
 #define RP_MSM_MAX_T 128
 
 // ------------------------------------------------------------------------------------------------ CTA reductions
-__device__ __forceinline__ void block_reduce_ge(ge &acc, uint32_t *sh /*[blockDim.x][32]*/) {
-    uint32_t tid = threadIdx.x;
-    rp_store_ext(sh + 32 * tid, acc);
+// Sum of the per-thread partial points of a CTA, result in thread 0.  Inside a warp the partials move by shuffles; only
+// the (<= 8) warp sums go through shared memory (1 KB), so the resident CTAs per SM are not capped by shared memory --
+// the small shapes (N = 64: one or two warps per CTA) need many CTAs per SM to keep the multiply pipe busy.
+#define RP_REDUCE_SH_WORDS (RP_MSM_MAX_T / 32 * 32)
+__device__ __forceinline__ void shfl_down_ge(ge &o, const ge &a, int d) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        o.X.v[i] = __shfl_down_sync(0xffffffffu, a.X.v[i], d); o.Y.v[i] = __shfl_down_sync(0xffffffffu, a.Y.v[i], d);
+        o.Z.v[i] = __shfl_down_sync(0xffffffffu, a.Z.v[i], d); o.T.v[i] = __shfl_down_sync(0xffffffffu, a.T.v[i], d);
+    }
+}
+__device__ __forceinline__ void block_reduce_ge(ge &acc, uint32_t *sh /*[blockDim.x / 32][32]*/) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+        ge o;
+        shfl_down_ge(o, acc, d);
+        ge_add(acc, acc, o);  // lanes >= d compute a sum nobody reads
+    }
+    if (nwarps == 1) return;
+    if (lane == 0) rp_store_ext(sh + 32 * warp, acc);
     __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (tid < s) {
+    if (warp == 0) {
+        if (lane < nwarps) rp_load_ext(acc, sh + 32 * lane); else ge_identity(acc);
+#pragma unroll 1
+        for (int d = (int)nwarps >> 1; d > 0; d >>= 1) {
             ge o;
-            rp_load_ext(o, sh + 32 * (tid + s));
+            shfl_down_ge(o, acc, d);
             ge_add(acc, acc, o);
-            rp_store_ext(sh + 32 * tid, acc);
         }
-        __syncthreads();
     }
 }
 __device__ __forceinline__ void block_reduce_sc(sc &acc, uint32_t *sh /*[blockDim.x][8]*/) {
@@ -120,7 +138,7 @@ __global__ void __launch_bounds__(128) k_rp_p2(RpBatch b) {
 }
 template <int W>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p3(RpBatch b) {
-    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     rp_p3_partial<W>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
     block_reduce_ge(acc, sh);
@@ -169,7 +187,7 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p9(RpBatch b, int rnd) {
 }
 template <int W>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p10(RpBatch b, int rnd) {
-    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     rp_p10_partial<W>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
     block_reduce_ge(acc, sh);
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(64) k_rp_v1(RpBatch b, int nv) {
 }
 template <int W>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_v2(RpBatch b) {
-    __shared__ uint32_t sh[RP_MSM_MAX_T * 32];
+    __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     uint64_t p = blockIdx.x;
     rp_v2_partial<W>(acc, b, p, threadIdx.x, blockDim.x);
@@ -297,10 +315,10 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     tm.begin(1);
     k_rp_p0<<<grid_for(K, 64), 64, 0, st>>>(b);
     switch (ctx->W) {
-        case 4: k_rp_p1<4><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
-        case 8: k_rp_p1<8><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
-        case 10: k_rp_p1<10><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
-        default: k_rp_p1<12><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+#define W_CASE(w) case w: k_rp_p1<w><<<grid_for(K * b.m, 64), 64, 0, st>>>(b, ctx->tab_b, ctx->tab_bbl); break;
+        DAPOL_W_CASES(W_CASE)
+#undef W_CASE
+        default: return DAPOL_ERR_BAD_ARG;
     }
     k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     tm.end();

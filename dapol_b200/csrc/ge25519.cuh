@@ -23,6 +23,9 @@ DAPOL_HD_INLINE void ge_identity(ge &p) {
 DAPOL_HD_INLINE void ge_basepoint(ge &p) {
     p.X = fe_const_bx(); p.Y = fe_const_by(); fe_set1(p.Z); p.T = fe_const_bt();
 }
+DAPOL_HD_INLINE void ge_basepoint_half(ge &p) {  // (1/2 mod l) * B: v * B as a half point needs no scalar halving
+    p.X = fe_const_bhx(); p.Y = fe_const_bhy(); fe_set1(p.Z); p.T = fe_const_bht();
+}
 DAPOL_HD_INLINE void ge_bblinding(ge &p) {  // PedersenGens::default().B_blinding (bulletproofs generators.rs)
     p.X = fe_const_bblx(); p.Y = fe_const_bbly(); fe_set1(p.Z); p.T = fe_const_bblt();
 }
@@ -303,8 +306,32 @@ DAPOL_HD_INLINE void load_niels(ge_niels &q, const ge_niels *src) {
 
 // ---- fixed-base signed-window comb: table[k][e] = (e+1) * 2^(W k) * P as affine Niels ------------
 // acc += sum_k d[k] * 2^(W k) * P, digits from sc_signed_digits<W, NW>.
+#ifndef DAPOL_COMB_PREFETCH
+#define DAPOL_COMB_PREFETCH 1
+#endif
 template <int W, int NW>
 DAPOL_HD_INLINE void ge_comb_accumulate(ge &acc, const ge_niels *__restrict__ table, const int32_t d[NW]) {
+#if DAPOL_COMB_PREFETCH
+    // software pipeline: the table entry of window k + 1 is requested before the addition of window k starts, so the
+    // L2 / HBM latency of the 96-byte look-up overlaps ~500 multiplies instead of stalling the few resident warps
+    ge_niels q, qn;
+    {
+        int32_t d0 = d[0];
+        uint32_t e0 = d0 ? (uint32_t)(d0 < 0 ? -d0 : d0) - 1u : 0u;
+        load_niels(qn, table + e0);
+    }
+#pragma unroll 1
+    for (int k = 0; k < NW; k++) {
+        int32_t dk = d[k];
+        q = qn;
+        if (k + 1 < NW) {
+            int32_t dn = d[k + 1];
+            uint32_t en = dn ? (uint32_t)(dn < 0 ? -dn : dn) - 1u : 0u;
+            load_niels(qn, table + ((size_t)(k + 1) * (1u << (W - 1)) + en));
+        }
+        if (dk != 0) ge_madd(acc, acc, q, dk < 0);
+    }
+#else
 #pragma unroll 1
     for (int k = 0; k < NW; k++) {
         int32_t dk = d[k];
@@ -316,4 +343,5 @@ DAPOL_HD_INLINE void ge_comb_accumulate(ge &acc, const ge_niels *__restrict__ ta
             ge_madd(acc, acc, q, neg);
         }
     }
+#endif
 }

@@ -351,24 +351,30 @@ DAPOL_HD_INLINE void rp_p0_body(const RpBatch &b, uint64_t p) {
     b.tr[p] = tr;
     b.status[p] = 0;
 }
-// P1 (thread per (proof, party)): V_j = commit(v_j, r_j) compressed, with the tree's comb tables (window WT)
+// P1 (thread per (proof, party)): V_j = commit(v_j, r_j) compressed, with the tree's comb tables (window WT):
+// tab_b holds multiples of B/2 and the blinding is halved mod l, so the sum is the half point of V_j and
+// compress(V_j) is the batched double-and-compress with a batch of one
 template <int WT>
 DAPOL_HD_INLINE void rp_p1_body(const RpBatch &b, uint64_t p, int j, const ge_niels *tab_b, const ge_niels *tab_bbl) {
     constexpr int NWR = 253 / WT + 1, NWV = 64 / WT + 1;
-    sc r;
+    sc r, rh;
     rp_ld(r, b.blind + (p * b.m + j) * 8);
-    sc_reduce256(r, r);
+    sc_half256(rh, r);
     uint64_t v = b.values[p * b.m + j];
     uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
     int32_t dr[NWR], dv[NWV];
-    sc_signed_digits<WT, NWR>(dr, r.v, 8);
+    sc_signed_digits<WT, NWR>(dr, rh.v, 8);
     sc_signed_digits<WT, NWV>(dv, vw, 2);
     ge acc;
     ge_identity(acc);
     ge_comb_accumulate<WT, NWV>(acc, tab_b, dv);
     ge_comb_accumulate<WT, NWR>(acc, tab_bbl, dr);
+    ge_dc_batch<1> dc;
+    dc.init();
+    dc.push(acc);
+    dc.solve();
     uint32_t cc[8];
-    ge_compress(cc, acc);
+    dc.get(0, cc);
     store8(b.Vc + (p * b.m + j) * 8, cc);
 }
 // P2 (thread per (proof, k)): s_L[k], s_R[k]

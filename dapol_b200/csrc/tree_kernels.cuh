@@ -151,7 +151,7 @@ template <int W, int B>
 DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, uint64_t level_off, const uint32_t *pos,
                                      int hash_id, const uint64_t *values, const uint32_t *blind /*[n][8]*/, const ge_niels *tab_b,
                                      const ge_niels *tab_bbl) {
-    constexpr int NWR = 253 / W + 1;
+    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
     ge_dc_batch<B> dc;
     dc.init();
 #pragma unroll 1
@@ -160,18 +160,17 @@ DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, co
         if (i >= n) break;
         uint32_t rw[8];
         load8(rw, blind + 8 * i);
-        sc rs, rh, vs, vh;
+        sc rs, rh;
 #pragma unroll
         for (int k = 0; k < 8; k++) rs.v[k] = rw[k];
         sc_half256(rh, rs);  // blinding may be unreduced (Scalar::from_bits, mod.rs:385)
         uint64_t v = values[i];
-        sc_set_u64(vs, v);
-        sc_half256(vh, vs);
+        uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
         int32_t d[NWR];
         ge acc;
         ge_identity(acc);
-        sc_signed_digits<W, NWR>(d, vh.v, 8);
-        ge_comb_accumulate<W, NWR>(acc, tab_b, d);
+        sc_signed_digits<W, NWV>(d, vw, 2);  // tab_b holds multiples of B/2: v * (B/2) is the half point of v * B
+        ge_comb_accumulate<W, NWV>(acc, tab_b, d);
         sc_signed_digits<W, NWR>(d, rh.v, 8);
         ge_comb_accumulate<W, NWR>(acc, tab_bbl, d);
         uint64_t g = level_off + pos[i];
@@ -288,14 +287,15 @@ DAPOL_HD_INLINE void merge_batch_body(uint64_t t, uint64_t stride, uint64_t n, c
     }
 }
 
-// comb table entry (k, e): (e+1) * 2^(W k) * P in affine Niels form
+// comb table entry (k, e): (e+1) * 2^(W k) * P in affine Niels form; P = B/2 (which = 0, 64/W + 1 windows: values are
+// 64-bit) or B_blinding (which = 1, 253/W + 1 windows, used with halved scalars)
 template <int W>
 DAPOL_HD_INLINE void comb_table_body(uint64_t t, ge_niels *table, int nw, int which /*0 = B, 1 = B_blinding*/) {
     uint32_t half = 1u << (W - 1);
     uint32_t k = (uint32_t)(t / half), e = (uint32_t)(t % half);
     if ((int)k >= nw) return;
     ge base;
-    if (which == 0) ge_basepoint(base); else ge_bblinding(base);
+    if (which == 0) ge_basepoint_half(base); else ge_bblinding(base);
 #pragma unroll 1
     for (uint32_t i = 0; i < k * W; i++) ge_dbl(base, base);
     // (e+1) * base by left-to-right double-and-add
