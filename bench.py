@@ -32,9 +32,21 @@ AUDIT_SEED = b"dapol-b200-bench"
 PAD_SEED = hashlib.sha256(b"dapol-b200").digest()
 # algorithmic work per unit, MAC32 = one 32x32->64 multiply-accumulate (SURVEY.md 8(d) / BASELINE.md / DESIGN.md)
 MAC32_LEAF, MAC32_PAD, MAC32_MERGE = 53.6e3, 45.5e3, 13.9e3
-# what the kernels here actually execute per unit (window-12 comb on half points, batched
-# double-and-compress with one inversion per 8 nodes); roofline.frac uses these, survey_unit_frac the figures above
-MAC32_LEAF_EXEC, MAC32_PAD_EXEC, MAC32_MERGE_EXEC = 25.6e3, 14.5e3, 4.0e3
+
+
+def executed_mac32(comb_window, node_batch):
+    """Field-arithmetic MAC32 the kernels here execute per unit: fixed-base comb on half points
+    (253/W + 1 mixed additions of 7 FM for a 253-bit scalar, 64/W + 1 for a 64-bit value), batched double-and-compress
+    (prepare 4 FS + 5 FM, 3 FM of Montgomery's trick, finish 11 FM, one inversion of 254 FS + 11 FM per node_batch nodes).
+    roofline.frac uses these; survey_unit_frac uses SURVEY 8(d)'s figures for the reference's algorithm."""
+    FM, FS, SCMUL = 72, 44, 128
+    madd, full_add = 7 * FM, 9 * FM
+    compress = (4 * FS + 5 * FM) + 3 * FM + 11 * FM + (254 * FS + 11 * FM) / node_batch
+    nwr, nwv = 253 // comb_window + 1, 64 // comb_window + 1
+    pad = nwr * madd + 3 * SCMUL + compress          # ChaCha draw -> wide reduce, halve; comb; compress
+    leaf = (nwr + nwv) * madd + SCMUL + compress     # halve r; two combs; compress
+    merge = full_add + 2 * SCMUL + compress          # point add; r_L + r_R mod l; compress
+    return leaf, pad, merge
 NODE_BYTES = 104  # com 32 + hash 32 + v 8 + r 32
 
 
@@ -355,6 +367,8 @@ def main():
         internal = (nodes - 1) // 2  # every internal node has exactly two children
         leaves_here = nodes - pads - internal
         med = {kk: statistics.median(v) for kk, v in phase_ms.items()}
+        params = ctx.params()
+        MAC32_LEAF_EXEC, MAC32_PAD_EXEC, MAC32_MERGE_EXEC = executed_mac32(params["comb_window"], params["node_batch"])
         achieved = pads * MAC32_PAD_EXEC / (med["padding"] * 1e-3) / 1e9  # GMAC32/s
         build_exec = leaves_here * MAC32_LEAF_EXEC + pads * MAC32_PAD_EXEC + internal * MAC32_MERGE_EXEC
         build_survey = leaves_here * MAC32_LEAF + pads * MAC32_PAD + internal * MAC32_MERGE
@@ -370,7 +384,7 @@ def main():
             "config": {"workload": f"DAPOL+ tree build from liabilities, 2^{args.users_log2} users/GPU, one tree of height {H} over "
                                    f"{world * n} users, D=blake3 (leaf derivation + commit + hash + merge + padding)",
                        "users_per_gpu": n, "height": H, "nodes_rank0": nodes, "padding_nodes_rank0": pads,
-                       "comb_window": args.comb_window or "default",
+                       "comb_window": params["comb_window"], "nodes_per_inversion": params["node_batch"],
                        "parallelism": (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs: all-gather of user records "
                                        f"(112 B/user) + all-gather of {world} subtree roots (232 B)") if world > 1 else "single GPU",
                        "l2": "per-step working set (node store + half points ~%.1f GB) >> 126 MB L2; no reuse across steps" % (nodes * 232 / 1e9)},

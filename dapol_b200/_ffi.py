@@ -60,6 +60,7 @@ def lib():
     L.dapol_kernel_launches.argtypes = [vp]
     L.dapol_kernel_launches.restype = u64
     L.dapol_last_build_times.argtypes = [vp, vp]
+    L.dapol_ctx_params.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.dapol_inclusion_proof_size.argtypes = [C.c_int, u64, C.c_int]
     L.dapol_inclusion_proof_size.restype = u64
     L.dapol_prove_batch.argtypes = [vp, u64, vp, u64, C.c_int, vp, vp, u64, C.POINTER(u64)]

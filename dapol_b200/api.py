@@ -67,6 +67,12 @@ class Context:
     def kernel_launches(self) -> int:
         return _ffi.lib().dapol_kernel_launches(self._h)
 
+    def params(self):
+        """Tuning parameters in effect: comb window of the tree tables, nodes per shared inversion, range-proof window."""
+        w, b, r = C.c_int(), C.c_int(), C.c_int()
+        _check(_ffi.lib().dapol_ctx_params(self._h, C.byref(w), C.byref(b), C.byref(r)))
+        return dict(comb_window=w.value, node_batch=b.value, rangeproof_window=r.value)
+
     def last_build_times(self):
         ms = np.zeros(5, np.float32)
         _check(_ffi.lib().dapol_last_build_times(self._h, _p(ms)))

@@ -43,6 +43,7 @@ struct dapol_ctx {
     unsigned long long *scratch = nullptr;  // 1 KB of device scratch (histograms, counters)
     // range proofs: window tables of the Bulletproof generators G_j[i], H_j[i] (j < rp_mcap, i < 64) and of B, B_blinding
     int rp_W = 12;
+    bool rp_W_auto = true;  // pick the widest window whose tables fit the HBM budget when they are built
     int rp_mcap = 0;
     ge_niels *rp_tab = nullptr;  // [(128 mcap + 2)][NW][2^(W-1)]
     float rp_last_ms[4] = {0, 0, 0, 0};  // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build

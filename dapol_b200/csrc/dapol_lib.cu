@@ -213,14 +213,14 @@ __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t 
 
 // units per thread of the node passes = batch size of the shared inversion (ge_dc_batch)
 #ifndef NODE_BATCH
-#define NODE_BATCH 8
+#define NODE_BATCH 24
 #endif
 // minimum resident 128-thread CTAs per SM the node kernels are compiled for (register cap = 65536 / (128 * MINB))
 #ifndef DAPOL_LEAF_MINB
 #define DAPOL_LEAF_MINB 3
 #endif
 #ifndef DAPOL_PAD_MINB
-#define DAPOL_PAD_MINB 4
+#define DAPOL_PAD_MINB 3
 #endif
 #ifndef DAPOL_MERGE_MINB
 #define DAPOL_MERGE_MINB 4
@@ -417,6 +417,13 @@ extern "C" int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream) {
     return DAPOL_OK;
 }
 extern "C" uint64_t dapol_kernel_launches(const dapol_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int dapol_ctx_params(const dapol_ctx *ctx, int *comb_window, int *node_batch, int *rangeproof_window) {
+    if (!ctx) return DAPOL_ERR_BAD_ARG;
+    if (comb_window) *comb_window = ctx->W;
+    if (node_batch) *node_batch = NODE_BATCH;
+    if (rangeproof_window) *rangeproof_window = ctx->rp_W;
+    return DAPOL_OK;
+}
 extern "C" int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]) {
     if (!ctx) return DAPOL_ERR_BAD_ARG;
     memcpy(ms, ctx->last_ms, sizeof(float) * 5);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include "dapol_internal.h"
 #include "rp_kernels.cuh"
 
@@ -80,6 +81,11 @@ __global__ void __launch_bounds__(128) k_rp_tab_chunk(uint64_t items, const uint
     if (it < items) rp_tab_chunk_body<W>(it, wb, tab);
 }
 
+// windows of the generator tables that are instantiated (dapol_ctx_set_rangeproof_window; 0 = pick by HBM budget)
+#define RP_W_CASES(X) X(8) X(12) X(13) X(14) X(16)
+static size_t rp_table_bytes(int W, int mcap) {
+    return (128ull * mcap + 2) * (size_t)(253 / W + 1) * (1ull << (W - 1)) * sizeof(ge_niels);
+}
 template <int W>
 static int rp_build_tables(dapol_ctx *ctx, int mcap) {
     constexpr int NW = 253 / W + 1;
@@ -114,7 +120,23 @@ static int rp_ensure_tables(dapol_ctx *ctx, int m) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, ctx->stream);
-    int rc = ctx->rp_W == 8 ? rp_build_tables<8>(ctx, mc) : rp_build_tables<12>(ctx, mc);
+    if (ctx->rp_W_auto) {  // widest window whose tables fit the HBM budget: fewer additions per scalar multiplication
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (ctx->rp_tab) free_b += rp_table_bytes(ctx->rp_W, ctx->rp_mcap);
+        const size_t budget = std::min<size_t>(64ull << 30, free_b / 2);
+        static const int widths[] = {16, 14, 13, 12};
+        int w = 8;
+        for (int cand : widths) if (rp_table_bytes(cand, mc) <= budget) { w = cand; break; }
+        ctx->rp_W = w;
+    }
+    int rc;
+    switch (ctx->rp_W) {
+#define W_CASE(w) case w: rc = rp_build_tables<w>(ctx, mc); break;
+        RP_W_CASES(W_CASE)
+#undef W_CASE
+        default: rc = DAPOL_ERR_BAD_ARG;
+    }
     cudaEventRecord(b, ctx->stream);
     cudaEventSynchronize(b);
     cudaEventElapsedTime(&ctx->rp_last_ms[3], a, b);
@@ -311,7 +333,7 @@ template <int W>
 static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     cudaStream_t st = ctx->stream;
     const uint64_t K = b.K, N = b.N;
-    const unsigned T = msm_threads(N + 1), TS = msm_threads(2 * N + 1);
+    const unsigned T = msm_threads(N), TS = msm_threads(2 * N);
     tm.begin(1);
     k_rp_p0<<<grid_for(K, 64), 64, 0, st>>>(b);
     switch (ctx->W) {
@@ -364,7 +386,7 @@ static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     tm.end();
     tm.begin(0);
     k_rp_v1<<<grid_for(K * nv, 64), 64, 0, st>>>(b, nv);
-    k_rp_v2<W><<<(unsigned)K, msm_threads(2 * N + 2 + nv), 0, st>>>(b);
+    k_rp_v2<W><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
     tm.end();
     ctx->launches += 5;
     CUDA_TRY(cudaGetLastError());
@@ -396,7 +418,12 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
         b.blind = reinterpret_cast<const uint32_t *>(d_blind) + first * m * 8;
         b.stream = d_stream + first; b.base_block = d_base + first;
         memcpy(b.seed, seed, 32);
-        rc = ctx->rp_W == 8 ? rp_prove_chunk<8>(ctx, b, tm) : rp_prove_chunk<12>(ctx, b, tm);
+        switch (ctx->rp_W) {
+#define W_CASE(w) case w: rc = rp_prove_chunk<w>(ctx, b, tm); break;
+            RP_W_CASES(W_CASE)
+#undef W_CASE
+            default: rc = DAPOL_ERR_BAD_ARG;
+        }
         if (rc) { dfree(pl.mem, st); return rc; }
         CUDA_TRY(cudaMemcpyAsync(d_proofs + first * plen, b.proof, kc * plen, cudaMemcpyDeviceToDevice, st));
         std::vector<int> status(kc);
@@ -439,7 +466,12 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
         RpBatch &b = pl.b;
         b.proof_in = reinterpret_cast<const uint32_t *>(d_proofs + first * plen);
         b.coms = reinterpret_cast<const uint32_t *>(d_coms) + first * m * 8;
-        rc = ctx->rp_W == 8 ? rp_verify_chunk<8>(ctx, b, tm) : rp_verify_chunk<12>(ctx, b, tm);
+        switch (ctx->rp_W) {
+#define W_CASE(w) case w: rc = rp_verify_chunk<w>(ctx, b, tm); break;
+            RP_W_CASES(W_CASE)
+#undef W_CASE
+            default: rc = DAPOL_ERR_BAD_ARG;
+        }
         if (rc) { dfree(pl.mem, st); return rc; }
         k_status_to_ok<<<grid_for(kc, 128), 128, 0, st>>>(kc, b.status, d_ok + first);
         ctx->launches++;
@@ -528,7 +560,15 @@ extern "C" int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]) {
     return DAPOL_OK;
 }
 extern "C" int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window) {
-    if (!ctx || (window != 8 && window != 12)) return DAPOL_ERR_BAD_ARG;
+    if (!ctx || (window != 0 && window != 8 && window != 12 && window != 13 && window != 14 && window != 16)) return DAPOL_ERR_BAD_ARG;
+    ctx->rp_W_auto = window == 0;
+    if (window == 0) {  // the width is chosen when the tables are (re)built
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (ctx->rp_tab) cudaFree(ctx->rp_tab);
+        ctx->rp_tab = nullptr; ctx->rp_mcap = 0;
+        return DAPOL_OK;
+    }
     if (ctx->rp_W != window) {
         CUDA_TRY(cudaSetDevice(ctx->device));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));

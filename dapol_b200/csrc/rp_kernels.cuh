@@ -242,6 +242,26 @@ DAPOL_HD_INLINE void rp_fixed_mul_acc(ge &acc, const ge_niels *tab, uint64_t g, 
     sc_signed_digits<W, NW>(d, s.v, 8);
     ge_comb_accumulate<W, NW>(acc, tab + g * (uint64_t)NW * (1u << (W - 1)), d);
 }
+// The lone extra term of an MSM (c * B, s_bl * B_blinding, ...) spread over the CTA: thread tid adds window tid of
+// s * P_g.  One more addition per thread instead of one thread doing all 253/W + 1 of them in an extra pass while
+// the rest of the CTA idles (at N = 64 that extra pass was a third of the MSM's time).
+template <int W>
+DAPOL_HD_INLINE void rp_fixed_mul_spread(ge &acc, const ge_niels *tab, uint64_t g, const sc &s, uint32_t tid, uint32_t T) {
+    constexpr int NW = 253 / W + 1;
+    int32_t d[NW];
+    sc_signed_digits<W, NW>(d, s.v, 8);
+#pragma unroll 1
+    for (uint32_t k = tid; k < (uint32_t)NW; k += T) {
+        int32_t dk = d[k];
+        if (dk != 0) {
+            int neg = dk < 0;
+            uint32_t e = (uint32_t)(neg ? -dk : dk) - 1u;
+            ge_niels q;
+            load_niels(q, tab + (g * (uint64_t)NW + k) * (1u << (W - 1)) + e);
+            ge_madd(acc, acc, q, neg);
+        }
+    }
+}
 // acc += (+/-) P_g   (unit scalar: entry (window 0, multiple 1))
 template <int W>
 DAPOL_HD_INLINE void rp_fixed_unit_acc(ge &acc, const ge_niels *tab, uint64_t g, int neg) {
@@ -400,19 +420,19 @@ DAPOL_HD_INLINE void rp_p3_partial(ge &acc, const RpBatch &b, uint64_t p, int wh
             int bit = (int)((v >> (k % n)) & 1);
             rp_fixed_unit_acc<W>(acc, bit ? b.tabG : b.tabH, rp_gen_of(b, k), !bit);
         }
-        if (tid == 0) {
-            sc s;
-            rp_ld(s, rp_ch(b, p, CH_ABL));
-            rp_fixed_mul_acc<W>(acc, b.tabBbl, 0, s);
-        }
+        sc s;
+        rp_ld(s, rp_ch(b, p, CH_ABL));
+        rp_fixed_mul_spread<W>(acc, b.tabBbl, 0, s, tid, T);
     } else {
 #pragma unroll 1
-        for (uint32_t t = tid; t < 2 * N + 1; t += T) {
+        for (uint32_t t = tid; t < 2 * N; t += T) {
             sc s;
             if (t < N) { rp_ld(s, b.vecA + (p * N + t) * 8); rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, t), s); }
-            else if (t < 2 * N) { rp_ld(s, b.vecB + (p * N + (t - N)) * 8); rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, t - N), s); }
-            else { rp_ld(s, rp_ch(b, p, CH_SBL)); rp_fixed_mul_acc<W>(acc, b.tabBbl, 0, s); }
+            else { rp_ld(s, b.vecB + (p * N + (t - N)) * 8); rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, t - N), s); }
         }
+        sc s;
+        rp_ld(s, rp_ch(b, p, CH_SBL));
+        rp_fixed_mul_spread<W>(acc, b.tabBbl, 0, s, tid, T);
     }
 }
 // write the sum point of an MSM pass
@@ -584,7 +604,7 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
     const uint32_t *cu = b.cu[cur] + p * half * 8, *cui = b.cui[cur] + p * half * 8;
     const int sh = b.lg - rnd;  // log2 h
 #pragma unroll 1
-    for (uint32_t t = tid; t < N + 1; t += T) {
+    for (uint32_t t = tid; t < N; t += T) {
         sc s, c;
         if (t < half) {         // G terms: positions with bit = 1 - which ... L uses G_hi (bit 1), R uses G_lo (bit 0)
             uint32_t pfx = t >> sh, i = t & (h - 1);
@@ -594,7 +614,7 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
             rp_ld(c, cu + pfx * 8);
             sc_mul(s, s, c);
             rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, I), s);
-        } else if (t < N) {     // H terms: L uses H_lo (bit 0) with b_hi, R uses H_hi (bit 1) with b_lo
+        } else {                // H terms: L uses H_lo (bit 0) with b_hi, R uses H_hi (bit 1) with b_lo
             uint32_t tt = t - half;
             uint32_t pfx = tt >> sh, i = tt & (h - 1);
             uint32_t bit = which ? 1u : 0u;
@@ -605,13 +625,13 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
             rp_ld(c, b.ypow + (p * N + I) * 8);
             sc_mul(s, s, c);
             rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, I), s);
-        } else {
-            rp_ld(s, rp_ch(b, p, which ? CH_CR : CH_CL));
-            rp_ld(c, rp_ch(b, p, CH_W));
-            sc_mul(s, s, c);
-            rp_fixed_mul_acc<W>(acc, b.tabB, 0, s);
         }
     }
+    sc s, c;  // + c_L/R * w * B, one window per thread
+    rp_ld(s, rp_ch(b, p, which ? CH_CR : CH_CL));
+    rp_ld(c, rp_ch(b, p, CH_W));
+    sc_mul(s, s, c);
+    rp_fixed_mul_spread<W>(acc, b.tabB, 0, s, tid, T);
 }
 // P11 (thread per proof): L, R -> u, u^-1
 DAPOL_HD_INLINE void rp_p11_body(const RpBatch &b, uint64_t p, int rnd) {
@@ -786,13 +806,13 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
     sc z, mz, a, bb;
     rp_ld(z, rp_ch(b, p, CH_Z)); rp_ld(mz, rp_ch(b, p, CH_MZ)); rp_ld(a, rp_ch(b, p, CH_A)); rp_ld(bb, rp_ch(b, p, CH_B));
 #pragma unroll 1
-    for (uint32_t t = tid; t < 2 * N + 2 + (uint32_t)nv; t += T) {
+    for (uint32_t t = tid; t < 2 * N; t += T) {
         sc s, c;
         if (t < N) {
             rp_ld(s, b.svec + (p * N + t) * 8);
             sc_mul(s, a, s); sc_sub(s, mz, s);
             rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, t), s);
-        } else if (t < 2 * N) {
+        } else {
             uint32_t I = t - N;
             rp_ld(s, b.svec + (p * N + (N - 1 - I)) * 8);
             sc_mul(s, bb, s);
@@ -802,16 +822,17 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
             sc_mul(s, s, c);
             sc_add(s, z, s);
             rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, I), s);
-        } else if (t == 2 * N) {
-            rp_ld(s, rp_ch(b, p, CH_SB));
-            rp_fixed_mul_acc<W>(acc, b.tabB, 0, s);
-        } else if (t == 2 * N + 1) {
-            rp_ld(s, rp_ch(b, p, CH_SBBL));
-            rp_fixed_mul_acc<W>(acc, b.tabBbl, 0, s);
-        } else {
-            ge q;
-            rp_load_ext(q, b.varpts + (p * nv + (t - 2 * N - 2)) * 32);
-            ge_add(acc, acc, q);
         }
+    }
+    sc s;  // the B and B_blinding terms, one window per thread; the variable-base partial points, one per thread
+    rp_ld(s, rp_ch(b, p, CH_SB));
+    rp_fixed_mul_spread<W>(acc, b.tabB, 0, s, tid, T);
+    rp_ld(s, rp_ch(b, p, CH_SBBL));
+    rp_fixed_mul_spread<W>(acc, b.tabBbl, 0, s, tid, T);
+#pragma unroll 1
+    for (uint32_t t = tid; t < (uint32_t)nv; t += T) {
+        ge q;
+        rp_load_ext(q, b.varpts + (p * nv + t) * 32);
+        ge_add(acc, acc, q);
     }
 }

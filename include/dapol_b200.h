@@ -195,7 +195,8 @@ DAPOL_API int dapol_rangeproof_prove_batch_dev(dapol_ctx *ctx, int nbits, int m,
                                                const uint8_t seed[32], const uint64_t *d_streams, const uint64_t *d_base_blocks, uint8_t *d_proofs);
 DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *d_proofs, uint64_t proof_len,
                                                 const uint8_t *d_commitments, uint8_t *d_ok);
-/* window (8 or 12 bits) of the generator tables; drops tables already built.  Default 12. */
+/* window (8, 12, 13, 14 or 16 bits) of the generator tables; drops tables already built.  0 (the default) = the widest
+ * window whose tables fit half of the free HBM, at most 64 GB (16 bits up to m = 4 ... 14 bits at m = 32, 12 at m = 64). */
 DAPOL_API int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window);
 /* device time of the last range-proof batch on this ctx (ms): [0] total, [1] MSM passes, [2] other passes, [3] last table build */
 DAPOL_API int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]);
@@ -205,6 +206,9 @@ DAPOL_API int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *val
 DAPOL_API int dapol_imad_peak(dapol_ctx *ctx, int variant, double *gmac_per_s); /* measured 32x32->64 MAC/s, variant 0..3 */
 DAPOL_API int dapol_fe_bench(dapol_ctx *ctx, int op, double *gop_per_s);        /* field mul(0)/sq(1) throughput, Gop/s */
 DAPOL_API uint64_t dapol_kernel_launches(const dapol_ctx *ctx);                 /* kernels launched so far on this ctx */
+/* tuning parameters in effect (for the work model of the roofline report): comb window of the tree tables, nodes per
+ * thread sharing one field inversion, window of the range-proof generator tables.  Any pointer may be NULL. */
+DAPOL_API int dapol_ctx_params(const dapol_ctx *ctx, int *comb_window, int *node_batch, int *rangeproof_window);
 /* device-time of the last tree build on this ctx, split per phase (ms, CUDA events on the ctx stream):
  * [0] structure, [1] leaves, [2] padding, [3] merges, [4] total */
 DAPOL_API int dapol_last_build_times(const dapol_ctx *ctx, float ms[5]);

@@ -119,7 +119,7 @@ static void comb_entry(uint64_t t, ge_niels *table, int nw, int which) {  // sam
     uint32_t k = (uint32_t)(t / half), e = (uint32_t)(t % half);
     if ((int)k >= nw) return;
     ge base;
-    if (which == 0) ge_basepoint(base); else ge_bblinding(base);
+    if (which == 0) ge_basepoint_half(base); else ge_bblinding(base);  // tab_b = multiples of B/2 (tree_kernels.cuh)
     for (uint32_t i = 0; i < k * WT; i++) ge_dbl(base, base);
     ge acc = base;
     for (uint32_t i = 0; i < e; i++) ge_add(acc, acc, base);
