@@ -42,7 +42,8 @@ def executed_mac32(comb_window, node_batch):
     FM, FS, SCMUL = 72, 44, 128
     madd, full_add = 7 * FM, 9 * FM
     compress = (4 * FS + 5 * FM) + 3 * FM + 11 * FM + (254 * FS + 11 * FM) / node_batch
-    nwr, nwv = 253 // comb_window + 1, 64 // comb_window + 1
+    value_window = comb_window if comb_window <= 16 else 22      # comb_value_window in tree_kernels.cuh
+    nwr, nwv = 253 // comb_window + 1, 64 // value_window + 1
     pad = nwr * madd + 3 * SCMUL + compress          # ChaCha draw -> wide reduce, halve; comb; compress
     leaf = (nwr + nwv) * madd + SCMUL + compress     # halve r; two combs; compress
     merge = full_add + 2 * SCMUL + compress          # point add; r_L + r_R mod l; compress

@@ -29,7 +29,14 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 #ifndef DAPOL_DEFAULT_COMB_WINDOW
 #define DAPOL_DEFAULT_COMB_WINDOW 15
 #endif
-#define DAPOL_W_CASES(X) X(4) X(8) X(10) X(12) X(13) X(14) X(15) X(16)
+// comb_window 0 picks the wide HBM-resident window when at least this much device memory is free, else the default
+#ifndef DAPOL_WIDE_COMB_WINDOW
+#define DAPOL_WIDE_COMB_WINDOW 24
+#endif
+#ifndef DAPOL_WIDE_COMB_MIN_FREE_GB
+#define DAPOL_WIDE_COMB_MIN_FREE_GB 48
+#endif
+#define DAPOL_W_CASES(X) X(4) X(8) X(12) X(15) X(16) X(20) X(22) X(24)
 
 struct dapol_ctx {
     int device = 0;

@@ -41,6 +41,16 @@ __global__ void k_comb_table(ge_niels *table, int nw, int which, uint64_t total)
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < total) comb_table_body<W>(t, table, nw, which);
 }
+template <int W>
+__global__ void k_comb_bases(ge *bases, int nw, int which) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) comb_bases_body<W>(bases, nw, which);
+}
+#define COMB_RUN 32
+template <int W>
+__global__ void __launch_bounds__(64) k_comb_table_run(ge_niels *table, int nw, const ge *bases, uint64_t total_runs) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total_runs) comb_table_run_body<W, COMB_RUN>(t, table, nw, bases);
+}
 // adjacent-leaf msb histogram (hist[0..63]) + input validation (hist[64] = bad flag)
 __global__ void k_leaf_msb_hist(const uint64_t *idx, uint64_t n, int height, unsigned long long *hist) {
     __shared__ unsigned int sh[65];
@@ -246,11 +256,23 @@ __global__ void k_leaf_records(uint64_t n, NodeStore ns, uint64_t level_off, con
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) record_leaf_body(i, ns, level_off, pos, recs);
 }
-template <int B>
-__global__ void __launch_bounds__(128, DAPOL_MERGE_MINB) k_merge(uint64_t n, uint64_t stride, NodeStore ns, uint64_t child_off, uint64_t parent_off,
-                                               const uint32_t *parent_pos, int hash_id) {
+// merge step 1 (per level): value, blinding and point sums of the parents
+__global__ void __launch_bounds__(128) k_merge_sum(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < stride) merge_batch_body<B>(j, stride, n, ns, child_off, parent_off, parent_pos, hash_id);
+    if (j < n) merge_sum_body(j, ns, child_off, parent_off, parent_pos);
+}
+// merge step 2 (once per tree): compress every internal node, B per shared inversion
+template <int B>
+__global__ void __launch_bounds__(128, DAPOL_MERGE_MINB) k_compress_internal(uint64_t n, uint64_t stride, NodeStore ns,
+                                                                              const __grid_constant__ InternalMap m) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < stride) compress_internal_body<B>(t, stride, n, ns, m);
+}
+// merge step 3 (per level): parent hashes
+__global__ void __launch_bounds__(128) k_merge_hash(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos,
+                                                    int hash_id) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) merge_hash_body(j, ns, child_off, parent_off, parent_pos, hash_id);
 }
 // leaves only (no tree): commitments for dapol_commit_batch
 template <int W>
@@ -258,7 +280,8 @@ __global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *valu
                                                 const ge_niels *tab_b, const ge_niels *tab_bbl) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    constexpr int WV = comb_value_window<W>::value;
+    constexpr int NWR = 253 / W + 1, NWV = 64 / WV + 1;
     sc rs, rh;
     load8(rs.v, blind + 8 * i);
     sc_half256(rh, rs);
@@ -266,10 +289,10 @@ __global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *valu
     uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
     int32_t dr[NWR], dv[NWV];
     sc_signed_digits<W, NWR>(dr, rh.v, 8);
-    sc_signed_digits<W, NWV>(dv, vw, 2);
+    sc_signed_digits<WV, NWV>(dv, vw, 2);
     ge acc;  // half point of the commitment: v * (B/2) + (r/2) * B_blinding
     ge_identity(acc);
-    ge_comb_accumulate<W, NWV>(acc, tab_b, dv);
+    ge_comb_accumulate<WV, NWV>(acc, tab_b, dv);
     ge_comb_accumulate<W, NWR>(acc, tab_bbl, dr);
     ge_dc_batch<1> dc;
     dc.init();
@@ -355,17 +378,38 @@ __global__ void __launch_bounds__(256) k_fe_bench(uint32_t *out, int iters) {
 }
 
 // ------------------------------------------------------------------------------------------------ ctx
+// table of `which` (0 = B/2, 1 = B_blinding) at window W with nw windows
+template <int W>
+static int build_one_table(dapol_ctx *ctx, ge_niels **tab, int nw, int which) {
+    constexpr uint64_t half = 1ull << (W - 1);
+    uint64_t total = (uint64_t)nw * half;
+    CUDA_TRY(cudaMalloc(tab, total * sizeof(ge_niels)));
+    if constexpr (W >= 10) {  // a run of consecutive multiples per thread (one addition per entry, one inversion per run)
+        ge *bases = nullptr;
+        CUDA_TRY(cudaMalloc(&bases, (size_t)nw * sizeof(ge)));
+        k_comb_bases<W><<<1, 32, 0, ctx->stream>>>(bases, nw, which);
+        uint64_t runs = total / COMB_RUN;
+        k_comb_table_run<W><<<grid_for(runs, 64), 64, 0, ctx->stream>>>(*tab, nw, bases, runs);
+        ctx->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaFree(bases);
+    } else {
+        k_comb_table<W><<<grid_for(total, 64), 64, 0, ctx->stream>>>(*tab, nw, which, total);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DAPOL_OK;
+}
 template <int W>
 static int build_tables(dapol_ctx *ctx) {
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;  // B/2 multiples for 64-bit values, B_blinding for halved 253-bit scalars
-    uint64_t half = 1ull << (W - 1);
-    uint64_t nb = (uint64_t)NWV * half, nbl = (uint64_t)NWR * half;
-    CUDA_TRY(cudaMalloc(&ctx->tab_b, nb * sizeof(ge_niels)));
-    CUDA_TRY(cudaMalloc(&ctx->tab_bbl, nbl * sizeof(ge_niels)));
-    k_comb_table<W><<<grid_for(nb, 64), 64, 0, ctx->stream>>>(ctx->tab_b, NWV, 0, nb);
-    k_comb_table<W><<<grid_for(nbl, 64), 64, 0, ctx->stream>>>(ctx->tab_bbl, NWR, 1, nbl);
-    ctx->launches += 2;
-    CUDA_TRY(cudaGetLastError());
+    // B/2 multiples for 64-bit values (window WV), B_blinding multiples for halved 253-bit scalars (window W)
+    constexpr int WV = comb_value_window<W>::value;
+    constexpr int NWR = 253 / W + 1, NWV = 64 / WV + 1;
+    int rc = build_one_table<WV>(ctx, &ctx->tab_b, NWV, 0);
+    if (rc) return rc;
+    rc = build_one_table<W>(ctx, &ctx->tab_bbl, NWR, 1);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DAPOL_OK;
 }
@@ -379,7 +423,14 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     CUDA_TRY(cudaSetDevice(device));
     dapol_ctx *ctx = new dapol_ctx();
     ctx->device = device;
-    ctx->W = comb_window ? comb_window : DAPOL_DEFAULT_COMB_WINDOW;
+    ctx->W = comb_window;
+    if (comb_window == 0) {
+        // the wide window keeps 9.5 GB of tables in HBM (11 additions per blinding instead of 17); a device that is short
+        // of memory (or shared with other contexts) stays with the L2-resident 27 MB tables
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        ctx->W = free_b >= (size_t)DAPOL_WIDE_COMB_MIN_FREE_GB << 30 ? DAPOL_WIDE_COMB_WINDOW : DAPOL_DEFAULT_COMB_WINDOW;
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto &e : ctx->ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaMalloc(&ctx->scratch, 1024));
@@ -599,20 +650,34 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
         }
         TRY_T(cudaEventRecord(ctx->ev[2 + phase], st));
     }
-    // ---- merges, level by level
-    for (int h = H; h >= 1; h--) {
-        uint64_t np = t->n_real[h - 1];
-        uint64_t stride = batch_stride(np, k_merge<NODE_BATCH>, 2.5);
-        k_merge<NODE_BATCH><<<grid_for(stride, 128), 128, 0, st>>>(np, stride, t->ns, t->level_off[h], t->level_off[h - 1],
-                                                                   h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
-        ctx->launches++;
-    }
-    TRY_T(cudaEventRecord(ctx->ev[4], st));
-    // pointer tables for path extraction
+    // pointer tables for the compress pass and path extraction
     TRY_T(dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *), st));
     TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
     TRY_T(dmalloc(&t->d_level_off, (H + 1) * 8, st));
     TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
+    // ---- merges: sums level by level, one compress pass over all internal nodes, hashes level by level
+    if (H >= 1) {
+        for (int h = H; h >= 1; h--) {
+            uint64_t np = t->n_real[h - 1];
+            k_merge_sum<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr);
+            ctx->launches++;
+        }
+        InternalMap im;
+        memset(&im, 0, sizeof(im));
+        im.levels = H; im.level_off = t->d_level_off; im.pos = t->d_pos;
+        uint64_t n_int = 0;
+        for (int h = 0; h < H; h++) { im.start[h] = n_int; n_int += t->n_real[h]; }
+        im.start[H] = n_int;
+        uint64_t stride = batch_stride(n_int, k_compress_internal<NODE_BATCH>, 2.0);
+        k_compress_internal<NODE_BATCH><<<grid_for(stride, 128), 128, 0, st>>>(n_int, stride, t->ns, im);
+        ctx->launches++;
+        for (int h = H; h >= 1; h--) {
+            uint64_t np = t->n_real[h - 1];
+            k_merge_hash<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
+            ctx->launches++;
+        }
+    }
+    TRY_T(cudaEventRecord(ctx->ev[4], st));
     TRY_T(cudaMemcpyAsync(t->root_ext, t->ns.ext, 128, cudaMemcpyDeviceToHost, st));  // root = global node 0
     TRY_T(cudaGetLastError());
     TRY_T(cudaStreamSynchronize(st));

@@ -304,14 +304,70 @@ DAPOL_HD_INLINE void load_niels(ge_niels &q, const ge_niels *src) {
 }
 
 
+// acc = sign * q (q affine Niels): X = 2x, Y = 2y, Z = 2, T = 2xy = t2d / d -- one multiplication instead of the seven of a
+// mixed addition into the identity (the first window of every comb)
+DAPOL_HD_INLINE void ge_from_niels(ge &r, const ge_niels &q, int neg) {
+    fe_sub(r.X, q.ypx, q.ymx);
+    fe_add(r.Y, q.ypx, q.ymx);
+    fe_set_u32(r.Z, 2);
+    fe_mul(r.T, q.t2d, fe_const_dinv());
+    fe_cneg(r.X, neg); fe_cneg(r.T, neg);
+}
+
+// Window of the table of B/2 (values are 64-bit) that goes with window W of the B_blinding table.  Up to 16 bits
+// both tables use W (L2-resident tables); the wide HBM-resident windows pair with 22 bits for the value table
+// (3 windows, 0.6 GB: a wider one would cost HBM without saving an addition).
+template <int W>
+struct comb_value_window {
+    static constexpr int value = W <= 16 ? W : 22;
+};
+
+struct NodeStore {
+    uint64_t *idx;     // [T] tree index (path bits) of the node inside its level
+    uint64_t *v;       // [T] liability sum
+    uint32_t *r;       // [T][8] blinding factor words (leaves: as given, possibly unreduced; else canonical)
+    uint32_t *comc;    // [T][8] compress(com)
+    uint32_t *hash;    // [T][8] node hash
+    uint32_t *ext;     // [T][32] com in extended coordinates X,Y,Z,T (build-time only)
+    uint8_t *is_pad;   // [T]
+};
+
+DAPOL_HD_INLINE void store_ge(uint32_t *dst, const ge &p) {
+    store8(dst, p.X.v); store8(dst + 8, p.Y.v); store8(dst + 16, p.Z.v); store8(dst + 24, p.T.v);
+}
+DAPOL_HD_INLINE void load_ge(ge &p, const uint32_t *src) {
+    load8(p.X.v, src); load8(p.Y.v, src + 8); load8(p.Z.v, src + 16); load8(p.T.v, src + 24);
+}
+
 // ---- fixed-base signed-window comb: table[k][e] = (e+1) * 2^(W k) * P as affine Niels ------------
 // acc += sum_k d[k] * 2^(W k) * P, digits from sc_signed_digits<W, NW>.
-#ifndef DAPOL_COMB_PREFETCH
-#define DAPOL_COMB_PREFETCH 1
+// FRESH: acc is known to be the identity on entry, so the first non-zero window initialises it (ge_from_niels).
+// Windows wider than the L2-resident ones (W > 16: tables of GBs in HBM) first request every entry of the scalar into L2
+// (prefetch.global.L2: no registers held), then run the same one-window-ahead register pipeline against L2 latency.
+#ifndef DAPOL_COMB_L2_PREFETCH_MIN_W
+#define DAPOL_COMB_L2_PREFETCH_MIN_W 17
 #endif
-template <int W, int NW>
+DAPOL_HD_INLINE void prefetch_l2_96(const void *p) {
+#ifdef __CUDA_ARCH__
+    const char *c = static_cast<const char *>(p);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c));  // entries are 32-byte aligned: three sectors, one or two lines
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 64));
+#else
+    (void)p;
+#endif
+}
+template <int W, int NW, bool FRESH = false, bool L2PF = (W >= DAPOL_COMB_L2_PREFETCH_MIN_W)>
 DAPOL_HD_INLINE void ge_comb_accumulate(ge &acc, const ge_niels *__restrict__ table, const int32_t d[NW]) {
-#if DAPOL_COMB_PREFETCH
+    int fresh = FRESH;
+    if (L2PF) {
+#pragma unroll
+        for (int k = 1; k < NW; k++) {
+            int32_t dk = d[k];
+            uint32_t ek = dk ? (uint32_t)(dk < 0 ? -dk : dk) - 1u : 0u;
+            prefetch_l2_96(table + ((size_t)k * (1u << (W - 1)) + ek));
+        }
+    }
     // software pipeline: the table entry of window k + 1 is requested before the addition of window k starts, so the
     // L2 / HBM latency of the 96-byte look-up overlaps ~500 multiplies instead of stalling the few resident warps
     ge_niels q, qn;
@@ -329,19 +385,9 @@ DAPOL_HD_INLINE void ge_comb_accumulate(ge &acc, const ge_niels *__restrict__ ta
             uint32_t en = dn ? (uint32_t)(dn < 0 ? -dn : dn) - 1u : 0u;
             load_niels(qn, table + ((size_t)(k + 1) * (1u << (W - 1)) + en));
         }
-        if (dk != 0) ge_madd(acc, acc, q, dk < 0);
-    }
-#else
-#pragma unroll 1
-    for (int k = 0; k < NW; k++) {
-        int32_t dk = d[k];
         if (dk != 0) {
-            int neg = dk < 0;
-            uint32_t e = (uint32_t)(neg ? -dk : dk) - 1u;
-            ge_niels q;
-            load_niels(q, table + ((size_t)k * (1u << (W - 1)) + e));
-            ge_madd(acc, acc, q, neg);
+            if (fresh) { ge_from_niels(acc, q, dk < 0); fresh = 0; }
+            else ge_madd(acc, acc, q, dk < 0);
         }
     }
-#endif
 }

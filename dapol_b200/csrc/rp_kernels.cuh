@@ -234,13 +234,17 @@ DAPOL_HD_INLINE void rp_tab_chunk_body(uint64_t item, const uint32_t *wb, ge_nie
     }
 }
 
+#ifndef DAPOL_RP_L2_PREFETCH
+#define DAPOL_RP_L2_PREFETCH 1
+#endif
 // acc += s * P_g using the window table of base g (s canonical)
 template <int W>
 DAPOL_HD_INLINE void rp_fixed_mul_acc(ge &acc, const ge_niels *tab, uint64_t g, const sc &s) {
     constexpr int NW = 253 / W + 1;
     int32_t d[NW];
     sc_signed_digits<W, NW>(d, s.v, 8);
-    ge_comb_accumulate<W, NW>(acc, tab + g * (uint64_t)NW * (1u << (W - 1)), d);
+    // the generator tables are HBM-resident at every window (0.5 .. 60 GB): L2 prefetch of all entries of the scalar first
+    ge_comb_accumulate<W, NW, false, DAPOL_RP_L2_PREFETCH != 0>(acc, tab + g * (uint64_t)NW * (1u << (W - 1)), d);
 }
 // The lone extra term of an MSM (c * B, s_bl * B_blinding, ...) spread over the CTA: thread tid adds window tid of
 // s * P_g.  One more addition per thread instead of one thread doing all 253/W + 1 of them in an extra pass while
@@ -376,7 +380,8 @@ DAPOL_HD_INLINE void rp_p0_body(const RpBatch &b, uint64_t p) {
 // compress(V_j) is the batched double-and-compress with a batch of one
 template <int WT>
 DAPOL_HD_INLINE void rp_p1_body(const RpBatch &b, uint64_t p, int j, const ge_niels *tab_b, const ge_niels *tab_bbl) {
-    constexpr int NWR = 253 / WT + 1, NWV = 64 / WT + 1;
+    constexpr int WV = comb_value_window<WT>::value;
+    constexpr int NWR = 253 / WT + 1, NWV = 64 / WV + 1;
     sc r, rh;
     rp_ld(r, b.blind + (p * b.m + j) * 8);
     sc_half256(rh, r);
@@ -384,10 +389,10 @@ DAPOL_HD_INLINE void rp_p1_body(const RpBatch &b, uint64_t p, int j, const ge_ni
     uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
     int32_t dr[NWR], dv[NWV];
     sc_signed_digits<WT, NWR>(dr, rh.v, 8);
-    sc_signed_digits<WT, NWV>(dv, vw, 2);
+    sc_signed_digits<WV, NWV>(dv, vw, 2);
     ge acc;
     ge_identity(acc);
-    ge_comb_accumulate<WT, NWV>(acc, tab_b, dv);
+    ge_comb_accumulate<WV, NWV>(acc, tab_b, dv);
     ge_comb_accumulate<WT, NWR>(acc, tab_bbl, dr);
     ge_dc_batch<1> dc;
     dc.init();

@@ -15,23 +15,10 @@
 #pragma once
 #include "ge25519.cuh"
 #include "hash_dev.cuh"
+#ifndef DAPOL_MAX_TREE_HEIGHT
+#define DAPOL_MAX_TREE_HEIGHT 64  // include/dapol_b200.h
+#endif
 
-struct NodeStore {
-    uint64_t *idx;     // [T] tree index (path bits) of the node inside its level
-    uint64_t *v;       // [T] liability sum
-    uint32_t *r;       // [T][8] blinding factor words (leaves: as given, possibly unreduced; else canonical)
-    uint32_t *comc;    // [T][8] compress(com)
-    uint32_t *hash;    // [T][8] node hash
-    uint32_t *ext;     // [T][32] com in extended coordinates X,Y,Z,T (build-time only)
-    uint8_t *is_pad;   // [T]
-};
-
-DAPOL_HD_INLINE void store_ge(uint32_t *dst, const ge &p) {
-    store8(dst, p.X.v); store8(dst + 8, p.Y.v); store8(dst + 16, p.Z.v); store8(dst + 24, p.T.v);
-}
-DAPOL_HD_INLINE void load_ge(ge &p, const uint32_t *src) {
-    load8(p.X.v, src); load8(p.Y.v, src + 8); load8(p.Z.v, src + 16); load8(p.T.v, src + 24);
-}
 // ------------------------------------------------------------------------------------------------
 // structure pass, level h: idx[0..c) = sorted tree indexes of the real (non-padding) nodes
 // flags[k] = (starts_new_parent << 32) | is_lone
@@ -151,7 +138,8 @@ template <int W, int B>
 DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, uint64_t level_off, const uint32_t *pos,
                                      int hash_id, const uint64_t *values, const uint32_t *blind /*[n][8]*/, const ge_niels *tab_b,
                                      const ge_niels *tab_bbl) {
-    constexpr int NWR = 253 / W + 1, NWV = 64 / W + 1;
+    constexpr int WV = comb_value_window<W>::value;
+    constexpr int NWR = 253 / W + 1, NWV = 64 / WV + 1;
     ge_dc_batch<B> dc;
     dc.init();
 #pragma unroll 1
@@ -166,11 +154,11 @@ DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, co
         sc_half256(rh, rs);  // blinding may be unreduced (Scalar::from_bits, mod.rs:385)
         uint64_t v = values[i];
         uint32_t vw[2] = {(uint32_t)v, (uint32_t)(v >> 32)};
-        int32_t d[NWR];
+        int32_t d[NWR > NWV ? NWR : NWV];
         ge acc;
         ge_identity(acc);
-        sc_signed_digits<W, NWV>(d, vw, 2);  // tab_b holds multiples of B/2: v * (B/2) is the half point of v * B
-        ge_comb_accumulate<W, NWV>(acc, tab_b, d);
+        sc_signed_digits<WV, NWV>(d, vw, 2);  // tab_b holds multiples of B/2: v * (B/2) is the half point of v * B
+        ge_comb_accumulate<WV, NWV, true>(acc, tab_b, d);
         sc_signed_digits<W, NWR>(d, rh.v, 8);
         ge_comb_accumulate<W, NWR>(acc, tab_bbl, d);
         uint64_t g = level_off + pos[i];
@@ -212,7 +200,7 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         sc_signed_digits<W, NWR>(d, rh.v, 8);
         ge acc;
         ge_identity(acc);
-        ge_comb_accumulate<W, NWR>(acc, tab_bbl, d);
+        ge_comb_accumulate<W, NWR, true>(acc, tab_bbl, d);
         uint64_t dest = pad_dest[g];
         ns.v[dest] = 0;
         store8(ns.r + 8 * dest, r.v);
@@ -246,44 +234,75 @@ DAPOL_HD_INLINE void record_leaf_body(uint64_t i, const NodeStore &ns, uint64_t 
     ns.v[g] = (uint64_t)rec[56] | ((uint64_t)rec[57] << 32);
 }
 
-// Mergeable::merge (node.rs:64-80) for the parents j of the level whose children start at child_off:
-// hash = D(C(L)||C(R)||H(L)||H(R)); v, r, com = sums.  parent_pos == nullptr: the single root at slot parent_off.
+// Mergeable::merge (node.rs:64-80) in three data-parallel steps, so that the compressions of ALL internal nodes form one
+// perfectly balanced batch instead of one latency-bound batch per level (the sums need no compressed point; only the
+// parent HASH needs the children's):
+//   1. per level, bottom-up:  v, r, com = sums           (merge_sum_body; one full addition per parent)
+//   2. once:                  compress(com) of every internal node, one shared inversion per thread batch
+//   3. per level, bottom-up:  hash = D(C(L)||C(R)||H(L)||H(R))   (merge_hash_body; HBM-bound)
+// parent_pos == nullptr: the single root at slot parent_off.
+DAPOL_HD_INLINE void merge_sum_body(uint64_t j, const NodeStore &ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos) {
+    uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
+    uint64_t l = child_off + 2 * j, r = l + 1;
+    ns.v[dest] = ns.v[l] + ns.v[r];  // u64 wrapping add, as release-mode Rust
+    sc a, c, s;
+    load8(a.v, ns.r + 8 * l); load8(c.v, ns.r + 8 * r);
+    sc_reduce256(a, a); sc_reduce256(c, c);  // leaf blindings may be unreduced (Scalar::from_bits)
+    sc_add(s, a, c);
+    store8(ns.r + 8 * dest, s.v);
+    ge p, q, sum;
+    load_ge(p, ns.ext + 32 * l); load_ge(q, ns.ext + 32 * r);
+    ge_add(sum, p, q);
+    store_ge(ns.ext + 32 * dest, sum);
+}
+DAPOL_HD_INLINE void merge_hash_body(uint64_t j, const NodeStore &ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos,
+                                     int hash_id) {
+    uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
+    uint64_t l = child_off + 2 * j, r = l + 1;
+    uint32_t cl[8], cr[8], hl[8], hr[8], hh[8];
+    load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
+    load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
+    dapol_hash128(hash_id, hh, cl, cr, hl, hr);
+    store8(ns.hash + 8 * dest, hh);
+}
+// Internal (non-leaf, non-padding) nodes of all levels as one flat unit range: unit u of level h (start[h] <= u <
+// start[h + 1], h = 0 .. H - 1) is the (u - start[h])-th real node of that level.
+struct InternalMap {
+    uint64_t start[DAPOL_MAX_TREE_HEIGHT + 2];
+    int levels;                   // H
+    const uint64_t *level_off;    // [H + 1]
+    uint32_t *const *pos;         // [H + 1], pos[0] unused
+};
+DAPOL_HD_INLINE uint64_t internal_node_of(const InternalMap &m, uint64_t u) {
+    int lo = 0, hi = m.levels - 1;
+    while (lo < hi) {  // last level whose start <= u
+        int mid = (lo + hi + 1) >> 1;
+        if (m.start[mid] <= u) lo = mid; else hi = mid - 1;
+    }
+    uint64_t j = u - m.start[lo];
+    return m.level_off[lo] + (lo ? (uint64_t)m.pos[lo][j] : 0);
+}
 template <int B>
-DAPOL_HD_INLINE void merge_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, uint64_t child_off, uint64_t parent_off,
-                                      const uint32_t *parent_pos, int hash_id) {
+DAPOL_HD_INLINE void compress_internal_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, const InternalMap &m) {
     ge_dc_batch<B> dc;
+    uint64_t dest[B];
     dc.init();
 #pragma unroll 1
     for (int b = 0; b < B; b++) {
-        uint64_t j = t + (uint64_t)b * stride;
-        if (j >= n) break;
-        uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
-        uint64_t l = child_off + 2 * j, r = l + 1;
-        uint32_t cl[8], cr[8], hl[8], hr[8], hh[8];
-        load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
-        load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
-        dapol_hash128(hash_id, hh, cl, cr, hl, hr);
-        store8(ns.hash + 8 * dest, hh);
-        ns.v[dest] = ns.v[l] + ns.v[r];  // u64 wrapping add, as release-mode Rust
-        sc a, c, s;
-        load8(a.v, ns.r + 8 * l); load8(c.v, ns.r + 8 * r);
-        sc_reduce256(a, a); sc_reduce256(c, c);  // leaf blindings may be unreduced (Scalar::from_bits)
-        sc_add(s, a, c);
-        store8(ns.r + 8 * dest, s.v);
-        ge p, q, sum;
-        load_ge(p, ns.ext + 32 * l); load_ge(q, ns.ext + 32 * r);
-        ge_add(sum, p, q);
-        store_ge(ns.ext + 32 * dest, sum);
-        dc.push(sum);
+        uint64_t u = t + (uint64_t)b * stride;
+        if (u >= n) break;
+        uint64_t g = internal_node_of(m, u);
+        dest[b] = g;
+        ge p;
+        load_ge(p, ns.ext + 32 * g);
+        dc.push(p);
     }
     dc.solve();
 #pragma unroll 1
     for (int b = 0; b < dc.n; b++) {
-        uint64_t j = t + (uint64_t)b * stride;
-        uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
         uint32_t cc[8];
         dc.get(b, cc);
-        store8(ns.comc + 8 * dest, cc);
+        store8(ns.comc + 8 * dest[b], cc);
     }
 }
 
@@ -311,6 +330,67 @@ DAPOL_HD_INLINE void comb_table_body(uint64_t t, ge_niels *table, int nw, int wh
     ge_niels n;
     ge_to_niels(n, acc);
     table[t] = n;
+}
+
+// The same table built a RUN of consecutive multiples per thread: entry e0 + i of window k = (e0 + 1) * base_k + i * base_k,
+// one addition per entry and one inversion per RUN entries (the wide HBM-resident windows have 10^7 .. 10^8 entries).
+// bases[k] = 2^(W k) * P (comb_bases_body).  Entries are stored canonical, so both builders give identical bytes.
+template <int W>
+DAPOL_HD_INLINE void comb_bases_body(ge *bases, int nw, int which) {
+    ge base;
+    if (which == 0) ge_basepoint_half(base); else ge_bblinding(base);
+    for (int k = 0; k < nw; k++) {
+        bases[k] = base;
+#pragma unroll 1
+        for (int i = 0; i < W; i++) ge_dbl(base, base);
+    }
+}
+template <int W, int RUN>
+DAPOL_HD_INLINE void comb_table_run_body(uint64_t t, ge_niels *table, int nw, const ge *bases) {
+    constexpr uint64_t half = 1ull << (W - 1);
+    static_assert(half % RUN == 0, "run length must divide the window size");
+    constexpr uint64_t runs = half / RUN;
+    uint32_t k = (uint32_t)(t / runs);
+    uint64_t e0 = (t % runs) * RUN;
+    if ((int)k >= nw) return;
+    ge base = bases[k];
+    ge_cached cb;
+    ge_to_cached(cb, base);
+    uint64_t m = e0 + 1;  // first multiple by left-to-right double-and-add
+    ge acc = base;
+    int top = 63;
+    while (!((m >> top) & 1ull)) top--;
+#pragma unroll 1
+    for (int b = top - 1; b >= 0; b--) {
+        ge_dbl(acc, acc);
+        if ((m >> b) & 1ull) ge_cadd(acc, acc, cb, 0);
+    }
+    fe X[RUN], Y[RUN], Z[RUN], pre[RUN], prod;  // local memory; Montgomery's trick over the RUN values of Z
+    fe_set1(prod);
+#pragma unroll 1
+    for (int i = 0; i < RUN; i++) {
+        if (i) ge_cadd(acc, acc, cb, 0);
+        X[i] = acc.X; Y[i] = acc.Y; Z[i] = acc.Z;
+        pre[i] = prod;
+        fe_mul(prod, prod, acc.Z);  // Z != 0 on the curve
+    }
+    fe inv;
+    fe_invert(inv, prod);
+#pragma unroll 1
+    for (int i = RUN - 1; i >= 0; i--) {
+        fe zi, x, y;
+        fe_mul(zi, inv, pre[i]);
+        fe_mul(inv, inv, Z[i]);
+        fe_mul(x, X[i], zi); fe_mul(y, Y[i], zi);
+        ge_niels n;
+        fe_add(n.ypx, y, x); fe_sub(n.ymx, y, x);
+        fe_mul(n.t2d, x, y); fe_mul(n.t2d, n.t2d, fe_const_d2());
+        uint32_t w[8];
+        fe_canon(w, n.ypx); fe_fromwords(n.ypx, w);
+        fe_canon(w, n.ymx); fe_fromwords(n.ymx, w);
+        fe_canon(w, n.t2d); fe_fromwords(n.t2d, w);
+        table[(uint64_t)k * half + e0 + i] = n;
+    }
 }
 
 // path extraction (Dapol::generate_proof's get_merkle_path_ref_batch, mod.rs:173): siblings leaf level

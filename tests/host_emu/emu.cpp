@@ -100,8 +100,24 @@ static void commit_w(uint64_t v, const uint8_t r[32], uint8_t out[32]) {
     static std::vector<ge_niels> tb, tbbl;
     if (tb.empty()) {
         tb.resize((size_t)NWR * half); tbbl.resize((size_t)NWR * half);
-        for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWR, 0);
-        for (uint64_t t = 0; t < tbbl.size(); t++) comb_table_body<W>(t, tbbl.data(), NWR, 1);
+        if (W == 8) {  // the run builder of the wide windows (RUN consecutive multiples per thread, shared inversion)
+            constexpr int RUN = W == 8 ? 16 : 1;
+            std::vector<ge> bases(NWR);
+            for (int which = 0; which < 2; which++) {
+                comb_bases_body<W>(bases.data(), NWR, which);
+                std::vector<ge_niels> &dst = which ? tbbl : tb;
+                for (uint64_t t = 0; t < dst.size() / RUN; t++) comb_table_run_body<W, RUN>(t, dst.data(), NWR, bases.data());
+            }
+            // both builders must give identical table bytes
+            std::vector<ge_niels> chk(tb.size());
+            for (uint64_t t = 0; t < 300; t++) {
+                comb_table_body<W>(t * 7, chk.data(), NWR, 1);
+                if (memcmp(&chk[t * 7], &tbbl[t * 7], sizeof(ge_niels))) abort();
+            }
+        } else {
+            for (uint64_t t = 0; t < tb.size(); t++) comb_table_body<W>(t, tb.data(), NWR, 0);
+            for (uint64_t t = 0; t < tbbl.size(); t++) comb_table_body<W>(t, tbbl.data(), NWR, 1);
+        }
     }
     // one-node store
     uint64_t idx = 0, vv = 0; uint32_t rr[8], cc[8], hh[8], ext[32], blind[8]; uint8_t pad = 0; uint32_t pos = 0;
@@ -174,9 +190,22 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     for (uint64_t i = 0, st = threads(n); i < st; i++)
         leaf_batch_body<W, BT>(i, st, n, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
     for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_rng.data(), tbbl.data());
+    // merges: sums per level, one compress pass over all internal nodes, hashes per level (as tree_build_dev)
     for (int h = height; h >= 1; h--)
-        for (uint64_t j = 0, st = threads(nparents[h]); j < st; j++)
-            merge_batch_body<BT>(j, st, nparents[h], ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);
+        for (uint64_t j = 0; j < nparents[h]; j++)
+            merge_sum_body(j, ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data());
+    std::vector<uint32_t *> pos_ptr(height + 1, nullptr);
+    for (int h = 1; h <= height; h++) pos_ptr[h] = pos[h].data();
+    InternalMap im;
+    memset(&im, 0, sizeof(im));
+    im.levels = height; im.level_off = t->level_off.data(); im.pos = pos_ptr.data();
+    uint64_t n_int = 0;
+    for (int h = 0; h < height; h++) { im.start[h] = n_int; n_int += n_real[h]; }
+    im.start[height] = n_int;
+    for (uint64_t j = 0, st = threads(n_int); j < st; j++) compress_internal_body<BT>(j, st, n_int, ns, im);
+    for (int h = height; h >= 1; h--)
+        for (uint64_t j = 0; j < nparents[h]; j++)
+            merge_hash_body(j, ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);
     return t;
 }
 // leaf derivation through the kernel bodies, with the sort/fix-point orchestration mirrored serially

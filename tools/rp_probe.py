@@ -8,8 +8,9 @@ SEED = hashlib.sha256(b"dapol-b200").digest()
 shapes = [(64, 1, 8192), (64, 16, 1024), (64, 32, 512)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
-for W in (12, 8):
-    ctx = Context(0)
+WINDOWS = [int(w) for w in os.environ.get("RP_WINDOWS", "12,8").split(",")]
+for W in WINDOWS:
+    ctx = Context(0, int(os.environ.get("COMB_WINDOW", "15")))
     ctx.set_rangeproof_window(W)
     for nbits, m, k in shapes:
         rng = np.random.default_rng(1)
