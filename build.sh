@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 mkdir -p dapol_b200/lib build
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden ${DAPOL_PTXAS_V:+-Xptxas -v}"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -split-compile 0 -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden ${DAPOL_PTXAS_V:+-Xptxas -v}"
 newest_hdr=$(ls -t dapol_b200/csrc/*.cuh dapol_b200/csrc/*.h dapol_b200/csrc/*.inc include/*.h build.sh | head -1)
 pids=(); tus=()
 for tu in dapol_lib dapol_rp dapol_proof; do

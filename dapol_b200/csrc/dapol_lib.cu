@@ -498,11 +498,11 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
 // size is chosen to minimise waves x thread cost -- small levels keep one unit per thread and spread over the SMs, and a
 // level of a few waves does not end on a nearly empty one.
 template <typename K>
-static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, double inv_cost = 12.0) {
+static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, size_t smem = 0, double inv_cost = 12.0) {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     int resident = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 128, 0) != cudaSuccess || resident <= 0) resident = 3;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 128, smem) != cudaSuccess || resident <= 0) resident = 3;
     const double wave = (double)sms * resident;
     double best = 1e300;
     uint64_t best_threads = n;

@@ -9,6 +9,9 @@
 #include "rp_kernels.cuh"
 
 #define RP_MSM_MAX_T 128
+#ifndef RP_INL_MIN_T
+#define RP_INL_MIN_T 128  // CTAs of at least this many threads use the MSM kernels with inlined products
+#endif
 
 // ------------------------------------------------------------------------------------------------ CTA reductions
 // Sum of the per-thread partial points of a CTA, result in thread 0.  Inside a warp the partials move by shuffles; only
@@ -158,11 +161,13 @@ __global__ void __launch_bounds__(128) k_rp_p2(RpBatch b) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < b.K * b.N) rp_p2_body(b, t / b.N, (uint32_t)(t % b.N));
 }
-template <int W>
+// MSM kernels (CTA per proof).  INL: 128-thread CTAs of the large shapes run the mixed additions with inlined products; the
+// single-warp CTAs of the small shapes share the called multiplication (see ge25519.cuh, ge_madd_inl).
+template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p3(RpBatch b) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
-    rp_p3_partial<W>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    rp_p3_partial<W, INL>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
     block_reduce_ge(acc, sh);
     if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
 }
@@ -207,11 +212,11 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p9(RpBatch b, int rnd) {
     block_reduce_sc(cl, sh); block_reduce_sc(cr, sh);
     if (threadIdx.x == 0) { rp_st(rp_ch(b, p, CH_CL), cl); rp_st(rp_ch(b, p, CH_CR), cr); }
 }
-template <int W>
+template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p10(RpBatch b, int rnd) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
-    rp_p10_partial<W>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
+    rp_p10_partial<W, INL>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
     block_reduce_ge(acc, sh);
     if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
 }
@@ -232,12 +237,12 @@ __global__ void __launch_bounds__(64) k_rp_v1(RpBatch b, int nv) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < b.K * nv) rp_v1_body(b, t / nv, (int)(t % nv));
 }
-template <int W>
+template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_v2(RpBatch b) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     uint64_t p = blockIdx.x;
-    rp_v2_partial<W>(acc, b, p, threadIdx.x, blockDim.x);
+    rp_v2_partial<W, INL>(acc, b, p, threadIdx.x, blockDim.x);
     block_reduce_ge(acc, sh);
     if (threadIdx.x == 0) b.status[p] = b.status[p] && ge_is_identity(acc);
 }
@@ -345,7 +350,8 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     tm.end();
     tm.begin(0);
-    k_rp_p3<W><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
+    if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
+    else k_rp_p3<W, false><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
     tm.end();
     tm.begin(1);
     k_rp_p4<<<grid_for(K, 64), 64, 0, st>>>(b);
@@ -363,7 +369,8 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         k_rp_p9<<<(unsigned)K, msm_threads(h), 0, st>>>(b, rnd);
         tm.end();
         tm.begin(0);
-        k_rp_p10<W><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
+        if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
+        else k_rp_p10<W, false><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
         tm.end();
         tm.begin(1);
         k_rp_p11<<<grid_for(K, 64), 64, 0, st>>>(b, rnd);
@@ -386,7 +393,8 @@ static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     tm.end();
     tm.begin(0);
     k_rp_v1<<<grid_for(K * nv, 64), 64, 0, st>>>(b, nv);
-    k_rp_v2<W><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
+    if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rp_v2<W, true><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
+    else k_rp_v2<W, false><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
     tm.end();
     ctx->launches += 5;
     CUDA_TRY(cudaGetLastError());

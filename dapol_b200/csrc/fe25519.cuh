@@ -77,16 +77,40 @@ DAPOL_HD_INLINE void fe_set0(fe &r) {
 DAPOL_HD_INLINE void fe_set1(fe &r) { fe_set0(r); r.v[0] = 1; }
 DAPOL_HD_INLINE void fe_set_u32(fe &r, uint32_t x) { fe_set0(r); r.v[0] = x; }
 
-DAPOL_HD_INLINE void fe_mul(fe &r, const fe &a, const fe &b) {
+DAPOL_HD_INLINE void fe_mul_inl(fe &r, const fe &a, const fe &b) {
     uint32_t R[16];
     mul_wide_8x8(R, a.v, b.v);
     fold38(r.v, R);
 }
-DAPOL_HD_INLINE void fe_sq(fe &r, const fe &a) {
+DAPOL_HD_INLINE void fe_sq_inl(fe &r, const fe &a) {
     uint32_t R[16];
     sqr_wide_8(R, a.v);
     fold38(r.v, R);
 }
+// On the device the multiplication and the squaring are CALLED, not inlined: a product is ~135 instructions (2 KB) and a
+// node kernel contains a few hundred of them, so the fully inlined kernels were 150 .. 215 KB of straight-line code against a
+// 32 KB instruction cache per SM -- ncu showed 46 % of all warp stalls of k_pad as no_instruction.  Arguments and result
+// travel in registers (structs of 8 words by value: no stack traffic), and every warp of the SM now runs the same 3.5 KB.
+#ifndef DAPOL_FE_CALL
+#define DAPOL_FE_CALL 1
+#endif
+#if defined(__CUDA_ARCH__) && DAPOL_FE_CALL
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
+    fe r;
+    fe_mul_inl(r, a, b);
+    return r;
+}
+static __device__ __noinline__ fe fe_sq_call(fe a) {
+    fe r;
+    fe_sq_inl(r, a);
+    return r;
+}
+__device__ __forceinline__ void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
+__device__ __forceinline__ void fe_sq(fe &r, const fe &a) { r = fe_sq_call(a); }
+#else
+DAPOL_HD_INLINE void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inl(r, a, b); }
+DAPOL_HD_INLINE void fe_sq(fe &r, const fe &a) { fe_sq_inl(r, a); }
+#endif
 // r = a^(2^n), n >= 1 (loop kept rolled: the body is ~110 instructions)
 DAPOL_HD_INLINE void fe_sqn(fe &r, const fe &a, int n) {
     fe_sq(r, a);

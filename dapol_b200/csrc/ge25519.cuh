@@ -52,19 +52,28 @@ DAPOL_HD_INLINE void ge_sub(ge &r, const ge &p, const ge &q) {
     ge_add(r, p, n);
 }
 // r = p + sign*q with q affine-Niels: 7M.  neg != 0 subtracts.
+// MUL = fe_mul (a called function on the device, fe25519.cuh) or fe_mul_inl (inlined)
+#define DAPOL_GE_MADD_BODY(MUL)                                      \
+    fe A, B, C, D, t0, t1, qa, qb;                                   \
+    qa = q.ymx; qb = q.ypx;                                          \
+    fe_cmov(qa, q.ypx, neg); fe_cmov(qb, q.ymx, neg);                \
+    fe_sub(t0, p.Y, p.X); MUL(A, t0, qa);                            \
+    fe_add(t0, p.Y, p.X); MUL(B, t0, qb);                            \
+    MUL(C, p.T, q.t2d); fe_cneg(C, neg);                             \
+    fe_dbl(D, p.Z);                                                  \
+    fe_sub(t0, B, A); /* E */                                        \
+    fe_sub(t1, D, C); /* F */                                        \
+    fe_add(D, D, C);  /* G */                                        \
+    fe_add(B, B, A);  /* H */                                        \
+    MUL(r.X, t0, t1); MUL(r.Y, D, B); MUL(r.Z, t1, D); MUL(r.T, t0, B);
 DAPOL_HD_INLINE void ge_madd(ge &r, const ge &p, const ge_niels &q, int neg) {
-    fe A, B, C, D, t0, t1, qa, qb;
-    qa = q.ymx; qb = q.ypx;
-    fe_cmov(qa, q.ypx, neg); fe_cmov(qb, q.ymx, neg);
-    fe_sub(t0, p.Y, p.X); fe_mul(A, t0, qa);
-    fe_add(t0, p.Y, p.X); fe_mul(B, t0, qb);
-    fe_mul(C, p.T, q.t2d); fe_cneg(C, neg);
-    fe_dbl(D, p.Z);
-    fe_sub(t0, B, A);  // E
-    fe_sub(t1, D, C);  // F
-    fe_add(D, D, C);   // G
-    fe_add(B, B, A);   // H
-    fe_mul(r.X, t0, t1); fe_mul(r.Y, D, B); fe_mul(r.Z, t1, D); fe_mul(r.T, t0, B);
+    DAPOL_GE_MADD_BODY(fe_mul)
+}
+// the same with the seven products inlined (19 KB of code): for loops that every warp of the SM runs in step (the MSM kernels
+// of the aggregated range proofs: 128-thread CTAs, hundreds of terms per thread), where the instruction cache holds the one
+// loop body and the register moves of a call are pure overhead on the multiply pipe
+DAPOL_HD_INLINE void ge_madd_inl(ge &r, const ge &p, const ge_niels &q, int neg) {
+    DAPOL_GE_MADD_BODY(fe_mul_inl)
 }
 DAPOL_HD_INLINE void ge_to_cached(ge_cached &c, const ge &p) {
     fe_add(c.YpX, p.Y, p.X); fe_sub(c.YmX, p.Y, p.X); fe_dbl(c.Z2, p.Z); fe_mul(c.T2d, p.T, fe_const_d2());
@@ -342,51 +351,31 @@ DAPOL_HD_INLINE void load_ge(ge &p, const uint32_t *src) {
 // ---- fixed-base signed-window comb: table[k][e] = (e+1) * 2^(W k) * P as affine Niels ------------
 // acc += sum_k d[k] * 2^(W k) * P, digits from sc_signed_digits<W, NW>.
 // FRESH: acc is known to be the identity on entry, so the first non-zero window initialises it (ge_from_niels).
-// Windows wider than the L2-resident ones (W > 16: tables of GBs in HBM) first request every entry of the scalar into L2
-// (prefetch.global.L2: no registers held), then run the same one-window-ahead register pipeline against L2 latency.
-#ifndef DAPOL_COMB_L2_PREFETCH_MIN_W
-#define DAPOL_COMB_L2_PREFETCH_MIN_W 17
-#endif
-DAPOL_HD_INLINE void prefetch_l2_96(const void *p) {
-#ifdef __CUDA_ARCH__
-    const char *c = static_cast<const char *>(p);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c));  // entries are 32-byte aligned: three sectors, one or two lines
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 32));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 64));
-#else
-    (void)p;
-#endif
+//
+// Table look-ups are 96-byte reads at data-dependent addresses (L2 hits for the 27 MB tables of window 15, HBM reads for the
+// wide windows): the entry of window k + 1 is requested before the addition of window k starts.  Measured and rejected
+// (profiles/r01d_variants.txt): prefetch.global.L2 of all entries of a scalar up front (+8 % time: 60 MB of prefetched lines
+// do not survive in L2 until used), and staging through shared memory with a cp.async ring of 4 / 6 entries per thread
+// (+6 .. 14 %: the wait / ld.shared pair per window costs more than the latency it hides).
+template <int W, int NW>
+DAPOL_HD_INLINE const ge_niels *comb_entry(const ge_niels *table, const int32_t d[NW], int k) {
+    int32_t dk = d[k];
+    uint32_t e = dk ? (uint32_t)(dk < 0 ? -dk : dk) - 1u : 0u;
+    return table + ((size_t)k * (1u << (W - 1)) + e);
 }
-template <int W, int NW, bool FRESH = false, bool L2PF = (W >= DAPOL_COMB_L2_PREFETCH_MIN_W)>
+template <int W, int NW, bool FRESH = false, bool INL = false>
 DAPOL_HD_INLINE void ge_comb_accumulate(ge &acc, const ge_niels *__restrict__ table, const int32_t d[NW]) {
     int fresh = FRESH;
-    if (L2PF) {
-#pragma unroll
-        for (int k = 1; k < NW; k++) {
-            int32_t dk = d[k];
-            uint32_t ek = dk ? (uint32_t)(dk < 0 ? -dk : dk) - 1u : 0u;
-            prefetch_l2_96(table + ((size_t)k * (1u << (W - 1)) + ek));
-        }
-    }
-    // software pipeline: the table entry of window k + 1 is requested before the addition of window k starts, so the
-    // L2 / HBM latency of the 96-byte look-up overlaps ~500 multiplies instead of stalling the few resident warps
     ge_niels q, qn;
-    {
-        int32_t d0 = d[0];
-        uint32_t e0 = d0 ? (uint32_t)(d0 < 0 ? -d0 : d0) - 1u : 0u;
-        load_niels(qn, table + e0);
-    }
+    load_niels(qn, comb_entry<W, NW>(table, d, 0));
 #pragma unroll 1
     for (int k = 0; k < NW; k++) {
         int32_t dk = d[k];
         q = qn;
-        if (k + 1 < NW) {
-            int32_t dn = d[k + 1];
-            uint32_t en = dn ? (uint32_t)(dn < 0 ? -dn : dn) - 1u : 0u;
-            load_niels(qn, table + ((size_t)(k + 1) * (1u << (W - 1)) + en));
-        }
+        if (k + 1 < NW) load_niels(qn, comb_entry<W, NW>(table, d, k + 1));
         if (dk != 0) {
             if (fresh) { ge_from_niels(acc, q, dk < 0); fresh = 0; }
+            else if (INL) ge_madd_inl(acc, acc, q, dk < 0);
             else ge_madd(acc, acc, q, dk < 0);
         }
     }

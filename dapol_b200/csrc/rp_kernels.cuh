@@ -234,17 +234,13 @@ DAPOL_HD_INLINE void rp_tab_chunk_body(uint64_t item, const uint32_t *wb, ge_nie
     }
 }
 
-#ifndef DAPOL_RP_L2_PREFETCH
-#define DAPOL_RP_L2_PREFETCH 1
-#endif
-// acc += s * P_g using the window table of base g (s canonical)
-template <int W>
+// acc += s * P_g using the window table of base g (s canonical); INL: mixed additions with inlined products (ge_madd_inl)
+template <int W, bool INL = false>
 DAPOL_HD_INLINE void rp_fixed_mul_acc(ge &acc, const ge_niels *tab, uint64_t g, const sc &s) {
     constexpr int NW = 253 / W + 1;
     int32_t d[NW];
     sc_signed_digits<W, NW>(d, s.v, 8);
-    // the generator tables are HBM-resident at every window (0.5 .. 60 GB): L2 prefetch of all entries of the scalar first
-    ge_comb_accumulate<W, NW, false, DAPOL_RP_L2_PREFETCH != 0>(acc, tab + g * (uint64_t)NW * (1u << (W - 1)), d);
+    ge_comb_accumulate<W, NW, false, INL>(acc, tab + g * (uint64_t)NW * (1u << (W - 1)), d);
 }
 // The lone extra term of an MSM (c * B, s_bl * B_blinding, ...) spread over the CTA: thread tid adds window tid of
 // s * P_g.  One more addition per thread instead of one thread doing all 253/W + 1 of them in an extra pass while
@@ -414,7 +410,7 @@ DAPOL_HD_INLINE void rp_p2_body(const RpBatch &b, uint64_t p, uint32_t k) {
 }
 // P3 (CTA per (proof, which)): which = 0: A = a_bl * B_bl + sum_k (bit_k ? G_k : -H_k)
 //                               which = 1: S = s_bl * B_bl + <s_L, G> + <s_R, H>          -- per-thread partial sums
-template <int W>
+template <int W, bool INL = false>
 DAPOL_HD_INLINE void rp_p3_partial(ge &acc, const RpBatch &b, uint64_t p, int which, uint32_t tid, uint32_t T) {
     ge_identity(acc);
     const uint32_t N = (uint32_t)b.N, n = (uint32_t)b.nbits;
@@ -432,8 +428,8 @@ DAPOL_HD_INLINE void rp_p3_partial(ge &acc, const RpBatch &b, uint64_t p, int wh
 #pragma unroll 1
         for (uint32_t t = tid; t < 2 * N; t += T) {
             sc s;
-            if (t < N) { rp_ld(s, b.vecA + (p * N + t) * 8); rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, t), s); }
-            else { rp_ld(s, b.vecB + (p * N + (t - N)) * 8); rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, t - N), s); }
+            if (t < N) { rp_ld(s, b.vecA + (p * N + t) * 8); rp_fixed_mul_acc<W, INL>(acc, b.tabG, rp_gen_of(b, t), s); }
+            else { rp_ld(s, b.vecB + (p * N + (t - N)) * 8); rp_fixed_mul_acc<W, INL>(acc, b.tabH, rp_gen_of(b, t - N), s); }
         }
         sc s;
         rp_ld(s, rp_ch(b, p, CH_SBL));
@@ -601,7 +597,7 @@ DAPOL_HD_INLINE void rp_p9_partial(sc &cl, sc &cr, const RpBatch &b, uint64_t p,
 // With I = original position, pfx = its top rnd-1 bits, bit = its rnd-th bit, i = its low lg-rnd bits:
 //   folded G_i = sum cu[pfx] G_I,  cu[pfx] = prod_{r<rnd} u_r^(2 b_r - 1);  folded H_i = sum y^-I cui[pfx] H_I, cui = 1/cu
 //   L = <a_lo, G_hi> + <b_hi, H_lo> + c_L w B      R = <a_hi, G_lo> + <b_lo, H_hi> + c_R w B     (Q = w B)
-template <int W>
+template <int W, bool INL = false>
 DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int rnd, int which, uint32_t tid, uint32_t T) {
     ge_identity(acc);
     const uint32_t N = (uint32_t)b.N, h = N >> rnd, half = N / 2;
@@ -618,7 +614,7 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
             rp_ld(s, b.vecA + (p * N + (which ? h + i : i)) * 8);
             rp_ld(c, cu + pfx * 8);
             sc_mul(s, s, c);
-            rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, I), s);
+            rp_fixed_mul_acc<W, INL>(acc, b.tabG, rp_gen_of(b, I), s);
         } else {                // H terms: L uses H_lo (bit 0) with b_hi, R uses H_hi (bit 1) with b_lo
             uint32_t tt = t - half;
             uint32_t pfx = tt >> sh, i = tt & (h - 1);
@@ -629,7 +625,7 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
             sc_mul(s, s, c);
             rp_ld(c, b.ypow + (p * N + I) * 8);
             sc_mul(s, s, c);
-            rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, I), s);
+            rp_fixed_mul_acc<W, INL>(acc, b.tabH, rp_gen_of(b, I), s);
         }
     }
     sc s, c;  // + c_L/R * w * B, one window per thread
@@ -803,7 +799,7 @@ DAPOL_HD_INLINE void rp_v1_body(const RpBatch &b, uint64_t p, int q) {
 }
 // V2 (CTA per proof, partial sums): the fixed-base part of the verification equation plus the variable partial points
 //   G_I: -z - a s_I      H_I: z + y^-I (z^(2+j) 2^i - b s_{N-1-I})      B, B_blinding: scalars from V0
-template <int W>
+template <int W, bool INL = false>
 DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32_t tid, uint32_t T) {
     ge_identity(acc);
     const uint32_t N = (uint32_t)b.N;
@@ -816,7 +812,7 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
         if (t < N) {
             rp_ld(s, b.svec + (p * N + t) * 8);
             sc_mul(s, a, s); sc_sub(s, mz, s);
-            rp_fixed_mul_acc<W>(acc, b.tabG, rp_gen_of(b, t), s);
+            rp_fixed_mul_acc<W, INL>(acc, b.tabG, rp_gen_of(b, t), s);
         } else {
             uint32_t I = t - N;
             rp_ld(s, b.svec + (p * N + (N - 1 - I)) * 8);
@@ -826,7 +822,7 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
             rp_ld(c, b.ypow + (p * N + I) * 8);
             sc_mul(s, s, c);
             sc_add(s, z, s);
-            rp_fixed_mul_acc<W>(acc, b.tabH, rp_gen_of(b, I), s);
+            rp_fixed_mul_acc<W, INL>(acc, b.tabH, rp_gen_of(b, I), s);
         }
     }
     sc s;  // the B and B_blinding terms, one window per thread; the variable-base partial points, one per thread
