@@ -227,10 +227,10 @@ __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t 
 #endif
 // minimum resident 128-thread CTAs per SM the node kernels are compiled for (register cap = 65536 / (128 * MINB))
 #ifndef DAPOL_LEAF_MINB
-#define DAPOL_LEAF_MINB 3
+#define DAPOL_LEAF_MINB 4
 #endif
 #ifndef DAPOL_PAD_MINB
-#define DAPOL_PAD_MINB 3
+#define DAPOL_PAD_MINB 4
 #endif
 #ifndef DAPOL_MERGE_MINB
 #define DAPOL_MERGE_MINB 4

@@ -9,6 +9,13 @@
 #include "rp_kernels.cuh"
 
 #define RP_MSM_MAX_T 128
+// minimum resident CTAs per SM the MSM kernels are compiled for (register cap = 65536 / (128 * RP_MSM_MINB))
+#ifndef RP_MSM_MINB
+#define RP_MSM_MINB 4      // single-warp .. 64-thread CTAs, called products: 128 registers, 16 warps per SM (m = 1: MSM passes 26.5 -> 25.1 ms)
+#endif
+#ifndef RP_MSM_MINB_INL
+#define RP_MSM_MINB_INL 3  // 128-thread CTAs, inlined products
+#endif
 #ifndef RP_INL_MIN_T
 #define RP_INL_MIN_T 128  // CTAs of at least this many threads use the MSM kernels with inlined products
 #endif
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(128) k_rp_tab_chunk(uint64_t items, const uint
 }
 
 // windows of the generator tables that are instantiated (dapol_ctx_set_rangeproof_window; 0 = pick by HBM budget)
-#define RP_W_CASES(X) X(8) X(12) X(13) X(14) X(16)
+#define RP_W_CASES(X) X(8) X(12) X(13) X(14) X(15) X(16)
 static size_t rp_table_bytes(int W, int mcap) {
     return (128ull * mcap + 2) * (size_t)(253 / W + 1) * (1ull << (W - 1)) * sizeof(ge_niels);
 }
@@ -98,10 +105,12 @@ static int rp_build_tables(dapol_ctx *ctx, int mcap) {
     uint64_t ngen = 128ull * mcap, nb = ngen + 2;
     uint32_t *uniform = nullptr, *ext = nullptr, *wb = nullptr;
     ge_niels *tab = nullptr;
-    CUDA_TRY(cudaMalloc(&tab, nb * NW * HALF * sizeof(ge_niels)));
-    CUDA_TRY(cudaMalloc(&uniform, 2ull * mcap * 64 * 64));
-    CUDA_TRY(cudaMalloc(&ext, nb * 128));
-    CUDA_TRY(cudaMalloc(&wb, nb * NW * 128));
+    if (cudaMalloc(&tab, nb * NW * HALF * sizeof(ge_niels)) != cudaSuccess || cudaMalloc(&uniform, 2ull * mcap * 64 * 64) != cudaSuccess ||
+        cudaMalloc(&ext, nb * 128) != cudaSuccess || cudaMalloc(&wb, nb * NW * 128) != cudaSuccess) {
+        dapol_cuda_err() = "range-proof generator tables: out of device memory";
+        cudaFree(tab); cudaFree(uniform); cudaFree(ext); cudaFree(wb);
+        return DAPOL_ERR_CUDA;
+    }
     k_rp_gen_chain<<<grid_for(2 * mcap, 32), 32, 0, st>>>(mcap, uniform);
     k_rp_gen_point<<<grid_for(nb, 64), 64, 0, st>>>(ngen, uniform, ext);
     k_rp_tab_windows<W><<<grid_for(nb, 64), 64, 0, st>>>(nb, ext, wb);
@@ -111,7 +120,6 @@ static int rp_build_tables(dapol_ctx *ctx, int mcap) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(uniform); cudaFree(ext); cudaFree(wb);
-    if (ctx->rp_tab) cudaFree(ctx->rp_tab);
     ctx->rp_tab = tab;
     ctx->rp_mcap = mcap;
     return DAPOL_OK;
@@ -123,22 +131,35 @@ static int rp_ensure_tables(dapol_ctx *ctx, int m) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, ctx->stream);
+    // the old tables go first: they are being replaced, and their HBM may be what the new ones need
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->rp_tab) { cudaFree(ctx->rp_tab); ctx->rp_tab = nullptr; ctx->rp_mcap = 0; }
+    auto build = [&](int w) {
+        switch (w) {
+#define W_CASE(w_) case w_: return rp_build_tables<w_>(ctx, mc);
+            RP_W_CASES(W_CASE)
+#undef W_CASE
+        }
+        return (int)DAPOL_ERR_BAD_ARG;
+    };
+    int rc = DAPOL_ERR_CUDA;
     if (ctx->rp_W_auto) {  // widest window whose tables fit the HBM budget: fewer additions per scalar multiplication
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);  // cached scratch of earlier batches
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (ctx->rp_tab) free_b += rp_table_bytes(ctx->rp_W, ctx->rp_mcap);
-        const size_t budget = std::min<size_t>(64ull << 30, free_b / 2);
-        static const int widths[] = {16, 14, 13, 12};
-        int w = 8;
-        for (int cand : widths) if (rp_table_bytes(cand, mc) <= budget) { w = cand; break; }
-        ctx->rp_W = w;
-    }
-    int rc;
-    switch (ctx->rp_W) {
-#define W_CASE(w) case w: rc = rp_build_tables<w>(ctx, mc); break;
-        RP_W_CASES(W_CASE)
-#undef W_CASE
-        default: rc = DAPOL_ERR_BAD_ARG;
+        // up to 70 % of the free HBM (at most 128 GB): the node store of a 2^21-user shard is 16 GB, the batch scratch 6 GB
+        const size_t budget = std::min<size_t>(128ull << 30, free_b / 10 * 7);
+        static const int widths[] = {16, 15, 14, 13, 12, 8};
+        for (int cand : widths) {
+            if (cand != 8 && rp_table_bytes(cand, mc) > budget) continue;
+            ctx->rp_W = cand;
+            rc = build(cand);
+            if (rc != DAPOL_ERR_CUDA) break;
+            cudaGetLastError();  // out of memory after all (fragmentation, another context): next narrower window
+        }
+    } else {
+        rc = build(ctx->rp_W);
     }
     cudaEventRecord(b, ctx->stream);
     cudaEventSynchronize(b);
@@ -164,7 +185,7 @@ __global__ void __launch_bounds__(128) k_rp_p2(RpBatch b) {
 // MSM kernels (CTA per proof).  INL: 128-thread CTAs of the large shapes run the mixed additions with inlined products; the
 // single-warp CTAs of the small shapes share the called multiplication (see ge25519.cuh, ge_madd_inl).
 template <int W, bool INL>
-__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p3(RpBatch b) {
+__global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rp_p3(RpBatch b) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     rp_p3_partial<W, INL>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p9(RpBatch b, int rnd) {
     if (threadIdx.x == 0) { rp_st(rp_ch(b, p, CH_CL), cl); rp_st(rp_ch(b, p, CH_CR), cr); }
 }
 template <int W, bool INL>
-__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_p10(RpBatch b, int rnd) {
+__global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rp_p10(RpBatch b, int rnd) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     rp_p10_partial<W, INL>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
@@ -233,12 +254,12 @@ __global__ void __launch_bounds__(64) k_rp_v0(RpBatch b) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < b.K) rp_v0_body(b, p);
 }
-__global__ void __launch_bounds__(64) k_rp_v1(RpBatch b, int nv) {
+__global__ void __launch_bounds__(64) k_rp_v1(RpBatch b) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < b.K * nv) rp_v1_body(b, t / nv, (int)(t % nv));
+    if (t < b.K * b.vgroups) rp_v1_body(b, t / b.vgroups, (int)(t % b.vgroups));
 }
 template <int W, bool INL>
-__global__ void __launch_bounds__(RP_MSM_MAX_T) k_rp_v2(RpBatch b) {
+__global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rp_v2(RpBatch b) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     uint64_t p = blockIdx.x;
@@ -266,7 +287,7 @@ static size_t rp_per_proof_bytes(int N, int m, int lg, bool verify) {
     size_t s = sizeof(merlin) + 2 * (size_t)m * 32 + CH_COUNT * 32 + (size_t)m * 32 + 3 * 32 * 32 + 256 + 4 + 4 * 256;
     s += (size_t)N * 32 * (verify ? 2 : 3);          // ypow, svec | vecA, vecB, ypow
     if (!verify) s += 4 * (size_t)(N / 2) * 32;      // cu, cui ping-pong
-    if (verify) s += (size_t)rp_nvar(lg, m) * (128 + 32);
+    if (verify) s += (size_t)rp_nvar(lg, m) * (128 + 32 + 8 * 128);  // partial points, scalars, cached multiples
     return s;
 }
 struct RpPlan {
@@ -284,7 +305,7 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
     Arena ar;
     ar.size = Arena::need(K, sizeof(merlin)) + 3 * Arena::need(K * m, 32) + Arena::need(K * CH_COUNT, 32) + Arena::need(K * 3 * 32, 32) +
               4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * nv, 128) +
-              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4);
+              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : 0);
     CUDA_TRY(dmalloc(&pl.mem, ar.size, ctx->stream));
     ar.base = pl.mem;
     b.tr = ar.take<merlin>(K);
@@ -296,6 +317,13 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
         b.svec = ar.take<uint32_t>(K * N * 8);
         b.varpts = ar.take<uint32_t>(K * nv * 32);
         b.varsc = ar.take<uint32_t>(K * nv * 8);
+        b.vartab = ar.take<uint32_t>(K * nv * 8 * 32);
+        // threads per proof of V1: enough threads to fill the GPU for small batches, one shared doubling chain per thread
+        // (a small batch of many-point proofs ends at one point per thread, a large batch at one thread per proof)
+        int g = 1;
+        while (g < nv && K * g < 65536) g <<= 1;
+        while (g * RP_V1_PMAX < nv) g <<= 1;
+        b.vgroups = g < nv ? g : nv;
     } else {
         b.vecA = ar.take<uint32_t>(K * N * 8); b.vecB = ar.take<uint32_t>(K * N * 8);
         for (int i = 0; i < 2; i++) { b.cu[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); b.cui[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); }
@@ -392,7 +420,7 @@ static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     tm.end();
     tm.begin(0);
-    k_rp_v1<<<grid_for(K * nv, 64), 64, 0, st>>>(b, nv);
+    k_rp_v1<<<grid_for(K * b.vgroups, 64), 64, 0, st>>>(b);
     if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rp_v2<W, true><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
     else k_rp_v2<W, false><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
     tm.end();
@@ -568,7 +596,7 @@ extern "C" int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]) {
     return DAPOL_OK;
 }
 extern "C" int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window) {
-    if (!ctx || (window != 0 && window != 8 && window != 12 && window != 13 && window != 14 && window != 16)) return DAPOL_ERR_BAD_ARG;
+    if (!ctx || (window != 0 && window != 8 && window != 12 && window != 13 && window != 14 && window != 15 && window != 16)) return DAPOL_ERR_BAD_ARG;
     ctx->rp_W_auto = window == 0;
     if (window == 0) {  // the width is chosen when the tables are (re)built
         CUDA_TRY(cudaSetDevice(ctx->device));

@@ -325,8 +325,10 @@ struct RpBatch {
     uint32_t *svec;             // [K][N][8]   verifier s vector
     uint32_t *cu[2], *cui[2];   // [K][N/2][8] coefficient tables, ping-pong
     uint32_t *pts;              // [K][2][32]  extended points out of the MSM passes
-    uint32_t *varpts;           // [K][nvar][32] verifier: s_q * P_q partial points
+    uint32_t *varpts;           // [K][nvar][32] verifier: partial sums of s_q * P_q (the first vgroups entries are used)
     uint32_t *varsc;            // [K][nvar][8]  verifier: scalars of the variable points
+    uint32_t *vartab;           // [K][nvar][8][32] verifier: cached multiples 1..8 of the variable points
+    int vgroups;                // verifier: threads per proof of V1 (each runs Straus over every vgroups-th variable point)
     uint32_t *proof;            // [K][plen/4]  output (prover)
     int *status;                // [K] prover: 0 ok, else error; verifier: 1 accept / 0 reject
     // generator tables
@@ -778,24 +780,71 @@ DAPOL_HD_INLINE void rp_v0_body(const RpBatch &b, uint64_t p) {
     rp_st(rp_ch(b, p, CH_Z), z); rp_st(rp_ch(b, p, CH_MZ), mz); rp_st(rp_ch(b, p, CH_A), a); rp_st(rp_ch(b, p, CH_B), bb);
     b.status[p] = ok;
 }
-// V1 (thread per (proof, q)): decompress the q-th variable point and multiply by its scalar
-DAPOL_HD_INLINE void rp_v1_body(const RpBatch &b, uint64_t p, int q) {
-    const int lg = b.lg, m = b.m, nv = rp_nvar(lg, m);
-    const uint32_t *src;
-    if (q < 4) src = b.proof_in + p * (b.plen / 4) + 8 * q;
-    else if (q < 4 + 2 * lg) src = b.proof_in + p * (b.plen / 4) + 56 + 8 * (q - 4);
-    else src = b.coms + (p * m + (q - 4 - 2 * lg)) * 8;
-    uint32_t w[8];
-    load8(w, src);
-    ge pt, r;
-    int ok = ge_decompress(pt, w);
-    if (!ok) { b.status[p] = 0; ge_identity(r); }
-    else {
+// V1 (vgroups threads per proof): sum of s_q * P_q over the variable points q = grp, grp + vgroups, ... of the proof, by
+// Straus' interleaving -- ONE chain of 252 doublings shared by the thread's points (signed 4-bit windows over 8 cached
+// multiples per point, kept in HBM scratch) instead of one chain per point: at m = 1 (17 points) 4 threads of 4 .. 5 points
+// do 1.4 M MAC32 per proof where a thread per point did 3.0 M.  dalek's vartime multiscalar_mul does the same on the CPU
+// (Straus below 190 points).  A point that fails to decompress rejects the proof (RangeProof::verify -> Err).
+#define RP_V1_PMAX 8
+DAPOL_HD_INLINE void rp_store_cached(uint32_t *dst, const ge_cached &c) {
+    store8(dst, c.YpX.v); store8(dst + 8, c.YmX.v); store8(dst + 16, c.Z2.v); store8(dst + 24, c.T2d.v);
+}
+DAPOL_HD_INLINE void rp_load_cached(ge_cached &c, const uint32_t *src) {
+    load8(c.YpX.v, src); load8(c.YmX.v, src + 8); load8(c.Z2.v, src + 16); load8(c.T2d.v, src + 24);
+}
+DAPOL_HD_INLINE void rp_v1_body(const RpBatch &b, uint64_t p, int grp) {
+    const int lg = b.lg, m = b.m, nv = rp_nvar(lg, m), G = b.vgroups;
+    int8_t dig[RP_V1_PMAX][64];
+    int cnt = 0;
+#pragma unroll 1
+    for (int q = grp; q < nv && cnt < RP_V1_PMAX; q += G, cnt++) {
+        const uint32_t *src;
+        if (q < 4) src = b.proof_in + p * (b.plen / 4) + 8 * q;
+        else if (q < 4 + 2 * lg) src = b.proof_in + p * (b.plen / 4) + 56 + 8 * (q - 4);
+        else src = b.coms + (p * m + (q - 4 - 2 * lg)) * 8;
+        uint32_t w[8];
+        load8(w, src);
+        ge cur;
+        if (!ge_decompress(cur, w)) {
+            b.status[p] = 0;
+#pragma unroll 1
+            for (int k = 0; k < 64; k++) dig[cnt][k] = 0;
+            continue;
+        }
+        uint32_t *tb = b.vartab + (p * nv + q) * 8 * 32;
+        ge_cached c1, c;
+        ge_to_cached(c1, cur);
+        rp_store_cached(tb, c1);
+#pragma unroll 1
+        for (int i = 1; i < 8; i++) {
+            ge_cadd(cur, cur, c1, 0);
+            ge_to_cached(c, cur);
+            rp_store_cached(tb + 32 * i, c);
+        }
         sc s;
         rp_ld(s, b.varsc + (p * nv + q) * 8);
-        ge_scalarmult_var(r, s, pt);
+        int32_t d[64];
+        sc_signed_digits<4, 64>(d, s.v, 8);
+#pragma unroll 1
+        for (int k = 0; k < 64; k++) dig[cnt][k] = (int8_t)d[k];
     }
-    rp_store_ext(b.varpts + (p * nv + q) * 32, r);
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int k = 63; k >= 0; k--) {
+        if (k != 63) { ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); }
+#pragma unroll 1
+        for (int c = 0; c < cnt; c++) {
+            int dk = dig[c][k];
+            if (dk != 0) {
+                int neg = dk < 0;
+                ge_cached e;
+                rp_load_cached(e, b.vartab + ((p * nv + (uint64_t)(grp + c * G)) * 8 + (uint32_t)((neg ? -dk : dk) - 1)) * 32);
+                ge_cadd(acc, acc, e, neg);
+            }
+        }
+    }
+    rp_store_ext(b.varpts + (p * nv + grp) * 32, acc);
 }
 // V2 (CTA per proof, partial sums): the fixed-base part of the verification equation plus the variable partial points
 //   G_I: -z - a s_I      H_I: z + y^-I (z^(2+j) 2^i - b s_{N-1-I})      B, B_blinding: scalars from V0
@@ -825,13 +874,13 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
             rp_fixed_mul_acc<W, INL>(acc, b.tabH, rp_gen_of(b, I), s);
         }
     }
-    sc s;  // the B and B_blinding terms, one window per thread; the variable-base partial points, one per thread
+    sc s;  // the B and B_blinding terms, one window per thread; the partial sums of the variable points (V1), one per thread
     rp_ld(s, rp_ch(b, p, CH_SB));
     rp_fixed_mul_spread<W>(acc, b.tabB, 0, s, tid, T);
     rp_ld(s, rp_ch(b, p, CH_SBBL));
     rp_fixed_mul_spread<W>(acc, b.tabBbl, 0, s, tid, T);
 #pragma unroll 1
-    for (uint32_t t = tid; t < (uint32_t)nv; t += T) {
+    for (uint32_t t = tid; t < (uint32_t)b.vgroups; t += T) {
         ge q;
         rp_load_ext(q, b.varpts + (p * nv + t) * 32);
         ge_add(acc, acc, q);

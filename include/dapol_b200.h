@@ -195,8 +195,9 @@ DAPOL_API int dapol_rangeproof_prove_batch_dev(dapol_ctx *ctx, int nbits, int m,
                                                const uint8_t seed[32], const uint64_t *d_streams, const uint64_t *d_base_blocks, uint8_t *d_proofs);
 DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *d_proofs, uint64_t proof_len,
                                                 const uint8_t *d_commitments, uint8_t *d_ok);
-/* window (8, 12, 13, 14 or 16 bits) of the generator tables; drops tables already built.  0 (the default) = the widest
- * window whose tables fit half of the free HBM, at most 64 GB (16 bits up to m = 4 ... 14 bits at m = 32, 12 at m = 64). */
+/* window (8, 12, 13, 14, 15 or 16 bits) of the generator tables; drops tables already built.  0 (the default) = the widest
+ * window whose tables fit 70 % of the free HBM, at most 128 GB (16 bits up to m = 8 ... 15 bits at m = 32, 14 at m = 64);
+ * if the allocation fails after all, the next narrower window is tried. */
 DAPOL_API int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window);
 /* device time of the last range-proof batch on this ctx (ms): [0] total, [1] MSM passes, [2] other passes, [3] last table build */
 DAPOL_API int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]);

@@ -78,7 +78,7 @@ EX void emu_merlin_test(const uint8_t *label, uint32_t llen, const uint8_t *mlab
 
 struct Bufs {
     std::vector<merlin> tr;
-    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, varpts, varsc, proof;
+    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, varpts, varsc, vartab, proof;
     std::vector<int> status;
 };
 static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
@@ -93,12 +93,12 @@ static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
     u.tr.resize(K); u.Vc.resize(K * m * 8); u.blr.resize(K * m * 8); u.chal.resize(K * CH_COUNT * 8); u.zpow.resize(K * m * 8);
     u.mult.resize(K * 3 * 32 * 8); u.vecA.resize(K * N * 8); u.vecB.resize(K * N * 8); u.ypow.resize(K * N * 8); u.svec.resize(K * N * 8);
     u.cu0.resize(K * N / 2 * 8); u.cu1.resize(K * N / 2 * 8); u.cui0.resize(K * N / 2 * 8); u.cui1.resize(K * N / 2 * 8);
-    u.pts.resize(K * 2 * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.proof.resize(K * b.plen / 4);
+    u.pts.resize(K * 2 * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.vartab.resize(K * nv * 8 * 32); u.proof.resize(K * b.plen / 4);
     u.status.resize(K);
     b.tr = u.tr.data(); b.Vc = u.Vc.data(); b.blr = u.blr.data(); b.chal = u.chal.data(); b.zpow = u.zpow.data(); b.mult = u.mult.data();
     b.vecA = u.vecA.data(); b.vecB = u.vecB.data(); b.ypow = u.ypow.data(); b.svec = u.svec.data();
     b.cu[0] = u.cu0.data(); b.cu[1] = u.cu1.data(); b.cui[0] = u.cui0.data(); b.cui[1] = u.cui1.data();
-    b.pts = u.pts.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.proof = u.proof.data(); b.status = u.status.data();
+    b.pts = u.pts.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.vartab = u.vartab.data(); b.proof = u.proof.data(); b.status = u.status.data();
     uint64_t per = (uint64_t)NW * HALF;
     b.tabG = g_tab.tab.data();
     b.tabH = b.tabG + 64ull * g_tab.mcap * per;
@@ -185,6 +185,8 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
     return rc;
 }
 
+static int g_vgroups = 8;
+EX void emu_rp_set_vgroups(int g) { g_vgroups = g; }
 EX void emu_rp_verify(int nbits, int m, uint64_t K, const uint8_t *proofs, const uint8_t *coms, int T, uint8_t *ok) {
     RpBatch b;
     Bufs u;
@@ -195,7 +197,12 @@ EX void emu_rp_verify(int nbits, int m, uint64_t K, const uint8_t *proofs, const
     for (uint64_t p = 0; p < K; p++) rp_v0_body(b, p);
     expand(b, b.svec, 2);
     expand(b, b.ypow, 1);
-    for (uint64_t p = 0; p < K; p++) for (int q = 0; q < nv; q++) rp_v1_body(b, p, q);
+    // threads per proof of V1 as rp_plan picks them for a small batch (8, or more when a thread would exceed RP_V1_PMAX points);
+    // odd proofs exercise other group counts through the same body
+    int g = g_vgroups;
+    while (g * RP_V1_PMAX < nv) g <<= 1;
+    b.vgroups = g < nv ? g : nv;
+    for (uint64_t p = 0; p < K; p++) for (int q = 0; q < b.vgroups; q++) rp_v1_body(b, p, q);
     for (uint64_t p = 0; p < K; p++) {
         ge sum, part;
         ge_identity(sum);

@@ -49,9 +49,14 @@ def emu_verify(E, nbits, m, proofs, coms, T=3):
     K = len(proofs)
     pr = np.frombuffer(b"".join(proofs), np.uint8).copy()
     cm = np.frombuffer(b"".join(b"".join(c) for c in coms), np.uint8).copy()
-    ok = np.zeros(K, np.uint8)
-    E.emu_rp_verify(nbits, m, C.c_uint64(K), pr.ctypes.data_as(C.c_void_p), cm.ctypes.data_as(C.c_void_p), T, ok.ctypes.data_as(C.c_void_p))
-    return [bool(x) for x in ok]
+    res = None
+    for groups in (8, 1, 4):  # threads per proof of V1 (Straus over every groups-th variable point): same verdicts
+        ok = np.zeros(K, np.uint8)
+        E.emu_rp_set_vgroups(groups)
+        E.emu_rp_verify(nbits, m, C.c_uint64(K), pr.ctypes.data_as(C.c_void_p), cm.ctypes.data_as(C.c_void_p), T, ok.ctypes.data_as(C.c_void_p))
+        assert res is None or res == [bool(x) for x in ok]
+        res = [bool(x) for x in ok]
+    return res
 
 
 def test_generators_and_tables(E, cref):
