@@ -36,17 +36,18 @@ MAC32_LEAF, MAC32_PAD, MAC32_MERGE = 53.6e3, 45.5e3, 13.9e3
 
 def executed_mac32(comb_window, node_batch):
     """Field-arithmetic MAC32 the kernels here execute per unit: fixed-base comb on half points
-    (253/W + 1 mixed additions of 7 FM for a 253-bit scalar, 64/W + 1 for a 64-bit value), batched double-and-compress
-    (prepare 4 FS + 5 FM, 3 FM of Montgomery's trick, finish 11 FM, one inversion of 254 FS + 11 FM per node_batch nodes).
+    (253/W + 1 windows for a 253-bit scalar, 64/WV + 1 for a 64-bit value; the first window initialises the accumulator
+    with one product, every other one is a mixed addition of 7 FM), batched double-and-compress (prepare 4 FS + 5 FM, 3 FM of
+    Montgomery's trick, finish 11 FM, one inversion of 254 FS + 11 FM per node_batch nodes).
     roofline.frac uses these; survey_unit_frac uses SURVEY 8(d)'s figures for the reference's algorithm."""
     FM, FS, SCMUL = 72, 44, 128
     madd, full_add = 7 * FM, 9 * FM
     compress = (4 * FS + 5 * FM) + 3 * FM + 11 * FM + (254 * FS + 11 * FM) / node_batch
-    value_window = comb_window if comb_window <= 16 else 22      # comb_value_window in tree_kernels.cuh
+    value_window = comb_window if comb_window <= 16 else 22      # comb_value_window in ge25519.cuh
     nwr, nwv = 253 // comb_window + 1, 64 // value_window + 1
-    pad = nwr * madd + 3 * SCMUL + compress          # ChaCha draw -> wide reduce, halve; comb; compress
-    leaf = (nwr + nwv) * madd + SCMUL + compress     # halve r; two combs; compress
-    merge = full_add + 2 * SCMUL + compress          # point add; r_L + r_R mod l; compress
+    pad = (nwr - 1) * madd + FM + 3 * SCMUL + compress          # ChaCha draw -> wide reduce, halve; comb; compress
+    leaf = (nwr + nwv - 1) * madd + FM + SCMUL + compress       # halve r; two combs; compress
+    merge = full_add + 2 * SCMUL + compress                     # point add; r_L + r_R mod l; compress
     return leaf, pad, merge
 NODE_BYTES = 104  # com 32 + hash 32 + v 8 + r 32
 
@@ -373,9 +374,11 @@ def main():
         achieved = pads * MAC32_PAD_EXEC / (med["padding"] * 1e-3) / 1e9  # GMAC32/s
         build_exec = leaves_here * MAC32_LEAF_EXEC + pads * MAC32_PAD_EXEC + internal * MAC32_MERGE_EXEC
         build_survey = leaves_here * MAC32_LEAF + pads * MAC32_PAD + internal * MAC32_MERGE
-        prof = {}
+        traffic = None  # DRAM bytes of one k_pad launch from the committed ncu --set full capture, if it is of this workload
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "k_pad_traffic.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01d_k_pad_ncu_full.json")))["launches"][0]
+            if int(cap["units_in_launch"]) == int(pads) and params["comb_window"] == 24:
+                traffic = cap["dram_bytes_per_launch"]
         except Exception:
             pass
         line = {
@@ -397,7 +400,7 @@ def main():
                          "algorithmic_mac32_per_launch": pads * MAC32_PAD_EXEC, "mac32_per_pad_executed": MAC32_PAD_EXEC,
                          "launch_ms": med["padding"],
                          "survey_unit_frac": pads * MAC32_PAD / (med["padding"] * 1e-3) / 1e9 / imad_peak,
-                         "traffic": prof.get("dram_bytes_per_launch"),
+                         "traffic": traffic,
                          "whole_build_frac": build_exec / (med["total"] * 1e-3) / 1e9 / imad_peak,
                          "whole_build_survey_unit_frac": build_survey / (med["total"] * 1e-3) / 1e9 / imad_peak,
                          "fe_mul_Gop_s": fe_rate[0], "fe_sq_Gop_s": fe_rate[1],

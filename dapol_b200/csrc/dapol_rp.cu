@@ -249,6 +249,34 @@ __global__ void __launch_bounds__(128) k_rp_p12(RpBatch b, int rnd, uint32_t cnt
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < b.K * cnt) rp_p12_body(b, t / cnt, rnd, (uint32_t)(t % cnt));
 }
+// hybrid rounds of the large aggregates (rp_kernels.cuh): materialise the folded generators, variable-base L / R, fold
+template <int W>
+__global__ void __launch_bounds__(64, 8) k_rp_pm(RpBatch b, int s) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * 2 * RP_FOLD_N) rp_pm_body<W, false>(b, t / (2 * RP_FOLD_N), (int)((t / RP_FOLD_N) & 1), (uint32_t)(t % RP_FOLD_N), s);
+}
+template <int W>
+__global__ void __launch_bounds__(128) k_rp_pv(RpBatch b, int rnd) {
+    const uint32_t g = 2u * ((uint32_t)b.N >> rnd);  // terms per (proof, L|R): a power of two <= 32, so groups never straddle a warp
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t pw = idx / g;
+    uint32_t t = (uint32_t)(idx % g);
+    ge acc;
+    if (pw < 2 * b.K) rp_pv_partial<W>(acc, b, pw >> 1, rnd, (int)(pw & 1), t, g);
+    else ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t d = g >> 1; d > 0; d >>= 1) {  // segmented reduction inside the group
+        ge o;
+        shfl_down_ge(o, acc, (int)d);
+        ge_add(acc, acc, o);
+    }
+    if (pw < 2 * b.K && t == 0) rp_store_point(b, pw >> 1, (int)(pw & 1), acc);
+}
+__global__ void __launch_bounds__(64) k_rp_pf(RpBatch b, int rnd) {
+    const uint32_t h = (uint32_t)b.N >> rnd;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < b.K * 2 * h) rp_pf_body(b, t / (2 * h), rnd, (int)((t / h) & 1), (uint32_t)(t % h));
+}
 // ------------------------------------------------------------------------------------------------ verifier kernels
 __global__ void __launch_bounds__(64) k_rp_v0(RpBatch b) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,7 +314,7 @@ extern "C" uint64_t dapol_rangeproof_size(int nbits, int m) {
 static size_t rp_per_proof_bytes(int N, int m, int lg, bool verify) {
     size_t s = sizeof(merlin) + 2 * (size_t)m * 32 + CH_COUNT * 32 + (size_t)m * 32 + 3 * 32 * 32 + 256 + 4 + 4 * 256;
     s += (size_t)N * 32 * (verify ? 2 : 3);          // ypow, svec | vecA, vecB, ypow
-    if (!verify) s += 4 * (size_t)(N / 2) * 32;      // cu, cui ping-pong
+    if (!verify) s += 4 * (size_t)(N / 2) * 32 + 2 * RP_FOLD_N * 128;  // cu, cui ping-pong; folded generators
     if (verify) s += (size_t)rp_nvar(lg, m) * (128 + 32 + 8 * 128);  // partial points, scalars, cached multiples
     return s;
 }
@@ -305,7 +333,7 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
     Arena ar;
     ar.size = Arena::need(K, sizeof(merlin)) + 3 * Arena::need(K * m, 32) + Arena::need(K * CH_COUNT, 32) + Arena::need(K * 3 * 32, 32) +
               4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * nv, 128) +
-              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : 0);
+              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : Arena::need(K * 2 * RP_FOLD_N, 128));
     CUDA_TRY(dmalloc(&pl.mem, ar.size, ctx->stream));
     ar.base = pl.mem;
     b.tr = ar.take<merlin>(K);
@@ -328,6 +356,7 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
         b.vecA = ar.take<uint32_t>(K * N * 8); b.vecB = ar.take<uint32_t>(K * N * 8);
         for (int i = 0; i < 2; i++) { b.cu[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); b.cui[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); }
         b.pts = ar.take<uint32_t>(K * 2 * 32);
+        b.gfold = ar.take<uint32_t>(K * 2 * RP_FOLD_N * 32);
         b.proof = ar.take<uint32_t>(K * b.plen / 4);
     }
     b.status = ar.take<int>(K);
@@ -391,13 +420,16 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     tm.end();
     ctx->launches += 10;
+    const int sw = rp_switch_round(b.N, b.lg);  // first round over folded generators (large aggregates), else lg + 1
     for (int rnd = 1; rnd <= b.lg; rnd++) {
         uint32_t h = (uint32_t)(N >> rnd), cnt = std::max<uint32_t>(h, 1u << (rnd - 1));
         tm.begin(1);
         k_rp_p9<<<(unsigned)K, msm_threads(h), 0, st>>>(b, rnd);
         tm.end();
         tm.begin(0);
-        if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
+        if (rnd == sw) { k_rp_pm<W><<<grid_for(K * 2 * RP_FOLD_N, 64), 64, 0, st>>>(b, sw); ctx->launches++; }
+        if (rnd >= sw) k_rp_pv<W><<<grid_for(K * 4 * h, 128), 128, 0, st>>>(b, rnd);
+        else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
         else k_rp_p10<W, false><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
         tm.end();
         tm.begin(1);
@@ -405,6 +437,12 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         k_rp_p12<<<grid_for(K * cnt, 128), 128, 0, st>>>(b, rnd, cnt);
         tm.end();
         ctx->launches += 4;
+        if (rnd >= sw && rnd < b.lg) {
+            tm.begin(0);
+            k_rp_pf<<<grid_for(K * 2 * h, 64), 64, 0, st>>>(b, rnd);
+            tm.end();
+            ctx->launches++;
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return DAPOL_OK;

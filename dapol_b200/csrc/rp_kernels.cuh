@@ -297,6 +297,39 @@ DAPOL_HD_INLINE void ge_scalarmult_var(ge &r, const sc &s, const ge &p) {
     r = acc;
 }
 
+// r = s1 * P1 + s2 * P2 (Straus: one doubling chain for both, signed 4-bit windows over 8 cached multiples each)
+DAPOL_HD_INLINE void ge_double_scalarmult_var(ge &r, const sc &s1, const ge &p1, const sc &s2, const ge &p2) {
+    ge_cached tb[2][8];
+#pragma unroll 1
+    for (int j = 0; j < 2; j++) {
+        ge cur = j ? p2 : p1;
+        ge_to_cached(tb[j][0], cur);
+#pragma unroll 1
+        for (int i = 1; i < 8; i++) {
+            ge_cadd(cur, cur, tb[j][0], 0);
+            ge_to_cached(tb[j][i], cur);
+        }
+    }
+    int32_t d[2][64];
+    sc_signed_digits<4, 64>(d[0], s1.v, 8);
+    sc_signed_digits<4, 64>(d[1], s2.v, 8);
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int k = 63; k >= 0; k--) {
+        if (k != 63) { ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); ge_dbl(acc, acc); }
+#pragma unroll 1
+        for (int j = 0; j < 2; j++) {
+            int32_t dk = d[j][k];
+            if (dk != 0) {
+                int neg = dk < 0;
+                ge_cadd(acc, acc, tb[j][(neg ? -dk : dk) - 1], neg);
+            }
+        }
+    }
+    r = acc;
+}
+
 // ------------------------------------------------------------------------------------------------ batch layout
 // Scalars are 8 LE words, canonical unless noted.  Per-proof challenge slots (RpBatch::chal, CH_* below).
 enum {
@@ -325,6 +358,7 @@ struct RpBatch {
     uint32_t *svec;             // [K][N][8]   verifier s vector
     uint32_t *cu[2], *cui[2];   // [K][N/2][8] coefficient tables, ping-pong
     uint32_t *pts;              // [K][2][32]  extended points out of the MSM passes
+    uint32_t *gfold;            // [K][2][RP_FOLD_N][32] folded generators G^(k), H^(k) of the variable-base rounds (extended)
     uint32_t *varpts;           // [K][nvar][32] verifier: partial sums of s_q * P_q (the first vgroups entries are used)
     uint32_t *varsc;            // [K][nvar][8]  verifier: scalars of the variable points
     uint32_t *vartab;           // [K][nvar][8][32] verifier: cached multiples 1..8 of the variable points
@@ -676,6 +710,78 @@ DAPOL_HD_INLINE void rp_p12_body(const RpBatch &b, uint64_t p, int rnd, uint32_t
         sc_mul(r, c, u); rp_st(b.cui[nxt] + (p * half + 2 * i) * 8, r);
         sc_mul(r, c, ui); rp_st(b.cui[nxt] + (p * half + 2 * i + 1) * 8, r);
     }
+}
+
+// ---- hybrid inner-product argument for the large aggregates (N >= RP_HYBRID_MIN_N) --------------------------------------
+// A round over the ORIGINAL generators costs 2N fixed-base multiplications whatever the round; bulletproofs' own rounds
+// over the FOLDED generators cost 4 * N / 2^(k-1) variable-base ones (L, R and the folding of G, H).  A variable-base
+// multiplication is ~19 fixed-base ones, so the late rounds are cheaper folded: the rounds switch when the vectors are
+// RP_FOLD_N = 32 long (round lg - 4).  PM materialises the folded generators of that round -- still fixed-base:
+// G^(s)_j = sum_pfx cu[pfx] G_(pfx, j), H^(s)_j = sum_pfx y^-I cui[pfx] H_(pfx, j) -- and the remaining rounds are the
+// textbook ones (PV: L, R by variable-base multiplications; PF: G' = u^-1 G_lo + u G_hi, H' = u H_lo + u^-1 H_hi).  The
+// group elements L_k, R_k are the same, so the proof bytes are too.  At N = 2048 (m = 32): 16 N fixed-base + 184 variable-
+// base multiplications per proof instead of 22 N fixed-base ones.
+#define RP_FOLD_N 32
+#ifndef RP_HYBRID_MIN_N
+#define RP_HYBRID_MIN_N 1024
+#endif
+// first variable-base round (1-based), or lg + 1 when every round runs over the original generators
+DAPOL_HD_INLINE int rp_switch_round(int N, int lg) { return N >= RP_HYBRID_MIN_N ? lg - 4 : lg + 1; }
+DAPOL_HD_INLINE uint32_t *rp_gfold(const RpBatch &b, uint64_t p, int which, uint32_t j) { return b.gfold + ((p * 2 + which) * RP_FOLD_N + j) * 32; }
+// PM (thread per (proof, G|H, j < RP_FOLD_N)) at the switch round s
+template <int W, bool INL = false>
+DAPOL_HD_INLINE void rp_pm_body(const RpBatch &b, uint64_t p, int which, uint32_t j, int s) {
+    const uint32_t N = (uint32_t)b.N, half = N / 2, npfx = 1u << (s - 1);
+    const int cur = (s - 1) & 1, shj = b.lg - s + 1;  // log2 of the folded length
+    const uint32_t *co = (which ? b.cui[cur] : b.cu[cur]) + p * half * 8;
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint32_t pfx = 0; pfx < npfx; pfx++) {
+        uint32_t I = (pfx << shj) | j;
+        sc c;
+        rp_ld(c, co + pfx * 8);
+        if (which) {
+            sc y;
+            rp_ld(y, b.ypow + (p * N + I) * 8);
+            sc_mul(c, c, y);
+        }
+        rp_fixed_mul_acc<W, INL>(acc, which ? b.tabH : b.tabG, rp_gen_of(b, I), c);
+    }
+    rp_store_ext(rp_gfold(b, p, which, j), acc);
+}
+// PV (thread per (proof, L|R, t < 2h), h = N >> rnd): term t of
+//   L = <a_lo, G_hi> + <b_hi, H_lo> + c_L w B      R = <a_hi, G_lo> + <b_lo, H_hi> + c_R w B
+// plus this thread's windows of the B term; the 2h partial points of a (proof, L|R) are summed by the caller
+template <int W>
+DAPOL_HD_INLINE void rp_pv_partial(ge &acc, const RpBatch &b, uint64_t p, int rnd, int which, uint32_t t, uint32_t g) {
+    const uint32_t N = (uint32_t)b.N, h = N >> rnd;
+    sc s, c;
+    ge pt;
+    if (t < h) {
+        rp_ld(s, b.vecA + (p * N + (which ? h + t : t)) * 8);
+        rp_load_ext(pt, rp_gfold(b, p, 0, which ? t : h + t));
+    } else {
+        uint32_t tt = t - h;
+        rp_ld(s, b.vecB + (p * N + (which ? tt : h + tt)) * 8);
+        rp_load_ext(pt, rp_gfold(b, p, 1, which ? h + tt : tt));
+    }
+    ge_scalarmult_var(acc, s, pt);
+    rp_ld(s, rp_ch(b, p, which ? CH_CR : CH_CL));
+    rp_ld(c, rp_ch(b, p, CH_W));
+    sc_mul(s, s, c);
+    rp_fixed_mul_spread<W>(acc, b.tabB, 0, s, t, g);
+}
+// PF (thread per (proof, G|H, i < h)) after the round's challenge: fold the generators in place
+DAPOL_HD_INLINE void rp_pf_body(const RpBatch &b, uint64_t p, int rnd, int which, uint32_t i) {
+    const uint32_t h = (uint32_t)b.N >> rnd;
+    sc u, ui;
+    rp_ld(u, rp_ch(b, p, CH_U)); rp_ld(ui, rp_ch(b, p, CH_UINV));
+    ge lo, hi, r;
+    rp_load_ext(lo, rp_gfold(b, p, which, i)); rp_load_ext(hi, rp_gfold(b, p, which, h + i));
+    if (which) ge_double_scalarmult_var(r, u, lo, ui, hi);
+    else ge_double_scalarmult_var(r, ui, lo, u, hi);
+    rp_store_ext(rp_gfold(b, p, which, i), r);
 }
 
 // ------------------------------------------------------------------------------------------------ verifier passes

@@ -7,6 +7,10 @@
 #include <cstring>
 #include <map>
 #include <vector>
+// the switch to the folded-generator rounds (hybrid inner-product argument) is a run-time knob here, so that the small
+// shapes a CPU can afford exercise both the original-generator rounds and the hybrid ones
+static int g_hybrid_min_n = 1024;
+#define RP_HYBRID_MIN_N g_hybrid_min_n
 #include "../../dapol_b200/csrc/rp_kernels.cuh"
 
 #define EX extern "C" __attribute__((visibility("default")))
@@ -78,7 +82,7 @@ EX void emu_merlin_test(const uint8_t *label, uint32_t llen, const uint8_t *mlab
 
 struct Bufs {
     std::vector<merlin> tr;
-    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, varpts, varsc, vartab, proof;
+    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, varpts, varsc, vartab, gfold, proof;
     std::vector<int> status;
 };
 static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
@@ -93,12 +97,12 @@ static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
     u.tr.resize(K); u.Vc.resize(K * m * 8); u.blr.resize(K * m * 8); u.chal.resize(K * CH_COUNT * 8); u.zpow.resize(K * m * 8);
     u.mult.resize(K * 3 * 32 * 8); u.vecA.resize(K * N * 8); u.vecB.resize(K * N * 8); u.ypow.resize(K * N * 8); u.svec.resize(K * N * 8);
     u.cu0.resize(K * N / 2 * 8); u.cu1.resize(K * N / 2 * 8); u.cui0.resize(K * N / 2 * 8); u.cui1.resize(K * N / 2 * 8);
-    u.pts.resize(K * 2 * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.vartab.resize(K * nv * 8 * 32); u.proof.resize(K * b.plen / 4);
+    u.pts.resize(K * 2 * 32); u.gfold.resize(K * 2 * RP_FOLD_N * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.vartab.resize(K * nv * 8 * 32); u.proof.resize(K * b.plen / 4);
     u.status.resize(K);
     b.tr = u.tr.data(); b.Vc = u.Vc.data(); b.blr = u.blr.data(); b.chal = u.chal.data(); b.zpow = u.zpow.data(); b.mult = u.mult.data();
     b.vecA = u.vecA.data(); b.vecB = u.vecB.data(); b.ypow = u.ypow.data(); b.svec = u.svec.data();
     b.cu[0] = u.cu0.data(); b.cu[1] = u.cu1.data(); b.cui[0] = u.cui0.data(); b.cui[1] = u.cui1.data();
-    b.pts = u.pts.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.vartab = u.vartab.data(); b.proof = u.proof.data(); b.status = u.status.data();
+    b.pts = u.pts.data(); b.gfold = u.gfold.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.vartab = u.vartab.data(); b.proof = u.proof.data(); b.status = u.status.data();
     uint64_t per = (uint64_t)NW * HALF;
     b.tabG = g_tab.tab.data();
     b.tabH = b.tabG + 64ull * g_tab.mcap * per;
@@ -128,6 +132,7 @@ static void comb_entry(uint64_t t, ge_niels *table, int nw, int which) {  // sam
     table[t] = n;
 }
 
+EX void emu_rp_set_hybrid_min_n(int n) { g_hybrid_min_n = n; }
 EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const uint8_t *blindings, const uint8_t seed[32],
                     const uint64_t *stream, const uint64_t *base_block, int T, uint8_t *out) {
     RpBatch b;
@@ -166,6 +171,7 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
     for (uint64_t p = 0; p < K; p++) rp_p7_body(b, p);
     for (uint64_t p = 0; p < K; p++) for (uint32_t k = 0; k < N; k++) rp_p8_body(b, p, k);
     expand(b, b.ypow, 1);
+    const int sw = rp_switch_round(b.N, b.lg);
     for (int rnd = 1; rnd <= b.lg; rnd++) {
         for (uint64_t p = 0; p < K; p++) {
             sc cl, cr, a0, a1;
@@ -173,11 +179,25 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
             for (int t = 0; t < T; t++) { rp_p9_partial(a0, a1, b, p, rnd, (uint32_t)t, (uint32_t)T); sc_add(cl, cl, a0); sc_add(cr, cr, a1); }
             rp_st(rp_ch(b, p, CH_CL), cl); rp_st(rp_ch(b, p, CH_CR), cr);
         }
-        msm([&](ge &acc, uint64_t p, int which, uint32_t t) { rp_p10_partial<W>(acc, b, p, rnd, which, t, (uint32_t)T); });
-        for (uint64_t p = 0; p < K; p++) rp_p11_body(b, p, rnd);
         uint32_t h = N >> rnd, cnt = h > (1u << (rnd - 1)) ? h : (1u << (rnd - 1));
+        if (rnd == sw)
+            for (uint64_t p = 0; p < K; p++) for (int which = 0; which < 2; which++) for (uint32_t j = 0; j < RP_FOLD_N; j++) rp_pm_body<W>(b, p, which, j, sw);
+        if (rnd >= sw) {
+            for (uint64_t p = 0; p < K; p++)
+                for (int which = 0; which < 2; which++) {
+                    ge sum, part;
+                    ge_identity(sum);
+                    for (uint32_t t = 0; t < 2 * h; t++) { rp_pv_partial<W>(part, b, p, rnd, which, t, 2 * h); ge_add(sum, sum, part); }
+                    rp_store_point(b, p, which, sum);
+                }
+        } else {
+            msm([&](ge &acc, uint64_t p, int which, uint32_t t) { rp_p10_partial<W>(acc, b, p, rnd, which, t, (uint32_t)T); });
+        }
+        for (uint64_t p = 0; p < K; p++) rp_p11_body(b, p, rnd);
         // a thread reads a[i], a[h+i] and writes a[i]; table growth reads cur, writes nxt: any order is fine
         for (uint64_t p = 0; p < K; p++) for (uint32_t i = 0; i < cnt; i++) rp_p12_body(b, p, rnd, i);
+        if (rnd >= sw && rnd < b.lg)
+            for (uint64_t p = 0; p < K; p++) for (int which = 0; which < 2; which++) for (uint32_t i = 0; i < h; i++) rp_pf_body(b, p, rnd, which, i);
     }
     memcpy(out, b.proof, K * b.plen);
     int rc = 0;

@@ -39,10 +39,18 @@ def emu_prove(E, nbits, values, blindings, streams, bases, T=3):
     lg = (nbits * m).bit_length() - 1
     plen = 32 * (9 + 2 * lg)
     out = np.zeros(K * plen, np.uint8)
-    rc = E.emu_rp_prove(nbits, m, C.c_uint64(K), vals.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), B(SEED),
-                        st.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p), T, out.ctypes.data_as(C.c_void_p))
-    assert rc == 0
-    return [out[i * plen:(i + 1) * plen].tobytes() for i in range(K)]
+    res = None
+    # all rounds over the original generators, then (N >= 32) the hybrid rounds over folded generators: identical bytes
+    for hybrid_min_n in (1 << 30, 32):
+        E.emu_rp_set_hybrid_min_n(hybrid_min_n)
+        rc = E.emu_rp_prove(nbits, m, C.c_uint64(K), vals.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), B(SEED),
+                            st.ctypes.data_as(C.c_void_p), bs.ctypes.data_as(C.c_void_p), T, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        got = [out[i * plen:(i + 1) * plen].tobytes() for i in range(K)]
+        assert res is None or res == got, "hybrid inner-product rounds changed the proof bytes"
+        res = got
+    E.emu_rp_set_hybrid_min_n(1024)
+    return res
 
 
 def emu_verify(E, nbits, m, proofs, coms, T=3):
