@@ -68,6 +68,7 @@ def main():
     w = mine[:min(64, len(mine))].copy()
     assert L.dapol_prove_batch(tree.subtree, len(w), p(w), H, policy, sd, p(out), out.nbytes, C.byref(got)) == 0, L.dapol_last_cuda_error()
     prove_s = verify_s = 0.0
+    chunk_times = []
     n_ok = n_done = 0
     tampered_rejected = None
     barrier(); t_all = time.perf_counter()
@@ -84,6 +85,7 @@ def main():
         assert rc == 0, rc
         t4 = time.perf_counter()
         prove_s += t2 - t1; verify_s += t4 - t3
+        chunk_times.append((round(t2 - t1, 4), round(t3 - t2, 4), round(t4 - t3, 4)))
         n_ok += int(ok[:k].sum()); n_done += k
         if s == 0:  # one tampered proof must be rejected
             bad = out[:size].copy(); bad[100] ^= 1
@@ -102,7 +104,7 @@ def main():
             "n_gpus": world, "proofs": done, "all_verified": okc == done, "tampered_rejected": tampered_rejected, "proof_bytes": int(size),
             "tree_build_s_e2e": build_s, "prove_s_max_rank": mx[0].item(), "verify_s_max_rank": mx[1].item(), "prove_plus_verify_wall_s": mx[2].item(),
             "prove_per_s": done / mx[0].item(), "verify_per_s": done / mx[1].item(), "prove_plus_verify_per_s": done / mx[2].item(),
-            "root": root.com.hex()[:16], "chunk": chunk,
+            "root": root.com.hex()[:16], "chunk": chunk, "rank0_chunk_s_prove_paths_verify": chunk_times[:3] + chunk_times[-2:],
             "timing": "wall clock between barrier + synchronize pairs, max over ranks; host buffers (proofs D2H after prove, H2D for verify)"}), flush=True)
     tree.close(); ctx.close()
     if world > 1:
