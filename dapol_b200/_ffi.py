@@ -45,6 +45,7 @@ def lib():
     L.dapol_tree_attach_top.argtypes = [vp, vp, u64]
     L.dapol_tree_root.argtypes = [vp, vp, vp, C.POINTER(u64), vp]
     L.dapol_tree_height.argtypes = [vp]
+    L.dapol_tree_hash_id.argtypes = [vp]
     L.dapol_tree_num_nodes.argtypes = [vp]
     L.dapol_tree_num_nodes.restype = u64
     L.dapol_tree_num_padding.argtypes = [vp]
@@ -65,6 +66,9 @@ def lib():
     L.dapol_inclusion_proof_size.restype = u64
     L.dapol_prove_batch.argtypes = [vp, u64, vp, u64, C.c_int, vp, vp, u64, C.POINTER(u64)]
     L.dapol_verify_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, vp]
+    L.dapol_tree_save.argtypes = [vp, C.c_char_p]
+    L.dapol_tree_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.dapol_prove_to_file.argtypes = [vp, u64, vp, u64, C.c_int, vp, u64, C.c_char_p, C.POINTER(u64)]
     L.dapol_rangeproof_size.argtypes = [C.c_int, C.c_int]
     L.dapol_rangeproof_size.restype = u64
     L.dapol_rangeproof_prove_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp]

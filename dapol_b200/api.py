@@ -9,6 +9,7 @@ over the C ABI.  Names, argument meaning and error behaviour follow the referenc
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -20,7 +21,7 @@ POLICY_PADDING, POLICY_SPLITTING = 0, 1
 MAX_TREE_HEIGHT = 64
 
 _ERR_NAMES = {1: "TreeHeightTooBig", 2: "SparsityTooSmall", 3: "InvalidDigestSize", 4: "DuplicatedInternalId",
-              5: "FailedToMapIndex", 16: "BadArgument", 17: "NotFound", 18: "BufferTooSmall", 19: "Cuda", 20: "Decode"}
+              5: "FailedToMapIndex", 16: "BadArgument", 17: "NotFound", 18: "BufferTooSmall", 19: "Cuda", 20: "Decode", 21: "Io"}
 
 
 class DapolError(Exception):
@@ -281,6 +282,31 @@ class Dapol:
             return None
         _check(rc)
         return x.value
+
+    # -- persistence (no reference counterpart: the crate keeps the tree in memory only) ------------
+    def save(self, path: str):
+        """Whole node store + slot maps + id -> leaf-index map to one file (holds the secret blindings)."""
+        _check(_ffi.lib().dapol_tree_save(self._t, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, ctx, path: str, aggregation_factor: int, policy: int = POLICY_PADDING):
+        """The saved tree back in HBM on `ctx`: same levels, paths and inclusion proofs as the tree that was saved."""
+        h = C.c_void_p()
+        _check(_ffi.lib().dapol_tree_load(ctx._h, os.fsencode(path), C.byref(h)))
+        L = _ffi.lib()
+        self = cls(ctx, 0, L.dapol_tree_height(h), aggregation_factor, policy)
+        self._t = h
+        self.hash_id = int(L.dapol_tree_hash_id(h))
+        return self
+
+    def generate_proofs_to_file(self, leaf_idx, seed: bytes, path: str, chunk: int = 0) -> int:
+        """Dapol::generate_proof for every index, streamed to `path` (mod.rs:250 TODO); returns the size of one proof."""
+        li = np.ascontiguousarray(leaf_idx, np.uint64)
+        size = C.c_uint64()
+        sd = (C.c_uint8 * 32).from_buffer_copy(seed)
+        _check(_ffi.lib().dapol_prove_to_file(self._t, len(li), _p(li), self.aggregation_factor, self.policy, sd, chunk, os.fsencode(path),
+                                              C.byref(size)))
+        return size.value
 
     def _free(self):
         if getattr(self, "_t", None):

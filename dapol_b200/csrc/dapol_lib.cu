@@ -1,6 +1,7 @@
 // dapol_b200 C-ABI library: CUDA kernels (sm_100a) + host orchestration for the DAPOL+ hot path.
 // Interface: include/dapol_b200.h.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +31,7 @@ extern "C" const char *dapol_strerror(int code) {
         case DAPOL_ERR_BUFFER: return "buffer too small";
         case DAPOL_ERR_CUDA: return "CUDA error";
         case DAPOL_ERR_DECODE: return "decoding error";
+        case DAPOL_ERR_IO: return "file cannot be opened, read or written, or is not a tree file";
     }
     return "unknown";
 }
@@ -1007,8 +1009,152 @@ extern "C" int dapol_tree_attach_top(dapol_tree *t, const dapol_tree *top, uint6
     return DAPOL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ persistence
+namespace {
+constexpr char TREE_MAGIC[8] = {'D', 'A', 'P', 'O', 'L', 'T', '0', '1'};
+constexpr size_t IO_CHUNK = 64u << 20;
+struct TreeFileHeader {  // little-endian, 64 bytes
+    char magic[8];
+    uint32_t version;
+    int32_t hash_id, height;
+    uint32_t flags;  // bit 0: id -> leaf-index map present
+    uint64_t n_leaves, T, n_pads, pos_words;
+    uint64_t reserved;
+};
+static_assert(sizeof(TreeFileHeader) == 64, "tree file header layout");
+struct PinnedBuf {
+    void *p = nullptr;
+    PinnedBuf() { if (cudaMallocHost(&p, IO_CHUNK) != cudaSuccess) p = nullptr; }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
+// device array -> file / file -> device array through a pinned staging buffer
+int dev_to_file(FILE *f, const void *d, size_t bytes, PinnedBuf &buf, cudaStream_t st) {
+    const uint8_t *src = static_cast<const uint8_t *>(d);
+    for (size_t off = 0; off < bytes; off += IO_CHUNK) {
+        size_t n = std::min(IO_CHUNK, bytes - off);
+        CUDA_TRY(cudaMemcpyAsync(buf.p, src + off, n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (fwrite(buf.p, 1, n, f) != n) return DAPOL_ERR_IO;
+    }
+    return DAPOL_OK;
+}
+int file_to_dev(FILE *f, void *d, size_t bytes, PinnedBuf &buf, cudaStream_t st) {
+    uint8_t *dst = static_cast<uint8_t *>(d);
+    for (size_t off = 0; off < bytes; off += IO_CHUNK) {
+        size_t n = std::min(IO_CHUNK, bytes - off);
+        if (fread(buf.p, 1, n, f) != n) return DAPOL_ERR_IO;
+        CUDA_TRY(cudaMemcpyAsync(dst + off, buf.p, n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return DAPOL_OK;
+}
+// words of the slot-map allocation (tree_build_dev's layout: 64-word aligned pieces for levels 1..H)
+uint64_t pos_words_of(const std::vector<uint64_t> &n_real, int H, std::vector<uint64_t> *pos_off) {
+    std::vector<uint64_t> off(H + 2, 0);
+    for (int h = 1; h <= H; h++) off[h + 1] = off[h] + ((n_real[h] + 63) & ~63ull);
+    if (pos_off) *pos_off = off;
+    return off[H + 1] + 64;
+}
+}  // namespace
+
+extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
+    if (!t || !path) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(t->ctx->device));
+    cudaStream_t st = t->ctx->stream;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    PinnedBuf buf;
+    if (!buf.p) { g_cuda_err = "cudaMallocHost failed"; return DAPOL_ERR_CUDA; }
+    FILE *f = fopen(path, "wb");
+    if (!f) return DAPOL_ERR_IO;
+    const int H = t->height;
+    const uint64_t T = t->T;
+    TreeFileHeader h = {};
+    memcpy(h.magic, TREE_MAGIC, 8);
+    h.version = 1; h.hash_id = t->hash_id; h.height = H; h.flags = t->leaf_index_of ? 1u : 0u;
+    h.n_leaves = t->n_leaves; h.T = T; h.n_pads = t->n_pads; h.pos_words = pos_words_of(t->n_real, H, nullptr);
+    int rc = DAPOL_OK;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+    for (int l = 0; l <= H && ok; l++) {
+        uint64_t row[4] = {t->level_off[l], t->level_n[l], t->n_real[l], t->npads[l]};
+        ok = fwrite(row, sizeof row, 1, f) == 1;
+    }
+    ok = ok && fwrite(t->root_ext, sizeof t->root_ext, 1, f) == 1;
+    if (!ok) rc = DAPOL_ERR_IO;
+    const struct { const void *p; size_t bytes; } parts[] = {
+        {t->ns.idx, T * 8}, {t->ns.v, T * 8}, {t->ns.r, T * 32}, {t->ns.comc, T * 32}, {t->ns.hash, T * 32}, {t->ns.is_pad, T},
+        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, t->leaf_index_of ? t->n_leaves * 8 : 0}};
+    for (const auto &pt : parts)
+        if (rc == DAPOL_OK && pt.bytes) rc = dev_to_file(f, pt.p, pt.bytes, buf, st);
+    if (rc == DAPOL_OK && fwrite(TREE_MAGIC, 8, 1, f) != 1) rc = DAPOL_ERR_IO;  // trailer: a truncated file does not load
+    if (fclose(f) != 0 && rc == DAPOL_OK) rc = DAPOL_ERR_IO;
+    return rc;
+}
+extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **out) {
+    if (!ctx || !path || !out) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    PinnedBuf buf;
+    if (!buf.p) { g_cuda_err = "cudaMallocHost failed"; return DAPOL_ERR_CUDA; }
+    FILE *f = fopen(path, "rb");
+    if (!f) return DAPOL_ERR_IO;
+    TreeFileHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, TREE_MAGIC, 8) != 0 || h.version != 1 || h.height < 0 || h.height > DAPOL_MAX_TREE_HEIGHT ||
+        (h.hash_id != DAPOL_HASH_BLAKE3 && h.hash_id != DAPOL_HASH_BLAKE2S) || h.T == 0 || h.n_leaves == 0 || h.n_leaves >= (1ull << 31)) {
+        fclose(f);
+        return DAPOL_ERR_IO;
+    }
+    const int H = h.height;
+    dapol_tree *t = new dapol_tree();
+    t->ctx = ctx; t->hash_id = h.hash_id; t->height = H; t->n_leaves = h.n_leaves; t->T = h.T; t->n_pads = h.n_pads;
+    t->level_off.assign(H + 1, 0); t->level_n.assign(H + 1, 0); t->n_real.assign(H + 1, 0); t->npads.assign(H + 1, 0);
+    t->pos.assign(H + 1, nullptr);
+    int rc = DAPOL_OK;
+    uint64_t total = 0;
+    for (int l = 0; l <= H; l++) {
+        uint64_t row[4];
+        if (fread(row, sizeof row, 1, f) != 1) { rc = DAPOL_ERR_IO; break; }
+        t->level_off[l] = row[0]; t->level_n[l] = row[1]; t->n_real[l] = row[2]; t->npads[l] = row[3];
+        if (row[0] != total || row[2] > row[1]) { rc = DAPOL_ERR_IO; break; }  // levels are laid out back to back
+        total += row[1];
+    }
+    std::vector<uint64_t> pos_off;
+    if (rc == DAPOL_OK && (total != h.T || t->n_real[H] != h.n_leaves || pos_words_of(t->n_real, H, &pos_off) != h.pos_words)) rc = DAPOL_ERR_IO;
+    if (rc == DAPOL_OK && fread(t->root_ext, sizeof t->root_ext, 1, f) != 1) rc = DAPOL_ERR_IO;
+    const uint64_t T = h.T;
+    auto alloc = [&](auto **p, size_t bytes) {
+        if (rc != DAPOL_OK) return;
+        if (dmalloc(p, bytes, st) != cudaSuccess) { g_cuda_err = "tree load: out of device memory"; cudaGetLastError(); rc = DAPOL_ERR_CUDA; }
+    };
+    alloc(&t->ns.idx, T * 8); alloc(&t->ns.v, T * 8); alloc(&t->ns.r, T * 32); alloc(&t->ns.comc, T * 32); alloc(&t->ns.hash, T * 32);
+    alloc(&t->ns.is_pad, T); alloc(&t->pos_all, h.pos_words * 4);
+    if (h.flags & 1u) alloc(&t->leaf_index_of, h.n_leaves * 8);
+    const struct { void *p; size_t bytes; } parts[] = {
+        {t->ns.idx, T * 8}, {t->ns.v, T * 8}, {t->ns.r, T * 32}, {t->ns.comc, T * 32}, {t->ns.hash, T * 32}, {t->ns.is_pad, T},
+        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, (h.flags & 1u) ? h.n_leaves * 8 : 0}};
+    for (const auto &pt : parts)
+        if (rc == DAPOL_OK && pt.bytes) rc = file_to_dev(f, pt.p, pt.bytes, buf, st);
+    char tail[8];
+    if (rc == DAPOL_OK && (fread(tail, 8, 1, f) != 1 || memcmp(tail, TREE_MAGIC, 8) != 0)) rc = DAPOL_ERR_IO;
+    fclose(f);
+    if (rc == DAPOL_OK) {
+        if (H == 0) t->pos[0] = t->pos_all;
+        for (int l = 1; l <= H; l++) t->pos[l] = t->pos_all + pos_off[l];
+        if (dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *), st) != cudaSuccess || dmalloc(&t->d_level_off, (H + 1) * 8, st) != cudaSuccess ||
+            cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            g_cuda_err = "tree load: device tables"; cudaGetLastError(); rc = DAPOL_ERR_CUDA;
+        }
+    }
+    if (rc != DAPOL_OK) { dapol_tree_destroy(t); return rc; }
+    *out = t;
+    return DAPOL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ accessors
 extern "C" int dapol_tree_height(const dapol_tree *t) { return t ? t->height : -1; }
+extern "C" int dapol_tree_hash_id(const dapol_tree *t) { return t ? t->hash_id : -1; }
 extern "C" uint64_t dapol_tree_num_nodes(const dapol_tree *t) { return t ? t->T : 0; }
 extern "C" uint64_t dapol_tree_num_padding(const dapol_tree *t) { return t ? t->n_pads : 0; }
 extern "C" uint64_t dapol_tree_level_size(const dapol_tree *t, int level) {

@@ -328,3 +328,26 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
     }
     return DAPOL_OK;
 }
+
+// Inclusion proofs streamed to a file (the reference's TODO "write the proofs to a local file", src/dapol/mod.rs:250):
+// dapol_prove_batch in chunks, proof i at byte i * size.
+extern "C" int dapol_prove_to_file(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                   const uint8_t seed[32], uint64_t chunk, const char *path, uint64_t *proof_size) {
+    if (!t || !leaf_idx || !seed || !k || !path) return DAPOL_ERR_BAD_ARG;
+    const uint64_t size = dapol_inclusion_proof_size(dapol_total_height(t), aggregation_factor, policy);
+    if (proof_size) *proof_size = size;
+    if (size == 0) return DAPOL_ERR_BAD_ARG;
+    if (chunk == 0) chunk = 8192;
+    FILE *f = fopen(path, "wb");
+    if (!f) return DAPOL_ERR_IO;
+    std::vector<uint8_t> buf(std::min(chunk, k) * size);
+    int rc = DAPOL_OK;
+    for (uint64_t s = 0; s < k && rc == DAPOL_OK; s += chunk) {
+        const uint64_t n = std::min(chunk, k - s);
+        uint64_t got = 0;
+        rc = dapol_prove_batch(t, n, leaf_idx + s, aggregation_factor, policy, seed, buf.data(), buf.size(), &got);
+        if (rc == DAPOL_OK && fwrite(buf.data(), 1, n * size, f) != n * size) rc = DAPOL_ERR_IO;
+    }
+    if (fclose(f) != 0 && rc == DAPOL_OK) rc = DAPOL_ERR_IO;
+    return rc;
+}

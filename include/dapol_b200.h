@@ -45,6 +45,7 @@ extern "C" {
 #define DAPOL_ERR_BUFFER 18      /* caller buffer too small; required size is reported */
 #define DAPOL_ERR_CUDA 19        /* no device / CUDA runtime failure (see dapol_last_cuda_error) */
 #define DAPOL_ERR_DECODE 20      /* smtree DecodingError / bulletproofs ProofError::FormatError */
+#define DAPOL_ERR_IO 21          /* tree / proof file cannot be opened, read or written, or is not a tree file */
 
 #define DAPOL_HASH_BLAKE3 0   /* blake3::Hasher     (benches/dapol.rs:38, src/tests.rs:102-103) */
 #define DAPOL_HASH_BLAKE2S 1  /* blake2::Blake2s    (src/dapol/tests.rs:13,21) */
@@ -143,6 +144,7 @@ DAPOL_API int dapol_tree_root(const dapol_tree *tree, uint8_t com[32], uint8_t h
 /* Tree introspection for parity dumps: level 0 = root .. height = leaves; nodes of a level are in tree
  * order with the two children of a parent adjacent. */
 DAPOL_API int dapol_tree_height(const dapol_tree *tree);
+DAPOL_API int dapol_tree_hash_id(const dapol_tree *tree);  /* DAPOL_HASH_*, -1 for NULL */
 DAPOL_API uint64_t dapol_tree_num_nodes(const dapol_tree *tree);
 DAPOL_API uint64_t dapol_tree_num_padding(const dapol_tree *tree);
 DAPOL_API uint64_t dapol_tree_level_size(const dapol_tree *tree, int level);
@@ -156,6 +158,21 @@ DAPOL_API int dapol_tree_leaf_index_of(const dapol_tree *tree, uint64_t input_po
 DAPOL_API int dapol_tree_paths(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t *values /* k*h */,
                      uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*32 */,
                      uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*32 or NULL */);
+
+/* ---- persistence (the reference keeps the tree in memory only and leaves "write the proofs to a local
+ * file" as a TODO, src/dapol/mod.rs:250).  dapol_tree_save writes the whole node store of a built tree (every level: index,
+ * value, blinding, compressed commitment, hash, padding flag), the slot maps and the id -> leaf-index map to one
+ * little-endian file ("DAPOLT01" header; ~113 B per node: 2.9 GB at 2^20 users / height 32); dapol_tree_load brings it back
+ * into HBM on any context, bit-identical (levels, paths and inclusion proofs are those of the saved tree).  The file holds
+ * the SECRET blindings of every node: protect it like the liabilities themselves.  A shard's attachment to its top tree is
+ * not saved (re-attach with dapol_tree_attach_top). */
+DAPOL_API int dapol_tree_save(const dapol_tree *tree, const char *path);
+DAPOL_API int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **out);
+/* dapol_prove_batch for k leaves streamed to a file in chunks of `chunk` proofs (0 = 8192): proof i at byte i * size, no
+ * header; the GPU works on one chunk while nothing larger than a chunk is held on the host.  *proof_size (if not NULL)
+ * receives the size of one proof. */
+DAPOL_API int dapol_prove_to_file(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                  const uint8_t seed[32], uint64_t chunk, const char *path, uint64_t *proof_size);
 
 /* ---- inclusion proofs.
  * Dapol::generate_proof_batch-per-leaf (src/dapol/mod.rs:167-190) for k leaves, each serialised as DapolProof::serialize
