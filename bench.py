@@ -45,7 +45,7 @@ def executed_mac32(comb_window, node_batch):
     compress = (4 * FS + 5 * FM) + 3 * FM + 11 * FM + (254 * FS + 11 * FM) / node_batch
     value_window = comb_window if comb_window <= 16 else 22      # comb_value_window in ge25519.cuh
     nwr, nwv = 253 // comb_window + 1, 64 // value_window + 1
-    pad = (nwr - 1) * madd + FM + 3 * SCMUL + compress          # ChaCha draw -> wide reduce, halve; comb; compress
+    pad = (nwr - 1) * madd + FM + 2 * SCMUL + compress          # ChaCha draw -> wide reduce with the halving folded in; comb; compress
     leaf = (nwr + nwv - 1) * madd + FM + SCMUL + compress       # halve r; two combs; compress
     merge = full_add + 2 * SCMUL + compress                     # point add; r_L + r_R mod l; compress
     return leaf, pad, merge

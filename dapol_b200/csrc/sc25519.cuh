@@ -94,6 +94,27 @@ DAPOL_HD_INLINE void sc_from_wide(sc &r, const uint32_t w[16]) {
     x[8] = (uint32_t)c;
     sc_condsub(r, x);
 }
+// Scalar::from_bytes_mod_order_wide on 16 LE words together with its half: h = r / 2 mod l, r = 2 h mod l, both canonical.
+// The halving rides on the two Montgomery products of the wide reduction (constants 2^-1 R and 2^-1 R^2) instead of a third.
+DAPOL_HD_INLINE void sc_from_wide_with_half(sc &r, sc &h, const uint32_t w[16]) {
+    sc lo, hi;
+    const sc c1 = {{SC_INV2R_WORDS}}, c2 = {{SC_INV2RR_WORDS}};
+#pragma unroll
+    for (int i = 0; i < 8; i++) { lo.v[i] = w[i]; hi.v[i] = w[8 + i]; }
+    sc_montmul(lo, lo, c1);  // lo / 2 mod l
+    sc_montmul(hi, hi, c2);  // hi * 2^256 / 2 mod l
+    uint32_t x[9];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)lo.v[i] + hi.v[i]; x[i] = (uint32_t)c; c >>= 32; }
+    x[8] = (uint32_t)c;
+    sc_condsub(h, x);
+    c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c += (uint64_t)h.v[i] + h.v[i]; x[i] = (uint32_t)c; c >>= 32; }
+    x[8] = (uint32_t)c;
+    sc_condsub(r, x);
+}
 DAPOL_HD_INLINE void sc_add(sc &r, const sc &a, const sc &b) {  // a, b < l
     uint32_t x[9];
     uint64_t c = 0;

@@ -194,8 +194,7 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         uint32_t ks[16];
         chacha20_block(ks, seed, pad_rng[g], 0);
         sc r, rh;
-        sc_from_wide(r, ks);
-        sc_half256(rh, r);
+        sc_from_wide_with_half(r, rh, ks);
         int32_t d[NWR];
         sc_signed_digits<W, NWR>(d, rh.v, 8);
         ge acc;

@@ -71,6 +71,10 @@ def main():
             ms = float(t.item())
             ok = d_ok[:K].cpu().numpy().astype(bool)
             exact = bool((ok == ~bad[:K]).all())
+            if world > 1:  # every rank checks the verdicts of its own batch
+                e = torch.tensor([1 if exact else 0], device=dev)
+                dist.all_reduce(e, op=dist.ReduceOp.MIN)
+                exact = bool(e.item())
             line = {"config": "C5 batch range-proof verification", "nbits": nbits, "m": 1, "proofs_per_gpu": K, "n_gpus": world, "verify_ms": ms,
                     "verifies_per_s": world * K / ms * 1e3, "corrupted": int(bad[:K].sum()), "verdicts_exact": exact}
             if lg == 10 and rank == 0:  # CPU leg + reject parity on the first 1024 proofs
