@@ -44,6 +44,7 @@ def lib():
     L.dapol_tree_build_from_records.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, u64, C.POINTER(vp)]
     L.dapol_tree_attach_top.argtypes = [vp, vp, u64]
     L.dapol_tree_root.argtypes = [vp, vp, vp, C.POINTER(u64), vp]
+    L.dapol_ctx_set_padding_mode.argtypes = [vp, C.c_int]
     L.dapol_tree_height.argtypes = [vp]
     L.dapol_tree_hash_id.argtypes = [vp]
     L.dapol_tree_num_nodes.argtypes = [vp]

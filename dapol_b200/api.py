@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -50,11 +51,14 @@ class Context:
 
     def __init__(self, device: int = 0, comb_window: int = 0):
         self._h = C.c_void_p()
+        self._trees = weakref.WeakSet()  # trees built on this context: they must be destroyed before it (C-ABI contract)
         _check(_ffi.lib().dapol_ctx_create(device, comb_window, C.byref(self._h)))
         self.device = device
 
     def close(self):
         if getattr(self, "_h", None):
+            for t in list(getattr(self, "_trees", ())):
+                t._free()
             _ffi.lib().dapol_ctx_destroy(self._h)
             self._h = None
 
@@ -88,6 +92,11 @@ class Context:
         return out
 
     # -- range proofs (src/range/mod.rs:48-119), batched ----------------------------------------
+    def set_padding_mode(self, positional: bool):
+        """False (default): padding blindings from the creation-order stream (the reference's RNG, seeded).  True: keyed by
+        (level, index) -- Paddable::padding(idx, secret) as a function of its arguments (node.rs:85-88 TODO); opt-in."""
+        _check(_ffi.lib().dapol_ctx_set_padding_mode(self._h, 1 if positional else 0))
+
     def set_rangeproof_window(self, window: int):
         _check(_ffi.lib().dapol_ctx_set_rangeproof_window(self._h, window))
 
@@ -205,6 +214,7 @@ class Dapol:
         self.ctx, self.hash_id, self.height = ctx, hash_id, height
         self.aggregation_factor, self.policy = aggregation_factor, policy
         self._t = None
+        ctx._trees.add(self)
 
     # -- constructors -------------------------------------------------------------------------
     @classmethod
@@ -310,7 +320,8 @@ class Dapol:
 
     def _free(self):
         if getattr(self, "_t", None):
-            _ffi.lib().dapol_tree_destroy(self._t)
+            if getattr(self.ctx, "_h", None):  # a tree that outlived its context was already released with it
+                _ffi.lib().dapol_tree_destroy(self._t)
             self._t = None
 
     close = _free

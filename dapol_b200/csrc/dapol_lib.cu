@@ -128,7 +128,7 @@ __global__ void k_scan_tile_offsets(uint64_t *tile_sums, uint64_t ntiles) {  // 
 // pass 3: exclusive scan inside the tile + slots / parents / padding destinations
 __global__ void k_struct_apply(const uint64_t *idx, uint64_t c, const uint64_t *flags, const uint64_t *tile_offsets, uint32_t *pos,
                                uint64_t *parent_idx, uint64_t level_off, NodeStore ns, uint64_t *pad_dest, uint64_t pad_ord_base,
-                               uint64_t *pad_rng, uint64_t pad_rng_base) {
+                               uint64_t *pad_rng, uint64_t pad_rng_base, int positional) {
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t x[SCAN_ITEMS], s = 0;
 #pragma unroll
@@ -136,7 +136,7 @@ __global__ void k_struct_apply(const uint64_t *idx, uint64_t c, const uint64_t *
     uint64_t e = block_exclusive_scan(s, nullptr) + tile_offsets[blockIdx.x];
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; i++) {
-        if (base + i < c) struct_apply_body(base + i, idx, x[i], e, pos, parent_idx, level_off, ns, pad_dest, pad_ord_base, pad_rng, pad_rng_base);
+        if (base + i < c) struct_apply_body(base + i, idx, x[i], e, pos, parent_idx, level_off, ns, pad_dest, pad_ord_base, pad_rng, pad_rng_base, positional);
         e += x[i];
     }
 }
@@ -249,9 +249,9 @@ struct Seed8 {
 };
 template <int W>
 __global__ void __launch_bounds__(128, DAPOL_PAD_MINB) k_pad(uint64_t n, uint64_t stride, NodeStore ns, const uint64_t *pad_dest, int hash_id, Seed8 seed,
-                                             const uint64_t *pad_rng, const ge_niels *tab_bbl) {
+                                             const uint64_t *pad_rng, const ge_niels *tab_bbl, const __grid_constant__ PadStreams ps) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_rng, tab_bbl);
+    if (g < stride) pad_batch_body<W, NODE_BATCH>(g, stride, n, ns, pad_dest, hash_id, seed.w, pad_rng, tab_bbl, ps);
 }
 // leaves of a top tree: subtree-root records gathered from the shards
 __global__ void k_leaf_records(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, const uint32_t *recs) {
@@ -469,6 +469,11 @@ extern "C" int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     return DAPOL_OK;
 }
+extern "C" int dapol_ctx_set_padding_mode(dapol_ctx *ctx, int mode) {
+    if (!ctx || (mode != DAPOL_PADDING_STREAM && mode != DAPOL_PADDING_POSITIONAL)) return DAPOL_ERR_BAD_ARG;
+    ctx->pad_mode = mode;
+    return DAPOL_OK;
+}
 extern "C" uint64_t dapol_kernel_launches(const dapol_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int dapol_ctx_params(const dapol_ctx *ctx, int *comb_window, int *node_batch, int *rangeproof_window) {
     if (!ctx) return DAPOL_ERR_BAD_ARG;
@@ -519,7 +524,7 @@ static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, size
 }
 template <int W>
 static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
-                            const Seed8 &seed, const uint64_t *d_pad_rng, int phase) {
+                            const Seed8 &seed, const uint64_t *d_pad_rng, int phase, const PadStreams &ps) {
     int H = t->height;
     if (phase == 0) {
         uint64_t stride = batch_stride(t->n_leaves, k_leaf<W>, 24.0);
@@ -528,7 +533,7 @@ static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_val
         ctx->launches++;
     } else if (t->n_pads) {
         uint64_t stride = batch_stride(t->n_pads, k_pad<W>, 13.0);
-        k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, d_pad_rng, ctx->tab_bbl);
+        k_pad<W><<<grid_for(stride, 128), 128, 0, ctx->stream>>>(t->n_pads, stride, t->ns, d_pad_dest, t->hash_id, seed, d_pad_rng, ctx->tab_bbl, ps);
         ctx->launches++;
     }
 }
@@ -622,20 +627,27 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     }
     // ---- structure: per level flags -> scan -> slots, parents, padding destinations.  Padding RNG ordinal =
     // creation order of smtree's build: level H..1, left to right.
+    // padding randomness: creation-order stream (the reference's RNG, seeded) or keyed by position (ctx->pad_mode)
+    const int positional = ctx->pad_mode == DAPOL_PADDING_POSITIONAL;
+    PadStreams ps;
+    memset(&ps, 0, sizeof ps);
+    ps.positional = positional; ps.levels = H; ps.level0 = positional && pad_level_base ? (int)pad_level_base[0] : 0;
     const uint64_t *cur = d_leaf_idx;
     uint64_t ord = 0;
     for (int h = H; h >= 1; h--) {
+        ps.start[h] = ord;
         uint64_t c = t->n_real[h];
         uint64_t *next = (cur == realA) ? realB : realA;
         unsigned ntiles = (unsigned)((c + SCAN_TILE - 1) / SCAN_TILE);
         k_struct_flags_tiles<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles);
         k_scan_tile_offsets<<<1, SCAN_BLOCK, 0, st>>>(d_tiles, ntiles);
         k_struct_apply<<<ntiles, SCAN_BLOCK, 0, st>>>(cur, c, d_flags, d_tiles, t->pos[h], next, t->level_off[h], t->ns, d_pad_dest, ord,
-                                                      d_pad_rng, pad_level_base ? pad_level_base[h] : pad_base + ord);
+                                                      d_pad_rng, pad_level_base ? pad_level_base[h] : (positional ? 0 : pad_base + ord), positional);
         ctx->launches += 3;
         ord += npads[h];
         cur = next;
     }
+    ps.start[0] = ord;
     TRY_T(cudaEventRecord(ctx->ev[1], st));
     // ---- leaves, padding nodes
     Seed8 seed;
@@ -646,7 +658,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
             k_leaf_records<<<grid_for(n, 128), 128, 0, st>>>(n, t->ns, t->level_off[H], t->pos[H], d_records);
             ctx->launches++;
         } else switch (ctx->W) {
-#define W_CASE(w) case w: launch_leaf_pad<w>(ctx, t, d_values, d_blind, d_pad_dest, seed, d_pad_rng, phase); break;
+#define W_CASE(w) case w: launch_leaf_pad<w>(ctx, t, d_values, d_blind, d_pad_dest, seed, d_pad_rng, phase, ps); break;
             DAPOL_W_CASES(W_CASE)
 #undef W_CASE
         }

@@ -34,7 +34,7 @@ DAPOL_HD_INLINE uint64_t struct_flags_body(uint64_t k, const uint64_t *idx, uint
 // (pad_rng_base + rank inside the level: single tree = running creation ordinal; shard = the level's global base).
 DAPOL_HD_INLINE void struct_apply_body(uint64_t k, const uint64_t *idx, uint64_t f, uint64_t s, uint32_t *pos, uint64_t *parent_idx,
                                        uint64_t level_off, const NodeStore &ns, uint64_t *pad_dest, uint64_t pad_ord_base,
-                                       uint64_t *pad_rng, uint64_t pad_rng_base) {
+                                       uint64_t *pad_rng, uint64_t pad_rng_base, int positional = 0) {
     uint64_t x = idx[k];
     uint32_t newp = (uint32_t)(f >> 32), lone = (uint32_t)f;
     uint64_t j = (s >> 32) - (newp ? 0 : 1);
@@ -50,7 +50,9 @@ DAPOL_HD_INLINE void struct_apply_body(uint64_t k, const uint64_t *idx, uint64_t
         ns.idx[level_off + pp] = x ^ 1;
         ns.is_pad[level_off + pp] = 1;
         pad_dest[pad_ord_base + q] = level_off + pp;
-        pad_rng[pad_ord_base + q] = pad_rng_base + q;  // block of the seeded stream this padding node draws (RNG contract)
+        // block of the seeded stream this padding node draws: creation order (RNG contract) or, in the positional mode, the
+        // node's own index (pad_rng_base = index of the subtree's first node of the level inside the whole tree)
+        pad_rng[pad_ord_base + q] = positional ? pad_rng_base + (x ^ 1) : pad_rng_base + q;
     }
 }
 // Sizes of every level from one pass over adjacent leaves: msb of idx[k] ^ idx[k-1] (k >= 1).  The number
@@ -179,11 +181,26 @@ DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, co
     }
 }
 
+// ChaCha stream of the padding node with creation ordinal g.  Stream mode: always 0.  Positional mode: the
+// node's level inside the whole tree; ordinals run level H first, so level h owns [start[h], start[h - 1]).
+struct PadStreams {
+    int positional, levels, level0;                // levels = H; level0 = levels above this (sub)tree
+    uint64_t start[DAPOL_MAX_TREE_HEIGHT + 2];     // start[h], h = 1 .. H; start[0] = number of padding nodes
+};
+DAPOL_HD_INLINE uint64_t pad_stream_of(const PadStreams &ps, uint64_t g) {
+    if (!ps.positional) return 0;
+    int lo = 1, hi = ps.levels;  // smallest h with start[h] <= g
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ps.start[mid] <= g) hi = mid; else lo = mid + 1;
+    }
+    return (uint64_t)(ps.level0 + lo);
+}
 // DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng)); rng draw #g of the seeded stream =
 // from_bytes_mod_order_wide(ChaCha20(pad_seed) block pad_rng[g])   (RNG contract)
 template <int W, int B>
 DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, const NodeStore &ns, const uint64_t *pad_dest, int hash_id,
-                                    const uint32_t seed[8], const uint64_t *pad_rng, const ge_niels *tab_bbl) {
+                                    const uint32_t seed[8], const uint64_t *pad_rng, const ge_niels *tab_bbl, const PadStreams &ps) {
     constexpr int NWR = 253 / W + 1;
     ge_dc_batch<B> dc;
     dc.init();
@@ -192,7 +209,7 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         uint64_t g = t + (uint64_t)b * stride;
         if (g >= n) break;
         uint32_t ks[16];
-        chacha20_block(ks, seed, pad_rng[g], 0);
+        chacha20_block(ks, seed, pad_rng[g], pad_stream_of(ps, g));
         sc r, rh;
         sc_from_wide_with_half(r, rh, ks);
         int32_t d[NWR];

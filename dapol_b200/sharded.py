@@ -82,6 +82,11 @@ class CudaEngine:
         self.device = torch.device("cuda", ctx.device)
         self.L = _ffi.lib()
         self.last_shard_times = None  # device time per phase of the last dapol_tree_build_shard_dev on this engine
+        self.positional = False       # padding blindings keyed by position instead of the creation-order stream
+
+    def set_padding_mode(self, positional: bool):
+        self.ctx.set_padding_mode(positional)
+        self.positional = bool(positional)
 
     def to_dev(self, a, dtype):
         if isinstance(a, torch.Tensor):
@@ -154,7 +159,7 @@ class CudaEngine:
         _check(self.L.dapol_tree_attach_top(tree, top, prefix))
 
     def destroy(self, tree):
-        if tree:
+        if tree and getattr(self.ctx, "_h", None):  # trees die with their context at the latest
             self.L.dapol_tree_destroy(tree)
 
     def root_of(self, tree) -> DapolNode:
@@ -248,8 +253,14 @@ class ShardedDapol:
         E, comm, Hs = self.engine, self.comm, self.sub_height
         self.n_mine = len(idx)
         dev = getattr(E, "device", None)
-        counts_all = comm.all_gather_host(E.pad_counts(Hs, idx), dev)
-        level_base, top_base = shard_pad_bases(counts_all, comm.rank, pad_base)
+        if getattr(E, "positional", False):
+            # position-keyed padding: a padding blinding depends on (level, index) only, so the shards need
+            # no exchange of padding counts -- the shard passes its coordinates inside the whole tree instead
+            level_base = np.array([self.k] + [comm.rank << h for h in range(1, Hs + 1)], dtype=np.uint64)
+            top_base = 0
+        else:
+            counts_all = comm.all_gather_host(E.pad_counts(Hs, idx), dev)
+            level_base, top_base = shard_pad_bases(counts_all, comm.rank, pad_base)
         rec = np.zeros(RECORD_BYTES + 8, np.uint8)
         if self.n_mine:
             self.subtree = E.build_shard(self.hash_id, Hs, idx, v, bl, pad_seed, level_base)

@@ -62,10 +62,21 @@ typedef struct dapol_tree dapol_tree;
  * (PedersenGens::default(), src/dapol/node.rs:31; BulletproofGens::new, src/range/mod.rs:50,66 --
  * the reference re-derives them on every call, here once).  comb_window = 0 picks the default. */
 DAPOL_API int dapol_ctx_create(int device, int comb_window, dapol_ctx **out);
-DAPOL_API void dapol_ctx_destroy(dapol_ctx *ctx);
+DAPOL_API void dapol_ctx_destroy(dapol_ctx *ctx);  /* destroy the context's trees first: a tree holds a pointer to its context */
 /* Run this context's kernels and copies on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's
  * current stream, so the caller's events bracket the work.  The stream must outlive the context. */
 DAPOL_API int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream);
+/* Where a padding node's blinding comes from (all builds on this context; default DAPOL_PADDING_STREAM).
+ * STREAM: the reference's behaviour under the seeded-RNG contract -- the k-th padding node smtree creates draws block
+ *   pad_base + k of stream 0 of ChaCha20(pad_seed) (DapolNode::padding ignores idx and secret, src/dapol/node.rs:85-88).
+ * POSITIONAL (opt-in, NOT the reference's bytes): the padding node at (level h, index i) of the whole tree
+ *   draws block i of stream h of ChaCha20(pad_seed) -- padding(idx, secret) as a function of its arguments, which the
+ *   reference leaves as a TODO.  pad_seed is then the padding key derived from the secret and pad_base is ignored; shards need
+ *   no exchange of padding counts: dapol_tree_build_shard_dev takes pad_level_base[0] = number of levels above the shard and
+ *   pad_level_base[h] = prefix << h (index of the shard's first node of level h inside the whole tree). */
+#define DAPOL_PADDING_STREAM 0
+#define DAPOL_PADDING_POSITIONAL 1
+DAPOL_API int dapol_ctx_set_padding_mode(dapol_ctx *ctx, int mode);
 DAPOL_API const char *dapol_strerror(int code);
 DAPOL_API const char *dapol_last_cuda_error(void);
 

@@ -269,8 +269,21 @@ EXPORT void dor_tree_free(dor_tree *t) {
 static int is_pair(const node *cur, uint64_t cnt, uint64_t i) {
     return !(cur[i].idx & 1) && i + 1 < cnt && cur[i + 1].idx == cur[i].idx + 1;
 }
+/* pad_mode 0: the reference's behaviour under the seeded-RNG contract (above).  pad_mode 1 (opt-in): the
+ * padding node at (level h, index i) draws block i of stream h of ChaCha20(pad_seed) -- Paddable::padding(idx, secret) as a
+ * function of its arguments (src/dapol/node.rs:85-88 leaves that as a TODO); pad_base is ignored. */
+static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
+                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode, dor_tree **out);
 EXPORT int dor_tree_build(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, dor_tree **out) {
+    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, pad_base, nthreads, 0, out);
+}
+EXPORT int dor_tree_build_positional(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
+                                     const uint8_t *blindings, const uint8_t pad_key[32], int nthreads, dor_tree **out) {
+    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_key, 0, nthreads, 1, out);
+}
+static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
+                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode, dor_tree **out) {
     if (height > 64 || height < 0 || n == 0 || (height == 0 && n != 1)) return ERR_BAD_ARG;
     for (uint64_t i = 0; i < n; i++) {
         if (i && idx_sorted[i] <= idx_sorted[i - 1]) return ERR_BAD_ARG;
@@ -313,7 +326,9 @@ EXPORT int dor_tree_build(int hash_id, int height, uint64_t n, const uint64_t *i
             if (pad_draw[k] != NO_DRAW) { /* DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng)) */
                 node *pd = full[2 * k].is_pad ? &full[2 * k] : &full[2 * k + 1];
                 sc r; uint8_t rb[32];
-                rng_scalar(&r, pad_seed, pad_draw[k], 0); sc_tobytes(rb, &r);
+                if (pad_mode == 1) rng_scalar(&r, pad_seed, pd->idx, (uint64_t)h);
+                else rng_scalar(&r, pad_seed, pad_draw[k], 0);
+                sc_tobytes(rb, &r);
                 node_new(hash_id, pd, pd->idx, 0, rb, 1);
             }
             node_merge(hash_id, &par[k], &full[2 * k], &full[2 * k + 1]);

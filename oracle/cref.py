@@ -147,13 +147,17 @@ def derive_leaves(hash_id, iid_blob, iid_off, eid_blob, eid_off, audit_seed: byt
 
 
 class Tree:
-    def __init__(self, hash_id, height, idx_sorted, values, blindings, pad_seed: bytes, pad_base=0, nthreads=0):
+    def __init__(self, hash_id, height, idx_sorted, values, blindings, pad_seed: bytes, pad_base=0, nthreads=0, positional=False):
+        """positional=True: padding blindings keyed by (level, index) instead of the creation-order stream."""
         idx, ip = _np(idx_sorted, np.uint64)
         val, vp = _np(values, np.uint64)
         bl, bp = _np(blindings, np.uint8)
         assert bl.size == 32 * idx.size
         h = C.c_void_p()
-        rc = lib().dor_tree_build(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), C.c_uint64(pad_base), nthreads, C.byref(h))
+        if positional:
+            rc = lib().dor_tree_build_positional(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), nthreads, C.byref(h))
+        else:
+            rc = lib().dor_tree_build(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), C.c_uint64(pad_base), nthreads, C.byref(h))
         if rc:
             raise ValueError(f"dor_tree_build rc={rc}")
         self.h, self.hash_id, self.height = h, hash_id, height

@@ -553,8 +553,10 @@ class Tree:
         return [self.levels[h][(leaf_idx >> (H - h)) ^ 1] for h in range(H, 0, -1)]
 
 
-def build_tree(hash_id, height, leaves, pad_seed: bytes, pad_draw_base: int = 0) -> Tree:
-    """leaves: iterable of (idx, Node) at leaf level.  Dapol::build (mod.rs:206-208)."""
+def build_tree(hash_id, height, leaves, pad_seed: bytes, pad_draw_base: int = 0, positional: bool = False) -> Tree:
+    """leaves: iterable of (idx, Node) at leaf level.  Dapol::build (mod.rs:206-208).
+    positional (opt-in): the padding node at (level h, index i) draws block i of stream h instead of the next
+    block of the creation-order stream -- Paddable::padding(idx, secret) as a function of its arguments (node.rs:85-88 TODO)."""
     t = Tree(hash_id, height)
     cur = dict(sorted((i, n) for i, n in leaves))
     draw = pad_draw_base
@@ -567,7 +569,7 @@ def build_tree(hash_id, height, leaves, pad_seed: bytes, pad_draw_base: int = 0)
             sib = idx ^ 1
             if sib not in cur:
                 # DapolNode::padding (node.rs:86-88): new(0, Scalar::random(rng))
-                lvl[sib] = node_new(hash_id, 0, rng_scalar(pad_seed, draw))
+                lvl[sib] = node_new(hash_id, 0, rng_scalar(pad_seed, sib, h) if positional else rng_scalar(pad_seed, draw))
                 t.is_pad[h].add(sib)
                 draw += 1
             elif idx & 1:

@@ -136,6 +136,8 @@ struct EmuTree {
     std::vector<uint64_t> idx, v; std::vector<uint32_t> r, comc, hash, ext; std::vector<uint8_t> is_pad;
     uint64_t n_pads;
 };
+static int g_positional = 0;  // padding mode of the next emulated builds (dapol_ctx_set_padding_mode)
+EX void emu_set_padding_mode(int positional) { g_positional = positional; }
 EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *leaf_idx, const uint64_t *values,
                            const uint8_t *blind, const uint8_t pad_seed[32], uint64_t pad_base) {
     constexpr int W = 4;
@@ -168,20 +170,25 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     std::vector<std::vector<uint32_t>> pos(height + 1);
     real[height].assign(leaf_idx, leaf_idx + n);
     uint64_t ord = 0;
+    PadStreams ps;
+    memset(&ps, 0, sizeof ps);
+    ps.positional = g_positional; ps.levels = height; ps.level0 = 0;
     for (int h = height; h >= 1; h--) {
+        ps.start[h] = ord;
         uint64_t c = real[h].size();
         if (c != n_real[h]) abort();
         pos[h].resize(c); real[h - 1].assign(n_real[h - 1], ~0ull);
         uint64_t s = 0;
         for (uint64_t k = 0; k < c; k++) {
             uint64_t f = struct_flags_body(k, real[h].data(), c);
-            struct_apply_body(k, real[h].data(), f, s, pos[h].data(), real[h - 1].data(), t->level_off[h], ns, pad_dest.data(), ord, pad_rng.data(), pad_base + ord);
+            struct_apply_body(k, real[h].data(), f, s, pos[h].data(), real[h - 1].data(), t->level_off[h], ns, pad_dest.data(), ord, pad_rng.data(), g_positional ? 0 : pad_base + ord, g_positional);
             s += f;
         }
         if ((s >> 32) != nparents[h] || (s & 0xffffffffull) != npads[h]) abort();
         ord += npads[h];
     }
     t->n_pads = total_pads;
+    ps.start[0] = ord;
     uint32_t seed[8]; b2w(seed, pad_seed, 8);
     std::vector<uint32_t> bw(8 * n); b2w(bw.data(), blind, 8 * n);
     constexpr int BT = 3;  // units per emulated thread (exercises full and partial batches)
@@ -189,7 +196,7 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     if (height == 0) { uint32_t p0 = 0; leaf_batch_body<W, BT>(0, 1, 1, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0]; return t; }
     for (uint64_t i = 0, st = threads(n); i < st; i++)
         leaf_batch_body<W, BT>(i, st, n, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
-    for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_rng.data(), tbbl.data());
+    for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_rng.data(), tbbl.data(), ps);
     // merges: sums per level, one compress pass over all internal nodes, hashes per level (as tree_build_dev)
     for (int h = height; h >= 1; h--)
         for (uint64_t j = 0; j < nparents[h]; j++)

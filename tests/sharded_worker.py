@@ -158,7 +158,8 @@ class FakeEngine:
 
 def main():
     rank, world, port, engine, n, H, hash_id = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5]), int(sys.argv[6]), int(sys.argv[7])
-    uneven = len(sys.argv) > 8 and sys.argv[8] == "uneven"
+    uneven = "uneven" in sys.argv[8:]
+    positional = "positional" in sys.argv[8:]  # padding keyed by (level, index): SURVEY 8(f) N3 (cuda engine only)
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if world > 1:
@@ -172,7 +173,7 @@ def main():
     rc, gidx, gbl, _ = cref.derive_leaves(hash_id, ib, io, eb, eo, AUDIT_SEED, H)
     assert rc == 0
     order = np.argsort(gidx, kind="stable")
-    g = cref.Tree(hash_id, H, gidx[order], vals[order], gbl[order], PAD_SEED)
+    g = cref.Tree(hash_id, H, gidx[order], vals[order], gbl[order], PAD_SEED, positional=positional)
     # this rank's slice of the input
     cuts = [0] + [(n * (r + 1)) // world for r in range(world)]
     if uneven and world > 1:
@@ -186,6 +187,7 @@ def main():
         from dapol_b200 import Context
         from dapol_b200.sharded import CudaEngine
         E = CudaEngine(Context(0))
+        E.set_padding_mode(positional)
     agg = min(H, 3)
     t = ShardedDapol.new(E, comm, hash_id, sl, AUDIT_SEED, H, agg, PAD_SEED)
     root, oroot = t.root_raw(), g.root()

@@ -11,6 +11,6 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("world,n,H,hash_id,extra", [(1, 300, 12, 0, ()), (2, 500, 14, 0, ()), (4, 700, 16, 1, ()), (2, 65, 9, 0, ("uneven",)),
-                                                      (4, 5, 8, 0, ())])
+                                                      (4, 5, 8, 0, ()), (4, 300, 13, 0, ("positional",)), (2, 40, 8, 1, ("positional", "uneven"))])
 def test_sharded_build_matches_single_tree_oracle(world, n, H, hash_id, extra):
     run_world(world, "cuda", n, H, hash_id, extra, timeout=900)

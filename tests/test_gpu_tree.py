@@ -92,6 +92,30 @@ def test_every_comb_window_gives_the_same_tree(cref, W):
     c.close()
 
 
+@pytest.mark.parametrize("hash_id,H,n", [(0, 12, 300), (1, 6, 9), (0, 40, 50), (0, 64, 7), (0, 1, 1)])
+def test_positional_padding_mode(cref, hash_id, H, n):
+    """SURVEY 8(f) N3 (opt-in): padding blindings keyed by (level, index) -- Paddable::padding(idx, secret) as a function of its
+    arguments, which the reference leaves as a TODO (src/dapol/node.rs:85-88).  Every node equals the oracle's tree built in the
+    same mode; the creation-order mode on the same inputs gives a different root, and pad_base no longer matters."""
+    from dapol_b200 import Context, Dapol
+    c = Context(0, 15)
+    idx, vals, bl = _inputs(H, n, 777 + H)
+    stream_root = Dapol.new_blank(c, hash_id, H, min(H, 4)).build(idx, vals, bl, PAD_SEED, 3).root_raw().com
+    c.set_padding_mode(True)
+    gpu = Dapol.new_blank(c, hash_id, H, min(H, 4)).build(idx, vals, bl, PAD_SEED, 3)
+    _assert_same_tree(gpu, cref.Tree(hash_id, H, idx, vals, bl, PAD_SEED, positional=True), H)
+    again = Dapol.new_blank(c, hash_id, H, min(H, 4)).build(idx, vals, bl, PAD_SEED, 99)
+    assert again.root_raw().com == gpu.root_raw().com
+    if gpu.num_padding:
+        assert gpu.root_raw().com != stream_root
+    c.set_padding_mode(False)
+    back = Dapol.new_blank(c, hash_id, H, min(H, 4)).build(idx, vals, bl, PAD_SEED, 3)
+    assert back.root_raw().com == stream_root
+    for t in (gpu, again, back):
+        t.close()
+    c.close()
+
+
 def test_identity_commitments_in_batch(ctx, cref):
     """Identity commitments (v = 0, r = 0 mod l) zero the batched inversion's input; the kernels mask them out."""
     from dapol_b200 import Dapol

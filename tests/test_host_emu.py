@@ -133,15 +133,19 @@ def test_hashes(E, pyref):
     assert bytes(buf) == bytes(st2)
 
 
+@pytest.mark.parametrize("positional", [False, True])
 @pytest.mark.parametrize("hid,H,n", [(0, 6, 9), (1, 4, 4), (0, 10, 200), (0, 16, 64), (0, 3, 4), (0, 1, 1), (0, 1, 2), (0, 5, 1), (0, 40, 20), (0, 64, 6)])
-def test_tree_bodies_vs_oracle(E, cref, hid, H, n):
+def test_tree_bodies_vs_oracle(E, cref, hid, H, n, positional):
+    """positional: padding blindings keyed by (level, index) instead of the creation-order stream."""
     rnd = random.Random(100 + H + n)
     idx = np.array(sorted({rnd.randrange(2 ** H) for _ in range(n)} if H > 20 else rnd.sample(range(2 ** H), n)), dtype=np.uint64)
     n = len(idx)
     vals_ = np.array([rnd.randrange(2 ** 32) for _ in range(n)], dtype=np.uint64)
     bl = np.frombuffer(rnd.randbytes(32 * n), dtype=np.uint8).copy().reshape(n, 32); bl[:, 31] &= 0x7F
-    T = cref.Tree(hid, H, idx, vals_, bl, PAD_SEED, 5)
+    T = cref.Tree(hid, H, idx, vals_, bl, PAD_SEED, 5, positional=positional)
+    E.emu_set_padding_mode(int(positional))
     t = E.emu_tree_build(hid, H, C.c_uint64(n), idx.ctypes.data_as(C.c_void_p), vals_.ctypes.data_as(C.c_void_p), bl.ctypes.data_as(C.c_void_p), B(PAD_SEED), C.c_uint64(5))
+    E.emu_set_padding_mode(0)
     assert t
     assert E.emu_tree_num_pads(t) == T.num_pads
     for h in range(H + 1):
