@@ -7,7 +7,9 @@
 //   structure pass  (integer/HBM-bound): pair detection, parent ranks, padding-node slots + RNG ordinals
 //   leaf pass       (IMAD-bound): v*B + r*B_blinding by fixed-base comb, compress, D(com)
 //   padding pass    (IMAD-bound): ChaCha20 draw -> r*B_blinding, compress, D(com)     [dominant, SURVEY F7]
-//   merge pass/level(IMAD-bound): point add, compress, D(C_L||C_R||H_L||H_R), v and r sums
+//   merge sums/level(IMAD/HBM): v, r and point sums of the parents (no compressed point needed)
+//   compress pass   (IMAD-bound): compress of the internal nodes of ALL levels, one balanced launch
+//   merge hash/level(HBM-bound): D(C_L||C_R||H_L||H_R)
 //
 // Node store (struct of arrays, one global numbering): level h (0 = root .. H = leaves) occupies
 // [level_off[h], level_off[h] + n_h); inside a level the two children of parent j sit at 2j, 2j+1,

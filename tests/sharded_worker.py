@@ -41,8 +41,9 @@ class FakeEngine:
     """Test double of dapol_b200.sharded.CudaEngine on CPU tensors, from the oracle's primitives."""
     device = None
 
-    def __init__(self, global_tree, k, rank, hash_id):
+    def __init__(self, global_tree, k, rank, hash_id, positional=False):
         self.g, self.k, self.rank, self.hash_id = global_tree, k, rank, hash_id
+        self.positional = positional  # padding keyed by (level, index): no exchange of padding counts (SURVEY 8(f) N3)
 
     def to_dev(self, a, dtype):
         return a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a).view(dtype).copy())
@@ -106,8 +107,12 @@ class FakeEngine:
         return base, below
 
     def build_shard(self, hash_id, height, idx, values, blind, pad_seed, level_base):
-        exp, _ = self._expected_bases(height)
-        assert (np.asarray(level_base, np.uint64)[1:] == exp[1:]).all(), (level_base, exp)
+        if self.positional:  # the shard's coordinates inside the whole tree: levels above it, index of its first node per level
+            exp = np.array([self.k] + [self.rank << h for h in range(1, height + 1)], np.uint64)
+            assert (np.asarray(level_base, np.uint64) == exp).all(), (level_base, exp)
+        else:
+            exp, _ = self._expected_bases(height)
+            assert (np.asarray(level_base, np.uint64)[1:] == exp[1:]).all(), (level_base, exp)
         leaves = self.g.level(self.g.height)
         sel = (leaves["is_pad"] == 0) & ((leaves["idx"] >> np.uint64(height)) == self.rank)
         assert (leaves["idx"][sel] & np.uint64((1 << height) - 1) == idx.numpy().astype(np.uint64)).all()
@@ -122,16 +127,17 @@ class FakeEngine:
         return rec
 
     def build_top(self, hash_id, height, idx, records, pad_seed, pad_base):
-        _, below = self._expected_bases(self.g.height - self.k)
-        assert pad_base == below, (pad_base, below)
+        if not self.positional:
+            _, below = self._expected_bases(self.g.height - self.k)
+            assert pad_base == below, (pad_base, below)
         cur = {int(i): dict(comc=r[128:160].tobytes(), hash=r[160:192].tobytes(), r=int.from_bytes(r[192:224].tobytes(), "little"),
                             v=int.from_bytes(r[224:232].tobytes(), "little")) for i, r in zip(idx, records)}
         ordinal = pad_base
-        for _ in range(height, 0, -1):  # smtree build order: level by level, left to right
+        for lvl in range(height, 0, -1):  # smtree build order: level by level, left to right
             nxt = {}
             for x in sorted(cur):
                 if (x ^ 1) not in cur:
-                    r = cref.rng_scalar(pad_seed, ordinal)
+                    r = cref.rng_scalar(pad_seed, x ^ 1, lvl) if self.positional else cref.rng_scalar(pad_seed, ordinal)
                     ordinal += 1
                     c = cref.commit(0, r)
                     cur[x ^ 1] = dict(comc=c, hash=cref.hash(hash_id, c), r=int.from_bytes(r, "little"), v=0)
@@ -159,7 +165,7 @@ class FakeEngine:
 def main():
     rank, world, port, engine, n, H, hash_id = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], int(sys.argv[5]), int(sys.argv[6]), int(sys.argv[7])
     uneven = "uneven" in sys.argv[8:]
-    positional = "positional" in sys.argv[8:]  # padding keyed by (level, index): SURVEY 8(f) N3 (cuda engine only)
+    positional = "positional" in sys.argv[8:]  # padding keyed by (level, index): SURVEY 8(f) N3
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if world > 1:
@@ -182,7 +188,7 @@ def main():
     sl = (*cref.pack_ids(ids[lo:hi]), *cref.pack_ids(eids[lo:hi]), vals[lo:hi])
     sl = (sl[0], sl[1], sl[2], sl[3], sl[4])
     if engine == "fake":
-        E = FakeEngine(g, k, rank, hash_id)
+        E = FakeEngine(g, k, rank, hash_id, positional)
     else:
         from dapol_b200 import Context
         from dapol_b200.sharded import CudaEngine

@@ -41,7 +41,8 @@ def run_world(world, engine, n, H, hash_id, extra=(), timeout=600):
     return roots
 
 
-@pytest.mark.parametrize("world,n,H,hash_id,extra", [(2, 48, 9, 0, ()), (4, 40, 10, 1, ()), (2, 33, 8, 0, ("uneven",)), (1, 20, 7, 0, ())])
+@pytest.mark.parametrize("world,n,H,hash_id,extra", [(2, 48, 9, 0, ()), (4, 40, 10, 1, ()), (2, 33, 8, 0, ("uneven",)), (1, 20, 7, 0, ()),
+                                                      (4, 36, 9, 0, ("positional",))])
 def test_sharded_host_logic_gloo(world, n, H, hash_id, extra):
     run_world(world, "fake", n, H, hash_id, extra)
 
