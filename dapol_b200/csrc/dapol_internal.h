@@ -1,6 +1,7 @@
 // Internals shared by the translation units of libdapol_b200.so (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include "../../include/dapol_b200.h"
@@ -75,6 +76,47 @@ struct dapol_tree {
     uint64_t prefix = 0;
 };
 static inline int dapol_total_height(const dapol_tree *t) { return t->height + (t->top ? t->top->height : 0); }
+
+// units per thread of the node passes = batch size of the shared inversion (ge_dc_batch)
+#ifndef NODE_BATCH
+#define NODE_BATCH 24
+#endif
+// minimum resident 128-thread CTAs per SM the node kernels are compiled for (register cap = 65536 / (128 * MINB))
+#ifndef DAPOL_LEAF_MINB
+#define DAPOL_LEAF_MINB 4
+#endif
+#ifndef DAPOL_PAD_MINB
+#define DAPOL_PAD_MINB 4
+#endif
+#ifndef DAPOL_MERGE_MINB
+#define DAPOL_MERGE_MINB 4
+#endif
+
+// Threads for n units at 1..NODE_BATCH units each.  A thread's cost is per * unit_cost + inv_cost (the shared field
+// inversion of its batch; costs in thousands of MAC32); the grid runs in waves of 148 SMs x resident CTAs, so the batch
+// size is chosen to minimise waves x thread cost -- small levels keep one unit per thread and spread over the SMs, and a
+// level of a few waves does not end on a nearly empty one.
+template <typename K>
+static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, size_t smem = 0, double inv_cost = 12.0) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 128, smem) != cudaSuccess || resident <= 0) resident = 3;
+    const double wave = (double)sms * resident;
+    double best = 1e300;
+    uint64_t best_threads = n;
+    for (int per = 1; per <= NODE_BATCH; per++) {
+        uint64_t threads = (n + per - 1) / per, ctas = (threads + 127) / 128;
+        double waves = ctas / wave;
+        if (waves < 6.0) waves = ceil(waves);  // few waves: the last one costs a full wave
+        double cost = waves * (per * unit_cost + inv_cost);
+        if (cost < best) { best = cost; best_threads = threads; }
+    }
+    return best_threads;
+}
+
+// the three merge steps of a built structure (dapol_merge.cu: compiled with inlined field products)
+void dapol_launch_merges(dapol_ctx *ctx, dapol_tree *t);
 
 // bump allocator over one device allocation (256-byte aligned pieces)
 struct Arena {

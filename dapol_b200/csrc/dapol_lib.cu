@@ -223,20 +223,6 @@ __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t 
     store8(blind_sorted + 8 * j, w);
 }
 
-// units per thread of the node passes = batch size of the shared inversion (ge_dc_batch)
-#ifndef NODE_BATCH
-#define NODE_BATCH 24
-#endif
-// minimum resident 128-thread CTAs per SM the node kernels are compiled for (register cap = 65536 / (128 * MINB))
-#ifndef DAPOL_LEAF_MINB
-#define DAPOL_LEAF_MINB 4
-#endif
-#ifndef DAPOL_PAD_MINB
-#define DAPOL_PAD_MINB 4
-#endif
-#ifndef DAPOL_MERGE_MINB
-#define DAPOL_MERGE_MINB 4
-#endif
 template <int W>
 __global__ void __launch_bounds__(128, DAPOL_LEAF_MINB) k_leaf(uint64_t n, uint64_t stride, NodeStore ns, uint64_t level_off, const uint32_t *pos, int hash_id,
                                               const uint64_t *values, const uint32_t *blind, const ge_niels *tab_b,
@@ -257,24 +243,6 @@ __global__ void __launch_bounds__(128, DAPOL_PAD_MINB) k_pad(uint64_t n, uint64_
 __global__ void k_leaf_records(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, const uint32_t *recs) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) record_leaf_body(i, ns, level_off, pos, recs);
-}
-// merge step 1 (per level): value, blinding and point sums of the parents
-__global__ void __launch_bounds__(128) k_merge_sum(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) merge_sum_body(j, ns, child_off, parent_off, parent_pos);
-}
-// merge step 2 (once per tree): compress every internal node, B per shared inversion
-template <int B>
-__global__ void __launch_bounds__(128, DAPOL_MERGE_MINB) k_compress_internal(uint64_t n, uint64_t stride, NodeStore ns,
-                                                                              const __grid_constant__ InternalMap m) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < stride) compress_internal_body<B>(t, stride, n, ns, m);
-}
-// merge step 3 (per level): parent hashes
-__global__ void __launch_bounds__(128) k_merge_hash(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos,
-                                                    int hash_id) {
-    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) merge_hash_body(j, ns, child_off, parent_off, parent_pos, hash_id);
 }
 // leaves only (no tree): commitments for dapol_commit_batch
 template <int W>
@@ -500,28 +468,6 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     delete t;
 }
 
-// Threads for n units at 1..NODE_BATCH units each.  A thread's cost is per * unit_cost + inv_cost (the shared field
-// inversion of its batch; costs in thousands of MAC32); the grid runs in waves of 148 SMs x resident CTAs, so the batch
-// size is chosen to minimise waves x thread cost -- small levels keep one unit per thread and spread over the SMs, and a
-// level of a few waves does not end on a nearly empty one.
-template <typename K>
-static inline uint64_t batch_stride(uint64_t n, K kernel, double unit_cost, size_t smem = 0, double inv_cost = 12.0) {
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-    int resident = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, 128, smem) != cudaSuccess || resident <= 0) resident = 3;
-    const double wave = (double)sms * resident;
-    double best = 1e300;
-    uint64_t best_threads = n;
-    for (int per = 1; per <= NODE_BATCH; per++) {
-        uint64_t threads = (n + per - 1) / per, ctas = (threads + 127) / 128;
-        double waves = ctas / wave;
-        if (waves < 6.0) waves = ceil(waves);  // few waves: the last one costs a full wave
-        double cost = waves * (per * unit_cost + inv_cost);
-        if (cost < best) { best = cost; best_threads = threads; }
-    }
-    return best_threads;
-}
 template <int W>
 static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_values, const uint32_t *d_blind, const uint64_t *d_pad_dest,
                             const Seed8 &seed, const uint64_t *d_pad_rng, int phase, const PadStreams &ps) {
@@ -669,28 +615,8 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     TRY_T(cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st));
     TRY_T(dmalloc(&t->d_level_off, (H + 1) * 8, st));
     TRY_T(cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st));
-    // ---- merges: sums level by level, one compress pass over all internal nodes, hashes level by level
-    if (H >= 1) {
-        for (int h = H; h >= 1; h--) {
-            uint64_t np = t->n_real[h - 1];
-            k_merge_sum<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr);
-            ctx->launches++;
-        }
-        InternalMap im;
-        memset(&im, 0, sizeof(im));
-        im.levels = H; im.level_off = t->d_level_off; im.pos = t->d_pos;
-        uint64_t n_int = 0;
-        for (int h = 0; h < H; h++) { im.start[h] = n_int; n_int += t->n_real[h]; }
-        im.start[H] = n_int;
-        uint64_t stride = batch_stride(n_int, k_compress_internal<NODE_BATCH>, 2.0);
-        k_compress_internal<NODE_BATCH><<<grid_for(stride, 128), 128, 0, st>>>(n_int, stride, t->ns, im);
-        ctx->launches++;
-        for (int h = H; h >= 1; h--) {
-            uint64_t np = t->n_real[h - 1];
-            k_merge_hash<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
-            ctx->launches++;
-        }
-    }
+    // ---- merges: sums level by level, one compress pass over all internal nodes, hashes level by level (dapol_merge.cu)
+    dapol_launch_merges(ctx, t);
     TRY_T(cudaEventRecord(ctx->ev[4], st));
     TRY_T(cudaMemcpyAsync(t->root_ext, t->ns.ext, 128, cudaMemcpyDeviceToHost, st));  // root = global node 0
     TRY_T(cudaGetLastError());
