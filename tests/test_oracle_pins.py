@@ -142,22 +142,24 @@ def test_collision_rule_matches(pyref, cref):
     assert rc == 0 and list(idx) == [x[0] for x in lv] and len(set(idx.tolist())) == n
 
 
-def _rand_tree(pyref, cref, hash_id, H, n, seed):
+def _rand_tree(pyref, cref, hash_id, H, n, seed, positional=False):
     rnd = random.Random(seed)
     liab = [(bytes([i]), bytes([i, i]), rnd.randrange(2 ** 32)) for i in range(n)]
     lv = pyref.derive_leaves(hash_id, liab, b"seed", H)
     idx = np.array([x[0] for x in lv], np.uint64)
     order = np.argsort(idx)
     bl = np.array([list(x[2].to_bytes(32, "little")) for x in lv], np.uint8)
-    T = cref.Tree(hash_id, H, idx[order], np.array([x[1] for x in lv], np.uint64)[order], bl[order], PAD_SEED)
+    T = cref.Tree(hash_id, H, idx[order], np.array([x[1] for x in lv], np.uint64)[order], bl[order], PAD_SEED, positional=positional)
     return lv, T, idx[order]
 
 
+@pytest.mark.parametrize("positional", [False, True])
 @pytest.mark.parametrize("hash_id", [0, 1])
-def test_tree_c_vs_bigint(pyref, cref, hash_id):
+def test_tree_c_vs_bigint(pyref, cref, hash_id, positional):
+    """positional: the opt-in mode of SURVEY 8(f) N3 (padding blindings keyed by (level, index)); the restatements must agree."""
     H = 6
-    lv, T, _ = _rand_tree(pyref, cref, hash_id, H, 9, 1)
-    pt = pyref.build_tree(hash_id, H, [(i, pyref.node_new(hash_id, v, r)) for i, v, r in lv], PAD_SEED)
+    lv, T, _ = _rand_tree(pyref, cref, hash_id, H, 9, 1, positional)
+    pt = pyref.build_tree(hash_id, H, [(i, pyref.node_new(hash_id, v, r)) for i, v, r in lv], PAD_SEED, positional=positional)
     npads = 0
     for h in range(H + 1):
         L = T.level(h)
