@@ -196,6 +196,51 @@ def test_large_tree_properties(ctx, cref):
         assert ((g["idx"][0::2] ^ 1) == g["idx"][1::2]).all()
 
 
+def test_full_size_tree_properties(cref):
+    """BASELINE config 2 at its full size (2^20 users, height 32, from liabilities, the bench's synthetic set): properties that do
+    not need the oracle to rebuild the tree -- the root value is the sum of the liabilities; node and padding counts follow from
+    the leaf indexes; children of every parent are adjacent; the id -> index map is a permutation-free injection into the leaf
+    level; and inclusion proofs of sampled users verify under the ORACLE's verifier against the GPU root (the Merkle fold hashes
+    every level of the path, the range proofs cover every sibling commitment), and a proof against a wrong leaf does not."""
+    import hashlib
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import AUDIT_SEED, synth_liabilities
+    from dapol_b200 import Context, Dapol
+    c = Context(0)
+    c.set_rangeproof_window(8)  # 16 sampled proofs: no point in building wide tables
+    n, H, agg = 1 << 20, 32, 4
+    liab = synth_liabilities(n)
+    t = Dapol.new(c, 0, liab, AUDIT_SEED, H, agg, PAD_SEED)
+    root = t.root_raw()
+    assert root.value == int(liab[4].sum())  # src/dapol/tests.rs:24 at scale
+    leaf = t.level(H)
+    real = leaf["is_pad"] == 0
+    lidx = leaf["idx"][real]
+    assert len(lidx) == n and (np.diff(lidx.astype(np.int64)) > 0).all()  # sorted, distinct: no index collision survived
+    # node / padding counts from the leaf indexes alone (level h has one real node per distinct prefix)
+    nodes, pads, cur = 1, 0, lidx
+    for h in range(H, 0, -1):
+        par = np.unique(cur >> np.uint64(1))
+        nodes += 2 * len(par); pads += 2 * len(par) - len(cur)
+        cur = par
+    assert (t.num_nodes, t.num_padding) == (nodes, pads)
+    for h in (H, 24, 12):
+        g = t.level(h)
+        assert ((g["idx"][0::2] ^ 1) == g["idx"][1::2]).all() and (g["v"][g["is_pad"] == 1] == 0).all()
+    users = [0, 1, n // 3, n - 1] + [int(x) for x in np.random.default_rng(7).integers(0, n, 12)]
+    picks = [t.leaf_index_of(u) for u in users]
+    assert all(p is not None and lidx[np.searchsorted(lidx, np.uint64(p))] == p for p in picks)  # every mapped index is a real leaf
+    proofs = t.generate_proofs(picks, hashlib.sha256(b"full-size").digest())
+    paths = t.paths(picks)
+    for k, pr in enumerate(proofs):
+        lc, lh = paths["leaf_comc"][k].tobytes(), paths["leaf_hash"][k].tobytes()
+        assert cref.verify_inclusion(0, 0, pr.serialize(), root.com, root.hash, lc, lh)
+        other = paths["leaf_comc"][(k + 1) % len(picks)].tobytes()
+        assert not cref.verify_inclusion(0, 0, pr.serialize(), root.com, root.hash, other, lh)
+    t.close(); c.close()
+
+
 def _liabs(n, seed, dense=False):
     rnd = random.Random(seed)
     ids = [rnd.randbytes(rnd.randrange(0, 40)) + i.to_bytes(3, "little") for i in range(n)]
