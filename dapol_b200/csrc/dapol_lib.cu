@@ -410,12 +410,22 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
         uint64_t keep = ~0ull;
         CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    int rc;
-    switch (ctx->W) {
-#define W_CASE(w) case w: rc = build_tables<w>(ctx); break;
-        DAPOL_W_CASES(W_CASE)
+    auto build = [&](int w) {
+        switch (w) {
+#define W_CASE(w_) case w_: return build_tables<w_>(ctx);
+            DAPOL_W_CASES(W_CASE)
 #undef W_CASE
-        default: rc = DAPOL_ERR_BAD_ARG;
+        }
+        return (int)DAPOL_ERR_BAD_ARG;
+    };
+    int rc = build(ctx->W);
+    if (rc == DAPOL_ERR_CUDA && comb_window == 0 && ctx->W != DAPOL_DEFAULT_COMB_WINDOW) {
+        // the wide tables did not fit after all (fragmentation, another context grabbed the memory): the L2-resident ones do
+        cudaGetLastError();
+        cudaFree(ctx->tab_b); cudaFree(ctx->tab_bbl);
+        ctx->tab_b = ctx->tab_bbl = nullptr;
+        ctx->W = DAPOL_DEFAULT_COMB_WINDOW;
+        rc = build(ctx->W);
     }
     if (rc) { dapol_ctx_destroy(ctx); return rc; }
     *out = ctx;
