@@ -361,9 +361,10 @@ static int build_one_table(dapol_ctx *ctx, ge_niels **tab, int nw, int which) {
         uint64_t runs = total / COMB_RUN;
         k_comb_table_run<W><<<grid_for(runs, 64), 64, 0, ctx->stream>>>(*tab, nw, bases, runs);
         ctx->launches += 2;
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         cudaFree(bases);
+        CUDA_TRY(e);
     } else {
         k_comb_table<W><<<grid_for(total, 64), 64, 0, ctx->stream>>>(*tab, nw, which, total);
         ctx->launches++;
