@@ -45,6 +45,9 @@ EX void emu_sc_op(int op, const uint8_t a[64], const uint8_t b[32], uint8_t out[
         case 4: { uint32_t w[16]; b2w(w, a, 16); sc_from_wide(r, w); break; }
         case 5: sc_reduce256(r, x); break;
         case 6: sc_neg(r, x); break;
+        case 7: { uint32_t w[16]; sc h; b2w(w, a, 16); sc_from_wide_with_half(r, h, w); break; }  // the wide reduction ...
+        case 8: { uint32_t w[16]; sc h; b2w(w, a, 16); sc_from_wide_with_half(h, r, w); break; }  // ... and its half
+        case 9: sc_half256(r, x); break;
         default: sc_set_u64(r, 0);
     }
     w2b(out, r.v, 8);

@@ -80,8 +80,12 @@ def test_scalar_ops(E):
         assert sc_op(1, a % L, b) == (a + b) % L and sc_op(2, a % L, b) == (a - b) % L and sc_op(6, a % L) == (-a) % L
         w = rnd.randrange(2 ** 512)
         assert sc_op(4, w) == w % L
+        half = pow(2, -1, L)
+        assert sc_op(7, w) == w % L and sc_op(8, w) == w * half % L and sc_op(9, a) == a * half % L  # padding scalars: r and r / 2
         assert E.emu_sc_is_canonical(B(a.to_bytes(32, "little"))) == (1 if a < L else 0)
     assert sc_op(4, 2 ** 512 - 1) == (2 ** 512 - 1) % L
+    for w in (0, 1, L, L - 1, 2 ** 256, 2 ** 256 - 1, 2 ** 512 - 1, L << 256):
+        assert sc_op(7, w) == w % L and sc_op(8, w) == w * pow(2, -1, L) % L
     for a in sv[10:16]:
         assert sc_op(3, a % L) == pow(a % L, L - 2, L)
 
