@@ -171,7 +171,7 @@ def cpu_baseline_leg(args):
             "sample": f"2^{sample_log2} users at height {H} (same sparsity as the workload), {reps} builds, {dt:.1f} s, OpenMP over {cores} threads"}, (n, H, root)
 
 
-def rangeproof_leg(ctx, L, dev, world, dist, args):
+def rangeproof_leg(ctx, L, dev, world, dist, args, imad_peak):
     """Range proofs/s (BASELINE.json's second metric): K independent 64-bit Bulletproofs per GPU, prove then verify,
     device-resident (CUDA events) and end to end through the host-buffer C ABI.  Shapes: m = 1 (single proofs, C5) and
     m = 32 (the aggregated proof of one height-32 inclusion proof under the Padding policy, C3)."""
@@ -204,7 +204,9 @@ def rangeproof_leg(ctx, L, dev, world, dist, args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ev[0].record(); prove_dev(); ev[1].record(); verify_dev(); ev[2].record()
+        ev[0].record(); prove_dev(); ev[1].record()
+        kt_prove = ctx.rangeproof_last_kernel_times()   # prove_dev returned after its own stream sync
+        verify_dev(); ev[2].record()
         torch.cuda.synchronize()
         t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev)
         all_ok = bool(d_ok.all().item())
@@ -222,11 +224,117 @@ def rangeproof_leg(ctx, L, dev, world, dist, args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         pm, vm = t.tolist(); pe, ve = te.tolist()
+        # roofline of the dominant kernel k_rp_p10 (L / R of the inner-product rounds over the generator tables): executed
+        # field + scalar MAC32 / its device time (CUDA events on the launching stream, this rank)
+        N, lg = 64 * m, (64 * m).bit_length() - 1
+        rpw = ctx.params()["rangeproof_window"]
+        w = 253 // rpw + 1
+        tab_rounds = lg if N < 1024 else lg - 5       # rp_switch_round: large aggregates fold the generators from round lg - 4 on
+        mac_p10 = K * tab_rounds * (2 * N * w * 7 * 72 + 3 * N * 128)
+        kt = kt_prove
+        achieved = mac_p10 / (kt["p10"] * 1e-3) / 1e9 if kt["p10"] > 0 else None
         out[f"n64_m{m}"] = {"proofs_per_gpu": K, "prove_per_s": world * K / pm * 1e3, "verify_per_s": world * K / vm * 1e3,
                             "prove_plus_verify_per_s": world * K / (pm + vm) * 1e3,
                             "e2e_prove_per_s": world * K / pe * 1e3, "e2e_verify_per_s": world * K / ve * 1e3,
                             "e2e_prove_plus_verify_per_s": world * K / (pe + ve) * 1e3,
-                            "all_verified": all_ok and bool(h_ok.all()), "proof_bytes": int(size)}
+                            "all_verified": all_ok and bool(h_ok.all()), "proof_bytes": int(size),
+                            "roofline": {"bound": "imad", "kernel": "k_rp_p10 (L/R MSMs of the inner-product rounds over the generator tables)",
+                                         "achieved": achieved, "peak": imad_peak, "unit": "GMAC32/s",
+                                         "frac": achieved / imad_peak if achieved and imad_peak else None,
+                                         "launch_ms_total": kt["p10"], "launches": tab_rounds, "rangeproof_window": rpw,
+                                         "mac32_per_proof_p10": mac_p10 / K, "share_of_prove": kt["p10"] / kt["total"] if kt["total"] else None,
+                                         "kernel_class_ms": kt,
+                                         "whole_prover_mac32_per_proof": prover_mac32(m, rpw),
+                                         "whole_prover_frac": (prover_mac32(m, rpw) * K / (pm * 1e-3 / 1) / 1e9 / imad_peak) if imad_peak else None}}
+    return out
+
+
+def prover_mac32(m, rpw):
+    """Executed field + scalar MAC32 of one 64-bit, m-party proof: A and S (3N table multiplications worth of
+    mixed additions: A adds one table entry per bit = N/w multiplications' worth), the table rounds (2N multiplications each), the
+    hybrid late rounds of large aggregates (materialise: 2 * 32 * N/32 = 2N; then ~184 variable-base multiplications at ~19
+    table ones each), T1/T2 and the vector passes (~40 N scalar products)."""
+    N, lg = 64 * m, (64 * m).bit_length() - 1
+    w = 253 // rpw + 1
+    tmul = w * 7 * 72
+    tab_rounds = lg if N < 1024 else lg - 5
+    hybrid = (2 * N + 184 * 19) * tmul if N >= 1024 else 0
+    return (2 * N + N / w) * tmul + tab_rounds * (2 * N * tmul + 3 * N * 128) + hybrid + 40 * N * 128
+
+
+def rangeproof_cpu_baseline(budget_s=6.0):
+    """CPU port (oracle/c) of the prover and the verifier of BASELINE's second metric on all host threads, one proof per
+    thread at a time (the reference is single-threaded per proof): m = 1 and m = 32, a bounded sample each."""
+    import concurrent.futures as cf
+    from oracle import cref
+    cref.build(); cref.lib()
+    cores = os.cpu_count() or 1
+    out = {}
+    for m, per_thread in ((1, 8), (32, 1)):
+        k = cores * per_thread
+        rng = np.random.default_rng(99 + m)
+        vals = rng.integers(0, 1 << 63, size=(k, m), dtype=np.uint64)
+        bl = rng.integers(0, 256, size=(k, m, 32), dtype=np.uint8); bl[:, :, 31] &= 0x0F
+        coms = [[cref.commit(int(vals[i, j]), bl[i, j].tobytes()) for j in range(m)] for i in range(k)]
+
+        def prove(i):
+            return cref.rp_prove([int(x) for x in vals[i]], [b.tobytes() for b in bl[i]], PAD_SEED, i, 0, 64)
+        with cf.ThreadPoolExecutor(cores) as ex:
+            t0 = time.perf_counter(); proofs = list(ex.map(prove, range(k))); tp = time.perf_counter() - t0
+            t0 = time.perf_counter(); oks = list(ex.map(lambda i: cref.rp_verify(proofs[i], coms[i], 64), range(k))); tv = time.perf_counter() - t0
+        assert all(oks)
+        out[f"n64_m{m}"] = {"prove_per_s": k / tp, "verify_per_s": k / tv, "prove_plus_verify_per_s": k / (tp + tv), "unit": "proofs/s",
+                            "cores": cores, "kind": "port",
+                            "sample": f"{k} proofs ({per_thread} per thread), prove {tp:.1f} s, verify {tv:.1f} s; generators precomputed once (the reference "
+                                      f"re-derives BulletproofGens::new(64, m) per call, src/range/mod.rs:50,66,85,104)"}
+    return out
+
+
+def c1_leg(ctx, L):
+    """BASELINE config 1 (the only configuration the reference itself benchmarks, benches/dapol.rs:24-57,59-141,149-175):
+    1024 leaves at stride 2^16 / 1024 of a height-16 tree (new_blank + build from ready nodes), aggregation_factor = height,
+    ONE inclusion proof generated and verified, both policies.  Latencies are wall clock through the host-buffer C ABI
+    (median of repeats); the CPU port runs the same calls on one thread (the reference is single-threaded)."""
+    from dapol_b200 import Dapol, DapolProof, DapolProofNode
+    from oracle import cref
+    cref.build(); cref.lib()
+    n, H = 1024, 16
+    idx = (np.arange(n, dtype=np.uint64) * np.uint64((1 << H) // n))
+    vals = splitmix64(n) & np.uint64(0xFFFFFFFF)
+    bl = np.frombuffer(b"".join(cref.rng_scalar(PAD_SEED, i, 7) for i in range(n)), np.uint8).reshape(n, 32).copy()
+
+    def med(f, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); r = f(); ts.append(time.perf_counter() - t0)
+        return statistics.median(ts) * 1e3, r
+    out = {"workload": "1024 leaves, height 16, stride layout, aggregation_factor 16 (benches/dapol.rs:149-175)"}
+    tree = Dapol.new_blank(ctx, 0, H, H)
+    launches0 = ctx.kernel_launches
+    tree.build(idx, vals, bl, PAD_SEED)
+    out["build_launches"] = int(ctx.kernel_launches - launches0)
+    ms, _ = med(lambda: tree.build(idx, vals, bl, PAD_SEED), 20)
+    out["gpu_build_ms"] = ms
+    t0 = time.perf_counter(); ora = cref.Tree(0, H, idx, vals, bl, PAD_SEED, 0, 1); out["cpu_build_ms_1thread"] = (time.perf_counter() - t0) * 1e3
+    ro, rg = ora.root(), tree.root_raw()
+    out["gpu_root_matches"] = bool((rg.value, rg.com, rg.hash) == (ro["v"], ro["comc"], ro["hash"]))
+    leaf = int(idx[n // 2])
+    paths = tree.paths([leaf])
+    ln = DapolProofNode(paths["leaf_comc"][0].tobytes(), paths["leaf_hash"][0].tobytes())
+    for pol, name in ((0, "padding"), (1, "splitting")):
+        tree.policy = pol
+        tree.generate_proof(leaf, PAD_SEED)  # generator tables + warm-up
+        launches0 = ctx.kernel_launches
+        ms, pr = med(lambda: tree.generate_proof(leaf, PAD_SEED), 10)
+        out[f"gpu_prove_ms_{name}"] = ms
+        out[f"prove_launches_{name}"] = int((ctx.kernel_launches - launches0) // 10)
+        ms, ok = med(lambda: pr.verify(ctx, tree.root(), ln), 10)
+        out[f"gpu_verify_ms_{name}"] = ms
+        t0 = time.perf_counter(); want = ora.prove_inclusion(leaf, H, pol, PAD_SEED); out[f"cpu_prove_ms_{name}"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter(); okc = cref.verify_inclusion(0, pol, want, ro["comc"], ro["hash"], ln.com, ln.hash)
+        out[f"cpu_verify_ms_{name}"] = (time.perf_counter() - t0) * 1e3
+        out[f"proof_bytes_match_{name}"] = bool(pr.serialize() == want) and bool(ok) and bool(okc)
+    tree.close()
     return out
 
 
@@ -242,8 +350,9 @@ def main():
     ap.add_argument("--cpu-sample-log2", type=int, default=17)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c1", action="store_true", help="skip the BASELINE config-1 latency leg (1024 leaves / height 16)")
     ap.add_argument("--rp-singles", type=int, default=16384, help="single range proofs per GPU in the range-proof leg (0 = skip)")
-    ap.add_argument("--rp-aggregates", type=int, default=512, help="m = 32 aggregated range proofs per GPU (0 = skip)")
+    ap.add_argument("--rp-aggregates", type=int, default=2048, help="m = 32 aggregated range proofs per GPU (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -363,7 +472,7 @@ def main():
     h2d = int(iid.nbytes + io.nbytes + eid.nbytes + eo.nbytes + vals.nbytes)
     d2h = 104 + 65 * 8 + 32 * 4  # root record + level histogram + collision-round counters (approx. 4 rounds)
 
-    rp = rangeproof_leg(ctx, L, dev, world, dist, args) if (args.rp_singles or args.rp_aggregates) else None
+    rp = rangeproof_leg(ctx, L, dev, world, dist, args, imad_peak) if (args.rp_singles or args.rp_aggregates) else None
 
     if rank == 0:
         internal = (nodes - 1) // 2  # every internal node has exactly two children
@@ -421,6 +530,21 @@ def main():
             t = Dapol.new(ctx, 0, s, AUDIT_SEED, sH, sH, PAD_SEED)
             line["cpu_baseline"]["gpu_root_matches"] = bool(t.root_raw().com == sroot)
             t.close()
+            # the timed full-size build against the oracle's root of the same workload (tests/golden/full_size_golden.json,
+            # produced once on the CPU by tests/golden/gen_golden_full.py: the oracle needs minutes for this tree)
+            try:
+                gold = json.load(open(os.path.join(ROOT, "tests", "golden", "full_size_golden.json")))["c2_2p20_h32"]
+                if (gold["users_log2"], gold["height"]) == (args.users_log2, H):
+                    line["cpu_baseline"]["full_size_root_matches_oracle_golden"] = bool(root_com.hex() == gold["root"]["com"])
+            except (OSError, KeyError):
+                pass
+            if rp is not None:
+                rp["cpu_baseline"] = rangeproof_cpu_baseline()
+                for key, cb_rp in rp["cpu_baseline"].items():
+                    if key in rp:
+                        rp[key]["e2e_speedup_vs_cpu_port"] = rp[key]["e2e_prove_plus_verify_per_s"] / cb_rp["prove_plus_verify_per_s"]
+            if not args.no_c1:
+                line["c1"] = c1_leg(ctx, L)
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -78,6 +78,7 @@ def lib():
     L.dapol_rangeproof_verify_batch_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, u64, vp, vp]
     L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
     L.dapol_rangeproof_last_times.argtypes = [vp, vp]
+    L.dapol_rangeproof_last_kernel_times.argtypes = [vp, vp]
     _lib = L
     return L
 

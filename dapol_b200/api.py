@@ -105,6 +105,12 @@ class Context:
         _check(_ffi.lib().dapol_rangeproof_last_times(self._h, _p(ms)))
         return dict(zip(("total", "msm", "other", "table_build"), ms.tolist()))
 
+    def rangeproof_last_kernel_times(self):
+        """Device time of the last batch per kernel class (ms): the MSM passes split into k_rp_p10 / k_rp_p3 / hybrid rounds / verifier."""
+        ms = np.zeros(8, np.float32)
+        _check(_ffi.lib().dapol_rangeproof_last_kernel_times(self._h, _p(ms)))
+        return dict(zip(("total", "msm", "other", "table_build", "p10", "p3", "hybrid", "verifier"), ms.tolist()))
+
     def rangeproof_prove_batch(self, nbits: int, values, blindings, seed: bytes, streams, base_blocks) -> np.ndarray:
         """k x generate_aggregated_range_proof (m = values.shape[1] parties; m = 1 is generate_single_range_proof).
         values [k][m] u64, blindings [k][m][32] Scalar bytes; returns [k][proof_len] bytes."""

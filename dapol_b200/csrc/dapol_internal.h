@@ -55,7 +55,9 @@ struct dapol_ctx {
     bool rp_W_auto = true;  // pick the widest window whose tables fit the HBM budget when they are built
     int rp_mcap = 0;
     ge_niels *rp_tab = nullptr;  // [(128 mcap + 2)][NW][2^(W-1)]
-    float rp_last_ms[4] = {0, 0, 0, 0};  // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build
+    // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build, and the MSM passes split per
+    // kernel class: [4] k_rp_p10 (L / R of the table rounds), [5] k_rp_p3 (A, S), [6] hybrid rounds (pm, pv, pf), [7] verifier (v1, v2)
+    float rp_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct dapol_tree {
@@ -71,6 +73,7 @@ struct dapol_tree {
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
     std::vector<uint64_t> npads;        // padding nodes per level
     uint32_t root_ext[32] = {};         // half point of the root commitment (kept for the shard root record)
+    uint32_t root_comc[8] = {}, root_hash[8] = {};  // compressed commitment and hash of the root (host copy: prover nonce key)
     // sharded trees: this tree is the subtree under node `prefix` of level top->height of `top`
     const dapol_tree *top = nullptr;
     uint64_t prefix = 0;

@@ -630,6 +630,8 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     dapol_launch_merges(ctx, t);
     TRY_T(cudaEventRecord(ctx->ev[4], st));
     TRY_T(cudaMemcpyAsync(t->root_ext, t->ns.ext, 128, cudaMemcpyDeviceToHost, st));  // root = global node 0
+    TRY_T(cudaMemcpyAsync(t->root_comc, t->ns.comc, 32, cudaMemcpyDeviceToHost, st));
+    TRY_T(cudaMemcpyAsync(t->root_hash, t->ns.hash, 32, cudaMemcpyDeviceToHost, st));
     TRY_T(cudaGetLastError());
     TRY_T(cudaStreamSynchronize(st));
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ctx->last_ms[i], ctx->ev[i], ctx->ev[i + 1]);
@@ -1092,6 +1094,8 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
         if (dmalloc(&t->d_pos, (H + 1) * sizeof(uint32_t *), st) != cudaSuccess || dmalloc(&t->d_level_off, (H + 1) * 8, st) != cudaSuccess ||
             cudaMemcpyAsync(t->d_pos, t->pos.data(), (H + 1) * sizeof(uint32_t *), cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(t->root_comc, t->ns.comc, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(t->root_hash, t->ns.hash, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             g_cuda_err = "tree load: device tables"; cudaGetLastError(); rc = DAPOL_ERR_CUDA;
         }

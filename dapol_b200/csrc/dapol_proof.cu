@@ -62,7 +62,28 @@ __global__ void k_gather_group(uint64_t k, int H, uint64_t start, uint64_t count
     ov[t] = v;
     store8(orr + t * 8, w);
 }
-// RNG contract: range proof #q of the inclusion proof of leaf x draws from ChaCha20(seed) stream x from block q << 32
+// ChaCha20 key of the prover's nonce streams of one tree: BLAKE3(label || seed || root commitment || root hash || le64 policy ||
+// le64 aggregation factor || le64 height).  The root commits to every witness of every proof, so the caller's seed re-used for
+// another tree (next audit), another policy or another aggregation factor never meets a nonce twice with different witnesses
+// (two e_blinding = alpha + rho x for one (alpha, rho) would leak both), and it is domain-separated from the padding stream.
+static void prover_nonce_key(uint8_t key[32], const uint8_t seed[32], const dapol_tree *whole, int policy, uint64_t agg, uint64_t height) {
+    static const uint8_t label[30] = {'d', 'a', 'p', 'o', 'l', '-', 'b', '2', '0', '0', ' ', 'p', 'r', 'o', 'v', 'e', 'r', ' ', 'n', 'o', 'n', 'c', 'e', ' ',
+                                      'k', 'e', 'y', ' ', 'v', '1'};
+    const uint64_t w[3] = {(uint64_t)policy, agg, height};
+    uint8_t tail[24];
+    for (int i = 0; i < 3; i++) for (int b = 0; b < 8; b++) tail[8 * i + b] = (uint8_t)(w[i] >> (8 * b));
+    dapol_hasher hs;
+    uint32_t out[8];
+    hasher_init(hs, DAPOL_HASH_BLAKE3);
+    hasher_update(hs, label, 30);
+    hasher_update(hs, seed, 32);
+    hasher_update_words(hs, whole->root_comc, 8);
+    hasher_update_words(hs, whole->root_hash, 8);
+    hasher_update(hs, tail, 24);
+    hasher_final(hs, out);
+    memcpy(key, out, 32);
+}
+// RNG contract: range proof #q of the inclusion proof of leaf x draws from ChaCha20(prover_nonce_key) stream x from block q << 32
 __global__ void k_proof_streams(uint64_t k, uint64_t per, uint64_t q0, const uint64_t *leaf_idx, uint64_t *stream, uint64_t *base) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= k * per) return;
@@ -82,6 +103,9 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
     const uint64_t size = dapol_inclusion_proof_size((int)H, aggregation_factor, policy);
     if (proof_size) *proof_size = size;
     if (!out || cap < k * size) return DAPOL_ERR_BUFFER;
+    uint8_t key[32];
+    prover_nonce_key(key, seed, t->top ? t->top : t, policy, aggregation_factor, H);
+    seed = key;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint64_t kh = k * (H ? H : 1), nsingle = H - sf;

@@ -376,17 +376,27 @@ static uint64_t rp_chunk(int N, int m, int lg, bool verify, uint64_t K) {
     return std::min<uint64_t>(K, c);
 }
 
-struct PhaseTimer {  // device time of the MSM passes vs the rest, on the ctx stream
+// device time per kernel class, on the ctx stream.  Classes: TM_OTHER = thread-per-proof / per-element passes; the MSM
+// passes are split into TM_P10 (L / R of the table rounds), TM_P3 (A, S), TM_HYB (pm, pv, pf), TM_VER (v1, v2).
+enum { TM_P10 = 0, TM_OTHER = 1, TM_P3 = 2, TM_HYB = 3, TM_VER = 4, TM_CLASSES = 5 };
+struct PhaseTimer {
     cudaStream_t st;
     cudaEvent_t e[2];
-    float ms[2] = {0, 0};
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[2];
+    float ms[TM_CLASSES] = {};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[TM_CLASSES];
     explicit PhaseTimer(cudaStream_t s) : st(s) {}
+    ~PhaseTimer() { collect(); }  // error paths: the events do not leak
     void begin(int which) { cudaEventCreate(&e[0]); cudaEventCreate(&e[1]); cudaEventRecord(e[0], st); cur = which; }
     void end() { cudaEventRecord(e[1], st); spans[cur].push_back({e[0], e[1]}); }
     void collect() {
-        for (int w = 0; w < 2; w++)
+        for (int w = 0; w < TM_CLASSES; w++) {
             for (auto &s : spans[w]) { float t = 0; cudaEventElapsedTime(&t, s.first, s.second); ms[w] += t; cudaEventDestroy(s.first); cudaEventDestroy(s.second); }
+            spans[w].clear();
+        }
+    }
+    void publish(float out[8]) const {
+        out[1] = ms[TM_P10] + ms[TM_P3] + ms[TM_HYB] + ms[TM_VER]; out[2] = ms[TM_OTHER];
+        out[4] = ms[TM_P10]; out[5] = ms[TM_P3]; out[6] = ms[TM_HYB]; out[7] = ms[TM_VER];
     }
     int cur = 0;
 };
@@ -406,7 +416,7 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     }
     k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     tm.end();
-    tm.begin(0);
+    tm.begin(TM_P3);
     if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
     else k_rp_p3<W, false><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
     tm.end();
@@ -426,7 +436,7 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         tm.begin(1);
         k_rp_p9<<<(unsigned)K, msm_threads(h), 0, st>>>(b, rnd);
         tm.end();
-        tm.begin(0);
+        tm.begin(rnd >= sw ? TM_HYB : TM_P10);
         if (rnd == sw) { k_rp_pm<W><<<grid_for(K * 2 * RP_FOLD_N, 64), 64, 0, st>>>(b, sw); ctx->launches++; }
         if (rnd >= sw) k_rp_pv<W><<<grid_for(K * 4 * h, 128), 128, 0, st>>>(b, rnd);
         else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
@@ -438,7 +448,7 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         tm.end();
         ctx->launches += 4;
         if (rnd >= sw && rnd < b.lg) {
-            tm.begin(0);
+            tm.begin(TM_HYB);
             k_rp_pf<<<grid_for(K * 2 * h, 64), 64, 0, st>>>(b, rnd);
             tm.end();
             ctx->launches++;
@@ -457,7 +467,7 @@ static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.svec, 2);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     tm.end();
-    tm.begin(0);
+    tm.begin(TM_VER);
     k_rp_v1<<<grid_for(K * b.vgroups, 64), 64, 0, st>>>(b);
     if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rp_v2<W, true><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
     else k_rp_v2<W, false><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
@@ -511,7 +521,7 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
     cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     tm.collect();
-    ctx->rp_last_ms[1] = tm.ms[0]; ctx->rp_last_ms[2] = tm.ms[1];
+    tm.publish(ctx->rp_last_ms);
     return bad ? DAPOL_ERR_BAD_ARG : DAPOL_OK;
 }
 // Device-resident batch verify.  d_proofs [K][plen], d_coms [K][m][32], d_ok [K] out (1 accept, 0 reject).
@@ -556,7 +566,7 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
     cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     tm.collect();
-    ctx->rp_last_ms[1] = tm.ms[0]; ctx->rp_last_ms[2] = tm.ms[1];
+    tm.publish(ctx->rp_last_ms);
     CUDA_TRY(cudaGetLastError());
     return DAPOL_OK;
 }
@@ -631,6 +641,11 @@ extern "C" int dapol_rangeproof_verify_batch(dapol_ctx *ctx, int nbits, int m, u
 extern "C" int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]) {
     if (!ctx || !ms) return DAPOL_ERR_BAD_ARG;
     memcpy(ms, ctx->rp_last_ms, sizeof(float) * 4);
+    return DAPOL_OK;
+}
+extern "C" int dapol_rangeproof_last_kernel_times(const dapol_ctx *ctx, float ms[8]) {
+    if (!ctx || !ms) return DAPOL_ERR_BAD_ARG;
+    memcpy(ms, ctx->rp_last_ms, sizeof(float) * 8);
     return DAPOL_OK;
 }
 extern "C" int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window) {

@@ -15,8 +15,20 @@
  * bulletproofs' prove_*; bit-exactness is defined against an injected stream):
  *   ChaCha20 (rand_chacha::ChaCha20Rng layout: 64-bit block counter, 64-bit stream id);
  *   k-th Scalar::random = from_bytes_mod_order_wide(keystream block k).
- *   Padding nodes: stream 0, block pad_base + creation ordinal (level H..1, left to right).
- *   Range proof #q of the inclusion proof for leaf x: stream x, blocks (q << 32) + draw#.
+ *   Padding nodes: key pad_seed, stream 0, block pad_base + creation ordinal (level H..1, left to right).
+ *   Range proof #q of the inclusion proof for leaf x (dapol_prove_batch / dapol_prove_to_file): key =
+ *     BLAKE3("dapol-b200 prover nonce key v1" || seed || root commitment || root hash || le64 policy ||
+ *            le64 aggregation_factor || le64 tree height),  stream x, blocks (q << 32) + draw#
+ *     (bulletproofs' party / dealer draw order, 132 m draws per proof at 64 bits).  The key binds the caller's seed to the
+ *     tree (whose root commits to every witness), the policy and the aggregation factor: re-using one seed for the next
+ *     audit's tree or for another policy / factor never pairs a nonce with two different witnesses, and the prover streams
+ *     are domain-separated from the padding stream even if the same 32 bytes are passed as pad_seed and seed.
+ *     A Rust-side comparison seeds rand_chacha::ChaCha20Rng with that key, set_stream(x), set_word_pos(q << 36).
+ *   The raw range-proof entry points (dapol_rangeproof_prove_batch*) take (seed, stream, base block) as given: the caller
+ *     must never prove two different witnesses under the same triple.
+ * SECRETS: seed and pad_seed must be secret, high-entropy and known only to the prover; the blindings they generate hide the
+ * liabilities.  Table look-ups and Straus windows are indexed by secret scalars (blindings, nonces): this library is NOT
+ * constant-time -- run it on hardware the prover controls (the reference's dalek code is constant-time for secrets).
  */
 #ifndef DAPOL_B200_H
 #define DAPOL_B200_H
@@ -231,6 +243,10 @@ DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m
 DAPOL_API int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window);
 /* device time of the last range-proof batch on this ctx (ms): [0] total, [1] MSM passes, [2] other passes, [3] last table build */
 DAPOL_API int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]);
+/* the same plus the MSM passes split per kernel class (CUDA events on the ctx stream; the roofline report of the dominant kernel):
+ * [4] k_rp_p10 (L / R of the inner-product rounds over the generator tables), [5] k_rp_p3 (A, S), [6] hybrid late rounds
+ * (k_rp_pm / pv / pf), [7] verifier (k_rp_v1 / v2) */
+DAPOL_API int dapol_rangeproof_last_kernel_times(const dapol_ctx *ctx, float ms[8]);
 
 /* Micro-entry points used by the parity tests and the roofline microbenchmark. */
 DAPOL_API int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *values, const uint8_t *blindings, uint8_t *coms /* n*32 */);

@@ -273,17 +273,27 @@ static int is_pair(const node *cur, uint64_t cnt, uint64_t i) {
  * padding node at (level h, index i) draws block i of stream h of ChaCha20(pad_seed) -- Paddable::padding(idx, secret) as a
  * function of its arguments (src/dapol/node.rs:85-88 leaves that as a TODO); pad_base is ignored. */
 static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
-                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode, dor_tree **out);
+                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode,
+                           const uint64_t *level_base, dor_tree **out);
 EXPORT int dor_tree_build(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, dor_tree **out) {
-    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, pad_base, nthreads, 0, out);
+    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, pad_base, nthreads, 0, NULL, out);
+}
+/* One shard of a tree split by leaf-index prefix: the subtree under one node of level k draws its padding
+ * blindings from the blocks the single-tree creation order (level H..1, left to right) gives them: the r-th padding node of
+ * the subtree's level h draws block level_base[h] + r of stream 0. */
+EXPORT int dor_tree_build_shard(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
+                                const uint8_t *blindings, const uint8_t pad_seed[32], const uint64_t *level_base /*[height+1]*/,
+                                int nthreads, dor_tree **out) {
+    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, 0, nthreads, 0, level_base, out);
 }
 EXPORT int dor_tree_build_positional(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
                                      const uint8_t *blindings, const uint8_t pad_key[32], int nthreads, dor_tree **out) {
-    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_key, 0, nthreads, 1, out);
+    return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_key, 0, nthreads, 1, NULL, out);
 }
 static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
-                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode, dor_tree **out) {
+                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode,
+                           const uint64_t *level_base, dor_tree **out) {
     if (height > 64 || height < 0 || n == 0 || (height == 0 && n != 1)) return ERR_BAD_ARG;
     for (uint64_t i = 0; i < n; i++) {
         if (i && idx_sorted[i] <= idx_sorted[i - 1]) return ERR_BAD_ARG;
@@ -298,7 +308,7 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
     t->hash_id = hash_id; t->height = height;
     t->lv = (level *)calloc((size_t)height + 1, sizeof(level));
     node *cur = (node *)calloc(n, sizeof(node));
-    uint64_t cnt = n, draw = pad_base;
+    uint64_t cnt = n, draw = pad_base, n_pads = 0;
 #pragma omp parallel for schedule(dynamic, 16)
     for (uint64_t i = 0; i < n; i++) node_new(hash_id, &cur[i], idx_sorted[i], values[i], blindings + 32 * i, 0);
     for (int h = height; h >= 1; h--) {
@@ -307,6 +317,7 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
         node *full = (node *)calloc(2 * np, sizeof(node));
         uint64_t *pad_draw = (uint64_t *)malloc(8 * np);
         uint64_t j = 0;
+        if (level_base) draw = level_base[h];
         for (uint64_t i = 0; i < cnt; j++) {
             if (is_pair(cur, cnt, i)) {
                 full[2 * j] = cur[i]; full[2 * j + 1] = cur[i + 1]; pad_draw[j] = NO_DRAW; i += 2;
@@ -315,7 +326,7 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
                 full[2 * j + side] = cur[i];
                 full[2 * j + (1 - side)].idx = cur[i].idx ^ 1;
                 full[2 * j + (1 - side)].is_pad = 1;
-                pad_draw[j] = draw++;
+                pad_draw[j] = draw++; n_pads++;
                 i += 1;
             }
         }
@@ -338,7 +349,7 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
         cur = par; cnt = np;
     }
     t->lv[0].nodes = cur; t->lv[0].count = cnt;
-    t->n_pads = draw - pad_base;
+    t->n_pads = n_pads;
     *out = t;
     return ERR_OK;
 }
@@ -668,9 +679,21 @@ EXPORT uint64_t dor_inclusion_proof_size(int height, uint64_t agg, int policy) {
     sz += 2 + 8 + ((uint64_t)height + 7) / 8 + 8 + 64 * (uint64_t)height;
     return sz;
 }
+/* ChaCha20 key of the prover's nonce streams of one tree (RNG contract, include/dapol_b200.h): BLAKE3(label || seed || root
+ * commitment || root hash || le64 policy || le64 aggregation factor || le64 height) -- the seed bound to the tree (its root
+ * commits to every witness), the policy and the factor, so a re-used seed never re-uses a nonce with another witness. */
+EXPORT void dor_prover_nonce_key(const uint8_t seed[32], const uint8_t root_com[32], const uint8_t root_hash[32], int policy, uint64_t agg,
+                                 int height, uint8_t key[32]) {
+    static const char label[] = "dapol-b200 prover nonce key v1";
+    uint8_t buf[30 + 96 + 24];
+    uint64_t w[3] = {(uint64_t)policy, agg, (uint64_t)height};
+    memcpy(buf, label, 30); memcpy(buf + 30, seed, 32); memcpy(buf + 62, root_com, 32); memcpy(buf + 94, root_hash, 32);
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 8; k++) buf[126 + 8 * i + k] = (uint8_t)(w[i] >> (8 * k));
+    hash_buf(0, buf, sizeof buf, key);
+}
 /* Dapol::generate_proof (mod.rs:167-190) + DapolProof::serialize (proof/mod.rs:68-73).
  * RNG contract: range proof #q of this DapolProof (aggregated first, then singles) draws from
- * ChaCha20(seed, stream = leaf_idx) starting at block q << 32. */
+ * ChaCha20(dor_prover_nonce_key(seed, root, policy, agg, height), stream = leaf_idx) starting at block q << 32. */
 EXPORT int dor_prove_inclusion(const dor_tree *t, uint64_t leaf_idx, uint64_t agg, int policy, const uint8_t seed[32],
                                uint8_t *out, uint64_t cap, uint64_t *out_len) {
     const node *sib[64];
@@ -681,6 +704,9 @@ EXPORT int dor_prove_inclusion(const dor_tree *t, uint64_t leaf_idx, uint64_t ag
     if (cap < need) return ERR_BUFFER;
     agg_group g[64]; int ng; uint64_t sf;
     policy_plan(H, agg, policy, g, &ng, &sf);
+    uint8_t key[32];
+    dor_prover_nonce_key(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, policy, agg, t->height, key);
+    seed = key;
     uint8_t *o = out; uint64_t q = 0, plen;
     if (policy == POLICY_SPLITTING) { put_be(o, (uint64_t)ng, 2); o += 2; }
     for (int i = 0; i < ng; i++) {

@@ -147,14 +147,20 @@ def derive_leaves(hash_id, iid_blob, iid_off, eid_blob, eid_off, audit_seed: byt
 
 
 class Tree:
-    def __init__(self, hash_id, height, idx_sorted, values, blindings, pad_seed: bytes, pad_base=0, nthreads=0, positional=False):
-        """positional=True: padding blindings keyed by (level, index) instead of the creation-order stream."""
+    def __init__(self, hash_id, height, idx_sorted, values, blindings, pad_seed: bytes, pad_base=0, nthreads=0, positional=False, level_base=None):
+        """positional=True: padding blindings keyed by (level, index) instead of the creation-order stream.
+        level_base (u64[height + 1]): one shard of a prefix-split tree -- the r-th padding node of level h draws block
+        level_base[h] + r (the blocks the single-tree creation order gives this subtree)."""
         idx, ip = _np(idx_sorted, np.uint64)
         val, vp = _np(values, np.uint64)
         bl, bp = _np(blindings, np.uint8)
         assert bl.size == 32 * idx.size
         h = C.c_void_p()
-        if positional:
+        if level_base is not None:
+            lb, lbp = _np(level_base, np.uint64)
+            assert lb.size == height + 1
+            rc = lib().dor_tree_build_shard(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), lbp, nthreads, C.byref(h))
+        elif positional:
             rc = lib().dor_tree_build_positional(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), nthreads, C.byref(h))
         else:
             rc = lib().dor_tree_build(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, _b(pad_seed), C.c_uint64(pad_base), nthreads, C.byref(h))

@@ -957,12 +957,24 @@ def merkle_deserialize(b: bytes, begin=0, dlen=32):
     return height, idx, sibs, begin
 
 
+PROVER_KEY_LABEL = b"dapol-b200 prover nonce key v1"
+
+
+def prover_nonce_key(seed: bytes, root_com: bytes, root_hash: bytes, policy: int, agg: int, height: int) -> bytes:
+    """ChaCha20 key of the prover's nonce streams of one tree (RNG contract, include/dapol_b200.h): the caller's seed bound to
+    the tree (its root commits to every witness), the policy, the aggregation factor and the height, so that re-using a seed
+    for another tree / policy / factor never re-uses a nonce with a different witness.  Always BLAKE3, whatever D is."""
+    return digest(HASH_BLAKE3, PROVER_KEY_LABEL, seed, root_com, root_hash, struct.pack("<QQQ", policy, agg, height))
+
+
 def prove_inclusion(tree: Tree, leaf_idx: int, agg: int, policy: int, seed: bytes) -> bytes:
     """Dapol::generate_proof -> DapolProof::serialize = range || merkle (proof/mod.rs:68-73)."""
     sibs = tree.path_siblings(leaf_idx)
     values = [s.v for s in sibs]
     blindings = [s.r % L for s in sibs]
-    aggregated, individual = policy_prove(values, blindings, agg, policy, seed, leaf_idx)
+    root = tree.root  # property
+    key = prover_nonce_key(seed, root.comc, root.hash, policy, agg, tree.height)
+    aggregated, individual = policy_prove(values, blindings, agg, policy, key, leaf_idx)
     return policy_serialize(aggregated, individual, policy) + merkle_serialize(
         tree.height, leaf_idx, [(s.comc, s.hash) for s in sibs])
 
