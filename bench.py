@@ -50,6 +50,8 @@ def executed_mac32(comb_window, node_batch):
     merge = full_add + 2 * SCMUL + compress                     # point add; r_L + r_R mod l; compress
     return leaf, pad, merge
 NODE_BYTES = 104  # com 32 + hash 32 + v 8 + r 32
+# ncu --set full capture of the k_pad launch of THIS kernel version on THIS workload (roofline.traffic); re-captured whenever k_pad changes
+PAD_NCU_CAPTURE = "r02a_k_pad_ncu_full.json"
 
 
 def splitmix64(n, seed=0xDA901):
@@ -270,7 +272,7 @@ def rangeproof_cpu_baseline(budget_s=6.0):
     cref.build(); cref.lib()
     cores = os.cpu_count() or 1
     out = {}
-    for m, per_thread in ((1, 8), (32, 1)):
+    for m, per_thread in ((1, 192), (32, 6)):  # ~4 s of proving per shape on every core
         k = cores * per_thread
         rng = np.random.default_rng(99 + m)
         vals = rng.integers(0, 1 << 63, size=(k, m), dtype=np.uint64)
@@ -485,7 +487,7 @@ def main():
         build_survey = leaves_here * MAC32_LEAF + pads * MAC32_PAD + internal * MAC32_MERGE
         traffic = None  # DRAM bytes of one k_pad launch from the committed ncu --set full capture, if it is of this workload
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01d_k_pad_ncu_full.json")))["launches"][0]
+            cap = json.load(open(os.path.join(ROOT, "profiles", PAD_NCU_CAPTURE)))["launches"][0]
             if int(cap["units_in_launch"]) == int(pads) and params["comb_window"] == 24:
                 traffic = cap["dram_bytes_per_launch"]
         except Exception:

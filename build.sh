@@ -8,7 +8,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -split-compile 0 -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden ${DAPOL_PTXAS_V:+-Xptxas -v}"
 newest_hdr=$(ls -t dapol_b200/csrc/*.cuh dapol_b200/csrc/*.h dapol_b200/csrc/*.inc include/*.h build.sh | head -1)
 pids=(); tus=()
-for tu in dapol_lib dapol_merge dapol_rp dapol_proof; do
+for tu in dapol_lib dapol_merge dapol_rp dapol_proof dapol_shard; do
   o=build/$tu.o
   if [ -n "$FORCE" ] || [ -n "$*" ] || [ ! -f $o ] || [ dapol_b200/csrc/$tu.cu -nt $o ] || [ "$newest_hdr" -nt $o ]; then
     $NVCC $FLAGS -c -o $o.tmp dapol_b200/csrc/$tu.cu "$@" > build/$tu.log 2>&1 && mv $o.tmp $o &
@@ -19,5 +19,5 @@ rc=0
 for p in "${pids[@]}"; do wait $p || rc=1; done
 for tu in "${tus[@]}"; do cat build/$tu.log; done
 [ $rc -eq 0 ] || { echo "build failed"; exit 1; }
-$NVCC -gencode arch=compute_100a,code=sm_100a --shared -o dapol_b200/lib/libdapol_b200.so build/dapol_lib.o build/dapol_merge.o build/dapol_rp.o build/dapol_proof.o
+$NVCC -gencode arch=compute_100a,code=sm_100a --shared -o dapol_b200/lib/libdapol_b200.so build/dapol_lib.o build/dapol_merge.o build/dapol_rp.o build/dapol_proof.o build/dapol_shard.o -ldl
 echo "built dapol_b200/lib/libdapol_b200.so (recompiled: ${tus[*]:-nothing})"

@@ -71,6 +71,7 @@ struct dapol_tree {
     uint32_t **d_pos = nullptr;   // device copy of the pointer table
     uint64_t *d_level_off = nullptr;
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
+    uint64_t index_map_first = 0, index_map_n = 0;  // sharded build: the map covers input positions [first, first + n) (0: all n_leaves)
     std::vector<uint64_t> npads;        // padding nodes per level
     uint32_t root_ext[32] = {};         // half point of the root commitment (kept for the shard root record)
     uint32_t root_comc[8] = {}, root_hash[8] = {};  // compressed commitment and hash of the root (host copy: prover nonce key)

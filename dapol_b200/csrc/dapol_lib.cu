@@ -1021,7 +1021,8 @@ extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
     const uint64_t T = t->T;
     TreeFileHeader h = {};
     memcpy(h.magic, TREE_MAGIC, 8);
-    h.version = 1; h.hash_id = t->hash_id; h.height = H; h.flags = t->leaf_index_of ? 1u : 0u;
+    const bool save_map = t->leaf_index_of && t->index_map_n == 0;  // a shard's local slice of the map is not saved
+    h.version = 1; h.hash_id = t->hash_id; h.height = H; h.flags = save_map ? 1u : 0u;
     h.n_leaves = t->n_leaves; h.T = T; h.n_pads = t->n_pads; h.pos_words = pos_words_of(t->n_real, H, nullptr);
     int rc = DAPOL_OK;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1;
@@ -1033,7 +1034,7 @@ extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
     if (!ok) rc = DAPOL_ERR_IO;
     const struct { const void *p; size_t bytes; } parts[] = {
         {t->ns.idx, T * 8}, {t->ns.v, T * 8}, {t->ns.r, T * 32}, {t->ns.comc, T * 32}, {t->ns.hash, T * 32}, {t->ns.is_pad, T},
-        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, t->leaf_index_of ? t->n_leaves * 8 : 0}};
+        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, save_map ? t->n_leaves * 8 : 0}};
     for (const auto &pt : parts)
         if (rc == DAPOL_OK && pt.bytes) rc = dev_to_file(f, pt.p, pt.bytes, buf, st);
     if (rc == DAPOL_OK && fwrite(TREE_MAGIC, 8, 1, f) != 1) rc = DAPOL_ERR_IO;  // trailer: a truncated file does not load
@@ -1131,8 +1132,10 @@ extern "C" int dapol_tree_root(const dapol_tree *t, uint8_t com[32], uint8_t has
 }
 extern "C" int dapol_tree_leaf_index_of(const dapol_tree *t, uint64_t input_pos, uint64_t *leaf_idx) {
     if (!t || !leaf_idx) return DAPOL_ERR_BAD_ARG;
-    if (!t->leaf_index_of || input_pos >= t->n_leaves) return DAPOL_ERR_NOT_FOUND;
-    CUDA_TRY(cudaMemcpy(leaf_idx, t->leaf_index_of + input_pos, 8, cudaMemcpyDeviceToHost));
+    const uint64_t first = t->index_map_first, cnt = t->index_map_n ? t->index_map_n : t->n_leaves;
+    if (!t->leaf_index_of || input_pos < first || input_pos - first >= cnt) return DAPOL_ERR_NOT_FOUND;
+    CUDA_TRY(cudaSetDevice(t->ctx->device));
+    CUDA_TRY(cudaMemcpy(leaf_idx, t->leaf_index_of + (input_pos - first), 8, cudaMemcpyDeviceToHost));
     return DAPOL_OK;
 }
 // device-resident path extraction (shared with the inclusion-proof path): all outputs are device pointers

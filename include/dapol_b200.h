@@ -161,6 +161,49 @@ DAPOL_API int dapol_tree_build_from_records(dapol_ctx *ctx, int hash_id, int hei
  * dapol_tree_paths / dapol_prove_batch then take whole-tree leaf indexes and emit whole-tree paths and proofs. */
 DAPOL_API int dapol_tree_attach_top(dapol_tree *tree, const dapol_tree *top, uint64_t prefix);
 
+/* ---- sharded build, ONE call per rank (what a multi-GPU host uses; the staged entry points above remain for hosts that
+ * bring their own exchange).  Collectives go through a communicator: the built-in backend is NCCL (resolved with dlopen
+ * at run time: the copy of libnccl.so.2 the process already holds, e.g. torch's, else the system one; no link-time
+ * dependency), or the host plugs its own transport as two callbacks on DEVICE buffers.
+ *   rank 0:      dapol_comm_nccl_unique_id(id);  -> ship the 128 bytes to every rank by any means (MPI, TCP, a file, ...)
+ *   every rank:  dapol_comm_nccl_create(ctx, id, rank, world, &comm);
+ *                dapol_sharded_build(ctx, comm, ..., &subtree, &top, ...);      (Dapol::new over all ranks' liabilities) */
+typedef struct dapol_comm dapol_comm;
+typedef struct dapol_comm_ops {
+    void *user;
+    /* every rank contributes `bytes` bytes at d_send; d_recv receives world * bytes in rank order.  Device pointers; the
+     * operation is ordered on cuda_stream (enqueue it there, or synchronise the stream, do it, and return when it is done) */
+    int (*all_gather)(void *user, const void *d_send, void *d_recv, uint64_t bytes, void *cuda_stream);
+    /* rank r is sent send_bytes[r] bytes from d_send + send_off[r] and sends recv_bytes[r] bytes to d_recv + recv_off[r]
+     * (host arrays of `world` entries; a rank's own block goes through the same call) */
+    int (*all_to_all)(void *user, const void *d_send, const uint64_t *send_off, const uint64_t *send_bytes, void *d_recv,
+                      const uint64_t *recv_off, const uint64_t *recv_bytes, void *cuda_stream);
+} dapol_comm_ops;
+#define DAPOL_NCCL_ID_BYTES 128
+DAPOL_API int dapol_comm_create(int rank, int world, const dapol_comm_ops *ops, dapol_comm **out);
+DAPOL_API int dapol_comm_nccl_unique_id(uint8_t id[DAPOL_NCCL_ID_BYTES]);
+DAPOL_API int dapol_comm_nccl_create(dapol_ctx *ctx, const uint8_t id[DAPOL_NCCL_ID_BYTES], int rank, int world, dapol_comm **out);
+DAPOL_API void dapol_comm_destroy(dapol_comm *comm);
+DAPOL_API int dapol_comm_rank(const dapol_comm *comm);
+DAPOL_API int dapol_comm_world(const dapol_comm *comm);
+/* Dapol::new(liabilities, options) (src/dapol/mod.rs:100-128) where the liabilities are the concatenation of every rank's
+ * slice in rank order (this rank passes ITS slice: device pointers, n_local may be 0) and the tree is split by the
+ * log2(world)-bit leaf-index prefix.  Bit-identical with dapol_tree_build_from_liabilities of the whole input for the same
+ * pad_seed / pad_base.  Per rank: 96 B per LOCAL user leave over the all-to-all (audit id for the duplicate check, claim =
+ * candidate index + position + value + blinding); index collisions are resolved by the owner of the index prefix, only the
+ * losers of a round travel again; then one all-gather of per-level padding counts and one of the 232-byte subtree roots.
+ * Outputs: *subtree = this rank's height-(H - k) subtree with *top attached (NULL if no leaf fell into the rank's prefix;
+ * world == 1: the whole tree, *top = NULL); *top = the top k levels (replicated); destroy subtree first, then top.
+ * dapol_tree_leaf_index_of(*top, pos) answers for the LOCAL slice, pos in [*first_pos, *first_pos + n_local).
+ * Errors are collective: every rank returns the same code (DUPLICATED_INTERNAL_ID / FAILED_TO_MAP_INDEX with *err_pos =
+ * the earliest offending input position of the whole input).  phase_ms (may be NULL): device time of [0] hashing,
+ * [1] exchange (duplicate check + claim rounds), [2] leaves + subtree build, [3] root gather + top tree. */
+DAPOL_API int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id, int height, uint64_t n_local, const uint8_t *d_iid_blob,
+                                  const uint64_t *d_iid_off, const uint8_t *d_eid_blob, const uint64_t *d_eid_off, const uint64_t *d_values,
+                                  const uint8_t *audit_seed, uint64_t audit_seed_len, const uint8_t pad_seed[32], uint64_t pad_base,
+                                  dapol_tree **subtree, dapol_tree **top, uint64_t *n_total, uint64_t *first_pos, uint64_t *err_pos,
+                                  float phase_ms[4]);
+
 DAPOL_API void dapol_tree_destroy(dapol_tree *tree);
 
 /* Dapol::root_raw / root   (src/dapol/mod.rs:134-141): commitment (compressed), hash, value, blinding. */
