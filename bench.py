@@ -353,6 +353,8 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c1", action="store_true", help="skip the BASELINE config-1 latency leg (1024 leaves / height 16)")
+    ap.add_argument("--staged-sharding", action="store_true", help="N > 1: the staged C-ABI calls orchestrated from Python (round-1 path) "
+                    "instead of the one-call dapol_sharded_build")
     ap.add_argument("--rp-singles", type=int, default=16384, help="single range proofs per GPU in the range-proof leg (0 = skip)")
     ap.add_argument("--rp-aggregates", type=int, default=2048, help="m = 32 aggregated range proofs per GPU (0 = skip)")
     args = ap.parse_args()
@@ -361,7 +363,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dapol_b200 import Comm, Context, CudaEngine, Dapol, ShardedDapol, _ffi
+    from dapol_b200 import Comm, Context, CudaEngine, Dapol, NativeComm, ShardedDapol, _ffi
     import ctypes as C
 
     rank = int(os.environ.get("RANK", "0"))
@@ -381,10 +383,14 @@ def main():
     engine = CudaEngine(ctx)
     k = (world - 1).bit_length()
     assert (1 << k) == world, "--gpus must be a power of two"
+    # N > 1: the library's own NCCL communicator; the whole sharded build is ONE C-ABI call per rank (dapol_sharded_build)
+    native = NativeComm(ctx, comm, "nccl") if world > 1 and not args.staged_sharding else None
+    exch_ms = []
 
     # Weak scaling: every rank holds 2^users_log2 users.  N GPUs build ONE tree over all N * 2^users_log2 users, of height
-    # height + log2 N (same sparsity, so per-GPU work is fixed): per-user hashing on the owner of the slice, one all-gather
-    # of the 112-byte user records, independent subtrees per leaf-index prefix, one all-gather of the N subtree roots.
+    # height + log2 N (same sparsity, so per-GPU work is fixed): per-user hashing on the owner of the slice, all-to-all of
+    # 96 B per local user (duplicate check + index claims; collisions resolved by the owner of the index prefix), independent
+    # subtrees per leaf-index prefix, one all-gather of the N subtree roots.
     n, H = 1 << args.users_log2, args.height + k
     iid, io, eid, eo, vals = synth_liabilities(n, first=rank * n)
     pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -404,7 +410,9 @@ def main():
             res = (L.dapol_tree_num_nodes(h), L.dapol_tree_num_padding(h), ctx.last_build_times())
             L.dapol_tree_destroy(h)
             return res
-        t = ShardedDapol.new(engine, comm, 0, (d_iid, d_io, d_eid, d_eo, d_vals), AUDIT_SEED, H, H, PAD_SEED)
+        t = ShardedDapol.new(engine, comm, 0, (d_iid, d_io, d_eid, d_eo, d_vals), AUDIT_SEED, H, H, PAD_SEED, native=native)
+        if t.phase_ms:
+            exch_ms.append(t.phase_ms)
         res = (L.dapol_tree_num_nodes(t.subtree) if t.subtree else 0, L.dapol_tree_num_padding(t.subtree) if t.subtree else 0,
                engine.last_shard_times or dict.fromkeys(phase_keys, 0.0))
         t.close()
@@ -421,7 +429,7 @@ def main():
             L.dapol_tree_root(h, com.ctypes.data, hs.ctypes.data, C.byref(v), bl.ctypes.data)  # D2H of the step's result
             L.dapol_tree_destroy(h)
             return com.tobytes(), v.value
-        t = ShardedDapol.new(engine, comm, 0, (h_iid, h_io, h_eid, h_eo, h_vals), AUDIT_SEED, H, H, PAD_SEED)
+        t = ShardedDapol.new(engine, comm, 0, (h_iid, h_io, h_eid, h_eo, h_vals), AUDIT_SEED, H, H, PAD_SEED, native=native)
         r = t.root_raw()
         t.close()
         return r.com, r.value
@@ -500,10 +508,14 @@ def main():
                                    f"{world * n} users, D=blake3 (leaf derivation + commit + hash + merge + padding)",
                        "users_per_gpu": n, "height": H, "nodes_rank0": nodes, "padding_nodes_rank0": pads,
                        "comb_window": params["comb_window"], "nodes_per_inversion": params["node_batch"],
-                       "parallelism": (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs: all-gather of user records "
-                                       f"(112 B/user) + all-gather of {world} subtree roots (232 B)") if world > 1 else "single GPU",
+                       "parallelism": ((f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs, one dapol_sharded_build call per rank "
+                                        f"(library-owned NCCL communicator): all-to-all of 96 B per local user (duplicate check + index claims), "
+                                        f"losers-only re-claim rounds, all-gather of padding counts and of {world} subtree roots (232 B)")
+                                       if native else (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs (staged C-ABI calls, "
+                                                       f"torch.distributed): all-gather of user records (112 B/user) + all-gather of {world} subtree roots"))
+                       if world > 1 else "single GPU",
                        "l2": "per-step working set (node store + half points ~%.1f GB) >> 126 MB L2; no reuse across steps" % (nodes * 232 / 1e9)},
-            "phase_ms": med,
+            "phase_ms": dict(med, **({"sharded_" + kk: statistics.median(x[kk] for x in exch_ms[-args.steps:]) for kk in exch_ms[-1]} if exch_ms else {})),
             "roofline": {"bound": "imad", "kernel": "k_pad (padding-node pass)", "achieved": achieved, "peak": imad_peak,
                          "unit": "GMAC32/s", "frac": achieved / imad_peak,
                          "peak_source": "measured live: IMAD.WIDE.U32 (64-bit addend) microbenchmark, dapol_imad_peak variant 1; "
@@ -550,6 +562,8 @@ def main():
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
+    if native is not None:
+        native.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ fallback: importing works anywhere, but every compute call needs the CUDA librar
 from .api import (Dapol, DapolError, DapolNode, DapolProof, DapolProofNode, HASH_BLAKE2S, HASH_BLAKE3, POLICY_PADDING, POLICY_SPLITTING,
                   Context)
 
-from .sharded import Comm, CudaEngine, ShardedDapol, shard_pad_bases
+from .sharded import Comm, CudaEngine, NativeComm, ShardedDapol, shard_pad_bases
 
-__all__ = ["Comm", "CudaEngine", "ShardedDapol", "shard_pad_bases", "Dapol", "DapolError", "DapolNode", "DapolProof", "DapolProofNode", "Context", "HASH_BLAKE3", "HASH_BLAKE2S",
+__all__ = ["Comm", "CudaEngine", "NativeComm", "ShardedDapol", "shard_pad_bases", "Dapol", "DapolError", "DapolNode", "DapolProof", "DapolProofNode", "Context", "HASH_BLAKE3", "HASH_BLAKE2S",
            "POLICY_PADDING", "POLICY_SPLITTING"]

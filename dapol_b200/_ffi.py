@@ -16,6 +16,15 @@ class LibraryMissing(RuntimeError):
     pass
 
 
+# dapol_comm_ops (include/dapol_b200.h): a host-provided transport for the sharded build's collectives
+ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, vp, vp, vp, u64, vp)
+ALL_TO_ALL_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.POINTER(u64), C.POINTER(u64), vp, C.POINTER(u64), C.POINTER(u64), vp)
+
+
+class CommOps(C.Structure):
+    _fields_ = [("user", vp), ("all_gather", ALL_GATHER_FN), ("all_to_all", ALL_TO_ALL_FN)]
+
+
 def lib():
     global _lib
     if _lib is not None:
@@ -79,6 +88,14 @@ def lib():
     L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
     L.dapol_rangeproof_last_times.argtypes = [vp, vp]
     L.dapol_rangeproof_last_kernel_times.argtypes = [vp, vp]
+    L.dapol_comm_create.argtypes = [C.c_int, C.c_int, C.POINTER(CommOps), C.POINTER(vp)]
+    L.dapol_comm_nccl_unique_id.argtypes = [vp]
+    L.dapol_comm_nccl_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.dapol_comm_destroy.argtypes = [vp]
+    L.dapol_comm_rank.argtypes = [vp]
+    L.dapol_comm_world.argtypes = [vp]
+    L.dapol_sharded_build.argtypes = [vp, vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, u64, vp, u64, C.POINTER(vp), C.POINTER(vp),
+                                      C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), vp]
     _lib = L
     return L
 

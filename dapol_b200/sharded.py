@@ -74,6 +74,99 @@ class Comm:
         return torch.cat([blocks[r, : int(counts[r])] for r in range(self.world)])
 
 
+class _DevView:
+    """Zero-copy torch view of raw device memory handed to a transport callback."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _dev_view(ptr, nbytes, device):
+    return torch.as_tensor(_DevView(ptr, nbytes), device=device)
+
+
+class NativeComm:
+    """dapol_comm (include/dapol_b200.h) for dapol_sharded_build.
+    `nccl`: the library's own NCCL communicator over NVLink (the 128-byte unique id travels through torch.distributed);
+    `torch`: the host-provided transport (dapol_comm_ops) on top of torch.distributed -- NCCL collectives on the device
+    buffers when the process group is nccl, host-staged gloo collectives otherwise (several ranks sharing one test GPU)."""
+
+    def __init__(self, ctx, comm: Comm, backend: str = "nccl"):
+        L = _ffi.lib()
+        self.comm, self.ctx, self.h = comm, ctx, C.c_void_p()
+        self.device = torch.device("cuda", ctx.device)
+        dist = comm.dist
+        if backend == "nccl":
+            ident = np.zeros(128, np.uint8)
+            if comm.rank == 0:
+                _check(L.dapol_comm_nccl_unique_id(_p(ident)))
+            if comm.world > 1:
+                box = [ident.tobytes()]
+                dist.broadcast_object_list(box, src=0, group=comm.group)
+                ident = np.frombuffer(box[0], np.uint8).copy()
+            _check(L.dapol_comm_nccl_create(ctx._h, _p(ident), comm.rank, comm.world, C.byref(self.h)))
+        else:
+            self._ag = _ffi.ALL_GATHER_FN(self._all_gather)
+            self._a2a = _ffi.ALL_TO_ALL_FN(self._all_to_all)
+            self._ops = _ffi.CommOps(None, self._ag, self._a2a)
+            _check(L.dapol_comm_create(comm.rank, comm.world, C.byref(self._ops), C.byref(self.h)))
+
+    # transport callbacks: device pointers in, ordered on the given stream (here: synchronise, do it, return when done)
+    def _all_gather(self, user, d_send, d_recv, nbytes, stream):
+        try:
+            dist, W = self.comm.dist, self.comm.world
+            torch.cuda.synchronize(self.device)
+            src = _dev_view(d_send, nbytes, self.device)
+            dst = _dev_view(d_recv, nbytes * W, self.device)
+            if W == 1:
+                dst.copy_(src)
+            elif self.comm.backend == "nccl":
+                dist.all_gather_into_tensor(dst, src, group=self.comm.group)
+            else:
+                h = src.cpu()
+                out = [torch.empty_like(h) for _ in range(W)]
+                dist.all_gather(out, h, group=self.comm.group)
+                dst.copy_(torch.cat(out))
+            torch.cuda.synchronize(self.device)
+            return 0
+        except Exception as e:  # never unwind through the C frames
+            print("dapol transport all_gather failed:", e, flush=True)
+            return 19
+
+    def _all_to_all(self, user, d_send, send_off, send_bytes, d_recv, recv_off, recv_bytes, stream):
+        try:
+            dist, W = self.comm.dist, self.comm.world
+            torch.cuda.synchronize(self.device)
+            so, sb = [int(send_off[r]) for r in range(W)], [int(send_bytes[r]) for r in range(W)]
+            ro, rb = [int(recv_off[r]) for r in range(W)], [int(recv_bytes[r]) for r in range(W)]
+            # the library packs both buffers densely in rank order (offsets = running sums): one all_to_all_single
+            assert so == [sum(sb[:r]) for r in range(W)] and ro == [sum(rb[:r]) for r in range(W)]
+            onhost = self.comm.backend != "nccl"
+            empty = torch.empty(0, dtype=torch.uint8, device=self.device)
+            src = _dev_view(d_send, sum(sb), self.device) if sum(sb) else empty
+            dst = _dev_view(d_recv, sum(rb), self.device) if sum(rb) else empty
+            if W == 1:
+                dst.copy_(src)
+            elif onhost:
+                out = torch.empty(sum(rb), dtype=torch.uint8)
+                dist.all_to_all_single(out, src.cpu(), rb, sb, group=self.comm.group)
+                dst.copy_(out)
+            else:
+                dist.all_to_all_single(dst, src, rb, sb, group=self.comm.group)
+            torch.cuda.synchronize(self.device)
+            return 0
+        except Exception as e:
+            print("dapol transport all_to_all failed:", e, flush=True)
+            return 19
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            _ffi.lib().dapol_comm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
 class CudaEngine:
     """The C-ABI calls of the sharded build, on torch device tensors."""
 
@@ -200,10 +293,13 @@ class ShardedDapol:
         self.n_total = 0
         self.n_mine = 0
         self.first_pos = 0
+        self.n_local = 0
+        self.native = False
+        self.phase_ms = None
 
     @classmethod
     def new(cls, engine, comm, hash_id, liabilities, audit_seed: bytes, tree_height: int, aggregation_factor: int, pad_seed: bytes,
-            policy=POLICY_PADDING, pad_base: int = 0):
+            policy=POLICY_PADDING, pad_base: int = 0, native: "NativeComm | None" = None):
         """Dapol::new(liabilities, options) (mod.rs:100-128) where `liabilities` is THIS rank's slice of the input, packed
         as (iid_blob, iid_off[n+1], eid_blob, eid_off[n+1], values[n]) (numpy, or torch tensors already on the device);
         input order = rank 0's slice, then rank 1's, ..."""
@@ -214,6 +310,28 @@ class ShardedDapol:
             raise DapolError(16)
         ib, io, eb, eo, vals = liabilities
         n = len(io) - 1
+        if native is not None:
+            # the whole protocol behind ONE C-ABI call (dapol_sharded_build): all-to-all of claims, per-prefix collision
+            # resolution, padding bases, subtree, root gather, top tree -- nothing of it runs in Python
+            E, L = engine, engine.L
+            d = (E.to_dev(ib, np.uint8), E.to_dev(io, np.int64), E.to_dev(eb, np.uint8), E.to_dev(eo, np.int64), E.to_dev(vals, np.int64))
+            sub, top = C.c_void_p(), C.c_void_p()
+            n_total, first, err = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            ms = np.zeros(4, np.float32)
+            seed = (C.c_uint8 * 32).from_buffer_copy(pad_seed)
+            aseed = (C.c_uint8 * max(len(audit_seed), 1)).from_buffer_copy(audit_seed or b"\0")
+            torch.cuda.current_stream(E.device).synchronize()
+            rc = L.dapol_sharded_build(E.ctx._h, native.h, hash_id, tree_height, n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(),
+                                       d[4].data_ptr(), aseed, len(audit_seed), seed, pad_base, C.byref(sub), C.byref(top), C.byref(n_total),
+                                       C.byref(first), C.byref(err), _p(ms))
+            _check(rc, err.value if rc in (4, 5) else None)
+            self.subtree = sub if sub.value else None
+            self.top = top if top.value else None
+            self.n_total, self.first_pos, self.n_local = int(n_total.value), int(first.value), n
+            self.phase_ms = dict(zip(("hash", "exchange", "subtree", "top"), ms.tolist()))
+            E.last_shard_times = E.ctx.last_build_times() if self.subtree else None
+            self.native = True
+            return self
         counts = comm.all_gather_host(np.array([n], np.uint64), getattr(engine, "device", None))[:, 0]
         self.n_total = int(counts.sum())
         self.first_pos = int(counts[: comm.rank].sum())
@@ -276,7 +394,7 @@ class ShardedDapol:
 
     # -- accessors (identical on every rank) ------------------------------------------------------
     def root_raw(self) -> DapolNode:
-        return self.engine.root_of(self.top)
+        return self.engine.root_of(self.top or self.subtree)  # one-rank native build: the whole tree is the `subtree`
 
     def root(self) -> DapolProofNode:
         return self.root_raw().get_proof_node()
@@ -286,6 +404,12 @@ class ShardedDapol:
 
     def leaf_index_of(self, input_pos: int):
         """id_to_idx_map lookup (mod.rs:148-151) by global input position."""
+        if getattr(self, "native", False):  # the native build keeps the map of the LOCAL slice only (on the top-tree handle)
+            if not (self.first_pos <= input_pos < self.first_pos + self.n_local):
+                return None
+            x = C.c_uint64()
+            _check(_ffi.lib().dapol_tree_leaf_index_of(self.top or self.subtree, input_pos, C.byref(x)))
+            return x.value
         if self.leaf_index_map is None or not (0 <= input_pos < self.n_total):
             return None
         return int(self.leaf_index_map[input_pos].item()) & 0xFFFFFFFFFFFFFFFF

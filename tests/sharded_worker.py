@@ -195,12 +195,21 @@ def main():
         E = CudaEngine(Context(0))
         E.set_padding_mode(positional)
     agg = min(H, 3)
-    t = ShardedDapol.new(E, comm, hash_id, sl, AUDIT_SEED, H, agg, PAD_SEED)
+    native = None
+    if engine == "cuda" and "native" in sys.argv[8:]:
+        # the one-call path (dapol_sharded_build): the library runs the whole exchange protocol; its collectives go through
+        # the host-provided transport (dapol_comm_ops) on top of this test's gloo group, the ranks share the box's one GPU
+        from dapol_b200.sharded import NativeComm
+        native = NativeComm(E.ctx, comm, backend="torch")
+    t = ShardedDapol.new(E, comm, hash_id, sl, AUDIT_SEED, H, agg, PAD_SEED, native=native)
     root, oroot = t.root_raw(), g.root()
     assert (root.value, root.com, root.hash) == (oroot["v"], oroot["comc"], oroot["hash"]), "sharded root != oracle single-tree root"
     assert int.from_bytes(root.blinding, "little") % L_ORDER == int.from_bytes(oroot["r"], "little") % L_ORDER
-    for pos in (0, n // 2, n - 1):
-        assert t.leaf_index_of(pos) == int(gidx[pos])
+    for pos in (0, n // 2, n - 1) + tuple(range(lo, min(hi, lo + 3))):
+        if native is None or lo <= pos < hi:  # the one-call build keeps the id -> index map of the rank's own slice
+            assert t.leaf_index_of(pos) == int(gidx[pos])
+        else:
+            assert t.leaf_index_of(pos) is None
     if engine == "cuda":
         import ctypes as C
         from dapol_b200 import _ffi
