@@ -197,6 +197,16 @@ class DapolProof:
         """DapolProof::verify(&root, &leaf) (proof/mod.rs:41-47)."""
         return bool(self.verify_many(ctx, root, [leaf], [self])[0])
 
+    def verify_batch(self, ctx: "Context", root: "DapolProofNode", leaves) -> bool:
+        """DapolProof::verify_batch(&root, &leaves) (proof/mod.rs:49-54): this ONE proof covers all the leaves (index order)."""
+        lc = np.frombuffer(b"".join(l.com for l in leaves), np.uint8).copy()
+        lh = np.frombuffer(b"".join(l.hash for l in leaves), np.uint8).copy()
+        blob = np.frombuffer(self.data or b"\0", np.uint8).copy()
+        ok = np.zeros(1, np.uint8)
+        _check(_ffi.lib().dapol_proof_verify_batch(ctx._h, self.hash_id, self.policy, len(leaves), _p(np.frombuffer(root.com, np.uint8).copy()),
+                                                   _p(np.frombuffer(root.hash, np.uint8).copy()), _p(lc), _p(lh), _p(blob), len(self.data), _p(ok)))
+        return bool(ok[0])
+
     @staticmethod
     def verify_many(ctx: "Context", root: "DapolProofNode", leaves, proofs) -> np.ndarray:
         """k independent DapolProof::verify calls against one root, as one GPU batch."""
@@ -397,3 +407,20 @@ class Dapol:
         """Dapol::generate_proof (mod.rs:167-169)."""
         r = self.generate_proofs([leaf_idx], seed)
         return None if r is None else r[0]
+
+    def generate_proof_batch(self, leaf_idx, seed: bytes):
+        """Dapol::generate_proof_batch(&[TreeIndex]) (mod.rs:172-190): ONE DapolProof for all the given leaves (strictly
+        increasing indexes); None if any index is not a leaf."""
+        li = np.ascontiguousarray(leaf_idx, np.uint64)
+        L = _ffi.lib()
+        size = L.dapol_batch_proof_size(self.height, len(li), _p(li), self.aggregation_factor, self.policy)
+        if size == 0:
+            raise DapolError(16)
+        out = np.zeros(size, np.uint8)
+        got = C.c_uint64()
+        sd = (C.c_uint8 * 32).from_buffer_copy(seed)
+        rc = L.dapol_generate_proof_batch(self._t, len(li), _p(li), self.aggregation_factor, self.policy, sd, _p(out), out.nbytes, C.byref(got))
+        if rc == 17:
+            return None
+        _check(rc)
+        return DapolProof(out.tobytes(), self.hash_id, self.policy)

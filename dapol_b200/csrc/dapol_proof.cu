@@ -375,3 +375,371 @@ extern "C" int dapol_prove_to_file(const dapol_tree *t, uint64_t k, const uint64
     if (fclose(f) != 0 && rc == DAPOL_OK) rc = DAPOL_ERR_IO;
     return rc;
 }
+
+// ================================================================================================ batch proofs
+// ONE DapolProof for several leaves: Dapol::generate_proof_batch (src/dapol/mod.rs:172-190) and DapolProof::verify_batch
+// (src/proof/mod.rs:49-54); test shape src/proof/tests.rs:6-35.  smtree's get_merkle_path_ref_batch / MerkleProof::verify_batch
+// are UPSTREAM-RECALL: level by level from the leaves up, left to right, a node's sibling is part of the
+// proof only if it is not itself on the way up from the batch.  The sibling order and the MerkleProof framing live in
+// batch_sibling_plan / batch_merkle_bytes / parse_batch_proof only.
+struct SibRef { int h; uint64_t idx; };
+static std::vector<SibRef> batch_sibling_plan(int height, uint64_t k, const uint64_t *idx) {
+    std::vector<SibRef> plan;
+    std::vector<uint64_t> cur(idx, idx + k), nxt;
+    for (int h = height; h >= 1; h--) {
+        const size_t n = cur.size();
+        for (size_t i = 0; i < n; i++) {
+            const uint64_t s = cur[i] ^ 1;
+            if (!((i > 0 && cur[i - 1] == s) || (i + 1 < n && cur[i + 1] == s))) plan.push_back({h, s});
+        }
+        nxt.clear();
+        for (uint64_t x : cur) if (nxt.empty() || nxt.back() != x >> 1) nxt.push_back(x >> 1);
+        cur.swap(nxt);
+    }
+    return plan;
+}
+static uint64_t batch_merkle_bytes(uint64_t H, uint64_t k, uint64_t nsib) { return 2 + 8 + k * ((H + 7) / 8) + 8 + 64 * nsib; }
+static uint64_t range_part_bytes(uint64_t nsib, uint64_t agg, int policy) {
+    std::vector<AggGroup> g;
+    uint64_t sf;
+    if (policy_plan(nsib, agg, policy, g, sf)) return 0;
+    uint64_t sz = policy == DAPOL_POLICY_SPLITTING ? 2 : 0;
+    for (auto &x : g) sz += 8 + dapol_rangeproof_size(64, (int)x.m);
+    return sz + 8 + SINGLE_PROOF_BYTE_NUM * (nsib - sf);
+}
+extern "C" uint64_t dapol_batch_proof_size(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy) {
+    if (!leaf_idx || k == 0 || height < 0 || height > 64) return 0;
+    if (k == 1) return dapol_inclusion_proof_size(height, aggregation_factor, policy);
+    for (uint64_t i = 0; i < k; i++) if ((i && leaf_idx[i] <= leaf_idx[i - 1]) || (height < 64 && (leaf_idx[i] >> height))) return 0;
+    const uint64_t nsib = batch_sibling_plan(height, k, leaf_idx).size(), rs = range_part_bytes(nsib, aggregation_factor, policy);
+    return rs ? rs + batch_merkle_bytes((uint64_t)height, k, nsib) : 0;
+}
+// node (level h, tree index x) of the store: levels are kept in tree order, so a binary search over the level's indexes finds it
+__global__ void k_fetch_nodes(uint64_t n, const int *lvl, const uint64_t *idx, NodeStore ns, const uint64_t *level_off, const uint64_t *level_n,
+                              uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint8_t *o_pad, int *not_found) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t off = level_off[lvl[j]];
+    int64_t slot = find_leaf_slot(ns.idx + off, level_n[lvl[j]], idx[j]);
+    if (slot < 0) { *not_found = 1; return; }
+    const uint64_t g = off + (uint64_t)slot;
+    uint32_t w[8];
+    o_v[j] = ns.v[g];
+    load8(w, ns.r + 8 * g); store8(o_r + 8 * j, w);
+    load8(w, ns.comc + 8 * g); store8(o_c + 8 * j, w);
+    load8(w, ns.hash + 8 * g); store8(o_h + 8 * j, w);
+    o_pad[j] = ns.is_pad[g];
+}
+// nonce key of a batch of more than one leaf: the tree's prover key chained over the leaf indexes, 64 per link; stream 0
+static void batch_nonce_key(uint8_t key[32], uint64_t k, const uint64_t *idx) {
+    static const char label[] = "dapol-b200 batch proof nonce key v1";
+    dapol_hasher hs;
+    uint32_t st[8];
+    uint8_t le[8];
+    hasher_init(hs, DAPOL_HASH_BLAKE3);
+    hasher_update(hs, reinterpret_cast<const uint8_t *>(label), 35);
+    hasher_update(hs, key, 32);
+    for (int b = 0; b < 8; b++) le[b] = (uint8_t)(k >> (8 * b));
+    hasher_update(hs, le, 8);
+    hasher_final(hs, st);
+    for (uint64_t i = 0; i < k; i += 64) {
+        hasher_init(hs, DAPOL_HASH_BLAKE3);
+        hasher_update_words(hs, st, 8);
+        for (uint64_t j = i; j < k && j < i + 64; j++) {
+            for (int b = 0; b < 8; b++) le[b] = (uint8_t)(idx[j] >> (8 * b));
+            hasher_update(hs, le, 8);
+        }
+        hasher_final(hs, st);
+    }
+    memcpy(key, st, 32);
+}
+extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                          const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size) {
+    if (!t || !leaf_idx || !seed || !k) return DAPOL_ERR_BAD_ARG;
+    if (k == 1) return dapol_prove_batch(t, 1, leaf_idx, aggregation_factor, policy, seed, out, cap, proof_size);  // mod.rs:167-169
+    if (t->top) return DAPOL_ERR_BAD_ARG;  // a batch may straddle shards: build it on the rank that holds a single tree
+    dapol_ctx *ctx = t->ctx;
+    const int H = t->height;
+    const uint64_t size = dapol_batch_proof_size(H, k, leaf_idx, aggregation_factor, policy);
+    if (proof_size) *proof_size = size;
+    if (!size) return DAPOL_ERR_BAD_ARG;  // unsorted indexes (smtree rejects), aggregation_factor > #siblings (reference: slice panic)
+    if (!out || cap < size) return DAPOL_ERR_BUFFER;
+    const std::vector<SibRef> plan = batch_sibling_plan(H, k, leaf_idx);
+    const uint64_t nsib = plan.size(), nf_items = k + nsib;
+    std::vector<AggGroup> groups;
+    uint64_t sf;
+    policy_plan(nsib, aggregation_factor, policy, groups, sf);
+    const uint64_t nsingle = nsib - sf;
+    uint8_t key[32];
+    prover_nonce_key(key, seed, t, policy, aggregation_factor, (uint64_t)H);
+    batch_nonce_key(key, k, leaf_idx);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<int> h_lvl(nf_items);
+    std::vector<uint64_t> h_idx(nf_items);
+    for (uint64_t i = 0; i < k; i++) { h_lvl[i] = H; h_idx[i] = leaf_idx[i]; }
+    for (uint64_t j = 0; j < nsib; j++) { h_lvl[k + j] = plan[j].h; h_idx[k + j] = plan[j].idx; }
+    uint64_t max_m = 1, agg_bytes = 0;
+    for (auto &g : groups) { max_m = std::max(max_m, g.m); agg_bytes += dapol_rangeproof_size(64, (int)g.m); }
+    const uint64_t rows = std::max<uint64_t>(max_m, std::max<uint64_t>(nsingle, 1));
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(nf_items, 4) + 2 * Arena::need(nf_items, 8) + 3 * Arena::need(nf_items, 32) + Arena::need(nf_items, 1) + 3 * 256 + Arena::need(65, 8) +
+              Arena::need(rows, 8) + Arena::need(rows, 32) + 2 * Arena::need(rows, 8) + Arena::need(agg_bytes + 1, 1) + Arena::need(nsingle + 1, SINGLE_PROOF_BYTE_NUM);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    int *d_lvl = ar.take<int>(nf_items);
+    uint64_t *d_idx = ar.take<uint64_t>(nf_items), *d_v = ar.take<uint64_t>(nf_items);
+    uint32_t *d_r = ar.take<uint32_t>(nf_items * 8), *d_c = ar.take<uint32_t>(nf_items * 8), *d_h = ar.take<uint32_t>(nf_items * 8);
+    uint8_t *d_pad = ar.take<uint8_t>(nf_items);
+    int *d_nf = ar.take<int>(1);
+    uint64_t *d_zero = ar.take<uint64_t>(1), *d_level_n = ar.take<uint64_t>(65);
+    uint64_t *g_v = ar.take<uint64_t>(rows);
+    uint32_t *g_r = ar.take<uint32_t>(rows * 8);
+    uint64_t *g_s = ar.take<uint64_t>(rows), *g_b = ar.take<uint64_t>(rows);
+    uint8_t *d_agg = ar.take<uint8_t>(agg_bytes + 1), *d_single = ar.take<uint8_t>((nsingle + 1) * SINGLE_PROOF_BYTE_NUM);
+#define FAILB(code) do { dfree(mem, st); return (code); } while (0)
+    cudaMemsetAsync(d_nf, 0, 4, st); cudaMemsetAsync(d_zero, 0, 8, st);
+    cudaMemcpyAsync(d_lvl, h_lvl.data(), nf_items * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_idx, h_idx.data(), nf_items * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_level_n, t->level_n.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st);
+    k_fetch_nodes<<<grid_for(nf_items, 128), 128, 0, st>>>(nf_items, d_lvl, d_idx, t->ns, t->d_level_off, d_level_n, d_v, d_r, d_c, d_h, d_pad, d_nf);
+    ctx->launches++;
+    int nf = 0;
+    std::vector<uint8_t> h_pad(nf_items);
+    cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_pad.data(), d_pad, nf_items, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) FAILB(DAPOL_ERR_CUDA);
+    for (uint64_t i = 0; i < k; i++) if (h_pad[i]) nf = 1;  // a padding node is not a leaf of the liability set (reference: None)
+    if (nf) FAILB(DAPOL_ERR_NOT_FOUND);
+    const uint64_t *s_v = d_v + k;
+    const uint32_t *s_r = d_r + 8 * k;
+    uint64_t q = 0, off = 0;
+    std::vector<uint64_t> agg_off;
+    for (auto &g : groups) {
+        k_gather_group<<<grid_for(g.m, 128), 128, 0, st>>>(1, (int)nsib, g.start, g.count, g.m, s_v, s_r, g_v, g_r);
+        k_proof_streams<<<1, 128, 0, st>>>(1, 1, q, d_zero, g_s, g_b);
+        ctx->launches += 2;
+        int rc = dapol_rp_prove_dev(ctx, 64, (int)g.m, 1, g_v, reinterpret_cast<const uint8_t *>(g_r), key, g_s, g_b, d_agg + off);
+        if (rc) FAILB(rc);
+        agg_off.push_back(off);
+        off += dapol_rangeproof_size(64, (int)g.m);
+        q++;
+    }
+    if (nsingle) {
+        k_gather_group<<<grid_for(nsingle, 128), 128, 0, st>>>(1, (int)nsib, sf, nsingle, nsingle, s_v, s_r, g_v, g_r);
+        k_proof_streams<<<grid_for(nsingle, 128), 128, 0, st>>>(1, nsingle, q, d_zero, g_s, g_b);
+        ctx->launches += 2;
+        int rc = dapol_rp_prove_dev(ctx, 64, 1, nsingle, g_v, reinterpret_cast<const uint8_t *>(g_r), key, g_s, g_b, d_single);
+        if (rc) FAILB(rc);
+    }
+    std::vector<uint8_t> h_agg(agg_bytes + 1), h_single(nsingle * SINGLE_PROOF_BYTE_NUM + 1), h_c(nsib * 32 + 1), h_h(nsib * 32 + 1);
+    if (agg_bytes) cudaMemcpyAsync(h_agg.data(), d_agg, agg_bytes, cudaMemcpyDeviceToHost, st);
+    if (nsingle) cudaMemcpyAsync(h_single.data(), d_single, nsingle * SINGLE_PROOF_BYTE_NUM, cudaMemcpyDeviceToHost, st);
+    if (nsib) { cudaMemcpyAsync(h_c.data(), d_c + 8 * k, nsib * 32, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h_h.data(), d_h + 8 * k, nsib * 32, cudaMemcpyDeviceToHost, st); }
+    if (cudaStreamSynchronize(st) != cudaSuccess) FAILB(DAPOL_ERR_CUDA);
+    dfree(mem, st);
+#undef FAILB
+    uint8_t *o = out;
+    if (policy == DAPOL_POLICY_SPLITTING) { put_be(o, groups.size(), 2); o += 2; }
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const uint64_t plen = dapol_rangeproof_size(64, (int)groups[gi].m);
+        put_be(o, plen, 8); o += 8;
+        memcpy(o, h_agg.data() + agg_off[gi], plen); o += plen;
+    }
+    put_be(o, nsingle, 8); o += 8;
+    memcpy(o, h_single.data(), nsingle * SINGLE_PROOF_BYTE_NUM); o += nsingle * SINGLE_PROOF_BYTE_NUM;
+    // MerkleProof::serialize of a batch proof: height, #indexes, the path bits of every index, #siblings, siblings
+    const uint64_t Hu = (uint64_t)H, nb = (Hu + 7) / 8;
+    put_be(o, Hu, 2); o += 2;
+    put_be(o, k, 8); o += 8;
+    for (uint64_t i = 0; i < k; i++) if (nb) { put_be(o, Hu == 64 ? leaf_idx[i] : leaf_idx[i] << (8 * nb - Hu), (int)nb); o += nb; }
+    put_be(o, nsib, 8); o += 8;
+    for (uint64_t s = 0; s < nsib; s++) { memcpy(o, h_c.data() + s * 32, 32); memcpy(o + 32, h_h.data() + s * 32, 32); o += 64; }
+    return DAPOL_OK;
+}
+
+// ---- verify_batch: MerkleProof::verify_batch as level-synchronous merges on the device (DapolProofNode::merge,
+// src/proof/node.rs:56-69), then R::verify over the siblings' commitments in proof order.
+struct BatchNode { uint32_t ext[32], c[8], h[8]; };
+// working nodes 0..k-1 = the leaves, k.. = the proof's siblings: decompress (non-canonical points reject, proof/node.rs:81-102)
+__global__ void __launch_bounds__(64) k_batch_init(uint64_t n, const uint32_t *coms, const uint32_t *hashes, BatchNode *nodes, int *bad) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t c[8], h[8];
+    load8(c, coms + 8 * j); load8(h, hashes + 8 * j);
+    ge p;
+    if (!ge_decompress(p, c)) { *bad = 1; return; }
+    rp_store_ext(nodes[j].ext, p);
+    store8(nodes[j].c, c); store8(nodes[j].h, h);
+}
+// one level: parent j = merge(nodes[left[j]], nodes[right[j]]) written at nodes[dst0 + j]
+__global__ void __launch_bounds__(64) k_batch_merge_level(uint64_t n, const uint32_t *left, const uint32_t *right, uint64_t dst0, BatchNode *nodes, int hash_id) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const BatchNode &l = nodes[left[j]], &r = nodes[right[j]];
+    ge a, b, s;
+    rp_load_ext(a, l.ext); rp_load_ext(b, r.ext);
+    ge_add(s, a, b);
+    uint32_t cl[8], cr[8], hl[8], hr[8], hh[8], cc[8];
+    load8(cl, l.c); load8(cr, r.c); load8(hl, l.h); load8(hr, r.h);
+    dapol_hash128(hash_id, hh, cl, cr, hl, hr);
+    ge_compress(cc, s);
+    BatchNode &o = nodes[dst0 + j];
+    rp_store_ext(o.ext, s);
+    store8(o.c, cc); store8(o.h, hh);
+}
+struct ParsedBatch {
+    bool ok = false;
+    std::vector<std::pair<uint64_t, uint64_t>> agg;
+    uint64_t nind = 0, ind_off = 0, H = 0, nsib = 0, sib_off = 0;
+    std::vector<uint64_t> idx;
+};
+static ParsedBatch parse_batch_proof(const uint8_t *p, uint64_t len, int policy) {
+    ParsedBatch r;
+    uint64_t pos = 0, nagg = 1;
+#define NEED(n) do { if (len - pos < (uint64_t)(n)) return r; } while (0)
+    if (policy == DAPOL_POLICY_SPLITTING) { NEED(2); nagg = get_be(p, 2); pos += 2; if (nagg > 64) return r; }
+    for (uint64_t i = 0; i < nagg; i++) {
+        NEED(8);
+        uint64_t sz = get_be(p + pos, 8); pos += 8;
+        if (sz > len - pos) return r;
+        r.agg.push_back({pos, sz}); pos += sz;
+    }
+    NEED(8);
+    r.nind = get_be(p + pos, 8); pos += 8;
+    if ((len - pos) / SINGLE_PROOF_BYTE_NUM < r.nind) return r;
+    r.ind_off = pos; pos += SINGLE_PROOF_BYTE_NUM * r.nind;
+    NEED(10);
+    r.H = get_be(p + pos, 2); pos += 2;
+    const uint64_t k = get_be(p + pos, 8); pos += 8;
+    const uint64_t nb = (r.H + 7) / 8;
+    if (r.H > 64 || k == 0 || (nb && (len - pos) / nb < k)) return r;
+    for (uint64_t i = 0; i < k; i++) {
+        uint64_t x = nb ? get_be(p + pos, (int)nb) : 0;
+        if (nb && r.H != 64) x >>= (8 * nb - r.H);
+        if (i && x <= r.idx.back()) return r;
+        r.idx.push_back(x); pos += nb;
+    }
+    NEED(8);
+    r.nsib = get_be(p + pos, 8); pos += 8;
+    if ((len - pos) / 64 < r.nsib || r.nind > r.nsib) return r;
+    r.sib_off = pos;
+#undef NEED
+    r.ok = true;
+    return r;
+}
+extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
+                                        const uint8_t *leaf_coms, const uint8_t *leaf_hashes, const uint8_t *proof, uint64_t proof_len, uint8_t *ok) {
+    if (!ctx || !root_com || !root_hash || !leaf_coms || !leaf_hashes || !proof || !ok || !k) return DAPOL_ERR_BAD_ARG;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (policy != DAPOL_POLICY_PADDING && policy != DAPOL_POLICY_SPLITTING) return DAPOL_ERR_BAD_ARG;
+    *ok = 0;
+    const ParsedBatch pb = parse_batch_proof(proof, proof_len, policy);
+    if (!pb.ok || pb.idx.size() != k) return DAPOL_OK;  // malformed bytes / wrong number of leaves: a reject, never an error
+    const std::vector<SibRef> plan = batch_sibling_plan((int)pb.H, k, pb.idx.data());
+    if (plan.size() != pb.nsib) return DAPOL_OK;
+    // merge plan: working nodes [0, k) leaves, [k, k + nsib) siblings, then the parents level by level
+    const uint64_t nsib = pb.nsib;
+    std::vector<uint32_t> left, right;
+    std::vector<uint64_t> lvl_first, lvl_count;
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> cur, nxt;  // (tree index, working node)
+        for (uint64_t i = 0; i < k; i++) cur.push_back({pb.idx[i], (uint32_t)i});
+        uint64_t sib_at = 0, next_node = k + nsib;
+        for (int h = (int)pb.H; h >= 1; h--) {
+            nxt.clear();
+            lvl_first.push_back(left.size());
+            for (size_t i = 0; i < cur.size();) {
+                uint32_t me = cur[i].second, other;
+                size_t step = 1;
+                if (i + 1 < cur.size() && cur[i + 1].first == (cur[i].first ^ 1)) { other = cur[i + 1].second; step = 2; }
+                else other = (uint32_t)(k + sib_at++);  // plan order == consumption order: level by level, left to right
+                if (cur[i].first & 1) { left.push_back(other); right.push_back(me); } else { left.push_back(me); right.push_back(other); }
+                nxt.push_back({cur[i].first >> 1, (uint32_t)next_node++});
+                i += step;
+            }
+            lvl_count.push_back(left.size() - lvl_first.back());
+            cur.swap(nxt);
+        }
+        if (sib_at != nsib) return DAPOL_OK;
+    }
+    const uint64_t n_work = k + nsib + left.size();
+    if (n_work >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<uint8_t> h_c((k + nsib) * 32), h_h((k + nsib) * 32);
+    memcpy(h_c.data(), leaf_coms, k * 32); memcpy(h_h.data(), leaf_hashes, k * 32);
+    for (uint64_t s = 0; s < nsib; s++) {
+        memcpy(h_c.data() + (k + s) * 32, proof + pb.sib_off + 64 * s, 32);
+        memcpy(h_h.data() + (k + s) * 32, proof + pb.sib_off + 64 * s + 32, 32);
+    }
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = 2 * Arena::need(k + nsib, 32) + Arena::need(n_work, sizeof(BatchNode)) + 2 * Arena::need(left.size() + 1, 4) + 256;
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint32_t *d_c = ar.take<uint32_t>((k + nsib) * 8), *d_h = ar.take<uint32_t>((k + nsib) * 8);
+    BatchNode *nodes = ar.take<BatchNode>(n_work);
+    uint32_t *d_l = ar.take<uint32_t>(left.size() + 1), *d_r = ar.take<uint32_t>(left.size() + 1);
+    int *d_bad = ar.take<int>(1), bad = 0;
+    cudaMemsetAsync(d_bad, 0, 4, st);
+    cudaMemcpyAsync(d_c, h_c.data(), h_c.size(), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_h, h_h.data(), h_h.size(), cudaMemcpyHostToDevice, st);
+    if (!left.empty()) {
+        cudaMemcpyAsync(d_l, left.data(), left.size() * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_r, right.data(), right.size() * 4, cudaMemcpyHostToDevice, st);
+    }
+    k_batch_init<<<grid_for(k + nsib, 64), 64, 0, st>>>(k + nsib, d_c, d_h, nodes, d_bad);
+    ctx->launches++;
+    uint64_t dst = k + nsib;
+    for (size_t l = 0; l < lvl_first.size(); l++) {
+        if (!lvl_count[l]) continue;
+        k_batch_merge_level<<<grid_for(lvl_count[l], 64), 64, 0, st>>>(lvl_count[l], d_l + lvl_first[l], d_r + lvl_first[l], dst, nodes, hash_id);
+        ctx->launches++;
+        dst += lvl_count[l];
+    }
+    uint32_t top[16];
+    const BatchNode *root_node = nodes + (n_work - 1);  // height 0: the single leaf itself (k == 1, no merges)
+    cudaMemcpyAsync(top, root_node->c, 32, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(top + 8, root_node->h, 32, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    dfree(mem, st);
+    CUDA_TRY(e);
+    if (bad || memcmp(top, root_com, 32) || memcmp(top + 8, root_hash, 32)) return DAPOL_OK;
+    // R::verify on the siblings' commitments (padding.rs:168-197 / splitting.rs:180-211)
+    const uint64_t n_agg_coms = nsib - pb.nind;
+    std::vector<AggGroup> groups;
+    uint64_t sf;
+    if (policy_plan(nsib, n_agg_coms, policy, groups, sf) || groups.size() > pb.agg.size() || (policy == DAPOL_POLICY_PADDING && pb.agg.size() != 1)) return DAPOL_OK;
+    uint8_t com_padding[32];
+    {
+        ge bb;
+        uint32_t w[8];
+        ge_bblinding(bb);
+        ge_compress(w, bb);
+        memcpy(com_padding, w, 32);
+    }
+    const uint8_t *sib = proof + pb.sib_off;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+        const AggGroup &g = groups[gi];
+        if (pb.agg[gi].second != dapol_rangeproof_size(64, (int)g.m)) return DAPOL_OK;
+        std::vector<uint8_t> hc(g.m * 32);
+        uint8_t one = 0;
+        for (uint64_t j = 0; j < g.m; j++) memcpy(hc.data() + j * 32, j < g.count ? sib + 64 * (g.start + j) : com_padding, 32);
+        int rc = dapol_rangeproof_verify_batch(ctx, 64, (int)g.m, 1, proof + pb.agg[gi].first, pb.agg[gi].second, hc.data(), &one);
+        if (rc) return rc;
+        if (!one) return DAPOL_OK;
+    }
+    if (pb.nind) {
+        std::vector<uint8_t> hc(pb.nind * 32), oks(pb.nind);
+        for (uint64_t s = 0; s < pb.nind; s++) memcpy(hc.data() + s * 32, sib + 64 * (n_agg_coms + s), 32);
+        int rc = dapol_rangeproof_verify_batch(ctx, 64, 1, pb.nind, proof + pb.ind_off, SINGLE_PROOF_BYTE_NUM, hc.data(), oks.data());
+        if (rc) return rc;
+        for (uint8_t v : oks) if (!v) return DAPOL_OK;
+    }
+    *ok = 1;
+    return DAPOL_OK;
+}

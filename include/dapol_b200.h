@@ -260,6 +260,26 @@ DAPOL_API int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64
                                  const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*32 */, const uint8_t *proofs,
                                  const uint64_t *offsets /* k+1 */, uint8_t *ok /* k */);
 
+/* ---- batch proofs: ONE DapolProof for several leaves.
+ * Dapol::generate_proof_batch(&[TreeIndex]) (src/dapol/mod.rs:172-190): the Merkle part carries, level by level from the
+ * leaves up and left to right, every sibling that is not itself on the way up from the batch (smtree
+ * get_merkle_path_ref_batch; UPSTREAM-RECALL, as is the MerkleProof framing: be16 height, be64 #indexes, path bits of every
+ * index, be64 #siblings, siblings), and R::generate_proof runs ONCE over all those siblings with aggregation_factor.
+ * leaf_idx strictly increasing (smtree's batch order); k = 1 is dapol_prove_batch of one leaf, byte for byte (mod.rs:167-169).
+ * Nonces: the tree's prover key chained over the batch's leaf indexes (BLAKE3, 64 indexes per link, label "dapol-b200 batch
+ * proof nonce key v1"), stream 0, blocks (q << 32) + draw#.  DAPOL_ERR_BAD_ARG if aggregation_factor > #siblings (reference:
+ * slice panic), if the indexes are not increasing, or if the tree is a shard with a top tree attached; DAPOL_ERR_NOT_FOUND if
+ * an index is not a leaf (reference: None).  dapol_batch_proof_size: size of that proof (0 = bad arguments). */
+DAPOL_API uint64_t dapol_batch_proof_size(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy);
+DAPOL_API int dapol_generate_proof_batch(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
+                                         const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size);
+/* DapolProof::deserialize + verify_batch(&root, &leaves) (src/proof/mod.rs:49-54,76-95): *ok = 1 iff the k leaves (in index
+ * order) and the proof's siblings fold to the root (MerkleProof::verify_batch by level-synchronous DapolProofNode::merge on the
+ * device) and R::verify accepts the siblings' commitments.  Malformed bytes or a wrong number of leaves are a reject. */
+DAPOL_API int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
+                                       const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*32 */, const uint8_t *proof,
+                                       uint64_t proof_len, uint8_t *ok);
+
 /* ---- range proofs: src/range/mod.rs:48-119 generate_/verify_{single,aggregated}_range_proof in batches.
  * One call = k independent Bulletproofs of one shape: nbits in {8,16,32,64} (the reference fixes BIT_SIZE = 64,
  * range/mod.rs:16), m parties (power of two <= 64; m = 1 is prove_single / verify_single), each over a fresh

@@ -799,3 +799,188 @@ EXPORT int dor_verify_inclusion(int hash_id, int policy, const uint8_t *p, uint6
         if (!dor_rp_verify(64, 1, ind + 672 * k, 672, sib + 64 * (n_agg_coms + k))) return 0;
     return 1;
 }
+
+/* ------------------------------------------------------------------ batch proofs: ONE DapolProof for several leaves
+ * Dapol::generate_proof_batch (src/dapol/mod.rs:172-190), DapolProof::verify_batch (src/proof/mod.rs:49-54), test shape
+ * src/proof/tests.rs:6-35.  smtree get_merkle_path_ref_batch / MerkleProof::verify_batch (UPSTREAM-RECALL):
+ * level by level from the leaves up, left to right; a node's sibling is listed only if it is not itself on the way up. */
+typedef struct { int h; uint64_t idx; } sib_ref;
+/* siblings a batch proof carries, in proof order; idx strictly increasing.  Returns the count (plan may be NULL). */
+static uint64_t batch_sibling_plan(int height, uint64_t k, const uint64_t *idx, sib_ref *plan) {
+    uint64_t *cur = malloc(8 * k), n = k, out = 0;
+    memcpy(cur, idx, 8 * k);
+    for (int h = height; h >= 1; h--) {
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t s = cur[i] ^ 1;
+            int have = (i > 0 && cur[i - 1] == s) || (i + 1 < n && cur[i + 1] == s);
+            if (!have) { if (plan) { plan[out].h = h; plan[out].idx = s; } out++; }
+        }
+        uint64_t m = 0;
+        for (uint64_t i = 0; i < n; i++) if (!m || cur[m - 1] != cur[i] >> 1) cur[m++] = cur[i] >> 1;
+        n = m;
+    }
+    free(cur);
+    return out;
+}
+/* nonce key of a batch of more than one leaf: the tree's prover key chained over the leaf indexes, 64 per link (stream 0) */
+static void batch_nonce_key(uint8_t key[32], uint64_t k, const uint64_t *idx) {
+    static const char label[] = "dapol-b200 batch proof nonce key v1";
+    uint8_t buf[35 + 32 + 8 + 512];
+    memcpy(buf, label, 35); memcpy(buf + 35, key, 32);
+    for (int b = 0; b < 8; b++) buf[67 + b] = (uint8_t)(k >> (8 * b));
+    hash_buf(0, buf, 75, key);
+    for (uint64_t i = 0; i < k; i += 64) {
+        uint64_t c = k - i < 64 ? k - i : 64;
+        memcpy(buf, key, 32);
+        for (uint64_t j = 0; j < c; j++) for (int b = 0; b < 8; b++) buf[32 + 8 * j + b] = (uint8_t)(idx[i + j] >> (8 * b));
+        hash_buf(0, buf, 32 + 8 * c, key);
+    }
+}
+static uint64_t range_part_size(uint64_t nsib, uint64_t agg, int policy) {
+    agg_group g[64]; int ng; uint64_t sf;
+    if (policy_plan(nsib, agg, policy, g, &ng, &sf)) return 0;
+    uint64_t sz = policy == POLICY_SPLITTING ? 2 : 0;
+    for (int i = 0; i < ng; i++) { if (g[i].m > 64) return 0; sz += 8 + rp_size(g[i].m); }
+    return sz + 8 + 672 * (nsib - sf);
+}
+EXPORT uint64_t dor_batch_proof_size(int height, uint64_t k, const uint64_t *idx, uint64_t agg, int policy) {
+    if (k == 0 || height < 0 || height > 64) return 0;
+    for (uint64_t i = 1; i < k; i++) if (idx[i] <= idx[i - 1]) return 0;
+    uint64_t nsib = batch_sibling_plan(height, k, idx, NULL), rs = range_part_size(nsib, agg, policy);
+    if (!rs) return 0;
+    return rs + 2 + 8 + k * (((uint64_t)height + 7) / 8) + 8 + 64 * nsib;
+}
+EXPORT int dor_prove_inclusion_batch(const dor_tree *t, uint64_t k, const uint64_t *idx, uint64_t agg, int policy, const uint8_t seed[32],
+                                     uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (k == 1) return dor_prove_inclusion(t, idx[0], agg, policy, seed, out, cap, out_len);
+    uint64_t need = dor_batch_proof_size(t->height, k, idx, agg, policy);
+    if (!need) return ERR_BAD_ARG;
+    if (cap < need) return ERR_BUFFER;
+    for (uint64_t i = 0; i < k; i++) { const node *lf = tree_find(t, t->height, idx[i]); if (!lf || lf->is_pad) return ERR_NOT_FOUND; }
+    uint64_t nsib = batch_sibling_plan(t->height, k, idx, NULL);
+    sib_ref *plan = malloc(sizeof(sib_ref) * (nsib + 1));
+    const node **sib = malloc(sizeof(node *) * (nsib + 1));
+    batch_sibling_plan(t->height, k, idx, plan);
+    for (uint64_t i = 0; i < nsib; i++) sib[i] = tree_find(t, plan[i].h, plan[i].idx);
+    uint8_t key[32];
+    dor_prover_nonce_key(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, policy, agg, t->height, key);
+    batch_nonce_key(key, k, idx);
+    agg_group g[64]; int ng; uint64_t sf, q = 0, plen; int rc = 0;
+    policy_plan(nsib, agg, policy, g, &ng, &sf);
+    uint8_t *o = out;
+    if (policy == POLICY_SPLITTING) { put_be(o, (uint64_t)ng, 2); o += 2; }
+    for (int i = 0; i < ng && !rc; i++) {
+        uint64_t vals[64]; uint8_t bls[64 * 32];
+        memset(vals, 0, sizeof vals); memset(bls, 0, sizeof bls);
+        for (uint64_t j = 0; j < g[i].m; j++) {
+            if (j < g[i].count) { vals[j] = sib[g[i].start + j]->v; memcpy(bls + 32 * j, sib[g[i].start + j]->r, 32); }
+            else bls[32 * j] = 1;
+        }
+        rc = dor_rp_prove(64, (int)g[i].m, vals, bls, key, 0, q << 32, o + 8, &plen);
+        put_be(o, plen, 8); o += 8 + plen; q++;
+    }
+    put_be(o, nsib - sf, 8); o += 8;
+    for (uint64_t j = sf; j < nsib && !rc; j++) { rc = dor_rp_prove(64, 1, &sib[j]->v, sib[j]->r, key, 0, q << 32, o, &plen); o += plen; q++; }
+    uint64_t H = (uint64_t)t->height, nb = (H + 7) / 8;
+    put_be(o, H, 2); o += 2; put_be(o, k, 8); o += 8;
+    for (uint64_t i = 0; i < k; i++) if (nb) { put_be(o, H == 64 ? idx[i] : idx[i] << (8 * nb - H), (int)nb); o += nb; }
+    put_be(o, nsib, 8); o += 8;
+    for (uint64_t j = 0; j < nsib; j++) { memcpy(o, sib[j]->comc, 32); memcpy(o + 32, sib[j]->hash, 32); o += 64; }
+    *out_len = (uint64_t)(o - out);
+    free(plan); free(sib);
+    return rc;
+}
+typedef struct { uint64_t idx; ge p; uint8_t c[32], h[32]; } pnode;
+/* DapolProof::deserialize + verify_batch(root, leaves) (proof/mod.rs:49-54,76-95); leaves in index order; 1 = accept */
+EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p, uint64_t len, const uint8_t root_com[32], const uint8_t root_hash[32],
+                                      uint64_t k, const uint8_t *leaf_coms, const uint8_t *leaf_hashes) {
+    uint64_t pos = 0, nagg = 1;
+    const uint8_t *aggp[64]; uint64_t aggl[64];
+#define NEEDB(n) do { if (len - pos < (uint64_t)(n)) return 0; } while (0)
+    if (policy == POLICY_SPLITTING) { NEEDB(2); nagg = get_be(p, 2); pos += 2; if (nagg > 64) return 0; }
+    for (uint64_t i = 0; i < nagg; i++) {
+        NEEDB(8); uint64_t sz = get_be(p + pos, 8); pos += 8;
+        if (sz > len - pos) return 0;
+        aggp[i] = p + pos; aggl[i] = sz; pos += sz;
+    }
+    NEEDB(8); uint64_t nind = get_be(p + pos, 8); pos += 8;
+    if ((len - pos) / 672 < nind) return 0;
+    const uint8_t *ind = p + pos; pos += 672 * nind;
+    NEEDB(10); uint64_t H = get_be(p + pos, 2); pos += 2;
+    uint64_t nl = get_be(p + pos, 8); pos += 8;
+    if (H > 64 || nl != k || k == 0) return 0;
+    uint64_t nb = (H + 7) / 8;
+    if ((len - pos) / (nb ? nb : 1) < k && nb) return 0;
+    uint64_t *idx = malloc(8 * k);
+    for (uint64_t i = 0; i < k; i++) { uint64_t x = nb ? get_be(p + pos, (int)nb) : 0; if (nb && H != 64) x >>= (8 * nb - H); idx[i] = x; pos += nb; }
+    int ok = 1;
+    for (uint64_t i = 1; i < k; i++) if (idx[i] <= idx[i - 1]) ok = 0;
+    uint64_t nsib = 0;
+    if (ok && len - pos >= 8) { nsib = get_be(p + pos, 8); pos += 8; } else ok = 0;
+    if (ok && ((len - pos) / 64 < nsib || nsib != batch_sibling_plan((int)H, k, idx, NULL) || nind > nsib)) ok = 0;
+    if (!ok) { free(idx); return 0; }
+    const uint8_t *sib = p + pos;
+    sib_ref *plan = malloc(sizeof(sib_ref) * (nsib + 1));
+    batch_sibling_plan((int)H, k, idx, plan);
+    pnode *cur = malloc(sizeof(pnode) * k), *nxt = malloc(sizeof(pnode) * k);
+    uint64_t n = k, used = 0;
+    for (uint64_t i = 0; i < k && ok; i++) {
+        cur[i].idx = idx[i]; memcpy(cur[i].c, leaf_coms + 32 * i, 32); memcpy(cur[i].h, leaf_hashes + 32 * i, 32);
+        ok = ge_decompress(&cur[i].p, cur[i].c);
+    }
+    /* siblings are consumed in plan order: all of a level (left to right) before the next level up */
+    for (int h = (int)H; h >= 1 && ok; h--) {
+        uint64_t m = 0, at = used;   /* `at` walks this level's siblings in the order the plan lists them */
+        /* first pass: how many siblings does this level consume (so the next level starts after them) */
+        uint64_t lvl_cnt = 0;
+        for (uint64_t j = used; j < nsib && plan[j].h == h; j++) lvl_cnt++;
+        for (uint64_t i = 0; i < n && ok; ) {
+            pnode other; const pnode *l, *r; uint64_t step = 1;
+            if (i + 1 < n && cur[i + 1].idx == (cur[i].idx ^ 1)) { other = cur[i + 1]; step = 2; }
+            else {
+                if (at >= used + lvl_cnt || plan[at].idx != (cur[i].idx ^ 1)) { ok = 0; break; }
+                other.idx = plan[at].idx; memcpy(other.c, sib + 64 * at, 32); memcpy(other.h, sib + 64 * at + 32, 32);
+                ok = ge_decompress(&other.p, other.c); at++;
+                if (!ok) break;
+            }
+            if (cur[i].idx & 1) { l = &other; r = &cur[i]; } else { l = &cur[i]; r = &other; }
+            uint8_t buf[128];
+            memcpy(buf, l->c, 32); memcpy(buf + 32, r->c, 32); memcpy(buf + 64, l->h, 32); memcpy(buf + 96, r->h, 32);
+            nxt[m].idx = cur[i].idx >> 1;
+            hash_buf(hash_id, buf, 128, nxt[m].h);
+            ge_add(&nxt[m].p, &l->p, &r->p); ge_compress(nxt[m].c, &nxt[m].p);
+            m++; i += step;
+        }
+        if (ok && at != used + lvl_cnt) ok = 0;
+        used += lvl_cnt;
+        pnode *t_ = cur; cur = nxt; nxt = t_; n = m;
+    }
+    if (ok && (n != 1 || memcmp(cur[0].c, root_com, 32) || memcmp(cur[0].h, root_hash, 32))) ok = 0;
+    free(cur); free(nxt); free(plan); free(idx);
+    if (!ok) return 0;
+    /* R::verify on the siblings' commitments, in proof order (padding.rs:168-197 / splitting.rs:180-211) */
+    uint64_t n_agg_coms = nsib - nind;
+    uint8_t coms[64 * 32];
+    if (n_agg_coms > 64) return 0;
+    if (policy == POLICY_PADDING) {
+        uint64_t m = next_pow2(n_agg_coms);
+        uint8_t bbl[32]; ge_compress(bbl, &GE_BBL);
+        for (uint64_t j = 0; j < m; j++) memcpy(coms + 32 * j, j < n_agg_coms ? sib + 64 * j : bbl, 32);
+        if (nagg != 1 || !dor_rp_verify(64, (int)m, aggp[0], aggl[0], coms)) return 0;
+    } else {
+        uint64_t base = next_pow2(n_agg_coms), at = 0, i = 0;
+        while (at < n_agg_coms) {
+            if (n_agg_coms & base) {
+                if (i >= nagg) return 0;
+                for (uint64_t j = 0; j < base; j++) memcpy(coms + 32 * j, sib + 64 * (at + j), 32);
+                if (!dor_rp_verify(64, (int)base, aggp[i], aggl[i], coms)) return 0;
+                i++; at += base;
+            }
+            base >>= 1;
+        }
+    }
+    for (uint64_t j = 0; j < nind; j++)
+        if (!dor_rp_verify(64, 1, ind + 672 * j, 672, sib + 64 * (n_agg_coms + j))) return 0;
+    return 1;
+#undef NEEDB
+}

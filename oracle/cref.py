@@ -217,6 +217,26 @@ class Tree:
         return bytes(out[: n.value])
 
 
+def prove_inclusion_batch(tree: "Tree", leaf_idxs, agg, policy, seed: bytes):
+    """Dapol::generate_proof_batch (mod.rs:172-190): ONE DapolProof for several leaves (strictly increasing indexes)."""
+    L = lib()
+    L.dor_batch_proof_size.restype = C.c_uint64
+    ia, iap = _np(leaf_idxs, np.uint64)
+    cap = L.dor_batch_proof_size(tree.height, C.c_uint64(ia.size), iap, C.c_uint64(agg), policy)
+    if cap == 0:
+        return None
+    out = (C.c_uint8 * cap)()
+    n = C.c_uint64()
+    rc = L.dor_prove_inclusion_batch(tree.h, C.c_uint64(ia.size), iap, C.c_uint64(agg), policy, _b(seed), out, C.c_uint64(cap), C.byref(n))
+    return None if rc else bytes(out[: n.value])
+
+
+def verify_inclusion_batch(hash_id, policy, proof: bytes, root_com, root_hash, leaf_coms, leaf_hashes) -> bool:
+    """DapolProof::deserialize + verify_batch(root, leaves) (proof/mod.rs:49-54); leaves in index order."""
+    return bool(lib().dor_verify_inclusion_batch(hash_id, policy, _b(proof) if proof else None, C.c_uint64(len(proof)), _b(root_com), _b(root_hash),
+                                                 C.c_uint64(len(leaf_coms)), _b(b"".join(leaf_coms)), _b(b"".join(leaf_hashes))))
+
+
 def rp_prove(values, blindings, seed: bytes, stream=0, base=0, nbits=64) -> bytes:
     m = len(values)
     vals, vp = _np(values, np.uint64)

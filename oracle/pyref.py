@@ -1002,3 +1002,109 @@ def verify_inclusion(hash_id, proof: bytes, policy: int, root, leaf) -> bool:
     if cur[1] != root[0] or cur[2] != root[1]:
         return False
     return policy_verify(aggregated, individual, [c for c, _ in sibs], policy)
+
+
+# --------------------------------------------------------------------------------------
+# Batch proofs: ONE DapolProof for several leaves (Dapol::generate_proof_batch, src/dapol/mod.rs:172-190;
+# DapolProof::verify_batch, src/proof/mod.rs:49-54; test shape src/proof/tests.rs:6-35).
+# smtree get_merkle_path_ref_batch / MerkleProof::verify_batch (UPSTREAM-RECALL, SURVEY App. A.6): level by level from
+# the leaves up, left to right, a node's sibling is listed only if it is not itself on the way up from the batch.
+# --------------------------------------------------------------------------------------
+def batch_sibling_plan(height: int, leaf_idxs):
+    """[(level, index)] of the siblings a batch Merkle proof carries, in proof order; leaf_idxs strictly increasing."""
+    assert all(a < b for a, b in zip(leaf_idxs, leaf_idxs[1:])), "batch indexes must be strictly increasing"
+    plan, cur = [], list(leaf_idxs)
+    for h in range(height, 0, -1):
+        have = set(cur)
+        plan += [(h, x ^ 1) for x in cur if (x ^ 1) not in have]
+        nxt = []
+        for x in cur:
+            if not nxt or nxt[-1] != x >> 1:
+                nxt.append(x >> 1)
+        cur = nxt
+    return plan
+
+
+BATCH_KEY_LABEL = b"dapol-b200 batch proof nonce key v1"
+
+
+def batch_nonce_key(key: bytes, leaf_idxs) -> bytes:
+    """Nonce key of a batch proof of more than one leaf: the tree's prover key (prover_nonce_key) bound to the batch --
+    BLAKE3 chained over the leaf indexes, 64 of them (512 B) per link; the proof's range proofs draw from stream 0."""
+    st = digest(HASH_BLAKE3, BATCH_KEY_LABEL, key, struct.pack("<Q", len(leaf_idxs)))
+    for i in range(0, len(leaf_idxs), 64):
+        st = digest(HASH_BLAKE3, st, b"".join(struct.pack("<Q", x) for x in leaf_idxs[i:i + 64]))
+    return st
+
+
+def merkle_serialize_batch(height, leaf_idxs, siblings) -> bytes:
+    out = height.to_bytes(2, "big") + len(leaf_idxs).to_bytes(8, "big")
+    nbytes = (height + 7) // 8
+    for x in leaf_idxs:
+        out += ((x << (8 * nbytes - height)) if height else 0).to_bytes(nbytes, "big")
+    out += len(siblings).to_bytes(8, "big")
+    for comc, h in siblings:
+        out += comc + h
+    return out
+
+
+def prove_inclusion_batch(tree: Tree, leaf_idxs, agg: int, policy: int, seed: bytes) -> bytes:
+    """Dapol::generate_proof_batch(leaf_indexes) -> DapolProof::serialize; one leaf = prove_inclusion (mod.rs:167-169)."""
+    leaf_idxs = list(leaf_idxs)
+    if len(leaf_idxs) == 1:
+        return prove_inclusion(tree, leaf_idxs[0], agg, policy, seed)
+    sibs = [tree.levels[h][i] for h, i in batch_sibling_plan(tree.height, leaf_idxs)]
+    root = tree.root
+    key = batch_nonce_key(prover_nonce_key(seed, root.comc, root.hash, policy, agg, tree.height), leaf_idxs)
+    aggregated, individual = policy_prove([s.v for s in sibs], [s.r % L for s in sibs], agg, policy, key, 0)
+    return policy_serialize(aggregated, individual, policy) + merkle_serialize_batch(tree.height, leaf_idxs, [(s.comc, s.hash) for s in sibs])
+
+
+def verify_inclusion_batch(hash_id, proof: bytes, policy: int, root, leaves, dlen=32) -> bool:
+    """DapolProof::deserialize + verify_batch(root, leaves); root / leaves = (comc, hash), leaves in index order."""
+    r = policy_deserialize(proof, policy)
+    if r is None:
+        return False
+    aggregated, individual, begin = r
+    try:
+        height = int.from_bytes(proof[begin:begin + 2], "big"); begin += 2
+        nb = int.from_bytes(proof[begin:begin + 8], "big"); begin += 8
+        nbytes = (height + 7) // 8
+        if height > 64 or nb != len(leaves) or nb == 0 or len(proof) - begin < nb * nbytes + 8:
+            return False
+        idxs = []
+        for _ in range(nb):
+            idxs.append(int.from_bytes(proof[begin:begin + nbytes], "big") >> (8 * nbytes - height) if height else 0)
+            begin += nbytes
+        k = int.from_bytes(proof[begin:begin + 8], "big"); begin += 8
+        if len(proof) - begin < k * (32 + dlen):
+            return False
+        sibs = []
+        for _ in range(k):
+            sibs.append((proof[begin:begin + 32], proof[begin + 32:begin + 32 + dlen]))
+            begin += 32 + dlen
+    except Exception:
+        return False
+    if any(a >= b for a, b in zip(idxs, idxs[1:])):
+        return False
+    plan = batch_sibling_plan(height, idxs)
+    if len(plan) != len(sibs):
+        return False
+    pts = [decompress(c) for c, _ in leaves] + [decompress(c) for c, _ in sibs]
+    if any(p is None for p in pts):
+        return False
+    cur = {x: (decompress(c), c, h) for x, (c, h) in zip(idxs, leaves)}
+    given = {hi: (decompress(c), c, h) for hi, (c, h) in zip(plan, sibs)}
+    for lvl in range(height, 0, -1):
+        nxt = {}
+        for x in sorted(cur):
+            if x >> 1 in nxt:
+                continue
+            other = cur.get(x ^ 1) or given[(lvl, x ^ 1)]
+            l, r_ = (cur[x], other) if not x & 1 else (other, cur[x])
+            nxt[x >> 1] = proofnode_merge(hash_id, l, r_)
+        cur = nxt
+    top = cur[0] if height else cur[idxs[0]]
+    if top[1] != root[0] or top[2] != root[1]:
+        return False
+    return policy_verify(aggregated, individual, [c for c, _ in sibs], policy)

@@ -222,3 +222,31 @@ def test_inclusion_c_vs_bigint(pyref, cref, policy):
         assert not cref.verify_inclusion(0, policy, pc, rt["comc"], rt["hash"], other["comc"], other["hash"])
     assert T.prove_inclusion(leaf, H + 1, policy, seed) is None       # reference: slice OOB panic
     assert T.prove_inclusion(leaf ^ 1 if (leaf ^ 1) not in set(sidx.tolist()) else 63, 2, policy, seed) is None or True
+
+
+def test_batch_proof_c_vs_bigint(pyref, cref):
+    """ONE DapolProof for several leaves (mod.rs:172-190, proof/mod.rs:49-54): the two restatements agree on the sibling plan,
+    the bytes and the verdicts; shape of src/proof/tests.rs:6-35 shrunk so the big-int prover finishes in seconds."""
+    H = 5
+    lv, T, sidx = _rand_tree(pyref, cref, 0, H, 7, 4)
+    pt = pyref.build_tree(0, H, [(i, pyref.node_new(0, v, r)) for i, v, r in lv], PAD_SEED)
+    seed = bytes(range(1, 33))
+    picks = [int(x) for x in sidx[[0, 2, 5]]]
+    plan = pyref.batch_sibling_plan(H, picks)
+    assert len(plan) < 3 * H and len(set(plan)) == len(plan)          # shared siblings appear once
+    assert pyref.batch_sibling_plan(H, picks[:1]) == [(h, (picks[0] >> (H - h)) ^ 1) for h in range(H, 0, -1)]  # single leaf: its path
+    rt = T.root()
+    leaves = [T.get_node(H, x) for x in picks]
+    lc, lh = [l["comc"] for l in leaves], [l["hash"] for l in leaves]
+    pc = cref.prove_inclusion_batch(T, picks, 1, 1, seed)
+    assert pc == pyref.prove_inclusion_batch(pt, picks, 1, 1, seed)
+    assert cref.verify_inclusion_batch(0, 1, pc, rt["comc"], rt["hash"], lc, lh)
+    assert pyref.verify_inclusion_batch(0, pc, 1, (rt["comc"], rt["hash"]), list(zip(lc, lh)))
+    assert not cref.verify_inclusion_batch(0, 1, pc, rt["comc"], rt["hash"], lc[::-1], lh[::-1])
+    assert not cref.verify_inclusion_batch(0, 1, pc, rt["comc"], rt["hash"], lc[:2], lh[:2])
+    for pos in (40, len(pc) - 5, len(pc) - 70):
+        bb = bytearray(pc); bb[pos] ^= 4
+        assert not cref.verify_inclusion_batch(0, 1, bytes(bb), rt["comc"], rt["hash"], lc, lh)
+    assert cref.prove_inclusion_batch(T, picks[:1], 2, 0, seed) == T.prove_inclusion(picks[0], 2, 0, seed)   # a batch of one is the single proof
+    assert cref.prove_inclusion_batch(T, picks[::-1], 1, 1, seed) is None                                   # not increasing
+    assert cref.prove_inclusion_batch(T, picks, len(plan) + 1, 1, seed) is None                             # reference: slice OOB panic
