@@ -408,6 +408,28 @@ class Dapol:
         r = self.generate_proofs([leaf_idx], seed)
         return None if r is None else r[0]
 
+    def index_of_ids(self, internal_ids):
+        """id_to_idx_map lookups (mod.rs:148-165) by the internal ids themselves; None if any id is unknown."""
+        blob, off = self.pack_ids(list(internal_ids))
+        k = len(off) - 1
+        idx = np.zeros(k, np.uint64); found = np.zeros(k, np.uint8)
+        rc = _ffi.lib().dapol_tree_index_of_batch(self._t, k, _p(blob), _p(off), _p(idx), _p(found))
+        if rc == 17:
+            return None
+        _check(rc)
+        return [int(x) for x in idx]
+
+    def generate_proof_for_id(self, internal_id: bytes, seed: bytes):
+        """Dapol::generate_proof_for_id (mod.rs:148-151)."""
+        idx = self.index_of_ids([internal_id])
+        return None if idx is None else self.generate_proof(idx[0], seed)
+
+    def generate_proof_batch_for_ids(self, internal_ids, seed: bytes):
+        """Dapol::generate_proof_batch_for_ids (mod.rs:155-165): one batch proof for the leaves of the given ids, in the ids' order
+        (the reference passes the indexes on as they come; smtree wants them increasing)."""
+        idx = self.index_of_ids(internal_ids)
+        return None if idx is None else self.generate_proof_batch(idx, seed)
+
     def generate_proof_batch(self, leaf_idx, seed: bytes):
         """Dapol::generate_proof_batch(&[TreeIndex]) (mod.rs:172-190): ONE DapolProof for all the given leaves (strictly
         increasing indexes); None if any index is not a leaf."""

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include "../../include/dapol_b200.h"
 #include <vector>
@@ -72,6 +73,13 @@ struct dapol_tree {
     uint64_t *d_level_off = nullptr;
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
     uint64_t index_map_first = 0, index_map_n = 0;  // sharded build: the map covers input positions [first, first + n) (0: all n_leaves)
+    // lookup by internal id (Dapol::generate_proof_for_id, mod.rs:148-165): audit ids of the mapped liabilities, the audit seed, and
+    // -- built on the first lookup -- the ids' 64-bit prefixes sorted with the input position of each
+    uint32_t *audit_ids = nullptr;
+    std::vector<uint8_t> audit_seed;
+    mutable uint64_t *akey_sorted = nullptr;
+    mutable uint32_t *akey_who = nullptr;
+    mutable std::mutex index_mu;
     std::vector<uint64_t> npads;        // padding nodes per level
     uint32_t root_ext[32] = {};         // half point of the root commitment (kept for the shard root record)
     uint32_t root_comc[8] = {}, root_hash[8] = {};  // compressed commitment and hash of the root (host copy: prover nonce key)

@@ -476,6 +476,7 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     dfree(t->ns.ext, st); dfree(t->ns.is_pad, st);
     dfree(t->pos_all, st);
     dfree(t->d_pos, st); dfree(t->d_level_off, st); dfree(t->leaf_index_of, st);
+    dfree(t->audit_ids, st); dfree(t->akey_sorted, st); dfree(t->akey_who, st);
     delete t;
 }
 
@@ -754,10 +755,11 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
     size_t cub_bytes = AssignScratch::cub_need(n, st);
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = 3 * Arena::need(n, 32) + Arena::need(n, 8) + Arena::need(n, 32) + AssignScratch::need(n, cub_bytes) + Arena::need(seed_len + 1, 1);
+    ar.size = 2 * Arena::need(n, 32) + Arena::need(n, 8) + Arena::need(n, 32) + AssignScratch::need(n, cub_bytes) + Arena::need(seed_len + 1, 1);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
-    uint32_t *audit = ar.take<uint32_t>(8 * n), *cur_seed = ar.take<uint32_t>(8 * n), *blind = ar.take<uint32_t>(8 * n);
+    uint32_t *audit = nullptr;  // survives in the tree: dapol_tree_index_of looks liabilities up by their audit id
+    uint32_t *cur_seed = ar.take<uint32_t>(8 * n), *blind = ar.take<uint32_t>(8 * n);
     uint64_t *values_sorted = ar.take<uint64_t>(n);
     uint32_t *blind_sorted = ar.take<uint32_t>(8 * n);
     AssignScratch sc;
@@ -769,24 +771,27 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
         cudaError_t e_ = (expr);                                             \
         if (e_ != cudaSuccess) {                                             \
             g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(e_); \
-            dfree(mem, st); dfree(cand, st); return DAPOL_ERR_CUDA;            \
+            dfree(mem, st); dfree(cand, st); dfree(audit, st); return DAPOL_ERR_CUDA; \
         }                                                                    \
     } while (0)
     TRY_L(dmalloc(&cand, n * 8, st));  // survives as the id -> leaf index map of the tree
+    TRY_L(dmalloc(&audit, n * 32, st));
     if (seed_len) TRY_L(cudaMemcpyAsync(d_seed, audit_seed, seed_len, cudaMemcpyHostToDevice, st));
     unsigned long long h_cnt[4] = {0, ~0ull, ~0ull, 0};
     TRY_L(cudaMemcpyAsync(sc.counters, h_cnt, 32, cudaMemcpyHostToDevice, st));
     rc = derive_stage(ctx, hash_id, height, n, d_iid_blob, d_iid_off, d_eid_blob, d_eid_off, d_seed, (uint32_t)seed_len, audit, cur_seed, cand, blind,
                       sc.tries, sc.akey, sc.iota, reinterpret_cast<int *>(sc.counters + 3));
     if (rc == DAPOL_OK) rc = assign_stage(ctx, hash_id, height, n, audit, cur_seed, cand, sc, err_pos);
-    if (rc != DAPOL_OK) { dfree(mem, st); dfree(cand, st); return rc; }
+    if (rc != DAPOL_OK) { dfree(mem, st); dfree(cand, st); dfree(audit, st); return rc; }
     // the last sort (no losers) is the final sorted order: result.sort_by_key(index) (mod.rs:396)
     k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, sc.who, d_values, blind, values_sorted, blind_sorted);
     ctx->launches++;
     rc = tree_build_dev(ctx, hash_id, height, n, sc.keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
     dfree(mem, st);
-    if (rc != DAPOL_OK) { dfree(cand, st); return rc; }
+    if (rc != DAPOL_OK) { dfree(cand, st); dfree(audit, st); return rc; }
     (*out)->leaf_index_of = cand;
+    (*out)->audit_ids = audit;
+    (*out)->audit_seed.assign(audit_seed, audit_seed + seed_len);
 #undef TRY_L
     return DAPOL_OK;
 }
@@ -1262,4 +1267,105 @@ extern "C" int dapol_fe_bench(dapol_ctx *ctx, int op, double *gop_per_s) {
     if (rc) return rc;
     *gop_per_s = (double)blocks * threads * iters * 2.0 / (ms * 1e-3) / 1e9;
     return DAPOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ lookup by internal id
+// Dapol::generate_proof_for_id / generate_proof_batch_for_ids (src/dapol/mod.rs:148-165) look the liability up in id_to_idx_map.
+// Here the map is keyed by the audit id D(audit_seed || internal_id) every liability already has (mod.rs:347-353): the ids' 64-bit
+// prefixes are sorted once, on the first lookup, and a query is a binary search + an exact 32-byte comparison.
+__global__ void k_index_keys(uint64_t n, const uint32_t *audit, uint64_t *keys, uint32_t *iota) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (uint64_t)audit[8 * i] | ((uint64_t)audit[8 * i + 1] << 32);
+    iota[i] = (uint32_t)i;
+}
+__global__ void k_lookup_ids(uint64_t k, const uint32_t *want /*[k][8]*/, uint64_t n, const uint64_t *keys_sorted, const uint32_t *who, const uint32_t *audit,
+                             const uint64_t *leaf_index_of, uint64_t *out_idx, uint8_t *found) {
+    uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= k) return;
+    uint32_t w[8], a[8];
+    load8(w, want + 8 * q);
+    const uint64_t key = (uint64_t)w[0] | ((uint64_t)w[1] << 32);
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (keys_sorted[mid] < key) lo = mid + 1; else hi = mid; }
+    found[q] = 0; out_idx[q] = 0;
+    for (; lo < n && keys_sorted[lo] == key; lo++) {
+        const uint64_t u = who[lo];
+        load8(a, audit + 8 * u);
+        uint32_t d = 0;
+        for (int i = 0; i < 8; i++) d |= a[i] ^ w[i];
+        if (d == 0) { found[q] = 1; out_idx[q] = leaf_index_of[u]; return; }
+    }
+}
+static int ensure_id_index(const dapol_tree *t) {
+    std::lock_guard<std::mutex> lk(t->index_mu);
+    if (t->akey_sorted) return DAPOL_OK;
+    dapol_ctx *ctx = t->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint64_t n = t->index_map_n ? t->index_map_n : t->n_leaves;
+    uint64_t *keys = nullptr, *keys_sorted = nullptr;
+    uint32_t *iota = nullptr, *who = nullptr;
+    uint8_t *tmp = nullptr;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys_sorted, iota, who, (int)n, 0, 64, st);
+    cudaError_t e = dmalloc(&keys, n * 8, st);
+    if (e == cudaSuccess) e = dmalloc(&keys_sorted, n * 8, st);
+    if (e == cudaSuccess) e = dmalloc(&iota, n * 4, st);
+    if (e == cudaSuccess) e = dmalloc(&who, n * 4, st);
+    if (e == cudaSuccess) e = dmalloc(&tmp, tb, st);
+    if (e == cudaSuccess) {
+        k_index_keys<<<grid_for(n, 256), 256, 0, st>>>(n, t->audit_ids, keys, iota);
+        cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys_sorted, iota, who, (int)n, 0, 64, st);
+        ctx->launches += 2;
+        e = cudaStreamSynchronize(st);
+    }
+    dfree(keys, st); dfree(iota, st); dfree(tmp, st);
+    if (e != cudaSuccess) { dfree(keys_sorted, st); dfree(who, st); CUDA_TRY(e); }
+    t->akey_sorted = keys_sorted;
+    t->akey_who = who;
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_index_of_batch(const dapol_tree *t, uint64_t k, const uint8_t *id_blob, const uint64_t *id_off, uint64_t *leaf_idx, uint8_t *found) {
+    if (!t || !id_off || !leaf_idx || !found || !k) return DAPOL_ERR_BAD_ARG;
+    if (!t->audit_ids || !t->leaf_index_of) { memset(found, 0, k); return DAPOL_ERR_NOT_FOUND; }  // not built from liabilities: no id map (reference: empty map)
+    dapol_ctx *ctx = t->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_id_index(t);
+    if (rc) return rc;
+    // audit ids of the queries on the host (the same D the tree was built with; ids of any length)
+    std::vector<uint32_t> want(8 * k);
+    for (uint64_t q = 0; q < k; q++) {
+        if (id_off[q + 1] < id_off[q] || id_off[q + 1] - id_off[q] > 0xffffffffull) return DAPOL_ERR_BAD_ARG;
+        dapol_hasher hs;
+        hasher_init(hs, t->hash_id);
+        if (!t->audit_seed.empty()) hasher_update(hs, t->audit_seed.data(), (uint32_t)t->audit_seed.size());
+        if (id_off[q + 1] > id_off[q]) hasher_update(hs, id_blob + id_off[q], (uint32_t)(id_off[q + 1] - id_off[q]));
+        if (hasher_final(hs, &want[8 * q])) return DAPOL_ERR_BAD_ARG;
+    }
+    cudaStream_t st = ctx->stream;
+    const uint64_t n = t->index_map_n ? t->index_map_n : t->n_leaves;
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(k, 32) + Arena::need(k, 8) + Arena::need(k, 1);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint32_t *d_want = ar.take<uint32_t>(8 * k);
+    uint64_t *d_out = ar.take<uint64_t>(k);
+    uint8_t *d_found = ar.take<uint8_t>(k);
+    cudaMemcpyAsync(d_want, want.data(), k * 32, cudaMemcpyHostToDevice, st);
+    k_lookup_ids<<<grid_for(k, 128), 128, 0, st>>>(k, d_want, n, t->akey_sorted, t->akey_who, t->audit_ids, t->leaf_index_of, d_out, d_found);
+    ctx->launches++;
+    cudaMemcpyAsync(leaf_idx, d_out, k * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(found, d_found, k, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    dfree(mem, st);
+    CUDA_TRY(e);
+    for (uint64_t q = 0; q < k; q++) if (!found[q]) return DAPOL_ERR_NOT_FOUND;  // reference: None if ANY id is unknown (mod.rs:155-165)
+    return DAPOL_OK;
+}
+extern "C" int dapol_tree_index_of(const dapol_tree *t, const uint8_t *internal_id, uint64_t len, uint64_t *leaf_idx) {
+    if (!leaf_idx) return DAPOL_ERR_BAD_ARG;
+    const uint64_t off[2] = {0, len};
+    uint8_t found = 0;
+    return dapol_tree_index_of_batch(t, 1, internal_id, off, leaf_idx, &found);
 }

@@ -665,6 +665,9 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
         b_cand.p = nullptr;  // ownership moved to the tree
         tp->index_map_first = my_first;
         tp->index_map_n = n;
+        tp->audit_ids = audit;  // dapol_tree_index_of on the top-tree handle: the ids of the local slice
+        b_audit.p = nullptr;
+        if (audit_seed_len) tp->audit_seed.assign(audit_seed, audit_seed + audit_seed_len);
     }
     memcpy(ctx->last_ms, build_ms, sizeof build_ms);  // dapol_last_build_times: the subtree build, not the tiny top tree
     CUDA_TRY(cudaEventRecord(ev[4], st));

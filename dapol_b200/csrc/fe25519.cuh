@@ -38,6 +38,11 @@
 #define EMU_ADDC_CC(d, x, y) EMU_SET_(d, (uint64_t)(x) + (uint64_t)(y) + cf_)
 #define EMU_ADDC(d, x, y) EMU_SETNC_(d, (uint64_t)(x) + (uint64_t)(y) + cf_)
 #define EMU_ADD(d, x, y) EMU_SETNC_(d, (uint64_t)(x) + (uint64_t)(y))
+// sub.cc / subc: CC.CF holds the borrow
+#define EMU_SETB_(d, t) do { uint64_t t__ = (t); (d) = (uint32_t)t__; cf_ = (uint32_t)(t__ >> 32) & 1u; } while (0)
+#define EMU_SUB_CC(d, x, y) EMU_SETB_(d, (uint64_t)(uint32_t)(x) - (uint64_t)(uint32_t)(y))
+#define EMU_SUBC_CC(d, x, y) EMU_SETB_(d, (uint64_t)(uint32_t)(x) - (uint64_t)(uint32_t)(y) - cf_)
+#define EMU_SUBC(d, x, y) EMU_SETNC_(d, (uint64_t)(uint32_t)(x) - (uint64_t)(uint32_t)(y) - cf_)
 #endif
 
 #ifdef DAPOL_FE_GEN_INC

@@ -36,6 +36,8 @@ DAPOL_HD_INLINE uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> ((6
 #define B3_CHUNK_START 1u
 #define B3_CHUNK_END 2u
 #define B3_ROOT 8u
+#define B3_PARENT 4u
+#define B3_MAX_DEPTH 16  // chaining-value stack of the tree mode: inputs of up to 2^16 chunks (64 MB)
 
 #define B3_ROUND(m0, m1, m2, m3, m4, m5, m6, m7, m8, m9, m10, m11, m12, m13, m14, m15) \
     BLAKE_G(s0, s4, s8, s12, m[m0], m[m1]);                                            \
@@ -47,10 +49,11 @@ DAPOL_HD_INLINE uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> ((6
     BLAKE_G(s2, s7, s8, s13, m[m12], m[m13]);                                          \
     BLAKE_G(s3, s4, s9, s14, m[m14], m[m15]);
 
-// cv <- compress(cv, m, counter = 0, block_len, flags); message schedule fully unrolled (indices static)
-DAPOL_HD_INLINE void blake3_compress(uint32_t cv[8], const uint32_t m[16], uint32_t block_len, uint32_t flags) {
+// cv <- compress(cv, m, counter, block_len, flags); message schedule fully unrolled (indices static).  The counter is the
+// chunk number (0 for every input of at most one chunk and for parent nodes).
+DAPOL_HD_INLINE void blake3_compress_t(uint32_t cv[8], const uint32_t m[16], uint32_t counter, uint32_t block_len, uint32_t flags) {
     uint32_t s0 = cv[0], s1 = cv[1], s2 = cv[2], s3 = cv[3], s4 = cv[4], s5 = cv[5], s6 = cv[6], s7 = cv[7];
-    uint32_t s8 = BLAKE_IV0, s9 = BLAKE_IV1, s10 = BLAKE_IV2, s11 = BLAKE_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = flags;
+    uint32_t s8 = BLAKE_IV0, s9 = BLAKE_IV1, s10 = BLAKE_IV2, s11 = BLAKE_IV3, s12 = counter, s13 = 0, s14 = block_len, s15 = flags;
     B3_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
     B3_ROUND(2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
     B3_ROUND(3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1)
@@ -60,6 +63,9 @@ DAPOL_HD_INLINE void blake3_compress(uint32_t cv[8], const uint32_t m[16], uint3
     B3_ROUND(11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13)
     cv[0] = s0 ^ s8; cv[1] = s1 ^ s9; cv[2] = s2 ^ s10; cv[3] = s3 ^ s11;
     cv[4] = s4 ^ s12; cv[5] = s5 ^ s13; cv[6] = s6 ^ s14; cv[7] = s7 ^ s15;
+}
+DAPOL_HD_INLINE void blake3_compress(uint32_t cv[8], const uint32_t m[16], uint32_t block_len, uint32_t flags) {
+    blake3_compress_t(cv, m, 0u, block_len, flags);
 }
 DAPOL_HD_INLINE void blake3_iv(uint32_t cv[8]) {
     cv[0] = BLAKE_IV0; cv[1] = BLAKE_IV1; cv[2] = BLAKE_IV2; cv[3] = BLAKE_IV3;
@@ -134,24 +140,57 @@ DAPOL_HD_INLINE void dapol_hash128(int hash_id, uint32_t out[8], const uint32_t 
     }
 }
 
-// Incremental D over a byte stream assembled from several parts (leaf derivation, mod.rs:347-384).
-// Buffer of <= 1024 bytes total for BLAKE3 single-chunk mode; returns 0 on success.
+// Incremental D over a byte stream assembled from several parts (leaf derivation, mod.rs:347-384): ids of any length hash as
+// the reference's D does.  BLAKE3 inputs longer than one 1024-byte chunk use the tree mode of the spec (chunk chaining values
+// on a small stack, left subtree = largest power of two of chunks); returns 0 on success.
 struct dapol_hasher {
     uint32_t h[8];
     uint32_t m[16];  // current block, little-endian packed
     uint32_t fill;   // bytes in m
-    uint32_t total;  // bytes compressed so far (before m)
+    uint32_t total;  // bytes compressed so far (before m); BLAKE3: inside the current chunk
     int hash_id;
+    uint32_t chunk;    // BLAKE3: number of the current chunk
+    uint32_t stack_n;  // BLAKE3: chaining values of completed subtrees
+    uint32_t stack[B3_MAX_DEPTH][8];
 };
+// parent node of the BLAKE3 tree: cv <- compress(IV, left || right, PARENT [| ROOT])
+DAPOL_HD_INLINE void blake3_parent(uint32_t cv[8], const uint32_t left[8], const uint32_t right[8], uint32_t root) {
+    uint32_t m[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { m[i] = left[i]; m[8 + i] = right[i]; }
+    blake3_iv(cv);
+    blake3_compress(cv, m, 64, B3_PARENT | root);
+}
 DAPOL_HD_INLINE void hasher_init(dapol_hasher &s, int hash_id) {
-    s.hash_id = hash_id; s.fill = 0; s.total = 0;
+    s.hash_id = hash_id; s.fill = 0; s.total = 0; s.chunk = 0; s.stack_n = 0;
     if (hash_id == DAPOL_HASH_BLAKE3) blake3_iv(s.h); else blake2s_iv(s.h);
 #pragma unroll
     for (int i = 0; i < 16; i++) s.m[i] = 0;
 }
-DAPOL_HD_INLINE void hasher_flush_full(dapol_hasher &s) {  // compress a full, non-final block
-    if (s.hash_id == DAPOL_HASH_BLAKE3) blake3_compress(s.h, s.m, 64, s.total == 0 ? B3_CHUNK_START : 0u);
-    else blake2s_compress(s.h, s.m, s.total + 64, 0);
+DAPOL_HD_INLINE void hasher_flush_full(dapol_hasher &s) {  // compress a full block that more input follows
+    if (s.hash_id == DAPOL_HASH_BLAKE3) {
+        if (s.total == 960) {  // last block of a chunk that is not the last chunk: its chaining value goes on the stack
+            blake3_compress_t(s.h, s.m, s.chunk, 64, B3_CHUNK_END);
+            uint32_t cv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) cv[i] = s.h[i];
+            for (uint32_t done = s.chunk + 1; (done & 1u) == 0 && s.stack_n > 0; done >>= 1) {  // merge completed subtrees
+                uint32_t l[8], p[8];
+                s.stack_n--;
+                for (int i = 0; i < 8; i++) l[i] = s.stack[s.stack_n][i];
+                blake3_parent(p, l, cv, 0u);
+                for (int i = 0; i < 8; i++) cv[i] = p[i];
+            }
+            if (s.stack_n < B3_MAX_DEPTH) { for (int i = 0; i < 8; i++) s.stack[s.stack_n][i] = cv[i]; }
+            s.stack_n++;
+            blake3_iv(s.h);
+            s.chunk++; s.fill = 0; s.total = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) s.m[i] = 0;
+            return;
+        }
+        blake3_compress_t(s.h, s.m, s.chunk, 64, s.total == 0 ? B3_CHUNK_START : 0u);
+    } else blake2s_compress(s.h, s.m, s.total + 64, 0);
     s.total += 64; s.fill = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) s.m[i] = 0;
@@ -174,8 +213,14 @@ DAPOL_HD_INLINE void hasher_update_words(dapol_hasher &s, const uint32_t *w, int
 }
 DAPOL_HD_INLINE int hasher_final(dapol_hasher &s, uint32_t out[8]) {
     if (s.hash_id == DAPOL_HASH_BLAKE3) {
-        if (s.total + s.fill > 1024) return -1;
-        blake3_compress(s.h, s.m, s.fill, (s.total == 0 ? B3_CHUNK_START : 0u) | B3_CHUNK_END | B3_ROOT);
+        if (s.stack_n > B3_MAX_DEPTH) return -1;  // longer than 2^16 chunks
+        blake3_compress_t(s.h, s.m, s.chunk, s.fill, (s.total == 0 ? B3_CHUNK_START : 0u) | B3_CHUNK_END | (s.stack_n == 0 ? B3_ROOT : 0u));
+        while (s.stack_n > 0) {  // fold the stack: the last parent is the root
+            uint32_t l[8], r[8];
+            s.stack_n--;
+            for (int i = 0; i < 8; i++) { l[i] = s.stack[s.stack_n][i]; r[i] = s.h[i]; }
+            blake3_parent(s.h, l, r, s.stack_n == 0 ? B3_ROOT : 0u);
+        }
     } else {
         blake2s_compress(s.h, s.m, s.total + s.fill, 1);
     }

@@ -220,6 +220,15 @@ DAPOL_API int dapol_tree_level_copy(const dapol_tree *tree, int level, uint64_t 
                           uint8_t *coms, uint8_t *hashes, uint8_t *is_padding); /* any pointer may be NULL */
 /* id -> TreeIndex map of Dapol::new (id_to_idx_map, mod.rs:80,389): leaf index of the i-th input liability */
 DAPOL_API int dapol_tree_leaf_index_of(const dapol_tree *tree, uint64_t input_pos, uint64_t *leaf_idx);
+/* ... and by the internal id itself: Dapol::generate_proof_for_id / generate_proof_batch_for_ids (mod.rs:148-165) =
+ * dapol_tree_index_of[_batch] followed by dapol_prove_batch / dapol_generate_proof_batch.  The library keeps the audit ids
+ * D(audit_seed || internal_id) of the liabilities it was built from (mod.rs:347-353) and sorts their prefixes on the first
+ * lookup; a query hashes the id (any length) and binary-searches.  DAPOL_ERR_NOT_FOUND if the id (batch: ANY id, found[i]
+ * says which) is not in the tree or the tree was built from ready nodes (reference: None).  On the handles of a sharded build
+ * (*top of dapol_sharded_build) the map covers the rank's own slice of the liabilities. */
+DAPOL_API int dapol_tree_index_of(const dapol_tree *tree, const uint8_t *internal_id, uint64_t len, uint64_t *leaf_idx);
+DAPOL_API int dapol_tree_index_of_batch(const dapol_tree *tree, uint64_t k, const uint8_t *id_blob, const uint64_t *id_off /* k+1 */,
+                                        uint64_t *leaf_idx /* k */, uint8_t *found /* k */);
 
 /* smtree get_merkle_path_ref_batch for one leaf (src/dapol/mod.rs:173-184): the K x height siblings,
  * leaf level first, with their secret (value, blinding) and public (com, hash) parts. */

@@ -26,12 +26,12 @@ static const uint32_t BLAKE_IV[8] = {0x6A09E667, 0xBB67AE85, 0x3C6EF372, 0xA54FF
 /* ---------------------------------------------------------------- BLAKE3 */
 static const uint8_t B3_PERM[16] = {2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8};
 
-static inline void blake3_compress(uint32_t cv[8], const uint8_t block[64], uint32_t block_len, uint32_t flags) {
+static inline void blake3_compress_t(uint32_t cv[8], const uint8_t block[64], uint64_t counter, uint32_t block_len, uint32_t flags) {
     uint32_t m[16], s[16], t[16];
     memcpy(m, block, 64);
     for (int i = 0; i < 8; i++) s[i] = cv[i];
     for (int i = 0; i < 4; i++) s[8 + i] = BLAKE_IV[i];
-    s[12] = 0; s[13] = 0; s[14] = block_len; s[15] = flags;
+    s[12] = (uint32_t)counter; s[13] = (uint32_t)(counter >> 32); s[14] = block_len; s[15] = flags;
     for (int r = 0; r < 7; r++) {
         BLAKE_G(s[0], s[4], s[8], s[12], m[0], m[1]);
         BLAKE_G(s[1], s[5], s[9], s[13], m[2], m[3]);
@@ -46,19 +46,40 @@ static inline void blake3_compress(uint32_t cv[8], const uint8_t block[64], uint
     }
     for (int i = 0; i < 8; i++) cv[i] = s[i] ^ s[i + 8];
 }
-/* returns 0 ok, -1 if len > 1024 (multi-chunk tree mode not needed on this path) */
-static inline int blake3_hash(const uint8_t *in, size_t len, uint8_t out[32]) {
-    if (len > 1024) return -1;
-    uint32_t cv[8];
+static inline void blake3_compress(uint32_t cv[8], const uint8_t block[64], uint32_t block_len, uint32_t flags) {
+    blake3_compress_t(cv, block, 0, block_len, flags);
+}
+/* chaining value of chunk #counter (<= 1024 bytes); root = 1 only for a single-chunk input */
+static inline void blake3_chunk_cv(uint32_t cv[8], const uint8_t *in, size_t len, uint64_t counter, int root) {
     memcpy(cv, BLAKE_IV, 32);
     size_t nblocks = len == 0 ? 1 : (len + 63) / 64;
     for (size_t b = 0; b < nblocks; b++) {
         uint8_t block[64] = {0};
         size_t off = b * 64, n = len - off < 64 ? len - off : 64;
         memcpy(block, in + off, n);
-        uint32_t flags = (b == 0 ? 1u : 0u) | (b == nblocks - 1 ? (2u | 8u) : 0u);
-        blake3_compress(cv, block, (uint32_t)n, flags);
+        uint32_t flags = (b == 0 ? 1u : 0u) | (b == nblocks - 1 ? (2u | (root ? 8u : 0u)) : 0u);
+        blake3_compress_t(cv, block, counter, (uint32_t)n, flags);
     }
+}
+static inline void blake3_parent(uint32_t out[8], const uint32_t l[8], const uint32_t r[8], int root) {
+    uint8_t block[64];
+    memcpy(block, l, 32); memcpy(block + 32, r, 32);
+    memcpy(out, BLAKE_IV, 32);
+    blake3_compress_t(out, block, 0, 64, 4u | (root ? 8u : 0u));
+}
+/* BLAKE3 hash of any length (the tree mode of the spec: 1024-byte chunks, left subtree = the largest power of two of
+ * chunks that leaves at least one for the right) -- ids of any length hash as blake3::Hasher does (mod.rs:347-353) */
+static inline int blake3_hash(const uint8_t *in, size_t len, uint8_t out[32]) {
+    uint32_t stack[64][8], cv[8];
+    int n = 0;
+    size_t nchunks = len == 0 ? 1 : (len + 1023) / 1024;
+    for (size_t c = 0; c + 1 < nchunks; c++) {  /* every chunk but the last: push, merging completed subtrees */
+        blake3_chunk_cv(cv, in + 1024 * c, 1024, c, 0);
+        for (size_t total = c + 1; (total & 1) == 0; total >>= 1) { n--; blake3_parent(cv, stack[n], cv, 0); }
+        memcpy(stack[n++], cv, 32);
+    }
+    blake3_chunk_cv(cv, in + 1024 * (nchunks - 1), len - 1024 * (nchunks - 1), nchunks - 1, n == 0);
+    while (n > 0) { n--; blake3_parent(cv, stack[n], cv, n == 0); }
     memcpy(out, cv, 32);
     return 0;
 }

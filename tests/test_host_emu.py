@@ -50,8 +50,17 @@ def test_field_ops(E):
         return int.from_bytes(bytes(out), "little")
     edge = [0, 1, 2, 19, 37, 38, P - 1, P, P + 1, 2 * P - 1, 2 * P, 2 * P + 37, 2 ** 256 - 1, 2 ** 256 - 38, 2 ** 255, 2 ** 255 - 1,
             2 ** 255 + 18, 2 ** 256 - 39, 0xFFFFFFFF, 2 ** 32, (2 ** 256 - 1) ^ (2 ** 32 - 1)]
+    # the product is one level of subtractive Karatsuba over the 128-bit halves: equal halves (zero difference), either sign of
+    # a0 - a1 and b1 - b0, extreme halves
+    M128 = 2 ** 128 - 1
+    halves = [0, 1, 2, M128, M128 - 1, 2 ** 127, 2 ** 64, 2 ** 64 - 1, 2 ** 96 + 5, rnd.randrange(2 ** 128), rnd.randrange(2 ** 128)]
+    edge += [lo | (hi << 128) for lo in halves for hi in halves]
     vals = edge + [rnd.randrange(2 ** 256) for _ in range(300)]
     out = (C.c_uint8 * 64)()
+    for a in edge[-121:]:
+        for b in edge[-121::7] + [rnd.randrange(2 ** 256)]:
+            E.emu_mul_wide(B(a.to_bytes(32, "little")), B(b.to_bytes(32, "little")), out, 0)
+            assert int.from_bytes(bytes(out), "little") == a * b, (hex(a), hex(b))
     for i, a in enumerate(vals):
         b = vals[(i * 7 + 3) % len(vals)]
         E.emu_mul_wide(B(a.to_bytes(32, "little")), B(b.to_bytes(32, "little")), out, 0)
@@ -122,10 +131,11 @@ def test_hashes(E, pyref):
     for hid, fn in ((0, lambda d: blake3.blake3(d).digest()), (1, lambda d: hashlib.blake2s(d).digest())):
         d = rnd.randbytes(32); E.emu_hash32(hid, B(d), out); assert bytes(out) == fn(d)
         d = rnd.randbytes(128); E.emu_hash128(hid, B(d), out); assert bytes(out) == fn(d)
-        for n in [0, 1, 3, 4, 31, 32, 63, 64, 65, 100, 127, 128, 129, 500, 1024]:
+        # ids of any length hash as the reference's D does (mod.rs:347-353): BLAKE3 beyond one 1024-byte chunk = tree mode
+        for n in [0, 1, 3, 4, 31, 32, 63, 64, 65, 100, 127, 128, 129, 500, 1023, 1024, 1025, 1088, 2047, 2048, 2049, 3072, 3073, 4096, 5000,
+                  7 * 1024, 8 * 1024 + 1, 31 * 1024 + 7, 65536, 100000]:
             d = rnd.randbytes(n)
             assert E.emu_hash_bytes(hid, B(d), n, out) == 0 and bytes(out) == fn(d), (hid, n)
-    assert E.emu_hash_bytes(0, B(bytes(1025)), 1025, out) != 0  # BLAKE3 single-chunk limit is reported, not ignored
     key = bytes(range(32))
     ks = (C.c_uint8 * 64)()
     E.emu_chacha(B(key), C.c_uint64(1 | (0x09000000 << 32)), C.c_uint64(0x4A000000), ks)
