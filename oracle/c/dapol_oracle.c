@@ -172,11 +172,17 @@ EXPORT int dor_derive_leaves(int hash_id, uint64_t n, const uint8_t *iid_blob, c
     if (height == 0 && n) return ERR_BAD_ARG;
     /* duplicate internal ids: detect via audit_id equality (same id <=> same audit_id, mod 2^-256) */
     uint8_t *audit = (uint8_t *)malloc(32 * (n ? n : 1));
-    uint8_t buf[2048];
+    /* ids of any length (the reference hashes whatever it is given, mod.rs:347-384): one buffer sized for the longest input */
+    uint64_t longest = 64;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t il = iid_off[i + 1] - iid_off[i], el = eid_off[i + 1] - eid_off[i];
+        if (seed_len + il > longest) longest = seed_len + il;
+        if (42 + el > longest) longest = 42 + el;
+    }
+    uint8_t *buf = (uint8_t *)malloc(longest);
     int rc = ERR_OK;
     for (uint64_t i = 0; i < n; i++) {
         uint64_t il = iid_off[i + 1] - iid_off[i];
-        if (seed_len + il > 1024) { free(audit); return ERR_BAD_ARG; }
         memcpy(buf, audit_seed, seed_len); memcpy(buf + seed_len, iid_blob + iid_off[i], il);
         hash_buf(hash_id, buf, seed_len + il, audit + 32 * i);
     }
@@ -200,7 +206,6 @@ EXPORT int dor_derive_leaves(int hash_id, uint64_t n, const uint8_t *iid_blob, c
     for (uint64_t i = 0; i < n && rc == ERR_OK; i++) {
         if (i == first_dup) { rc = ERR_DUPLICATED_INTERNAL_ID; if (err_pos) *err_pos = i; break; }
         uint64_t el = eid_off[i + 1] - eid_off[i];
-        if (42 + el > 1024) { rc = ERR_BAD_ARG; break; }
         uint8_t seed[32];
         memcpy(buf, audit + 32 * i, 32); memcpy(buf + 32, "index_seed", 10); memcpy(buf + 42, eid_blob + eid_off[i], el);
         hash_buf(hash_id, buf, 42 + el, seed);
@@ -218,7 +223,7 @@ EXPORT int dor_derive_leaves(int hash_id, uint64_t n, const uint8_t *iid_blob, c
         out_blind[32 * i + 31] &= 0x7f; /* Scalar::from_bits */
     }
     set_free(&used);
-    free(audit);
+    free(audit); free(buf);
     return rc;
 }
 

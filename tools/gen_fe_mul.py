@@ -277,7 +277,10 @@ def gen_mul_karatsuba():
 
 
 def gen_mul():
-    if os.environ.get("DAPOL_FE_MUL", "karatsuba") == "karatsuba":
+    # DAPOL_FE_MUL=karatsuba: measured and REJECTED on B200 (profiles/r02_variants.txt): 48 + 8 wide multiply-accumulates instead of
+    # 64 + 8, but ptxas turns the extra carry chains into IMAD.X / IMAD.MOV on the same multiply pipe and the product needs 207
+    # instructions instead of 139: fe_mul 112 -> 91 G/s, tree build 25.9 -> 28.7 ms.  The schoolbook product stays the default.
+    if os.environ.get("DAPOL_FE_MUL", "schoolbook") == "karatsuba":
         return gen_mul_karatsuba()
     s = "DAPOL_HD_INLINE void mul_wide_8x8(uint32_t R[16], const uint32_t a[8], const uint32_t b[8]) {\n"
     s += "    uint32_t E[16], O[15];\n"
