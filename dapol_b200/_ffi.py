@@ -88,6 +88,9 @@ def lib():
     L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
     L.dapol_rangeproof_last_times.argtypes = [vp, vp]
     L.dapol_rangeproof_last_kernel_times.argtypes = [vp, vp]
+    L.dapol_ctx_set_rangeproof_table_budget.argtypes = [vp, u64]
+    L.dapol_ctx_rangeproof_table_bytes.argtypes = [vp]
+    L.dapol_ctx_rangeproof_table_bytes.restype = u64
     L.dapol_tree_index_of.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.dapol_tree_index_of_batch.argtypes = [vp, u64, vp, vp, vp, vp]
     L.dapol_batch_proof_size.argtypes = [C.c_int, u64, vp, u64, C.c_int]

@@ -56,6 +56,8 @@ struct dapol_ctx {
     bool rp_W_auto = true;  // pick the widest window whose tables fit the HBM budget when they are built
     int rp_mcap = 0;
     ge_niels *rp_tab = nullptr;  // [(128 mcap + 2)][NW][2^(W-1)]
+    size_t rp_budget = 0;        // HBM budget of those tables in bytes (0 = 70 % of the free memory, at most 128 GB)
+    size_t rp_table_bytes = 0;   // size of the tables in place
     // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build, and the MSM passes split per
     // kernel class: [4] k_rp_p10 (L / R of the table rounds), [5] k_rp_p3 (A, S), [6] hybrid rounds (pm, pv, pf), [7] verifier (v1, v2)
     float rp_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

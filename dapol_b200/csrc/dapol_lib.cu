@@ -1013,6 +1013,38 @@ uint64_t pos_words_of(const std::vector<uint64_t> &n_real, int H, std::vector<ui
 }
 }  // namespace
 
+// A loaded file is data from outside: before any kernel indexes the node store through the slot maps, check that the maps are what
+// the build would have produced -- every slot inside its level and increasing, indexes increasing inside a level, the two children
+// of a parent adjacent with the parent's index = child index >> 1.  One thread per real node of a level.
+__global__ void k_validate_level(uint64_t n_real, uint64_t level_n, const uint32_t *pos, const uint64_t *idx_level, const uint64_t *idx_children,
+                                 uint64_t children_n, int is_root_level, int *bad) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_real) return;
+    uint64_t slot = is_root_level ? 0 : pos[j];
+    if (slot >= level_n || (!is_root_level && j && pos[j - 1] >= slot)) { *bad = 1; return; }
+    if (idx_children) {  // children of the j-th real node sit at 2j, 2j + 1 of the level below
+        if (2 * j + 1 >= children_n) { *bad = 1; return; }
+        uint64_t l = idx_children[2 * j], r = idx_children[2 * j + 1];
+        if ((l ^ 1) != r || (l & 1) || (l >> 1) != idx_level[slot] || (j && idx_children[2 * j - 1] >= l)) *bad = 1;
+    }
+}
+static int validate_loaded_tree(dapol_ctx *ctx, const dapol_tree *t) {
+    cudaStream_t st = ctx->stream;
+    const int H = t->height;
+    int *d_bad = reinterpret_cast<int *>(ctx->scratch), bad = 0;
+    CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, st));
+    for (int h = 0; h <= H; h++) {
+        if (t->n_real[h] == 0 || t->n_real[h] > t->level_n[h] || (h < H && t->level_n[h + 1] != 2 * t->n_real[h])) return DAPOL_ERR_IO;
+        k_validate_level<<<grid_for(t->n_real[h], 256), 256, 0, st>>>(t->n_real[h], t->level_n[h], h ? t->pos[h] : nullptr, t->ns.idx + t->level_off[h],
+                                                                      h < H ? t->ns.idx + t->level_off[h + 1] : nullptr, h < H ? t->level_n[h + 1] : 0, h == 0, d_bad);
+        ctx->launches++;
+    }
+    CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    return bad ? DAPOL_ERR_IO : DAPOL_OK;
+}
+
 extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
     if (!t || !path) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(t->ctx->device));
@@ -1106,6 +1138,7 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
             g_cuda_err = "tree load: device tables"; cudaGetLastError(); rc = DAPOL_ERR_CUDA;
         }
     }
+    if (rc == DAPOL_OK) rc = validate_loaded_tree(ctx, t);  // a corrupted or crafted file must not make later kernels read out of bounds
     if (rc != DAPOL_OK) { dapol_tree_destroy(t); return rc; }
     *out = t;
     return DAPOL_OK;
@@ -1189,8 +1222,9 @@ extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t 
     }
     if (leaf_coms) cudaMemcpyAsync(leaf_coms, d_lc, k * 32, cudaMemcpyDeviceToHost, st);
     if (leaf_hashes) cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st);
-    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaError_t e = cudaStreamSynchronize(st);
     dfree(mem, st);
+    CUDA_TRY(e);
     return nf ? DAPOL_ERR_NOT_FOUND : DAPOL_OK;
 }
 
@@ -1199,10 +1233,15 @@ extern "C" int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *va
     if (!ctx || !values || !blindings || !coms || n == 0) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    uint64_t *d_v = nullptr; uint32_t *d_b = nullptr, *d_o = nullptr;
-    CUDA_TRY(cudaMalloc(&d_v, n * 8)); CUDA_TRY(cudaMalloc(&d_b, n * 32)); CUDA_TRY(cudaMalloc(&d_o, n * 32));
-    CUDA_TRY(cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_b, blindings, n * 32, cudaMemcpyHostToDevice, st));
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(n, 8) + 2 * Arena::need(n, 32);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *d_v = ar.take<uint64_t>(n);
+    uint32_t *d_b = ar.take<uint32_t>(8 * n), *d_o = ar.take<uint32_t>(8 * n);
+    cudaMemcpyAsync(d_v, values, n * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_b, blindings, n * 32, cudaMemcpyHostToDevice, st);
     unsigned g = grid_for(n, 128);
     switch (ctx->W) {
 #define W_CASE(w) case w: k_commit<w><<<g, 128, 0, st>>>(n, d_v, d_b, d_o, ctx->tab_b, ctx->tab_bbl); break;
@@ -1210,10 +1249,11 @@ extern "C" int dapol_commit_batch(dapol_ctx *ctx, uint64_t n, const uint64_t *va
 #undef W_CASE
     }
     ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(coms, d_o, n * 32, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    cudaFree(d_v); cudaFree(d_b); cudaFree(d_o);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(coms, d_o, n * 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dfree(mem, st);  // released on the error path too
+    CUDA_TRY(e);
     return DAPOL_OK;
 }
 

@@ -144,22 +144,39 @@ static int rp_ensure_tables(dapol_ctx *ctx, int m) {
     };
     int rc = DAPOL_ERR_CUDA;
     if (ctx->rp_W_auto) {  // widest window whose tables fit the HBM budget: fewer additions per scalar multiplication
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);  // cached scratch of earlier batches
+        // HBM budget of the tables: what the caller set (dapol_ctx_set_rangeproof_table_budget), else 70 % of the memory that is
+        // free or cached-but-unused in the device's stream-ordered pool, at most 128 GB (the node store of a 2^21-user shard is
+        // 16 GB, the batch scratch 6 GB).  The shared default pool is NOT trimmed up front (a co-tenant, e.g. torch, may rely on
+        // its cache); only when an allocation that fits the budget fails is the pool's unused cache released, once.
+        cudaMemPool_t pool = nullptr;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        // up to 70 % of the free HBM (at most 128 GB): the node store of a 2^21-user shard is 16 GB, the batch scratch 6 GB
-        const size_t budget = std::min<size_t>(128ull << 30, free_b / 10 * 7);
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        }
+        const size_t avail = free_b + (size_t)(reserved > used ? reserved - used : 0);
+        const size_t budget = ctx->rp_budget ? ctx->rp_budget : std::min<size_t>(128ull << 30, avail / 10 * 7);
         static const int widths[] = {16, 15, 14, 13, 12, 8};
+        bool trimmed = false;
         for (int cand : widths) {
             if (cand != 8 && rp_table_bytes(cand, mc) > budget) continue;
             ctx->rp_W = cand;
             rc = build(cand);
+            if (rc == DAPOL_ERR_CUDA && !trimmed && pool) {  // the cache of earlier batches is in the way: release it and try this width again
+                cudaGetLastError();
+                cudaMemPoolTrimTo(pool, 0);
+                trimmed = true;
+                rc = build(cand);
+            }
             if (rc != DAPOL_ERR_CUDA) break;
             cudaGetLastError();  // out of memory after all (fragmentation, another context): next narrower window
         }
+        if (rc == DAPOL_OK) ctx->rp_table_bytes = rp_table_bytes(ctx->rp_W, mc);
     } else {
         rc = build(ctx->rp_W);
+        if (rc == DAPOL_OK) ctx->rp_table_bytes = rp_table_bytes(ctx->rp_W, mc);
     }
     cudaEventRecord(b, ctx->stream);
     cudaEventSynchronize(b);
@@ -379,6 +396,13 @@ static uint64_t rp_chunk(int N, int m, int lg, bool verify, uint64_t K) {
 // device time per kernel class, on the ctx stream.  Classes: TM_OTHER = thread-per-proof / per-element passes; the MSM
 // passes are split into TM_P10 (L / R of the table rounds), TM_P3 (A, S), TM_HYB (pm, pv, pf), TM_VER (v1, v2).
 enum { TM_P10 = 0, TM_OTHER = 1, TM_P3 = 2, TM_HYB = 3, TM_VER = 4, TM_CLASSES = 5 };
+struct EventPair {  // released on every exit path
+    cudaEvent_t a = nullptr, b = nullptr;
+    EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    EventPair(const EventPair &) = delete;
+    EventPair &operator=(const EventPair &) = delete;
+};
 struct PhaseTimer {
     cudaStream_t st;
     cudaEvent_t e[2];
@@ -488,8 +512,8 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
     const int N = nbits * m, lg = ilog2((uint64_t)N);
     const uint64_t plen = 32ull * (9 + 2 * lg), chunk = rp_chunk(N, m, lg, false, K);
     PhaseTimer tm(st);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    EventPair evp;
+    cudaEvent_t e0 = evp.a, e1 = evp.b;
     cudaEventRecord(e0, st);
     int bad = 0;
     for (uint64_t first = 0; first < K; first += chunk) {
@@ -509,17 +533,17 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
             default: rc = DAPOL_ERR_BAD_ARG;
         }
         if (rc) { dfree(pl.mem, st); return rc; }
-        CUDA_TRY(cudaMemcpyAsync(d_proofs + first * plen, b.proof, kc * plen, cudaMemcpyDeviceToDevice, st));
         std::vector<int> status(kc);
-        CUDA_TRY(cudaMemcpyAsync(status.data(), b.status, kc * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaError_t ce = cudaMemcpyAsync(d_proofs + first * plen, b.proof, kc * plen, cudaMemcpyDeviceToDevice, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(status.data(), b.status, kc * 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { dfree(pl.mem, st); CUDA_TRY(ce); }
         for (int s : status) bad |= s;
         dfree(pl.mem, st);
     }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     tm.collect();
     tm.publish(ctx->rp_last_ms);
     return bad ? DAPOL_ERR_BAD_ARG : DAPOL_OK;
@@ -539,8 +563,8 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
     const int N = nbits * m, lg = ilog2((uint64_t)N);
     const uint64_t plen = 32ull * (9 + 2 * lg), chunk = rp_chunk(N, m, lg, true, K);
     PhaseTimer tm(st);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    EventPair evp;
+    cudaEvent_t e0 = evp.a, e1 = evp.b;
     cudaEventRecord(e0, st);
     for (uint64_t first = 0; first < K; first += chunk) {
         uint64_t kc = std::min(chunk, K - first);
@@ -564,7 +588,6 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&ctx->rp_last_ms[0], e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     tm.collect();
     tm.publish(ctx->rp_last_ms);
     CUDA_TRY(cudaGetLastError());
@@ -648,6 +671,12 @@ extern "C" int dapol_rangeproof_last_kernel_times(const dapol_ctx *ctx, float ms
     memcpy(ms, ctx->rp_last_ms, sizeof(float) * 8);
     return DAPOL_OK;
 }
+extern "C" int dapol_ctx_set_rangeproof_table_budget(dapol_ctx *ctx, uint64_t bytes) {
+    if (!ctx) return DAPOL_ERR_BAD_ARG;
+    ctx->rp_budget = bytes;
+    return DAPOL_OK;
+}
+extern "C" uint64_t dapol_ctx_rangeproof_table_bytes(const dapol_ctx *ctx) { return ctx && ctx->rp_tab ? ctx->rp_table_bytes : 0; }
 extern "C" int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window) {
     if (!ctx || (window != 0 && window != 8 && window != 12 && window != 13 && window != 14 && window != 15 && window != 16)) return DAPOL_ERR_BAD_ARG;
     ctx->rp_W_auto = window == 0;

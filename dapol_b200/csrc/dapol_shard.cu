@@ -25,7 +25,11 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: every NCCL symbol is resolved with dlsym (no link-time dependency)
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -170,6 +174,19 @@ __global__ void k_pack_audit(uint64_t n, const uint32_t *audit, uint64_t first_p
     for (int w = 0; w < 8; w++) m[w] = audit[8 * i + w];
     m[8] = (uint32_t)pos; m[9] = (uint32_t)(pos >> 32);
 }
+// duplicate-id screen: insert the 64-bit audit-id prefix of every message into an open-addressing table (all ones = empty);
+// meeting an equal prefix (or the empty pattern itself) counts a suspect -- the exact pass then decides
+__global__ void k_dup_probe(uint64_t n, const uint32_t *msgs, unsigned long long *table, uint64_t mask, unsigned long long *suspects) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long key = (unsigned long long)msgs[10 * j] | ((unsigned long long)msgs[10 * j + 1] << 32);
+    if (key == ~0ull) { atomicAdd(suspects, 1ull); return; }
+    for (uint64_t slot = (key >> 20) & mask;; slot = (slot + 1) & mask) {
+        unsigned long long prev = atomicCAS(&table[slot], ~0ull, key);
+        if (prev == ~0ull) return;
+        if (prev == key) { atomicAdd(suspects, 1ull); return; }
+    }
+}
 __global__ void k_audit_keys(uint64_t n, const uint32_t *msgs, uint64_t *keys, uint32_t *iota) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -246,10 +263,17 @@ __global__ void k_claim_cand_keys(uint64_t n, const uint32_t *by_pos, ClaimStore
 }
 // live claims sorted by (candidate, position): every claim but the first of a group lost its slot -- its position goes
 // back to the user's home rank, the claim dies
-__global__ void k_claim_mark_losers(uint64_t n_live, const uint64_t *sorted_keys, const uint32_t *who, ClaimStore cs, unsigned long long *n_losers,
+__global__ void k_claim_composite_keys(uint64_t n, ClaimStore cs, int cand_bits, int pos_bits, uint64_t *keys, uint32_t *iota) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    keys[j] = ((((uint64_t)cs.dead[j] << cand_bits) | cs.cand[j]) << pos_bits) | cs.pos[j];
+    iota[j] = (uint32_t)j;
+}
+// key_shift: low bits of the sort key that hold the position (composite keys), 0 for plain candidate keys
+__global__ void k_claim_mark_losers(uint64_t n_live, const uint64_t *sorted_keys, int key_shift, const uint32_t *who, ClaimStore cs, unsigned long long *n_losers,
                                     uint64_t *loser_pos) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0 || j >= n_live || sorted_keys[j] != sorted_keys[j - 1]) return;
+    if (j == 0 || j >= n_live || (sorted_keys[j] >> key_shift) != (sorted_keys[j - 1] >> key_shift)) return;
     uint32_t o = who[j];
     cs.dead[o] = 1;
     loser_pos[atomicAdd(n_losers, 1ull)] = cs.pos[o];
@@ -296,6 +320,21 @@ __global__ void k_claims_to_leaves(uint64_t n_live, const uint32_t *who, ClaimSt
 
 // ------------------------------------------------------------------------------------------------ host orchestration
 namespace {
+// DAPOL_SHARD_TRACE=1: host time (us since the call began) at every point where the host waited for the stream, on rank 0
+struct Trace {
+    bool on = false;
+    std::chrono::steady_clock::time_point t0;
+    std::string log;
+    void start(int rank) { const char *e = getenv("DAPOL_SHARD_TRACE"); on = e && *e == '1' && rank == 0; t0 = std::chrono::steady_clock::now(); }
+    void mark(const char *what, uint64_t x = 0) {
+        if (!on) return;
+        double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        char b[96];
+        snprintf(b, sizeof b, "%9.1f us  %s %llu\n", us, what, (unsigned long long)x);
+        log += b;
+    }
+    ~Trace() { if (on) fprintf(stderr, "[dapol_sharded_build trace]\n%s", log.c_str()); }
+};
 struct DevBuf {  // stream-ordered allocation that frees itself
     void *p = nullptr;
     cudaStream_t st = nullptr;
@@ -416,6 +455,8 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
     struct EvGuard { cudaEvent_t *e; ~EvGuard() { for (int i = 0; i < 5; i++) cudaEventDestroy(e[i]); } } ev_guard{ev};
     CUDA_TRY(cudaEventRecord(ev[0], st));
     Shard S{ctx, comm, st, world, rank, k};
+    Trace tr;
+    tr.start(rank);
     int rc = S.init();
     if (rc) return rc;
 
@@ -446,6 +487,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
         if (all[2 * r + 1]) return (int)all[2 * r + 1];  // a rank could not hash its slice (id too long, CUDA error): same verdict everywhere
         first_pos[r + 1] = first_pos[r] + all[2 * r];
     }
+    tr.mark("hashed + sizes gathered", n);
     const uint64_t n_total = first_pos[world], my_first = first_pos[rank];
     if (n_total_out) *n_total_out = n_total;
     if (first_pos_out) *first_pos_out = my_first;
@@ -467,13 +509,29 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
     {
         if (n) { k_dest_audit<<<grid_for(n, 256), 256, 0, st>>>(n, audit, k, dest); ctx->launches++; }
         if ((rc = S.plan(n, dest))) return rc;
+        tr.mark("dup: planned", S.recv_total);
         if ((rc = S.slots(n, dest, slot))) return rc;
         DevBuf snd, rcv, keys, keys2, who, who2, tmp;
         CUDA_TRY(snd.alloc(40 * (size_t)(S.send_total + 1), st)); CUDA_TRY(rcv.alloc(40 * (size_t)(S.recv_total + 1), st));
         if (n) { k_pack_audit<<<grid_for(n, 256), 256, 0, st>>>(n, audit, my_first, slot, snd.as<uint32_t>()); ctx->launches++; }
         if ((rc = S.all_to_all(snd.p, rcv.p, 40))) return rc;
         const uint64_t nr = S.recv_total;
+        // fast path: the 64-bit prefixes go into an open-addressing table; two equal prefixes (practically: a real duplicate) make
+        // the exact sort-and-compare pass below run, otherwise the ids are all different and nothing more is needed
+        unsigned long long suspects = 0;
         if (nr > 1) {
+            uint64_t cap = 1024;
+            while (cap < 2 * nr) cap <<= 1;
+            DevBuf table;
+            CUDA_TRY(table.alloc(8 * cap, st));
+            CUDA_TRY(cudaMemsetAsync(table.p, 0xff, 8 * cap, st));
+            CUDA_TRY(cudaMemsetAsync(ctr, 0, 8, st));
+            k_dup_probe<<<grid_for(nr, 256), 256, 0, st>>>(nr, rcv.as<uint32_t>(), table.as<unsigned long long>(), cap - 1, ctr);
+            ctx->launches++;
+            CUDA_TRY(cudaMemcpyAsync(&suspects, ctr, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        if (suspects) {
             CUDA_TRY(keys.alloc(8 * nr, st)); CUDA_TRY(keys2.alloc(8 * nr, st)); CUDA_TRY(who.alloc(4 * nr, st)); CUDA_TRY(who2.alloc(4 * nr, st));
             size_t tb = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.as<uint64_t>(), keys2.as<uint64_t>(), who.as<uint32_t>(), who2.as<uint32_t>(), (int)nr, 0, 64, st);
@@ -484,12 +542,15 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
             ctx->launches += 3;
         }
         CUDA_TRY(cudaStreamSynchronize(st));  // the buffers of this block are released in stream order, the host vectors are reused
+        tr.mark("dup: exchanged + sorted + checked");
     }
 
     // ---- 3. claims: distributed fix-point of the first-come-first-served rule
     ClaimStore cs;
     struct CsGuard { ClaimStore &c; cudaStream_t s; ~CsGuard() { claims_free(c, s); } } cs_guard{cs, st};
     const uint64_t mask = Hs >= 64 ? ~0ull : (1ull << Hs) - 1;
+    int pos_bits = 1;  // bits of an input position
+    while ((1ull << pos_bits) < n_total) pos_bits++;
     const int shift = Hs;  // owner of a candidate = its top k bits
     DevBuf b_again, b_pkeys, b_pkeys2, b_who, b_who2, b_ckeys, b_ckeys2, b_who3, b_sorttmp, b_losers, b_ldest, b_lslot;
     CUDA_TRY(b_again.alloc(na * 4, st));
@@ -504,6 +565,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
         // 3a. route the claims of this round to the owners of their candidates
         if (n_claiming) { k_dest_claim<<<grid_for(n_claiming, 256), 256, 0, st>>>(n_claiming, claim_list, cand, shift, dest); ctx->launches++; }
         if ((rc = S.plan(n_claiming, dest))) return rc;
+        tr.mark("claims: planned, round", (uint64_t)round);
         if (round > 0 && S.grand_total() == 0) break;  // nobody re-hashed anywhere: fix-point
         if ((rc = S.slots(n_claiming, dest, slot))) return rc;
         {
@@ -539,21 +601,33 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
                 CUDA_TRY(b_sorttmp.alloc(sort_tmp_bytes, st));
             }
             size_t tb = sort_tmp_bytes;
-            k_claim_pos_keys<<<grid_for(nc, 256), 256, 0, st>>>(nc, cs.pos, b_pkeys.as<uint32_t>(), b_who.as<uint32_t>());
-            cub::DeviceRadixSort::SortPairs(b_sorttmp.p, tb, b_pkeys.as<uint32_t>(), b_pkeys2.as<uint32_t>(), b_who.as<uint32_t>(), b_who2.as<uint32_t>(), (int)nc, 0, 31, st);
-            k_claim_cand_keys<<<grid_for(nc, 256), 256, 0, st>>>(nc, b_who2.as<uint32_t>(), cs, Hs, b_ckeys.as<uint64_t>());
-            tb = sort_tmp_bytes;
-            cub::DeviceRadixSort::SortPairs(b_sorttmp.p, tb, b_ckeys.as<uint64_t>(), b_ckeys2.as<uint64_t>(), b_who2.as<uint32_t>(), b_who3.as<uint32_t>(), (int)nc, 0,
-                                            std::min(Hs + 1, 64), st);
+            int key_shift = 0;
+            if (Hs + 1 + pos_bits <= 64) {
+                // (dead, candidate, position) fits one 64-bit key: ONE radix sort orders the claims by candidate and, inside a group, by position
+                key_shift = pos_bits;
+                k_claim_composite_keys<<<grid_for(nc, 256), 256, 0, st>>>(nc, cs, Hs, pos_bits, b_ckeys.as<uint64_t>(), b_who2.as<uint32_t>());
+                cub::DeviceRadixSort::SortPairs(b_sorttmp.p, tb, b_ckeys.as<uint64_t>(), b_ckeys2.as<uint64_t>(), b_who2.as<uint32_t>(), b_who3.as<uint32_t>(), (int)nc, 0,
+                                                Hs + 1 + pos_bits, st);
+                ctx->launches += 2;
+            } else {  // tall shards: stable sort by candidate of the claims sorted by position
+                k_claim_pos_keys<<<grid_for(nc, 256), 256, 0, st>>>(nc, cs.pos, b_pkeys.as<uint32_t>(), b_who.as<uint32_t>());
+                cub::DeviceRadixSort::SortPairs(b_sorttmp.p, tb, b_pkeys.as<uint32_t>(), b_pkeys2.as<uint32_t>(), b_who.as<uint32_t>(), b_who2.as<uint32_t>(), (int)nc, 0, 31, st);
+                k_claim_cand_keys<<<grid_for(nc, 256), 256, 0, st>>>(nc, b_who2.as<uint32_t>(), cs, Hs, b_ckeys.as<uint64_t>());
+                tb = sort_tmp_bytes;
+                cub::DeviceRadixSort::SortPairs(b_sorttmp.p, tb, b_ckeys.as<uint64_t>(), b_ckeys2.as<uint64_t>(), b_who2.as<uint32_t>(), b_who3.as<uint32_t>(), (int)nc, 0,
+                                                std::min(Hs + 1, 64), st);
+                ctx->launches += 4;
+            }
             n_live = nc - n_dead;
             CUDA_TRY(cudaMemsetAsync(ctr, 0, 16, st));
-            if (n_live) k_claim_mark_losers<<<grid_for(n_live, 256), 256, 0, st>>>(n_live, b_ckeys2.as<uint64_t>(), b_who3.as<uint32_t>(), cs, ctr, b_losers.as<uint64_t>());
-            ctx->launches += 5;
+            if (n_live) k_claim_mark_losers<<<grid_for(n_live, 256), 256, 0, st>>>(n_live, b_ckeys2.as<uint64_t>(), key_shift, b_who3.as<uint32_t>(), cs, ctr, b_losers.as<uint64_t>());
+            ctx->launches += 1;
             unsigned long long h = 0;
             CUDA_TRY(cudaMemcpyAsync(&h, ctr, 8, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             n_losers = h;
             n_dead += n_losers;
+            tr.mark("claims: exchanged + sorted + losers marked", n_losers);
         } else {
             n_live = 0;
             CUDA_TRY(cudaMemsetAsync(ctr, 0, 16, st));
@@ -566,6 +640,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
             ctx->launches++;
         }
         if ((rc = S.plan(n_losers, ldest))) return rc;
+        tr.mark("losers: planned", S.grand_total());
         if (S.grand_total() == 0) { n_live = cs.n - n_dead; break; }  // no collision anywhere: fix-point (the last sort holds the leaves)
         if ((rc = S.slots(n_losers, ldest, lslot))) return rc;
         {
@@ -583,6 +658,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
                 CUDA_TRY(cudaMemcpyAsync(&h, ctr + 1, 8, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
                 n_claiming = h;
+                tr.mark("losers: exchanged + re-hashed", n_claiming);
             }
             claim_list = again;
         }
@@ -599,6 +675,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
         if (d != ~0ull && d <= f) { if (err_pos) *err_pos = d; return DAPOL_ERR_DUPLICATED_INTERNAL_ID; }
         if (f != ~0ull) { if (err_pos) *err_pos = f; return DAPOL_ERR_FAILED_TO_MAP_INDEX; }
     }
+    tr.mark("verdict gathered");
     CUDA_TRY(cudaEventRecord(ev[2], st));
 
     // ---- 4. the surviving claims, sorted by candidate, are this shard's leaves
@@ -637,6 +714,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
         if (rc == DAPOL_OK) rc = dapol_tree_root_record(sub, reinterpret_cast<uint8_t *>(rec));
         rec[DAPOL_RECORD_BYTES / 8] = rc == DAPOL_OK ? 1 : 2 + (uint64_t)rc;
     }
+    tr.mark("subtree built", n_mine);
     float build_ms[5] = {0, 0, 0, 0, 0};
     memcpy(build_ms, ctx->last_ms, sizeof build_ms);
     CUDA_TRY(cudaEventRecord(ev[3], st));
@@ -672,6 +750,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
     memcpy(ctx->last_ms, build_ms, sizeof build_ms);  // dapol_last_build_times: the subtree build, not the tiny top tree
     CUDA_TRY(cudaEventRecord(ev[4], st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    tr.mark("top tree built");
     if (phase_ms) for (int i = 0; i < 4; i++) cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]);
     *subtree = sub;
     *top = tp;

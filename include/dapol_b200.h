@@ -313,6 +313,13 @@ DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m
  * window whose tables fit 70 % of the free HBM, at most 128 GB (16 bits up to m = 8 ... 15 bits at m = 32, 14 at m = 64);
  * if the allocation fails after all, the next narrower window is tried. */
 DAPOL_API int dapol_ctx_set_rangeproof_window(dapol_ctx *ctx, int window);
+/* HBM budget (bytes) of the generator tables under window 0 (auto); 0 restores the default (70 % of the device memory that is free
+ * or cached-but-unused by the stream-ordered pool, at most 128 GB).  A process that shares the GPU (another framework, other
+ * contexts, large trees to come) sets it to what it can spare: e.g. 4 GB gives window 12 at m = 1 .. 8.  The shared default
+ * memory pool is never trimmed up front; its unused cache is released only if an allocation that fits the budget fails.
+ * dapol_ctx_rangeproof_table_bytes: size of the tables currently in place (0 = none built yet). */
+DAPOL_API int dapol_ctx_set_rangeproof_table_budget(dapol_ctx *ctx, uint64_t bytes);
+DAPOL_API uint64_t dapol_ctx_rangeproof_table_bytes(const dapol_ctx *ctx);
 /* device time of the last range-proof batch on this ctx (ms): [0] total, [1] MSM passes, [2] other passes, [3] last table build */
 DAPOL_API int dapol_rangeproof_last_times(const dapol_ctx *ctx, float ms[4]);
 /* the same plus the MSM passes split per kernel class (CUDA events on the ctx stream; the roofline report of the dominant kernel):

@@ -175,6 +175,29 @@ def main():
     k = (world - 1).bit_length()
     # the oracle's single tree over the whole liability set
     ids, eids, vals = liabilities(n)
+    if "dup" in sys.argv[8:]:
+        # duplicated internal ids on different ranks (mod.rs:345-349): every rank must report DuplicatedInternalId at the input
+        # position the sequential reference fails at (the oracle's err_pos) -- the exact pass behind the prefix screen decides
+        ids[n - 2] = ids[1]; ids[n // 2] = ids[3]
+        ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+        rc, _, _, err_pos = cref.derive_leaves(hash_id, ib, io, eb, eo, AUDIT_SEED, H)
+        assert rc == 4
+        cuts = [0] + [(n * (r + 1)) // world for r in range(world)]
+        lo, hi = cuts[rank], cuts[rank + 1]
+        sl = (*cref.pack_ids(ids[lo:hi]), *cref.pack_ids(eids[lo:hi]), vals[lo:hi])
+        from dapol_b200 import Context, DapolError
+        from dapol_b200.sharded import CudaEngine, NativeComm
+        E = CudaEngine(Context(0))
+        try:
+            ShardedDapol.new(E, comm, hash_id, sl, AUDIT_SEED, H, 1, PAD_SEED, native=NativeComm(E.ctx, comm, backend="torch"))
+            raise AssertionError("duplicate ids not detected")
+        except DapolError as e:
+            assert (e.code, e.detail) == (4, err_pos), (e.code, e.detail, err_pos)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        print("OK dup@%d" % err_pos, flush=True)
+        return
     ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
     rc, gidx, gbl, _ = cref.derive_leaves(hash_id, ib, io, eb, eo, AUDIT_SEED, H)
     assert rc == 0

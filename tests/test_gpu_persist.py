@@ -70,6 +70,19 @@ def test_bad_files_are_io_errors(ctx, tmp_path):
         with pytest.raises(DapolError) as e:
             Dapol.load(ctx, p, 4)
         assert e.value.code == 21
+    # consistent sizes but corrupted slot maps / indexes (a crafted file): rejected before any kernel can index out of bounds.
+    # Layout after the 64-byte header, the 9 x 32-byte level table and the 128-byte root point: idx u64[T], v, r, com, hash, is_pad, pos u32[]
+    T = t.num_nodes
+    idx_off = 64 + 9 * 32 + 128
+    pos_off = idx_off + T * (8 + 8 + 32 + 32 + 32 + 1)
+    for off, val in ((idx_off + 8 * 3, b"\xff" * 8), (idx_off + 8 * (T - 1), b"\x00" * 8), (pos_off + 4 * 64, b"\xff\xff\xff\x7f"),
+                     (pos_off + 4 * 65, b"\x00\x00\x00\x00")):
+        bad = bytearray(blob); bad[off:off + len(val)] = val
+        p = str(tmp_path / "crafted.dapol")
+        open(p, "wb").write(bytes(bad))
+        with pytest.raises(DapolError) as e:
+            Dapol.load(ctx, p, 4)
+        assert e.value.code == 21, off
     with pytest.raises(DapolError) as e:
         Dapol.load(ctx, str(tmp_path / "missing.dapol"), 4)
     assert e.value.code == 21

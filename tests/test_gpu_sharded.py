@@ -18,7 +18,8 @@ def test_sharded_build_matches_single_tree_oracle(world, n, H, hash_id, extra):
 
 @pytest.mark.parametrize("world,n,H,hash_id,extra", [(1, 300, 12, 0, ()), (2, 500, 14, 0, ()), (4, 700, 16, 1, ()), (2, 65, 9, 0, ("uneven",)),
                                                       (4, 5, 8, 0, ()), (4, 300, 13, 0, ("positional",)), (2, 40, 8, 1, ("positional", "uneven")),
-                                                      (4, 128, 8, 0, ()), (2, 512, 10, 1, ("uneven",)), (8, 2000, 16, 0, ())])
+                                                      (4, 128, 8, 0, ()), (2, 512, 10, 1, ("uneven",)), (8, 2000, 16, 0, ()), (4, 600, 14, 0, ("dup",)),
+                                                      (2, 300, 40, 0, ()), (4, 200, 64, 1, ())])
 def test_one_call_sharded_build_matches_single_tree_oracle(world, n, H, hash_id, extra):
     """dapol_sharded_build (the whole exchange protocol inside the library: all-to-all of claims, per-prefix collision
     resolution with only the losers travelling again, padding bases, subtree, root gather, top tree), its collectives on the
