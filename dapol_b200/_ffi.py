@@ -88,6 +88,7 @@ def lib():
     L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
     L.dapol_rangeproof_last_times.argtypes = [vp, vp]
     L.dapol_rangeproof_last_kernel_times.argtypes = [vp, vp]
+    L.dapol_ctx_set_leaf_hash_mode.argtypes = [vp, C.c_int]
     L.dapol_ctx_set_rangeproof_table_budget.argtypes = [vp, u64]
     L.dapol_ctx_rangeproof_table_bytes.argtypes = [vp]
     L.dapol_ctx_rangeproof_table_bytes.restype = u64

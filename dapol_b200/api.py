@@ -97,6 +97,19 @@ class Context:
         (level, index) -- Paddable::padding(idx, secret) as a function of its arguments (node.rs:85-88 TODO); opt-in."""
         _check(_ffi.lib().dapol_ctx_set_padding_mode(self._h, 1 if positional else 0))
 
+    def set_leaf_hash_mode(self, id_salt: bool):
+        """False (default): leaf hash = D(compress(com)), the reference (node.rs:33-36).  True: the DAPOL+ paper's leaf hash
+        D("leaf" || external_id || salt) with salt = D(audit_id || "salt_seed" || external_id) -- opt-in, not the reference's bytes."""
+        _check(_ffi.lib().dapol_ctx_set_leaf_hash_mode(self._h, 1 if id_salt else 0))
+
+    def set_rangeproof_table_budget(self, nbytes: int):
+        """HBM budget of the generator tables under the automatic window (0 = default: 70 % of the free memory, at most 128 GB)."""
+        _check(_ffi.lib().dapol_ctx_set_rangeproof_table_budget(self._h, nbytes))
+
+    @property
+    def rangeproof_table_bytes(self) -> int:
+        return _ffi.lib().dapol_ctx_rangeproof_table_bytes(self._h)
+
     def set_rangeproof_window(self, window: int):
         _check(_ffi.lib().dapol_ctx_set_rangeproof_window(self._h, window))
 

@@ -44,6 +44,7 @@ struct dapol_ctx {
     int device = 0;
     int W = 8;  // comb window of the tree tables
     int pad_mode = 0;  // DAPOL_PADDING_STREAM / DAPOL_PADDING_POSITIONAL (dapol_ctx_set_padding_mode)
+    int leaf_hash_mode = 0;  // DAPOL_LEAF_HASH_COMMITMENT / DAPOL_LEAF_HASH_ID_SALT (dapol_ctx_set_leaf_hash_mode)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     ge_niels *tab_b = nullptr, *tab_bbl = nullptr;  // comb tables for B and B_blinding at window W (253/W+1 windows each)

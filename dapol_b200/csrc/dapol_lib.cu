@@ -212,6 +212,41 @@ __global__ void k_resolve_collisions(uint64_t n, const uint64_t *sorted_cand, co
     if (rehash_body(u, hash_id, height, cur_seed, cand, tries)) atomicAdd(&counters[0], 1ull);
     else { tries[u] = 129; atomicMin(&counters[1], (unsigned long long)u); }
 }
+// Opt-in leaf hash of the DAPOL+ paper (NOT the reference's bytes, which hash the commitment only, node.rs:33-36):
+//   salt = D(audit_id || "salt_seed" || external_id),  leaf hash = D("leaf" || external_id || salt)
+// so that a leaf's hash binds the user's id and a per-user salt instead of being computable from the commitment alone.
+__global__ void k_leaf_id_hashes(uint64_t n, int hash_id, const uint32_t *audit, const uint8_t *eid_blob, const uint64_t *eid_off, uint32_t *out, int *too_long) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t tag_s[9] = {'s', 'a', 'l', 't', '_', 's', 'e', 'e', 'd'}, tag_l[4] = {'l', 'e', 'a', 'f'};
+    const uint8_t *eid = eid_blob + eid_off[i];
+    const uint32_t elen = (uint32_t)(eid_off[i + 1] - eid_off[i]);
+    dapol_hasher hs;
+    uint32_t a[8], salt[8], h[8];
+    load8(a, audit + 8 * i);
+    hasher_init(hs, hash_id);
+    hasher_update_words(hs, a, 8); hasher_update(hs, tag_s, 9); hasher_update(hs, eid, elen);
+    int rc = hasher_final(hs, salt);
+    hasher_init(hs, hash_id);
+    hasher_update(hs, tag_l, 4); hasher_update(hs, eid, elen); hasher_update_words(hs, salt, 8);
+    rc |= hasher_final(hs, h);
+    if (rc) *too_long = 1;
+    store8(out + 8 * i, h);
+}
+__global__ void k_gather_hashes(uint64_t n, const uint32_t *who, const uint32_t *src, uint32_t *dst) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t w[8];
+    load8(w, src + 8 * (uint64_t)who[j]);
+    store8(dst + 8 * j, w);
+}
+__global__ void k_set_leaf_hashes(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, const uint32_t *src) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t w[8];
+    load8(w, src + 8 * j);
+    store8(ns.hash + 8 * (level_off + pos[j]), w);
+}
 __global__ void k_gather_leaves(uint64_t n, const uint32_t *who, const uint64_t *values, const uint32_t *blind, uint64_t *values_sorted,
                                 uint32_t *blind_sorted) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,6 +483,11 @@ extern "C" int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream) {
     ctx->stream = static_cast<cudaStream_t>(cuda_stream);
     return DAPOL_OK;
 }
+extern "C" int dapol_ctx_set_leaf_hash_mode(dapol_ctx *ctx, int mode) {
+    if (!ctx || (mode != DAPOL_LEAF_HASH_COMMITMENT && mode != DAPOL_LEAF_HASH_ID_SALT)) return DAPOL_ERR_BAD_ARG;
+    ctx->leaf_hash_mode = mode;
+    return DAPOL_OK;
+}
 extern "C" int dapol_ctx_set_padding_mode(dapol_ctx *ctx, int mode) {
     if (!ctx || (mode != DAPOL_PADDING_STREAM && mode != DAPOL_PADDING_POSITIONAL)) return DAPOL_ERR_BAD_ARG;
     ctx->pad_mode = mode;
@@ -501,7 +541,7 @@ static void launch_leaf_pad(dapol_ctx *ctx, dapol_tree *t, const uint64_t *d_val
 // interleave with the other shards' in the single-tree creation order); nullptr: pad_base + running creation ordinal.
 static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, const uint64_t *d_leaf_idx, const uint64_t *d_values,
                           const uint8_t *d_blindings, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out,
-                          const uint64_t *pad_level_base = nullptr, const uint32_t *d_records = nullptr) {
+                          const uint64_t *pad_level_base = nullptr, const uint32_t *d_records = nullptr, const uint32_t *d_leaf_hashes = nullptr) {
     if (!ctx || !out || !d_leaf_idx || !pad_seed) return DAPOL_ERR_BAD_ARG;
     if (!d_records && (!d_values || !d_blindings)) return DAPOL_ERR_BAD_ARG;
     *out = nullptr;
@@ -619,6 +659,10 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
 #define W_CASE(w) case w: launch_leaf_pad<w>(ctx, t, d_values, d_blind, d_pad_dest, seed, d_pad_rng, phase, ps); break;
             DAPOL_W_CASES(W_CASE)
 #undef W_CASE
+        }
+        if (phase == 0 && d_leaf_hashes) {  // id / salt leaf hashes (opt-in mode) replace D(compress(com)) before any parent is hashed
+            k_set_leaf_hashes<<<grid_for(n, 256), 256, 0, st>>>(n, t->ns, t->level_off[H], t->pos[H], d_leaf_hashes);
+            ctx->launches++;
         }
         TRY_T(cudaEventRecord(ctx->ev[2 + phase], st));
     }
@@ -786,7 +830,17 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
     // the last sort (no losers) is the final sorted order: result.sort_by_key(index) (mod.rs:396)
     k_gather_leaves<<<grid_for(n, 256), 256, 0, st>>>(n, sc.who, d_values, blind, values_sorted, blind_sorted);
     ctx->launches++;
-    rc = tree_build_dev(ctx, hash_id, height, n, sc.keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out);
+    uint32_t *leaf_hashes = nullptr, *leaf_hashes_in = nullptr;
+    if (ctx->leaf_hash_mode == DAPOL_LEAF_HASH_ID_SALT) {
+        TRY_L(dmalloc(&leaf_hashes_in, n * 32, st));
+        if (dmalloc(&leaf_hashes, n * 32, st) != cudaSuccess) { dfree(leaf_hashes_in, st); dfree(mem, st); dfree(cand, st); dfree(audit, st); return DAPOL_ERR_CUDA; }
+        k_leaf_id_hashes<<<grid_for(n, 128), 128, 0, st>>>(n, hash_id, audit, d_eid_blob, d_eid_off, leaf_hashes_in, reinterpret_cast<int *>(sc.counters + 3));
+        k_gather_hashes<<<grid_for(n, 256), 256, 0, st>>>(n, sc.who, leaf_hashes_in, leaf_hashes);
+        ctx->launches += 2;
+    }
+    rc = tree_build_dev(ctx, hash_id, height, n, sc.keys_sorted, values_sorted, reinterpret_cast<const uint8_t *>(blind_sorted), pad_seed, pad_base, out,
+                        nullptr, nullptr, leaf_hashes);
+    dfree(leaf_hashes, st); dfree(leaf_hashes_in, st);
     dfree(mem, st);
     if (rc != DAPOL_OK) { dfree(cand, st); dfree(audit, st); return rc; }
     (*out)->leaf_index_of = cand;

@@ -433,6 +433,7 @@ extern "C" int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id
                                    float phase_ms[4]) {
     if (!ctx || !comm || !subtree || !top || !pad_seed) return DAPOL_ERR_BAD_ARG;
     *subtree = *top = nullptr;
+    if (comm->world > 1 && ctx->leaf_hash_mode != DAPOL_LEAF_HASH_COMMITMENT) return DAPOL_ERR_BAD_ARG;  // claims do not carry id / salt hashes
     const int world = comm->world, rank = comm->rank;
     int k = 0;
     while ((1 << k) < world) k++;

@@ -91,6 +91,15 @@ DAPOL_API int dapol_ctx_set_stream(dapol_ctx *ctx, void *cuda_stream);
 #define DAPOL_PADDING_STREAM 0
 #define DAPOL_PADDING_POSITIONAL 1
 DAPOL_API int dapol_ctx_set_padding_mode(dapol_ctx *ctx, int mode);
+/* What a LEAF's hash is, for trees built from liabilities on this context (default DAPOL_LEAF_HASH_COMMITMENT).
+ * COMMITMENT: the reference -- hash = D(compress(com)) (src/dapol/node.rs:33-36).
+ * ID_SALT (opt-in, NOT the reference's bytes): the leaf hash of the DAPOL+ paper,
+ *   salt = D(audit_id || "salt_seed" || external_id),  hash = D("leaf" || external_id || salt),
+ *   so a leaf's hash binds the user's id and a per-user salt.  Padding and internal nodes are unchanged; proofs and their
+ *   verification carry (com, hash) of the leaf as before.  Not available in the sharded builds (DAPOL_ERR_BAD_ARG). */
+#define DAPOL_LEAF_HASH_COMMITMENT 0
+#define DAPOL_LEAF_HASH_ID_SALT 1
+DAPOL_API int dapol_ctx_set_leaf_hash_mode(dapol_ctx *ctx, int mode);
 DAPOL_API const char *dapol_strerror(int code);
 DAPOL_API const char *dapol_last_cuda_error(void);
 

@@ -280,6 +280,32 @@ static int is_pair(const node *cur, uint64_t cnt, uint64_t i) {
 static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
                            const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, int pad_mode,
                            const uint64_t *level_base, dor_tree **out);
+/* leaf hashes given by the caller instead of D(compress(com)): the opt-in id / salt leaf hash (include/dapol_b200.h,
+ * DAPOL_LEAF_HASH_ID_SALT); NULL = the reference's rule (node.rs:33-36) */
+static const uint8_t *g_leaf_hash_override = NULL;
+EXPORT int dor_tree_build_leaf_hashes(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
+                                      const uint8_t *blindings, const uint8_t *leaf_hashes, const uint8_t pad_seed[32], uint64_t pad_base,
+                                      int nthreads, dor_tree **out) {
+    g_leaf_hash_override = leaf_hashes;  /* test infrastructure: single-threaded callers */
+    int rc = tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, pad_base, nthreads, 0, NULL, out);
+    g_leaf_hash_override = NULL;
+    return rc;
+}
+/* salt = D(audit_id || "salt_seed" || external_id), leaf hash = D("leaf" || external_id || salt), audit_id = D(audit_seed || internal_id) */
+EXPORT void dor_leaf_id_hashes(int hash_id, uint64_t n, const uint8_t *iid_blob, const uint64_t *iid_off, const uint8_t *eid_blob,
+                               const uint64_t *eid_off, const uint8_t *audit_seed, uint64_t seed_len, uint8_t *out) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t il = iid_off[i + 1] - iid_off[i], el = eid_off[i + 1] - eid_off[i];
+        uint8_t *buf = (uint8_t *)malloc(64 + seed_len + il + el), audit[32], salt[32];
+        memcpy(buf, audit_seed, seed_len); memcpy(buf + seed_len, iid_blob + iid_off[i], il);
+        hash_buf(hash_id, buf, seed_len + il, audit);
+        memcpy(buf, audit, 32); memcpy(buf + 32, "salt_seed", 9); memcpy(buf + 41, eid_blob + eid_off[i], el);
+        hash_buf(hash_id, buf, 41 + el, salt);
+        memcpy(buf, "leaf", 4); memcpy(buf + 4, eid_blob + eid_off[i], el); memcpy(buf + 4 + el, salt, 32);
+        hash_buf(hash_id, buf, 36 + el, out + 32 * i);
+        free(buf);
+    }
+}
 EXPORT int dor_tree_build(int hash_id, int height, uint64_t n, const uint64_t *idx_sorted, const uint64_t *values,
                           const uint8_t *blindings, const uint8_t pad_seed[32], uint64_t pad_base, int nthreads, dor_tree **out) {
     return tree_build_mode(hash_id, height, n, idx_sorted, values, blindings, pad_seed, pad_base, nthreads, 0, NULL, out);
@@ -315,7 +341,10 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
     node *cur = (node *)calloc(n, sizeof(node));
     uint64_t cnt = n, draw = pad_base, n_pads = 0;
 #pragma omp parallel for schedule(dynamic, 16)
-    for (uint64_t i = 0; i < n; i++) node_new(hash_id, &cur[i], idx_sorted[i], values[i], blindings + 32 * i, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        node_new(hash_id, &cur[i], idx_sorted[i], values[i], blindings + 32 * i, 0);
+        if (g_leaf_hash_override) memcpy(cur[i].hash, g_leaf_hash_override + 32 * i, 32);
+    }
     for (int h = height; h >= 1; h--) {
         uint64_t np = 0;
         for (uint64_t i = 0; i < cnt; np++) i += is_pair(cur, cnt, i) ? 2 : 1;

@@ -217,6 +217,31 @@ class Tree:
         return bytes(out[: n.value])
 
 
+def leaf_id_hashes(hash_id, iid_blob, iid_off, eid_blob, eid_off, audit_seed: bytes) -> np.ndarray:
+    """Opt-in leaf hash of the DAPOL+ paper (include/dapol_b200.h, DAPOL_LEAF_HASH_ID_SALT), per liability in input order."""
+    n = len(iid_off) - 1
+    out = np.zeros((max(n, 1), 32), np.uint8)
+    ib, ibp = _np(iid_blob, np.uint8); io, iop = _np(iid_off, np.uint64)
+    eb, ebp = _np(eid_blob, np.uint8); eo, eop = _np(eid_off, np.uint64)
+    lib().dor_leaf_id_hashes(hash_id, C.c_uint64(n), ibp, iop, ebp, eop, _b(audit_seed) if audit_seed else None, C.c_uint64(len(audit_seed)),
+                             out.ctypes.data_as(C.c_void_p))
+    return out[:n]
+
+
+def tree_with_leaf_hashes(hash_id, height, idx_sorted, values, blindings, leaf_hashes, pad_seed: bytes, pad_base=0) -> "Tree":
+    """dor_tree_build with the leaves' hashes given (sorted like the leaves) instead of D(compress(com))."""
+    idx, ip = _np(idx_sorted, np.uint64); val, vp = _np(values, np.uint64); bl, bp = _np(blindings, np.uint8)
+    lh, lp = _np(leaf_hashes, np.uint8)
+    assert bl.size == 32 * idx.size == lh.size
+    h = C.c_void_p()
+    rc = lib().dor_tree_build_leaf_hashes(hash_id, height, C.c_uint64(idx.size), ip, vp, bp, lp, _b(pad_seed), C.c_uint64(pad_base), 0, C.byref(h))
+    if rc:
+        raise ValueError(f"dor_tree_build_leaf_hashes rc={rc}")
+    t = Tree.__new__(Tree)
+    t.h, t.hash_id, t.height = h, hash_id, height
+    return t
+
+
 def prove_inclusion_batch(tree: "Tree", leaf_idxs, agg, policy, seed: bytes):
     """Dapol::generate_proof_batch (mod.rs:172-190): ONE DapolProof for several leaves (strictly increasing indexes)."""
     L = lib()

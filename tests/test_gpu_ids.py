@@ -73,3 +73,42 @@ def test_tree_from_nodes_has_no_id_map(ctx):
     t = Dapol.new_blank(ctx, 0, 6, 1).build([1, 5, 9], [1, 2, 3], np.zeros((3, 32), np.uint8), PAD_SEED)
     assert t.index_of_ids([b"a"]) is None      # new_blank: empty id_to_idx_map (mod.rs:196-204)
     t.close()
+
+
+@pytest.mark.parametrize("hash_id", [0, 1])
+def test_id_salt_leaf_hash_mode(cref, hash_id):
+    """Opt-in leaf hash of the DAPOL+ paper: every level of the GPU tree equals the oracle's tree built
+    with the same leaf hashes; inclusion proofs verify (the leaf's proof node carries the id / salt hash); the default mode
+    on the same liabilities gives a different root hash but the same commitments."""
+    from dapol_b200 import Context, Dapol, DapolProof, DapolProofNode
+    rnd = random.Random(5 + hash_id)
+    n, H, seed = 120, 10, b"id-salt"
+    ids = [b"user-%d" % i for i in range(n)]
+    eids = [rnd.randbytes(rnd.choice([0, 4, 33, 1200])) for _ in range(n)]
+    vals = [rnd.randrange(1 << 32) for _ in range(n)]
+    c = Context(0, 15)
+    c.set_rangeproof_window(8)
+    plain = Dapol.new(c, hash_id, list(zip(ids, eids, vals)), seed, H, 2, PAD_SEED)
+    c.set_leaf_hash_mode(True)
+    t = Dapol.new(c, hash_id, list(zip(ids, eids, vals)), seed, H, 2, PAD_SEED)
+    ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+    rc, idx, bl, _ = cref.derive_leaves(hash_id, ib, io, eb, eo, seed, H)
+    assert rc == 0
+    lh = cref.leaf_id_hashes(hash_id, ib, io, eb, eo, seed)
+    order = np.argsort(idx)
+    ora = cref.tree_with_leaf_hashes(hash_id, H, idx[order], np.array(vals, np.uint64)[order], bl[order], lh[order], PAD_SEED)
+    for h in range(H + 1):
+        g, o = t.level(h), ora.level(h)
+        for key in ("idx", "v", "comc", "hash", "is_pad"):
+            assert (g[key] == o[key]).all(), (h, key)
+    assert t.root_raw().com == plain.root_raw().com and t.root_raw().hash != plain.root_raw().hash
+    picks = [int(idx[i]) for i in (0, 17, n - 1)]
+    proofs = t.generate_proofs(picks, PROVE_SEED)
+    paths = t.paths(picks)
+    leaves = [DapolProofNode(paths["leaf_comc"][k].tobytes(), paths["leaf_hash"][k].tobytes()) for k in range(3)]
+    assert leaves[1].hash == lh[17].tobytes()
+    assert DapolProof.verify_many(c, t.root(), leaves, proofs).all()
+    r = ora.root()
+    for k in range(3):
+        assert cref.verify_inclusion(hash_id, 0, proofs[k].serialize(), r["comc"], r["hash"], leaves[k].com, leaves[k].hash)
+    t.close(); plain.close(); c.close()

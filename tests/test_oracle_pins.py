@@ -250,3 +250,18 @@ def test_batch_proof_c_vs_bigint(pyref, cref):
     assert cref.prove_inclusion_batch(T, picks[:1], 2, 0, seed) == T.prove_inclusion(picks[0], 2, 0, seed)   # a batch of one is the single proof
     assert cref.prove_inclusion_batch(T, picks[::-1], 1, 1, seed) is None                                   # not increasing
     assert cref.prove_inclusion_batch(T, picks, len(plan) + 1, 1, seed) is None                             # reference: slice OOB panic
+
+
+def test_id_salt_leaf_hash_pinned_to_hashlib(cref):
+    """Opt-in leaf hash (include/dapol_b200.h, DAPOL_LEAF_HASH_ID_SALT): salt = D(audit_id || "salt_seed" || eid), hash = D("leaf" || eid || salt),
+    audit_id = D(audit_seed || iid) (mod.rs:347-353) -- the C oracle against hashlib / the blake3 package."""
+    import blake3
+    ids = [b"alice", b"", b"x" * 1500]
+    eids = [b"ext-1", b"e" * 2000, b""]
+    ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+    for hid, D in ((0, lambda d: blake3.blake3(d).digest()), (1, lambda d: hashlib.blake2s(d).digest())):
+        got = cref.leaf_id_hashes(hid, ib, io, eb, eo, b"seed")
+        for i in range(3):
+            audit = D(b"seed" + ids[i])
+            salt = D(audit + b"salt_seed" + eids[i])
+            assert got[i].tobytes() == D(b"leaf" + eids[i] + salt)
