@@ -74,6 +74,11 @@ def lib():
     L.dapol_ctx_params.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.dapol_inclusion_proof_size.argtypes = [C.c_int, u64, C.c_int]
     L.dapol_inclusion_proof_size.restype = u64
+    L.dapol_inclusion_proof_size_d.argtypes = [C.c_int, u64, C.c_int, C.c_int]
+    L.dapol_inclusion_proof_size_d.restype = u64
+    L.dapol_batch_proof_size_d.argtypes = [C.c_int, u64, vp, u64, C.c_int, C.c_int]
+    L.dapol_batch_proof_size_d.restype = u64
+    L.dapol_digest_len.argtypes = [C.c_int]
     L.dapol_prove_batch.argtypes = [vp, u64, vp, u64, C.c_int, vp, vp, u64, C.POINTER(u64)]
     L.dapol_verify_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, vp]
     L.dapol_tree_save.argtypes = [vp, C.c_char_p]

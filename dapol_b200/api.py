@@ -17,7 +17,11 @@ import numpy as np
 
 from . import _ffi
 
-HASH_BLAKE3, HASH_BLAKE2S = 0, 1
+HASH_BLAKE3, HASH_BLAKE2S, HASH_BLAKE2B = 0, 1, 2  # Blake2b: 64-byte digests (src/tests.rs:104-105), new_blank + build trees only
+
+
+def digest_len(hash_id: int) -> int:
+    return 64 if hash_id == HASH_BLAKE2B else 32
 POLICY_PADDING, POLICY_SPLITTING = 0, 1
 MAX_TREE_HEIGHT = 64
 
@@ -359,7 +363,7 @@ class Dapol:
     # -- accessors ----------------------------------------------------------------------------
     def root_raw(self) -> DapolNode:
         """Dapol::root_raw (mod.rs:134-136)."""
-        com = np.zeros(32, np.uint8); hs = np.zeros(32, np.uint8); bl = np.zeros(32, np.uint8)
+        com = np.zeros(32, np.uint8); hs = np.zeros(digest_len(self.hash_id), np.uint8); bl = np.zeros(32, np.uint8)
         v = C.c_uint64()
         _check(_ffi.lib().dapol_tree_root(self._t, _p(com), _p(hs), C.byref(v), _p(bl)))
         return DapolNode(v.value, bl.tobytes(), com.tobytes(), hs.tobytes())
@@ -379,7 +383,7 @@ class Dapol:
     def level(self, h: int):
         n = _ffi.lib().dapol_tree_level_size(self._t, h)
         idx = np.zeros(n, np.uint64); v = np.zeros(n, np.uint64)
-        r = np.zeros((n, 32), np.uint8); c = np.zeros((n, 32), np.uint8); hs = np.zeros((n, 32), np.uint8)
+        r = np.zeros((n, 32), np.uint8); c = np.zeros((n, 32), np.uint8); hs = np.zeros((n, digest_len(self.hash_id)), np.uint8)
         pad = np.zeros(n, np.uint8)
         _check(_ffi.lib().dapol_tree_level_copy(self._t, h, _p(idx), _p(v), _p(r), _p(c), _p(hs), _p(pad)))
         return dict(idx=idx, v=v, r=r, comc=c, hash=hs, is_pad=pad)
@@ -389,8 +393,9 @@ class Dapol:
         li = np.ascontiguousarray(leaf_idx, np.uint64)
         k, H = len(li), max(self.height, 1)
         v = np.zeros((k, H), np.uint64)
-        r = np.zeros((k, H, 32), np.uint8); c = np.zeros((k, H, 32), np.uint8); hs = np.zeros((k, H, 32), np.uint8)
-        lc = np.zeros((k, 32), np.uint8); lh = np.zeros((k, 32), np.uint8)
+        dl = digest_len(self.hash_id)
+        r = np.zeros((k, H, 32), np.uint8); c = np.zeros((k, H, 32), np.uint8); hs = np.zeros((k, H, dl), np.uint8)
+        lc = np.zeros((k, 32), np.uint8); lh = np.zeros((k, dl), np.uint8)
         rc = _ffi.lib().dapol_tree_paths(self._t, k, _p(li), _p(v), _p(r), _p(c), _p(hs), _p(lc), _p(lh))
         if rc == 17:
             return None
@@ -404,7 +409,7 @@ class Dapol:
         li = np.ascontiguousarray(leaf_idx, np.uint64)
         k = len(li)
         L = _ffi.lib()
-        size = L.dapol_inclusion_proof_size(self.height, self.aggregation_factor, self.policy)
+        size = L.dapol_inclusion_proof_size_d(self.height, self.aggregation_factor, self.policy, self.hash_id)
         if size == 0:
             raise DapolError(16)
         out = np.zeros(k * size, np.uint8)
@@ -448,7 +453,7 @@ class Dapol:
         increasing indexes); None if any index is not a leaf."""
         li = np.ascontiguousarray(leaf_idx, np.uint64)
         L = _ffi.lib()
-        size = L.dapol_batch_proof_size(self.height, len(li), _p(li), self.aggregation_factor, self.policy)
+        size = L.dapol_batch_proof_size_d(self.height, len(li), _p(li), self.aggregation_factor, self.policy, self.hash_id)
         if size == 0:
             raise DapolError(16)
         out = np.zeros(size, np.uint8)

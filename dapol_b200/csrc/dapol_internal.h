@@ -85,7 +85,7 @@ struct dapol_tree {
     mutable std::mutex index_mu;
     std::vector<uint64_t> npads;        // padding nodes per level
     uint32_t root_ext[32] = {};         // half point of the root commitment (kept for the shard root record)
-    uint32_t root_comc[8] = {}, root_hash[8] = {};  // compressed commitment and hash of the root (host copy: prover nonce key)
+    uint32_t root_comc[8] = {}, root_hash[16] = {};  // compressed commitment and hash (32 or 64 bytes) of the root (host copy: prover nonce key)
     // sharded trees: this tree is the subtree under node `prefix` of level top->height of `top`
     const dapol_tree *top = nullptr;
     uint64_t prefix = 0;
@@ -155,4 +155,5 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
 // device-resident Merkle paths of k leaves (dapol_lib.cu): siblings leaf level first, [k][total height] each; leaf
 // indexes are those of the whole tree (prefix included when the tree is a shard with its top tree attached)
 int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
-                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found);
+                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found, uint32_t *d_hh = nullptr, uint32_t *d_lhh = nullptr);
+static inline int dapol_dlen(int hash_id) { return hash_id == DAPOL_HASH_BLAKE2B ? 64 : 32; }

@@ -240,6 +240,10 @@ __global__ void k_gather_hashes(uint64_t n, const uint32_t *who, const uint32_t 
     load8(w, src + 8 * (uint64_t)who[j]);
     store8(dst + 8 * j, w);
 }
+__global__ void k_leafpad_hash_b2b(uint64_t T, NodeStore ns, uint64_t leaf_level_off) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < T) leafpad_hash_b2b_body(g, ns, leaf_level_off);
+}
 __global__ void k_set_leaf_hashes(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, const uint32_t *src) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -312,7 +316,8 @@ __global__ void __launch_bounds__(128) k_commit(uint64_t n, const uint64_t *valu
 // the shard prefix above `height` bits when prefix_check is set.
 __global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, uint64_t fixed_idx, int prefix_check, uint64_t prefix, NodeStore ns,
                         const uint64_t *level_off, uint64_t n_leaf_level, uint32_t *const *pos, int height, int out_stride, int lvl0,
-                        uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint32_t *o_lc, uint32_t *o_lh, int *not_found) {
+                        uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint32_t *o_lc, uint32_t *o_lh, int *not_found,
+                        uint32_t *o_hh, uint32_t *o_lhh) {  // o_hh / o_lhh: upper halves of 64-byte hashes (Blake2b trees), else nullptr
     uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= k) return;
     uint64_t want = leaf_idx ? leaf_idx[q] : fixed_idx;
@@ -326,6 +331,7 @@ __global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, uint64_t fixed_idx
     uint32_t w[8];
     if (o_lc) { load8(w, ns.comc + 8 * (off + slot)); store8(o_lc + 8 * q, w); }
     if (o_lh) { load8(w, ns.hash + 8 * (off + slot)); store8(o_lh + 8 * q, w); }
+    if (o_lhh && ns.hash_hi) { load8(w, ns.hash_hi + 8 * (off + slot)); store8(o_lhh + 8 * q, w); }
     uint64_t p = (uint64_t)slot;
     for (int h = height, lvl = lvl0; h >= 1; h--, lvl++) {
         uint64_t g = level_off[h] + (p ^ 1), o = q * (uint64_t)out_stride + lvl;
@@ -333,6 +339,7 @@ __global__ void k_paths(uint64_t k, const uint64_t *leaf_idx, uint64_t fixed_idx
         load8(w, ns.r + 8 * g); store8(o_r + 8 * o, w);
         load8(w, ns.comc + 8 * g); store8(o_c + 8 * o, w);
         load8(w, ns.hash + 8 * g); store8(o_h + 8 * o, w);
+        if (o_hh && ns.hash_hi) { load8(w, ns.hash_hi + 8 * g); store8(o_hh + 8 * o, w); }
         if (h > 1) p = pos[h - 1][p >> 1];
     }
 }
@@ -512,7 +519,7 @@ extern "C" void dapol_tree_destroy(dapol_tree *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStream_t st = t->ctx->stream;
-    dfree(t->ns.idx, st); dfree(t->ns.v, st); dfree(t->ns.r, st); dfree(t->ns.comc, st); dfree(t->ns.hash, st);
+    dfree(t->ns.idx, st); dfree(t->ns.v, st); dfree(t->ns.r, st); dfree(t->ns.comc, st); dfree(t->ns.hash, st); dfree(t->ns.hash_hi, st);
     dfree(t->ns.ext, st); dfree(t->ns.is_pad, st);
     dfree(t->pos_all, st);
     dfree(t->d_pos, st); dfree(t->d_level_off, st); dfree(t->leaf_index_of, st);
@@ -545,7 +552,10 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     if (!ctx || !out || !d_leaf_idx || !pad_seed) return DAPOL_ERR_BAD_ARG;
     if (!d_records && (!d_values || !d_blindings)) return DAPOL_ERR_BAD_ARG;
     *out = nullptr;
-    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    // D = Blake2b (64-byte digests): new_blank + build only, as in the reference (Dapol::new insists on 32 bytes, mod.rs:101-103)
+    const bool b2b = hash_id == DAPOL_HASH_BLAKE2B;
+    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S && !b2b) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    if (b2b && (d_records || d_leaf_hashes || pad_level_base)) return DAPOL_ERR_INVALID_DIGEST_SIZE;
     if (height > DAPOL_MAX_TREE_HEIGHT) return DAPOL_ERR_TREE_HEIGHT_TOO_BIG;
     if (height < 0 || n == 0 || (height == 0 && n != 1) || n >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -602,6 +612,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     TRY_T(dmalloc(&t->ns.r, T * 32, st));
     TRY_T(dmalloc(&t->ns.comc, T * 32, st));
     TRY_T(dmalloc(&t->ns.hash, T * 32, st));
+    if (b2b) TRY_T(dmalloc(&t->ns.hash_hi, T * 32, st));
     TRY_T(dmalloc(&t->ns.ext, T * 128, st));
     TRY_T(dmalloc(&t->ns.is_pad, T, st));
     TRY_T(dmalloc(&t->pos_all, (pos_off[H + 1] + 64) * 4, st));
@@ -664,6 +675,10 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
             k_set_leaf_hashes<<<grid_for(n, 256), 256, 0, st>>>(n, t->ns, t->level_off[H], t->pos[H], d_leaf_hashes);
             ctx->launches++;
         }
+        if (phase == 1 && b2b) {  // 64-byte digests of the leaf-level and padding nodes (the node kernels left 32-byte placeholders)
+            k_leafpad_hash_b2b<<<grid_for(T, 128), 128, 0, st>>>(T, t->ns, t->level_off[H]);
+            ctx->launches++;
+        }
         TRY_T(cudaEventRecord(ctx->ev[2 + phase], st));
     }
     // pointer tables for the compress pass and path extraction
@@ -677,6 +692,7 @@ static int tree_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64_t n, c
     TRY_T(cudaMemcpyAsync(t->root_ext, t->ns.ext, 128, cudaMemcpyDeviceToHost, st));  // root = global node 0
     TRY_T(cudaMemcpyAsync(t->root_comc, t->ns.comc, 32, cudaMemcpyDeviceToHost, st));
     TRY_T(cudaMemcpyAsync(t->root_hash, t->ns.hash, 32, cudaMemcpyDeviceToHost, st));
+    if (b2b) TRY_T(cudaMemcpyAsync(t->root_hash + 8, t->ns.hash_hi, 32, cudaMemcpyDeviceToHost, st));
     TRY_T(cudaGetLastError());
     TRY_T(cudaStreamSynchronize(st));
     for (int i = 0; i < 4; i++) cudaEventElapsedTime(&ctx->last_ms[i], ctx->ev[i], ctx->ev[i + 1]);
@@ -987,6 +1003,7 @@ extern "C" int dapol_tree_build_shard_dev(dapol_ctx *ctx, int hash_id, int heigh
 }
 extern "C" int dapol_tree_root_record(const dapol_tree *t, uint8_t *rec) {
     if (!t || !rec) return DAPOL_ERR_BAD_ARG;
+    if (t->ns.hash_hi) return DAPOL_ERR_INVALID_DIGEST_SIZE;  // the record carries a 32-byte hash (sharded builds = Dapol::new: 32-byte digests)
     memcpy(rec, t->root_ext, 128);
     uint64_t v = 0;
     int rc = dapol_tree_level_copy(t, 0, nullptr, &v, rec + 192, rec + 128, rec + 160, nullptr);
@@ -1125,7 +1142,7 @@ extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
     if (!ok) rc = DAPOL_ERR_IO;
     const struct { const void *p; size_t bytes; } parts[] = {
         {t->ns.idx, T * 8}, {t->ns.v, T * 8}, {t->ns.r, T * 32}, {t->ns.comc, T * 32}, {t->ns.hash, T * 32}, {t->ns.is_pad, T},
-        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, save_map ? t->n_leaves * 8 : 0}};
+        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, save_map ? t->n_leaves * 8 : 0}, {t->ns.hash_hi, t->ns.hash_hi ? T * 32 : 0}};
     for (const auto &pt : parts)
         if (rc == DAPOL_OK && pt.bytes) rc = dev_to_file(f, pt.p, pt.bytes, buf, st);
     if (rc == DAPOL_OK && fwrite(TREE_MAGIC, 8, 1, f) != 1) rc = DAPOL_ERR_IO;  // trailer: a truncated file does not load
@@ -1143,7 +1160,7 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
     if (!f) return DAPOL_ERR_IO;
     TreeFileHeader h;
     if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, TREE_MAGIC, 8) != 0 || h.version != 1 || h.height < 0 || h.height > DAPOL_MAX_TREE_HEIGHT ||
-        (h.hash_id != DAPOL_HASH_BLAKE3 && h.hash_id != DAPOL_HASH_BLAKE2S) || h.T == 0 || h.n_leaves == 0 || h.n_leaves >= (1ull << 31)) {
+        (h.hash_id != DAPOL_HASH_BLAKE3 && h.hash_id != DAPOL_HASH_BLAKE2S && h.hash_id != DAPOL_HASH_BLAKE2B) || h.T == 0 || h.n_leaves == 0 || h.n_leaves >= (1ull << 31)) {
         fclose(f);
         return DAPOL_ERR_IO;
     }
@@ -1172,9 +1189,11 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
     alloc(&t->ns.idx, T * 8); alloc(&t->ns.v, T * 8); alloc(&t->ns.r, T * 32); alloc(&t->ns.comc, T * 32); alloc(&t->ns.hash, T * 32);
     alloc(&t->ns.is_pad, T); alloc(&t->pos_all, h.pos_words * 4);
     if (h.flags & 1u) alloc(&t->leaf_index_of, h.n_leaves * 8);
+    const bool b2b = h.hash_id == DAPOL_HASH_BLAKE2B;
+    if (b2b) alloc(&t->ns.hash_hi, T * 32);
     const struct { void *p; size_t bytes; } parts[] = {
         {t->ns.idx, T * 8}, {t->ns.v, T * 8}, {t->ns.r, T * 32}, {t->ns.comc, T * 32}, {t->ns.hash, T * 32}, {t->ns.is_pad, T},
-        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, (h.flags & 1u) ? h.n_leaves * 8 : 0}};
+        {t->pos_all, h.pos_words * 4}, {t->leaf_index_of, (h.flags & 1u) ? h.n_leaves * 8 : 0}, {t->ns.hash_hi, b2b ? T * 32 : 0}};
     for (const auto &pt : parts)
         if (rc == DAPOL_OK && pt.bytes) rc = file_to_dev(f, pt.p, pt.bytes, buf, st);
     char tail[8];
@@ -1188,6 +1207,7 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
             cudaMemcpyAsync(t->d_level_off, t->level_off.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
             cudaMemcpyAsync(t->root_comc, t->ns.comc, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
             cudaMemcpyAsync(t->root_hash, t->ns.hash, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            (b2b && cudaMemcpyAsync(t->root_hash + 8, t->ns.hash_hi, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
             cudaStreamSynchronize(st) != cudaSuccess) {
             g_cuda_err = "tree load: device tables"; cudaGetLastError(); rc = DAPOL_ERR_CUDA;
         }
@@ -1201,6 +1221,9 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
 // ------------------------------------------------------------------------------------------------ accessors
 extern "C" int dapol_tree_height(const dapol_tree *t) { return t ? t->height : -1; }
 extern "C" int dapol_tree_hash_id(const dapol_tree *t) { return t ? t->hash_id : -1; }
+extern "C" int dapol_digest_len(int hash_id) {
+    return hash_id == DAPOL_HASH_BLAKE2B ? 64 : (hash_id == DAPOL_HASH_BLAKE3 || hash_id == DAPOL_HASH_BLAKE2S) ? 32 : 0;
+}
 extern "C" uint64_t dapol_tree_num_nodes(const dapol_tree *t) { return t ? t->T : 0; }
 extern "C" uint64_t dapol_tree_num_padding(const dapol_tree *t) { return t ? t->n_pads : 0; }
 extern "C" uint64_t dapol_tree_level_size(const dapol_tree *t, int level) {
@@ -1215,7 +1238,11 @@ extern "C" int dapol_tree_level_copy(const dapol_tree *t, int level, uint64_t *i
     if (values) CUDA_TRY(cudaMemcpy(values, t->ns.v + o, n * 8, cudaMemcpyDeviceToHost));
     if (blindings) CUDA_TRY(cudaMemcpy(blindings, t->ns.r + 8 * o, n * 32, cudaMemcpyDeviceToHost));
     if (coms) CUDA_TRY(cudaMemcpy(coms, t->ns.comc + 8 * o, n * 32, cudaMemcpyDeviceToHost));
-    if (hashes) CUDA_TRY(cudaMemcpy(hashes, t->ns.hash + 8 * o, n * 32, cudaMemcpyDeviceToHost));
+    if (hashes && !t->ns.hash_hi) CUDA_TRY(cudaMemcpy(hashes, t->ns.hash + 8 * o, n * 32, cudaMemcpyDeviceToHost));
+    if (hashes && t->ns.hash_hi) {  // 64-byte digests: the halves are kept apart on the device
+        CUDA_TRY(cudaMemcpy2D(hashes, 64, t->ns.hash + 8 * o, 32, 32, n, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy2D(hashes + 32, 64, t->ns.hash_hi + 8 * o, 32, 32, n, cudaMemcpyDeviceToHost));
+    }
     if (is_padding) CUDA_TRY(cudaMemcpy(is_padding, t->ns.is_pad + o, n, cudaMemcpyDeviceToHost));
     return DAPOL_OK;
 }
@@ -1232,16 +1259,16 @@ extern "C" int dapol_tree_leaf_index_of(const dapol_tree *t, uint64_t input_pos,
 }
 // device-resident path extraction (shared with the inclusion-proof path): all outputs are device pointers
 int dapol_tree_paths_dev(const dapol_tree *t, uint64_t k, const uint64_t *d_leaf_idx, uint64_t *d_v, uint32_t *d_r, uint32_t *d_c, uint32_t *d_h,
-                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found) {
+                         uint32_t *d_lc, uint32_t *d_lh, int *d_not_found, uint32_t *d_hh, uint32_t *d_lhh) {
     dapol_ctx *ctx = t->ctx;
     const int Ht = dapol_total_height(t);
     k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, d_leaf_idx, 0, t->top != nullptr, t->prefix, t->ns, t->d_level_off, t->level_n[t->height],
-                                                       t->d_pos, t->height, Ht, 0, d_v, d_r, d_c, d_h, d_lc, d_lh, d_not_found);
+                                                       t->d_pos, t->height, Ht, 0, d_v, d_r, d_c, d_h, d_lc, d_lh, d_not_found, d_hh, d_lhh);
     ctx->launches++;
     if (t->top && t->top->height > 0) {  // the upper levels come from the (replicated) top tree: siblings of this shard's root
         const dapol_tree *u = t->top;
         k_paths<<<grid_for(k, 128), 128, 0, ctx->stream>>>(k, nullptr, t->prefix, 0, 0, u->ns, u->d_level_off, u->level_n[u->height], u->d_pos,
-                                                           u->height, Ht, t->height, d_v, d_r, d_c, d_h, nullptr, nullptr, d_not_found);
+                                                           u->height, Ht, t->height, d_v, d_r, d_c, d_h, nullptr, nullptr, d_not_found, d_hh, nullptr);
         ctx->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1256,26 +1283,35 @@ extern "C" int dapol_tree_paths(const dapol_tree *t, uint64_t k, const uint64_t 
     uint64_t H = (uint64_t)dapol_total_height(t), kh = k * (H ? H : 1);
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 3 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256;
+    const bool b2b = t->ns.hash_hi != nullptr;  // 64-byte digests: hashes / leaf_hashes are 64 bytes per node
+    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 4 * Arena::need(kh, 32) + 3 * Arena::need(k, 32) + 256;
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint64_t *d_li = ar.take<uint64_t>(k), *d_v = ar.take<uint64_t>(kh);
-    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8);
-    uint32_t *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8);
+    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8), *d_hh = ar.take<uint32_t>(kh * 8);
+    uint32_t *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8), *d_lhh = ar.take<uint32_t>(k * 8);
     int *d_nf = ar.take<int>(1), nf = 0;
     cudaMemsetAsync(d_nf, 0, 4, st);
     cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st);
-    int rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf);
+    int rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf, b2b ? d_hh : nullptr, b2b ? d_lhh : nullptr);
     if (rc) { dfree(mem, st); return rc; }
     cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st);
     if (H) {
         cudaMemcpyAsync(values, d_v, kh * 8, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(blindings, d_r, kh * 32, cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(coms, d_c, kh * 32, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(hashes, d_h, kh * 32, cudaMemcpyDeviceToHost, st);
+        if (!b2b) cudaMemcpyAsync(hashes, d_h, kh * 32, cudaMemcpyDeviceToHost, st);
+        else {
+            cudaMemcpy2DAsync(hashes, 64, d_h, 32, 32, kh, cudaMemcpyDeviceToHost, st);
+            cudaMemcpy2DAsync(hashes + 32, 64, d_hh, 32, 32, kh, cudaMemcpyDeviceToHost, st);
+        }
     }
     if (leaf_coms) cudaMemcpyAsync(leaf_coms, d_lc, k * 32, cudaMemcpyDeviceToHost, st);
-    if (leaf_hashes) cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st);
+    if (leaf_hashes && !b2b) cudaMemcpyAsync(leaf_hashes, d_lh, k * 32, cudaMemcpyDeviceToHost, st);
+    if (leaf_hashes && b2b) {
+        cudaMemcpy2DAsync(leaf_hashes, 64, d_lh, 32, 32, k, cudaMemcpyDeviceToHost, st);
+        cudaMemcpy2DAsync(leaf_hashes + 32, 64, d_lhh, 32, 32, k, cudaMemcpyDeviceToHost, st);
+    }
     cudaError_t e = cudaStreamSynchronize(st);
     dfree(mem, st);
     CUDA_TRY(e);

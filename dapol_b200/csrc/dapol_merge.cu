@@ -26,6 +26,11 @@ __global__ void __launch_bounds__(128) k_merge_hash(uint64_t n, NodeStore ns, ui
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) merge_hash_body(j, ns, child_off, parent_off, parent_pos, hash_id);
 }
+// D = Blake2b: 192-byte parent hashes over the two halves of the children's digests
+__global__ void __launch_bounds__(128) k_merge_hash_b2b(uint64_t n, NodeStore ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) merge_hash_b2b_body(j, ns, child_off, parent_off, parent_pos);
+}
 void dapol_launch_merges(dapol_ctx *ctx, dapol_tree *t) {
     const int H = t->height;
     const int hash_id = t->hash_id;
@@ -47,7 +52,10 @@ void dapol_launch_merges(dapol_ctx *ctx, dapol_tree *t) {
         ctx->launches++;
         for (int h = H; h >= 1; h--) {
             uint64_t np = t->n_real[h - 1];
-            k_merge_hash<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
+            if (hash_id == DAPOL_HASH_BLAKE2B)
+                k_merge_hash_b2b<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr);
+            else
+                k_merge_hash<<<grid_for(np, 128), 128, 0, st>>>(np, t->ns, t->level_off[h], t->level_off[h - 1], h - 1 >= 1 ? t->pos[h - 1] : nullptr, hash_id);
             ctx->launches++;
         }
     }

@@ -37,15 +37,19 @@ static int policy_plan(uint64_t nsib, uint64_t agg, int policy, std::vector<AggG
     for (auto &x : g) if (x.m > 64) return DAPOL_ERR_BAD_ARG;
     return DAPOL_OK;
 }
-static uint64_t merkle_bytes(uint64_t H) { return 2 + 8 + (H + 7) / 8 + 8 + 64 * H; }
-extern "C" uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy) {
+// a sibling on the wire is DapolProofNode::serialize = com (32) || hash (Dlen), src/proof/node.rs:74-79
+static uint64_t merkle_bytes(uint64_t H, uint64_t dl) { return 2 + 8 + (H + 7) / 8 + 8 + (32 + dl) * H; }
+extern "C" uint64_t dapol_inclusion_proof_size_d(int height, uint64_t aggregation_factor, int policy, int hash_id) {
     std::vector<AggGroup> g;
     uint64_t sf;
-    if (height < 0 || height > 64 || policy_plan((uint64_t)height, aggregation_factor, policy, g, sf)) return 0;
+    if (!dapol_digest_len(hash_id) || height < 0 || height > 64 || policy_plan((uint64_t)height, aggregation_factor, policy, g, sf)) return 0;
     uint64_t sz = policy == DAPOL_POLICY_SPLITTING ? 2 : 0;
     for (auto &x : g) sz += 8 + dapol_rangeproof_size(64, (int)x.m);
     sz += 8 + SINGLE_PROOF_BYTE_NUM * ((uint64_t)height - sf);
-    return sz + merkle_bytes((uint64_t)height);
+    return sz + merkle_bytes((uint64_t)height, (uint64_t)dapol_digest_len(hash_id));
+}
+extern "C" uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy) {
+    return dapol_inclusion_proof_size_d(height, aggregation_factor, policy, DAPOL_HASH_BLAKE3);
 }
 
 // ------------------------------------------------------------------------------------------------ prove
@@ -78,7 +82,7 @@ static void prover_nonce_key(uint8_t key[32], const uint8_t seed[32], const dapo
     hasher_update(hs, label, 30);
     hasher_update(hs, seed, 32);
     hasher_update_words(hs, whole->root_comc, 8);
-    hasher_update_words(hs, whole->root_hash, 8);
+    hasher_update_words(hs, whole->root_hash, dapol_dlen(whole->hash_id) / 4);
     hasher_update(hs, tail, 24);
     hasher_final(hs, out);
     memcpy(key, out, 32);
@@ -100,7 +104,8 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
     uint64_t sf;
     int rc = policy_plan(H, aggregation_factor, policy, groups, sf);
     if (rc) return rc;
-    const uint64_t size = dapol_inclusion_proof_size((int)H, aggregation_factor, policy);
+    const uint64_t size = dapol_inclusion_proof_size_d((int)H, aggregation_factor, policy, t->hash_id);
+    const bool b2b = t->ns.hash_hi != nullptr;  // 64-byte digests: a sibling is com || hash lo || hash hi
     if (proof_size) *proof_size = size;
     if (!out || cap < k * size) return DAPOL_ERR_BUFFER;
     uint8_t key[32];
@@ -116,12 +121,12 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
     for (auto &g : groups) agg_bytes += dapol_rangeproof_size(64, (int)g.m);
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 3 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256 + Arena::need(rows, 8) +
+    ar.size = Arena::need(k, 8) + Arena::need(kh, 8) + 4 * Arena::need(kh, 32) + 2 * Arena::need(k, 32) + 256 + Arena::need(rows, 8) +
               Arena::need(rows, 32) + 2 * Arena::need(rows, 8) + Arena::need(k * agg_bytes, 1) + Arena::need(k * nsingle + 1, SINGLE_PROOF_BYTE_NUM);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint64_t *d_li = ar.take<uint64_t>(k), *d_v = ar.take<uint64_t>(kh);
-    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8);
+    uint32_t *d_r = ar.take<uint32_t>(kh * 8), *d_c = ar.take<uint32_t>(kh * 8), *d_h = ar.take<uint32_t>(kh * 8), *d_hh = ar.take<uint32_t>(kh * 8);
     uint32_t *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8);
     int *d_nf = ar.take<int>(1), nf = 0;
     uint64_t *g_v = ar.take<uint64_t>(rows);
@@ -131,7 +136,7 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
 #define FAIL(code) do { dfree(mem, st); return (code); } while (0)
     cudaMemsetAsync(d_nf, 0, 4, st);
     cudaMemcpyAsync(d_li, leaf_idx, k * 8, cudaMemcpyHostToDevice, st);
-    rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf);
+    rc = dapol_tree_paths_dev(t, k, d_li, d_v, d_r, d_c, d_h, d_lc, d_lh, d_nf, b2b ? d_hh : nullptr, nullptr);
     if (rc) FAIL(rc);
     cudaMemcpyAsync(&nf, d_nf, 4, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) FAIL(DAPOL_ERR_CUDA);
@@ -158,10 +163,11 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
         if (rc) FAIL(rc);
     }
     // host assembly of DapolProof::serialize = R::serialize || MerkleProof::serialize
-    std::vector<uint8_t> h_agg(k * agg_bytes), h_single(k * nsingle * SINGLE_PROOF_BYTE_NUM), h_c(kh * 32), h_h(kh * 32);
+    std::vector<uint8_t> h_agg(k * agg_bytes), h_single(k * nsingle * SINGLE_PROOF_BYTE_NUM), h_c(kh * 32), h_h(kh * 32), h_hh(b2b ? kh * 32 : 0);
     if (agg_bytes) cudaMemcpyAsync(h_agg.data(), d_agg, h_agg.size(), cudaMemcpyDeviceToHost, st);
     if (nsingle) cudaMemcpyAsync(h_single.data(), d_single, h_single.size(), cudaMemcpyDeviceToHost, st);
     if (H) { cudaMemcpyAsync(h_c.data(), d_c, kh * 32, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h_h.data(), d_h, kh * 32, cudaMemcpyDeviceToHost, st); }
+    if (H && b2b) cudaMemcpyAsync(h_hh.data(), d_hh, kh * 32, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) FAIL(DAPOL_ERR_CUDA);
     dfree(mem, st);
 #undef FAIL
@@ -187,6 +193,7 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
             memcpy(o, h_c.data() + (p * H + s) * 32, 32);
             memcpy(o + 32, h_h.data() + (p * H + s) * 32, 32);
             o += 64;
+            if (b2b) { memcpy(o, h_hh.data() + (p * H + s) * 32, 32); o += 32; }
         }
     }
     return DAPOL_OK;
@@ -200,6 +207,36 @@ __global__ void __launch_bounds__(64) k_merkle_fold(uint64_t k, int hash_id, con
                                                     uint8_t *ok) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= k || !ok[p]) return;
+    if (hash_id == DAPOL_HASH_BLAKE2B) {  // 64-byte digests: leaf_h = [k][16], root = com (8) | hash (16), siblings of 96 bytes
+        uint32_t curc[8], curl[8], curu[8], sc_[8], sl[8], su[8];
+        load8(curc, leaf_c + 8 * p); load8(curl, leaf_h + 16 * p); load8(curu, leaf_h + 16 * p + 8);
+        ge cur, s;
+        int good = ge_decompress(cur, curc);
+        const uint8_t *sib = blob + sib_off[p];
+        const uint32_t H = heights[p];
+        const uint64_t x = idx[p];
+#pragma unroll 1
+        for (uint32_t lv = 0; lv < H && good; lv++) {
+            for (int i = 0; i < 8; i++) {
+                const uint8_t *a = sib + 96 * lv + 4 * i;
+                sc_[i] = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);
+                sl[i] = (uint32_t)a[32] | ((uint32_t)a[33] << 8) | ((uint32_t)a[34] << 16) | ((uint32_t)a[35] << 24);
+                su[i] = (uint32_t)a[64] | ((uint32_t)a[65] << 8) | ((uint32_t)a[66] << 16) | ((uint32_t)a[67] << 24);
+            }
+            good &= ge_decompress(s, sc_);
+            uint32_t lo[8], hi[8];
+            if ((x >> lv) & 1) dapol_b2b_hash192(lo, hi, sc_, curc, sl, su, curl, curu);
+            else dapol_b2b_hash192(lo, hi, curc, sc_, curl, curu, sl, su);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { curl[i] = lo[i]; curu[i] = hi[i]; }
+            ge_add(cur, cur, s);
+            ge_compress(curc, cur);
+        }
+        uint32_t d = 0;
+        for (int i = 0; i < 8; i++) d |= (curc[i] ^ root[i]) | (curl[i] ^ root[8 + i]) | (curu[i] ^ root[16 + i]);
+        ok[p] = (uint8_t)(good && d == 0);
+        return;
+    }
     uint32_t curc[8], curh[8], sc_[8], sh[8];
     load8(curc, leaf_c + 8 * p); load8(curh, leaf_h + 8 * p);
     ge cur, s;
@@ -234,7 +271,7 @@ struct ParsedProof {
     uint64_t nind = 0, ind_off = 0, H = 0, idx = 0, sib_off = 0;
 };
 // DapolProof::deserialize (src/proof/mod.rs:76-84): R::deserialize then MerkleProof::deserialize; any framing error rejects
-static ParsedProof parse_proof(const uint8_t *p, uint64_t base, uint64_t len, int policy) {
+static ParsedProof parse_proof(const uint8_t *p, uint64_t base, uint64_t len, int policy, uint64_t ss /* bytes of one sibling: 32 + Dlen */) {
     ParsedProof r;
     uint64_t pos = 0, nagg = 1;
 #define NEED(n) do { if (len - pos < (uint64_t)(n)) return r; } while (0)
@@ -259,7 +296,7 @@ static ParsedProof parse_proof(const uint8_t *p, uint64_t base, uint64_t len, in
     if (nb && r.H != 64) r.idx >>= (8 * nb - r.H);
     pos += nb;
     uint64_t nsib = get_be(p + pos, 8); pos += 8;
-    if (nsib != r.H || (len - pos) / 64 < nsib) return r;
+    if (nsib != r.H || (len - pos) / ss < nsib) return r;
     r.sib_off = base + pos;
     if (r.nind > nsib) return r;  // reference: usize underflow panic (padding.rs:171, splitting.rs:182)
 #undef NEED
@@ -271,7 +308,8 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
                                   const uint8_t *leaf_coms, const uint8_t *leaf_hashes, const uint8_t *proofs, const uint64_t *offsets,
                                   uint8_t *ok) {
     if (!ctx || !root_com || !root_hash || !leaf_coms || !leaf_hashes || !proofs || !offsets || !ok || !k) return DAPOL_ERR_BAD_ARG;
-    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    const uint64_t dl = (uint64_t)dapol_digest_len(hash_id), ss = 32 + dl;  // root_hash / leaf_hashes: dl bytes each
+    if (!dl) return DAPOL_ERR_INVALID_DIGEST_SIZE;
     if (policy != DAPOL_POLICY_PADDING && policy != DAPOL_POLICY_SPLITTING) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -281,7 +319,7 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
     std::vector<uint32_t> h_H(k);
     for (uint64_t p = 0; p < k; p++) {
         if (offsets[p + 1] < offsets[p] || offsets[p + 1] > total) return DAPOL_ERR_BAD_ARG;
-        pp[p] = parse_proof(proofs + offsets[p], offsets[p], offsets[p + 1] - offsets[p], policy);
+        pp[p] = parse_proof(proofs + offsets[p], offsets[p], offsets[p + 1] - offsets[p], policy, ss);
         ok[p] = pp[p].ok ? 1 : 0;
         h_sib[p] = pp[p].sib_off; h_idx[p] = pp[p].idx; h_H[p] = (uint32_t)pp[p].H;
     }
@@ -305,21 +343,21 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
     }
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = Arena::need(total + 1, 1) + 2 * Arena::need(k, 8) + Arena::need(k, 4) + 2 * Arena::need(k, 32) + 256 + Arena::need(k, 1);
+    ar.size = Arena::need(total + 1, 1) + 2 * Arena::need(k, 8) + Arena::need(k, 4) + 3 * Arena::need(k, 32) + 256 + Arena::need(k, 1);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     uint8_t *d_blob = ar.take<uint8_t>(total + 1);
     uint64_t *d_sib = ar.take<uint64_t>(k), *d_idx = ar.take<uint64_t>(k);
-    uint32_t *d_H = ar.take<uint32_t>(k), *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 8), *d_root = ar.take<uint32_t>(16);
+    uint32_t *d_H = ar.take<uint32_t>(k), *d_lc = ar.take<uint32_t>(k * 8), *d_lh = ar.take<uint32_t>(k * 16), *d_root = ar.take<uint32_t>(24);
     uint8_t *d_ok = ar.take<uint8_t>(k);
     cudaMemcpyAsync(d_blob, proofs, total, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_sib, h_sib.data(), k * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_idx, h_idx.data(), k * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_H, h_H.data(), k * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_lc, leaf_coms, k * 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_lh, leaf_hashes, k * 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_lh, leaf_hashes, k * dl, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_root, root_com, 32, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_root + 8, root_hash, 32, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_root + 8, root_hash, dl, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_ok, ok, k, cudaMemcpyHostToDevice, st);
     k_merkle_fold<<<grid_for(k, 64), 64, 0, st>>>(k, hash_id, d_blob, d_sib, d_H, d_idx, d_lc, d_lh, d_root, d_ok);
     ctx->launches++;
@@ -344,7 +382,7 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
             const Item &it = items[i];
             memcpy(hp.data() + i * plen, proofs + it.off, plen);
             const uint8_t *sib = proofs + pp[it.p].sib_off;
-            for (uint64_t j = 0; j < m; j++) memcpy(hc.data() + (i * m + j) * 32, j < it.count ? sib + 64 * (it.first + j) : com_padding, 32);
+            for (uint64_t j = 0; j < m; j++) memcpy(hc.data() + (i * m + j) * 32, j < it.count ? sib + ss * (it.first + j) : com_padding, 32);
         }
         int rc = dapol_rangeproof_verify_batch(ctx, 64, (int)m, items.size(), hp.data(), plen, hc.data(), hok.data());
         if (rc) return rc;
@@ -358,7 +396,7 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
 extern "C" int dapol_prove_to_file(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
                                    const uint8_t seed[32], uint64_t chunk, const char *path, uint64_t *proof_size) {
     if (!t || !leaf_idx || !seed || !k || !path) return DAPOL_ERR_BAD_ARG;
-    const uint64_t size = dapol_inclusion_proof_size(dapol_total_height(t), aggregation_factor, policy);
+    const uint64_t size = dapol_inclusion_proof_size_d(dapol_total_height(t), aggregation_factor, policy, t->hash_id);
     if (proof_size) *proof_size = size;
     if (size == 0) return DAPOL_ERR_BAD_ARG;
     if (chunk == 0) chunk = 8192;
@@ -398,7 +436,7 @@ static std::vector<SibRef> batch_sibling_plan(int height, uint64_t k, const uint
     }
     return plan;
 }
-static uint64_t batch_merkle_bytes(uint64_t H, uint64_t k, uint64_t nsib) { return 2 + 8 + k * ((H + 7) / 8) + 8 + 64 * nsib; }
+static uint64_t batch_merkle_bytes(uint64_t H, uint64_t k, uint64_t nsib, uint64_t dl) { return 2 + 8 + k * ((H + 7) / 8) + 8 + (32 + dl) * nsib; }
 static uint64_t range_part_bytes(uint64_t nsib, uint64_t agg, int policy) {
     std::vector<AggGroup> g;
     uint64_t sf;
@@ -408,15 +446,19 @@ static uint64_t range_part_bytes(uint64_t nsib, uint64_t agg, int policy) {
     return sz + 8 + SINGLE_PROOF_BYTE_NUM * (nsib - sf);
 }
 extern "C" uint64_t dapol_batch_proof_size(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy) {
-    if (!leaf_idx || k == 0 || height < 0 || height > 64) return 0;
-    if (k == 1) return dapol_inclusion_proof_size(height, aggregation_factor, policy);
+    return dapol_batch_proof_size_d(height, k, leaf_idx, aggregation_factor, policy, DAPOL_HASH_BLAKE3);
+}
+extern "C" uint64_t dapol_batch_proof_size_d(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy, int hash_id) {
+    const uint64_t dl = (uint64_t)dapol_digest_len(hash_id);
+    if (!dl || !leaf_idx || k == 0 || height < 0 || height > 64) return 0;
+    if (k == 1) return dapol_inclusion_proof_size_d(height, aggregation_factor, policy, hash_id);
     for (uint64_t i = 0; i < k; i++) if ((i && leaf_idx[i] <= leaf_idx[i - 1]) || (height < 64 && (leaf_idx[i] >> height))) return 0;
     const uint64_t nsib = batch_sibling_plan(height, k, leaf_idx).size(), rs = range_part_bytes(nsib, aggregation_factor, policy);
-    return rs ? rs + batch_merkle_bytes((uint64_t)height, k, nsib) : 0;
+    return rs ? rs + batch_merkle_bytes((uint64_t)height, k, nsib, dl) : 0;
 }
 // node (level h, tree index x) of the store: levels are kept in tree order, so a binary search over the level's indexes finds it
 __global__ void k_fetch_nodes(uint64_t n, const int *lvl, const uint64_t *idx, NodeStore ns, const uint64_t *level_off, const uint64_t *level_n,
-                              uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint8_t *o_pad, int *not_found) {
+                              uint64_t *o_v, uint32_t *o_r, uint32_t *o_c, uint32_t *o_h, uint8_t *o_pad, int *not_found, uint32_t *o_hh) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const uint64_t off = level_off[lvl[j]];
@@ -428,6 +470,7 @@ __global__ void k_fetch_nodes(uint64_t n, const int *lvl, const uint64_t *idx, N
     load8(w, ns.r + 8 * g); store8(o_r + 8 * j, w);
     load8(w, ns.comc + 8 * g); store8(o_c + 8 * j, w);
     load8(w, ns.hash + 8 * g); store8(o_h + 8 * j, w);
+    if (o_hh && ns.hash_hi) { load8(w, ns.hash_hi + 8 * g); store8(o_hh + 8 * j, w); }
     o_pad[j] = ns.is_pad[g];
 }
 // nonce key of a batch of more than one leaf: the tree's prover key chained over the leaf indexes, 64 per link; stream 0
@@ -460,7 +503,8 @@ extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const
     if (t->top) return DAPOL_ERR_BAD_ARG;  // a batch may straddle shards: build it on the rank that holds a single tree
     dapol_ctx *ctx = t->ctx;
     const int H = t->height;
-    const uint64_t size = dapol_batch_proof_size(H, k, leaf_idx, aggregation_factor, policy);
+    const uint64_t size = dapol_batch_proof_size_d(H, k, leaf_idx, aggregation_factor, policy, t->hash_id);
+    const bool b2b = t->ns.hash_hi != nullptr;
     if (proof_size) *proof_size = size;
     if (!size) return DAPOL_ERR_BAD_ARG;  // unsorted indexes (smtree rejects), aggregation_factor > #siblings (reference: slice panic)
     if (!out || cap < size) return DAPOL_ERR_BUFFER;
@@ -484,13 +528,14 @@ extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const
     const uint64_t rows = std::max<uint64_t>(max_m, std::max<uint64_t>(nsingle, 1));
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = Arena::need(nf_items, 4) + 2 * Arena::need(nf_items, 8) + 3 * Arena::need(nf_items, 32) + Arena::need(nf_items, 1) + 3 * 256 + Arena::need(65, 8) +
+    ar.size = Arena::need(nf_items, 4) + 2 * Arena::need(nf_items, 8) + 4 * Arena::need(nf_items, 32) + Arena::need(nf_items, 1) + 3 * 256 + Arena::need(65, 8) +
               Arena::need(rows, 8) + Arena::need(rows, 32) + 2 * Arena::need(rows, 8) + Arena::need(agg_bytes + 1, 1) + Arena::need(nsingle + 1, SINGLE_PROOF_BYTE_NUM);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     int *d_lvl = ar.take<int>(nf_items);
     uint64_t *d_idx = ar.take<uint64_t>(nf_items), *d_v = ar.take<uint64_t>(nf_items);
     uint32_t *d_r = ar.take<uint32_t>(nf_items * 8), *d_c = ar.take<uint32_t>(nf_items * 8), *d_h = ar.take<uint32_t>(nf_items * 8);
+    uint32_t *d_hh = ar.take<uint32_t>(nf_items * 8);
     uint8_t *d_pad = ar.take<uint8_t>(nf_items);
     int *d_nf = ar.take<int>(1);
     uint64_t *d_zero = ar.take<uint64_t>(1), *d_level_n = ar.take<uint64_t>(65);
@@ -503,7 +548,7 @@ extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const
     cudaMemcpyAsync(d_lvl, h_lvl.data(), nf_items * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_idx, h_idx.data(), nf_items * 8, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_level_n, t->level_n.data(), (H + 1) * 8, cudaMemcpyHostToDevice, st);
-    k_fetch_nodes<<<grid_for(nf_items, 128), 128, 0, st>>>(nf_items, d_lvl, d_idx, t->ns, t->d_level_off, d_level_n, d_v, d_r, d_c, d_h, d_pad, d_nf);
+    k_fetch_nodes<<<grid_for(nf_items, 128), 128, 0, st>>>(nf_items, d_lvl, d_idx, t->ns, t->d_level_off, d_level_n, d_v, d_r, d_c, d_h, d_pad, d_nf, b2b ? d_hh : nullptr);
     ctx->launches++;
     int nf = 0;
     std::vector<uint8_t> h_pad(nf_items);
@@ -533,10 +578,11 @@ extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const
         int rc = dapol_rp_prove_dev(ctx, 64, 1, nsingle, g_v, reinterpret_cast<const uint8_t *>(g_r), key, g_s, g_b, d_single);
         if (rc) FAILB(rc);
     }
-    std::vector<uint8_t> h_agg(agg_bytes + 1), h_single(nsingle * SINGLE_PROOF_BYTE_NUM + 1), h_c(nsib * 32 + 1), h_h(nsib * 32 + 1);
+    std::vector<uint8_t> h_agg(agg_bytes + 1), h_single(nsingle * SINGLE_PROOF_BYTE_NUM + 1), h_c(nsib * 32 + 1), h_h(nsib * 32 + 1), h_hh(nsib * 32 + 1);
     if (agg_bytes) cudaMemcpyAsync(h_agg.data(), d_agg, agg_bytes, cudaMemcpyDeviceToHost, st);
     if (nsingle) cudaMemcpyAsync(h_single.data(), d_single, nsingle * SINGLE_PROOF_BYTE_NUM, cudaMemcpyDeviceToHost, st);
     if (nsib) { cudaMemcpyAsync(h_c.data(), d_c + 8 * k, nsib * 32, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(h_h.data(), d_h + 8 * k, nsib * 32, cudaMemcpyDeviceToHost, st); }
+    if (nsib && b2b) cudaMemcpyAsync(h_hh.data(), d_hh + 8 * k, nsib * 32, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) FAILB(DAPOL_ERR_CUDA);
     dfree(mem, st);
 #undef FAILB
@@ -555,23 +601,27 @@ extern "C" int dapol_generate_proof_batch(const dapol_tree *t, uint64_t k, const
     put_be(o, k, 8); o += 8;
     for (uint64_t i = 0; i < k; i++) if (nb) { put_be(o, Hu == 64 ? leaf_idx[i] : leaf_idx[i] << (8 * nb - Hu), (int)nb); o += nb; }
     put_be(o, nsib, 8); o += 8;
-    for (uint64_t s = 0; s < nsib; s++) { memcpy(o, h_c.data() + s * 32, 32); memcpy(o + 32, h_h.data() + s * 32, 32); o += 64; }
+    for (uint64_t s = 0; s < nsib; s++) {
+        memcpy(o, h_c.data() + s * 32, 32); memcpy(o + 32, h_h.data() + s * 32, 32); o += 64;
+        if (b2b) { memcpy(o, h_hh.data() + s * 32, 32); o += 32; }
+    }
     return DAPOL_OK;
 }
 
 // ---- verify_batch: MerkleProof::verify_batch as level-synchronous merges on the device (DapolProofNode::merge,
 // src/proof/node.rs:56-69), then R::verify over the siblings' commitments in proof order.
-struct BatchNode { uint32_t ext[32], c[8], h[8]; };
+struct BatchNode { uint32_t ext[32], c[8], h[16]; };  // h: 8 words, or 16 (lo | hi) for 64-byte digests
 // working nodes 0..k-1 = the leaves, k.. = the proof's siblings: decompress (non-canonical points reject, proof/node.rs:81-102)
-__global__ void __launch_bounds__(64) k_batch_init(uint64_t n, const uint32_t *coms, const uint32_t *hashes, BatchNode *nodes, int *bad) {
+__global__ void __launch_bounds__(64) k_batch_init(uint64_t n, const uint32_t *coms, const uint32_t *hashes, BatchNode *nodes, int *bad, int hw /* words per hash */) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t c[8], h[8];
-    load8(c, coms + 8 * j); load8(h, hashes + 8 * j);
+    load8(c, coms + 8 * j); load8(h, hashes + (uint64_t)hw * j);
     ge p;
     if (!ge_decompress(p, c)) { *bad = 1; return; }
     rp_store_ext(nodes[j].ext, p);
     store8(nodes[j].c, c); store8(nodes[j].h, h);
+    if (hw == 16) { load8(h, hashes + 16 * j + 8); store8(nodes[j].h + 8, h); }
 }
 // one level: parent j = merge(nodes[left[j]], nodes[right[j]]) written at nodes[dst0 + j]
 __global__ void __launch_bounds__(64) k_batch_merge_level(uint64_t n, const uint32_t *left, const uint32_t *right, uint64_t dst0, BatchNode *nodes, int hash_id) {
@@ -583,9 +633,14 @@ __global__ void __launch_bounds__(64) k_batch_merge_level(uint64_t n, const uint
     ge_add(s, a, b);
     uint32_t cl[8], cr[8], hl[8], hr[8], hh[8], cc[8];
     load8(cl, l.c); load8(cr, r.c); load8(hl, l.h); load8(hr, r.h);
-    dapol_hash128(hash_id, hh, cl, cr, hl, hr);
-    ge_compress(cc, s);
     BatchNode &o = nodes[dst0 + j];
+    if (hash_id == DAPOL_HASH_BLAKE2B) {
+        uint32_t hlu[8], hru[8], hu[8];
+        load8(hlu, l.h + 8); load8(hru, r.h + 8);
+        dapol_b2b_hash192(hh, hu, cl, cr, hl, hlu, hr, hru);
+        store8(o.h + 8, hu);
+    } else dapol_hash128(hash_id, hh, cl, cr, hl, hr);
+    ge_compress(cc, s);
     rp_store_ext(o.ext, s);
     store8(o.c, cc); store8(o.h, hh);
 }
@@ -595,7 +650,7 @@ struct ParsedBatch {
     uint64_t nind = 0, ind_off = 0, H = 0, nsib = 0, sib_off = 0;
     std::vector<uint64_t> idx;
 };
-static ParsedBatch parse_batch_proof(const uint8_t *p, uint64_t len, int policy) {
+static ParsedBatch parse_batch_proof(const uint8_t *p, uint64_t len, int policy, uint64_t ss) {
     ParsedBatch r;
     uint64_t pos = 0, nagg = 1;
 #define NEED(n) do { if (len - pos < (uint64_t)(n)) return r; } while (0)
@@ -623,7 +678,7 @@ static ParsedBatch parse_batch_proof(const uint8_t *p, uint64_t len, int policy)
     }
     NEED(8);
     r.nsib = get_be(p + pos, 8); pos += 8;
-    if ((len - pos) / 64 < r.nsib || r.nind > r.nsib) return r;
+    if ((len - pos) / ss < r.nsib || r.nind > r.nsib) return r;
     r.sib_off = pos;
 #undef NEED
     r.ok = true;
@@ -632,10 +687,11 @@ static ParsedBatch parse_batch_proof(const uint8_t *p, uint64_t len, int policy)
 extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
                                         const uint8_t *leaf_coms, const uint8_t *leaf_hashes, const uint8_t *proof, uint64_t proof_len, uint8_t *ok) {
     if (!ctx || !root_com || !root_hash || !leaf_coms || !leaf_hashes || !proof || !ok || !k) return DAPOL_ERR_BAD_ARG;
-    if (hash_id != DAPOL_HASH_BLAKE3 && hash_id != DAPOL_HASH_BLAKE2S) return DAPOL_ERR_INVALID_DIGEST_SIZE;
+    const uint64_t dl = (uint64_t)dapol_digest_len(hash_id), ss = 32 + dl;  // root_hash / leaf_hashes: dl bytes each
+    if (!dl) return DAPOL_ERR_INVALID_DIGEST_SIZE;
     if (policy != DAPOL_POLICY_PADDING && policy != DAPOL_POLICY_SPLITTING) return DAPOL_ERR_BAD_ARG;
     *ok = 0;
-    const ParsedBatch pb = parse_batch_proof(proof, proof_len, policy);
+    const ParsedBatch pb = parse_batch_proof(proof, proof_len, policy, ss);
     if (!pb.ok || pb.idx.size() != k) return DAPOL_OK;  // malformed bytes / wrong number of leaves: a reject, never an error
     const std::vector<SibRef> plan = batch_sibling_plan((int)pb.H, k, pb.idx.data());
     if (plan.size() != pb.nsib) return DAPOL_OK;
@@ -668,18 +724,18 @@ extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy,
     if (n_work >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    std::vector<uint8_t> h_c((k + nsib) * 32), h_h((k + nsib) * 32);
-    memcpy(h_c.data(), leaf_coms, k * 32); memcpy(h_h.data(), leaf_hashes, k * 32);
+    std::vector<uint8_t> h_c((k + nsib) * 32), h_h((k + nsib) * dl);
+    memcpy(h_c.data(), leaf_coms, k * 32); memcpy(h_h.data(), leaf_hashes, k * dl);
     for (uint64_t s = 0; s < nsib; s++) {
-        memcpy(h_c.data() + (k + s) * 32, proof + pb.sib_off + 64 * s, 32);
-        memcpy(h_h.data() + (k + s) * 32, proof + pb.sib_off + 64 * s + 32, 32);
+        memcpy(h_c.data() + (k + s) * 32, proof + pb.sib_off + ss * s, 32);
+        memcpy(h_h.data() + (k + s) * dl, proof + pb.sib_off + ss * s + 32, dl);
     }
     uint8_t *mem = nullptr;
     Arena ar;
-    ar.size = 2 * Arena::need(k + nsib, 32) + Arena::need(n_work, sizeof(BatchNode)) + 2 * Arena::need(left.size() + 1, 4) + 256;
+    ar.size = 3 * Arena::need(k + nsib, 32) + Arena::need(n_work, sizeof(BatchNode)) + 2 * Arena::need(left.size() + 1, 4) + 256;
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
-    uint32_t *d_c = ar.take<uint32_t>((k + nsib) * 8), *d_h = ar.take<uint32_t>((k + nsib) * 8);
+    uint32_t *d_c = ar.take<uint32_t>((k + nsib) * 8), *d_h = ar.take<uint32_t>((k + nsib) * 16);
     BatchNode *nodes = ar.take<BatchNode>(n_work);
     uint32_t *d_l = ar.take<uint32_t>(left.size() + 1), *d_r = ar.take<uint32_t>(left.size() + 1);
     int *d_bad = ar.take<int>(1), bad = 0;
@@ -690,7 +746,7 @@ extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy,
         cudaMemcpyAsync(d_l, left.data(), left.size() * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_r, right.data(), right.size() * 4, cudaMemcpyHostToDevice, st);
     }
-    k_batch_init<<<grid_for(k + nsib, 64), 64, 0, st>>>(k + nsib, d_c, d_h, nodes, d_bad);
+    k_batch_init<<<grid_for(k + nsib, 64), 64, 0, st>>>(k + nsib, d_c, d_h, nodes, d_bad, (int)(dl / 4));
     ctx->launches++;
     uint64_t dst = k + nsib;
     for (size_t l = 0; l < lvl_first.size(); l++) {
@@ -699,16 +755,16 @@ extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy,
         ctx->launches++;
         dst += lvl_count[l];
     }
-    uint32_t top[16];
+    uint32_t top[24];
     const BatchNode *root_node = nodes + (n_work - 1);  // height 0: the single leaf itself (k == 1, no merges)
     cudaMemcpyAsync(top, root_node->c, 32, cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(top + 8, root_node->h, 32, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(top + 8, root_node->h, dl, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     dfree(mem, st);
     CUDA_TRY(e);
-    if (bad || memcmp(top, root_com, 32) || memcmp(top + 8, root_hash, 32)) return DAPOL_OK;
+    if (bad || memcmp(top, root_com, 32) || memcmp(top + 8, root_hash, dl)) return DAPOL_OK;
     // R::verify on the siblings' commitments (padding.rs:168-197 / splitting.rs:180-211)
     const uint64_t n_agg_coms = nsib - pb.nind;
     std::vector<AggGroup> groups;
@@ -728,14 +784,14 @@ extern "C" int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy,
         if (pb.agg[gi].second != dapol_rangeproof_size(64, (int)g.m)) return DAPOL_OK;
         std::vector<uint8_t> hc(g.m * 32);
         uint8_t one = 0;
-        for (uint64_t j = 0; j < g.m; j++) memcpy(hc.data() + j * 32, j < g.count ? sib + 64 * (g.start + j) : com_padding, 32);
+        for (uint64_t j = 0; j < g.m; j++) memcpy(hc.data() + j * 32, j < g.count ? sib + ss * (g.start + j) : com_padding, 32);
         int rc = dapol_rangeproof_verify_batch(ctx, 64, (int)g.m, 1, proof + pb.agg[gi].first, pb.agg[gi].second, hc.data(), &one);
         if (rc) return rc;
         if (!one) return DAPOL_OK;
     }
     if (pb.nind) {
         std::vector<uint8_t> hc(pb.nind * 32), oks(pb.nind);
-        for (uint64_t s = 0; s < pb.nind; s++) memcpy(hc.data() + s * 32, sib + 64 * (n_agg_coms + s), 32);
+        for (uint64_t s = 0; s < pb.nind; s++) memcpy(hc.data() + s * 32, sib + ss * (n_agg_coms + s), 32);
         int rc = dapol_rangeproof_verify_batch(ctx, 64, 1, pb.nind, proof + pb.ind_off, SINGLE_PROOF_BYTE_NUM, hc.data(), oks.data());
         if (rc) return rc;
         for (uint8_t v : oks) if (!v) return DAPOL_OK;

@@ -339,6 +339,7 @@ struct NodeStore {
     uint32_t *hash;    // [T][8] node hash
     uint32_t *ext;     // [T][32] com in extended coordinates X,Y,Z,T (build-time only)
     uint8_t *is_pad;   // [T]
+    uint32_t *hash_hi; // [T][8] upper half of a 64-byte node hash (D = Blake2b, DAPOL_HASH_BLAKE2B); nullptr for 32-byte digests
 };
 
 DAPOL_HD_INLINE void store_ge(uint32_t *dst, const ge &p) {

@@ -105,6 +105,85 @@ DAPOL_HD_INLINE void blake2s_iv(uint32_t h[8]) {
     h[0] ^= 0x01010020u;
 }
 
+// ---------------------------------------------------------------- BLAKE2b-512 (64-byte digests: blake2::Blake2b, src/tests.rs:104-105)
+// The reference reaches it through new_blank + build only (Dapol::new insists on 32-byte digests, mod.rs:101-103).  A node's
+// 64-byte hash is kept as two 32-byte halves (NodeStore::hash / hash_hi), so every 32-byte code path is untouched.
+#ifndef DAPOL_HASH_BLAKE2B
+#define DAPOL_HASH_BLAKE2B 2
+#endif
+#define B2B_G(a, b, c, d, x, y)                        \
+    a = a + b + (x); d = rotl64(d ^ a, 32);            \
+    c = c + d;       b = rotl64(b ^ c, 40);            \
+    a = a + b + (y); d = rotl64(d ^ a, 48);            \
+    c = c + d;       b = rotl64(b ^ c, 1);
+#define B2B_ROUND(a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15) \
+    B2B_G(v0, v4, v8, v12, m[a0], m[a1]);                                               \
+    B2B_G(v1, v5, v9, v13, m[a2], m[a3]);                                               \
+    B2B_G(v2, v6, v10, v14, m[a4], m[a5]);                                              \
+    B2B_G(v3, v7, v11, v15, m[a6], m[a7]);                                              \
+    B2B_G(v0, v5, v10, v15, m[a8], m[a9]);                                              \
+    B2B_G(v1, v6, v11, v12, m[a10], m[a11]);                                            \
+    B2B_G(v2, v7, v8, v13, m[a12], m[a13]);                                             \
+    B2B_G(v3, v4, v9, v14, m[a14], m[a15]);
+DAPOL_HD_INLINE void blake2b_compress(uint64_t h[8], const uint64_t m[16], uint64_t t, int last) {
+    uint64_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    uint64_t v8 = 0x6a09e667f3bcc908ull, v9 = 0xbb67ae8584caa73bull, v10 = 0x3c6ef372fe94f82bull, v11 = 0xa54ff53a5f1d36f1ull;
+    uint64_t v12 = 0x510e527fade682d1ull ^ t, v13 = 0x9b05688c2b3e6c1full, v14 = 0x1f83d9abfb41bd6bull, v15 = 0x5be0cd19137e2179ull;
+    if (last) v14 = ~v14;
+    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+    B2B_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+    B2B_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+    B2B_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+    B2B_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+    B2B_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+    B2B_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+    B2B_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+    B2B_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+    h[0] ^= v0 ^ v8; h[1] ^= v1 ^ v9; h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+    h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+DAPOL_HD_INLINE void blake2b_iv512(uint64_t h[8]) {
+    h[0] = 0x6a09e667f3bcc908ull ^ 0x01010040ull; h[1] = 0xbb67ae8584caa73bull; h[2] = 0x3c6ef372fe94f82bull; h[3] = 0xa54ff53a5f1d36f1ull;
+    h[4] = 0x510e527fade682d1ull; h[5] = 0x9b05688c2b3e6c1full; h[6] = 0x1f83d9abfb41bd6bull; h[7] = 0x5be0cd19137e2179ull;
+}
+DAPOL_HD_INLINE uint64_t b2b_pair(const uint32_t *w) { return (uint64_t)w[0] | ((uint64_t)w[1] << 32); }
+DAPOL_HD_INLINE void b2b_out(uint32_t lo[8], uint32_t hi[8], const uint64_t h[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        lo[2 * i] = (uint32_t)h[i]; lo[2 * i + 1] = (uint32_t)(h[i] >> 32);
+        hi[2 * i] = (uint32_t)h[4 + i]; hi[2 * i + 1] = (uint32_t)(h[4 + i] >> 32);
+    }
+}
+// Blake2b(32-byte string) -> 64 bytes as two halves        -- DapolNode::new: D(compress(com))   (node.rs:33-36)
+DAPOL_HD_INLINE void dapol_b2b_hash32(uint32_t lo[8], uint32_t hi[8], const uint32_t in[8]) {
+    uint64_t h[8], m[16];
+    blake2b_iv512(h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) m[i] = b2b_pair(in + 2 * i);
+#pragma unroll
+    for (int i = 4; i < 16; i++) m[i] = 0;
+    blake2b_compress(h, m, 32, 1);
+    b2b_out(lo, hi, h);
+}
+// Blake2b(C(L) || C(R) || H(L) || H(R)), 32 + 32 + 64 + 64 = 192 bytes   -- Mergeable::merge (node.rs:66-70)
+DAPOL_HD_INLINE void dapol_b2b_hash192(uint32_t lo[8], uint32_t hi[8], const uint32_t cl[8], const uint32_t cr[8], const uint32_t hl_lo[8],
+                                       const uint32_t hl_hi[8], const uint32_t hr_lo[8], const uint32_t hr_hi[8]) {
+    uint64_t h[8], m[16];
+    blake2b_iv512(h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { m[i] = b2b_pair(cl + 2 * i); m[4 + i] = b2b_pair(cr + 2 * i); m[8 + i] = b2b_pair(hl_lo + 2 * i); m[12 + i] = b2b_pair(hl_hi + 2 * i); }
+    blake2b_compress(h, m, 128, 0);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { m[i] = b2b_pair(hr_lo + 2 * i); m[4 + i] = b2b_pair(hr_hi + 2 * i); }
+#pragma unroll
+    for (int i = 8; i < 16; i++) m[i] = 0;
+    blake2b_compress(h, m, 192, 1);
+    b2b_out(lo, hi, h);
+}
+
 // ---------------------------------------------------------------- D over fixed-size node inputs
 // hash = D(32-byte string)          -- DapolNode::new: D(compress(com))        (node.rs:33-36)
 DAPOL_HD_INLINE void dapol_hash32(int hash_id, uint32_t out[8], const uint32_t in[8]) {

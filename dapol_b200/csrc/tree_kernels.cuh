@@ -283,6 +283,29 @@ DAPOL_HD_INLINE void merge_hash_body(uint64_t j, const NodeStore &ns, uint64_t c
     dapol_hash128(hash_id, hh, cl, cr, hl, hr);
     store8(ns.hash + 8 * dest, hh);
 }
+// D = Blake2b (64-byte digests, src/tests.rs:104-105; new_blank + build only, mod.rs:101-103).  The IMAD-bound leaf / padding
+// kernels stay as they are (they leave a 32-byte placeholder in ns.hash); one extra pass hashes the compressed commitment of
+// every leaf-level and padding node -- DapolNode::new: D(compress(com)), node.rs:33-36 -- and the parents' hashes take the
+// 192-byte form of Mergeable::merge (node.rs:66-70).  The halves of a digest live in ns.hash / ns.hash_hi.
+DAPOL_HD_INLINE void leafpad_hash_b2b_body(uint64_t g, const NodeStore &ns, uint64_t leaf_level_off) {
+    if (g < leaf_level_off && !ns.is_pad[g]) return;  // internal node: hashed by its merge
+    uint32_t cc[8], lo[8], hi[8];
+    load8(cc, ns.comc + 8 * g);
+    dapol_b2b_hash32(lo, hi, cc);
+    store8(ns.hash + 8 * g, lo);
+    store8(ns.hash_hi + 8 * g, hi);
+}
+DAPOL_HD_INLINE void merge_hash_b2b_body(uint64_t j, const NodeStore &ns, uint64_t child_off, uint64_t parent_off, const uint32_t *parent_pos) {
+    uint64_t dest = parent_pos ? parent_off + parent_pos[j] : parent_off;
+    uint64_t l = child_off + 2 * j, r = l + 1;
+    uint32_t cl[8], cr[8], hl[8], hlh[8], hr[8], hrh[8], lo[8], hi[8];
+    load8(cl, ns.comc + 8 * l); load8(cr, ns.comc + 8 * r);
+    load8(hl, ns.hash + 8 * l); load8(hr, ns.hash + 8 * r);
+    load8(hlh, ns.hash_hi + 8 * l); load8(hrh, ns.hash_hi + 8 * r);
+    dapol_b2b_hash192(lo, hi, cl, cr, hl, hlh, hr, hrh);
+    store8(ns.hash + 8 * dest, lo);
+    store8(ns.hash_hi + 8 * dest, hi);
+}
 // Internal (non-leaf, non-padding) nodes of all levels as one flat unit range: unit u of level h (start[h] <= u <
 // start[h + 1], h = 0 .. H - 1) is the (u - start[h])-th real node of that level.
 struct InternalMap {

@@ -2,8 +2,11 @@
  *
  * Drop-in boundary for the reference crate MystenLabs/dapol (/root/reference): each entry point
  * names the reference interface it replaces.  The reference is generic Rust over a digest D and a
- * range-proof policy R; here D is `hash_id` (BLAKE3 or BLAKE2s-256, 32-byte digests only --
- * src/dapol/mod.rs:101-103) and R is `policy`.
+ * range-proof policy R; here D is `hash_id` and R is `policy`.  BLAKE3 and BLAKE2s-256 (32-byte digests) work on every
+ * entry point; Blake2b (64-byte digests, the other half of the reference's test matrix, src/tests.rs:104-105) works where
+ * the reference allows it: trees built from ready nodes (new_blank + build), their paths, proofs and verification --
+ * Dapol::new insists on 32 bytes (src/dapol/mod.rs:101-103), so the liability / sharded builds return
+ * DAPOL_ERR_INVALID_DIGEST_SIZE for it.  Wherever a buffer holds node hashes, one hash is dapol_digest_len(hash_id) bytes.
  *
  * Conventions: plain pointers and sizes, caller-allocated little-endian flat buffers, `int` return
  * (0 = ok; 1..5 mirror src/errors.rs DapolError variants; >= 16 are boundary errors), never unwinds.
@@ -61,6 +64,7 @@ extern "C" {
 
 #define DAPOL_HASH_BLAKE3 0   /* blake3::Hasher     (benches/dapol.rs:38, src/tests.rs:102-103) */
 #define DAPOL_HASH_BLAKE2S 1  /* blake2::Blake2s    (src/dapol/tests.rs:13,21) */
+#define DAPOL_HASH_BLAKE2B 2  /* blake2::Blake2b, 64-byte digests (src/tests.rs:104-105); ready-node trees only */
 
 #define DAPOL_POLICY_PADDING 0    /* RangeProofPadding   (src/range/padding.rs) */
 #define DAPOL_POLICY_SPLITTING 1  /* RangeProofSplitting (src/range/splitting.rs) */
@@ -100,6 +104,7 @@ DAPOL_API int dapol_ctx_set_padding_mode(dapol_ctx *ctx, int mode);
 #define DAPOL_LEAF_HASH_COMMITMENT 0
 #define DAPOL_LEAF_HASH_ID_SALT 1
 DAPOL_API int dapol_ctx_set_leaf_hash_mode(dapol_ctx *ctx, int mode);
+DAPOL_API int dapol_digest_len(int hash_id); /* bytes of one node hash: 32, 64 for DAPOL_HASH_BLAKE2B, 0 for an unknown id */
 DAPOL_API const char *dapol_strerror(int code);
 DAPOL_API const char *dapol_last_cuda_error(void);
 
@@ -216,7 +221,7 @@ DAPOL_API int dapol_sharded_build(dapol_ctx *ctx, dapol_comm *comm, int hash_id,
 DAPOL_API void dapol_tree_destroy(dapol_tree *tree);
 
 /* Dapol::root_raw / root   (src/dapol/mod.rs:134-141): commitment (compressed), hash, value, blinding. */
-DAPOL_API int dapol_tree_root(const dapol_tree *tree, uint8_t com[32], uint8_t hash[32], uint64_t *value, uint8_t blinding[32]);
+DAPOL_API int dapol_tree_root(const dapol_tree *tree, uint8_t com[32], uint8_t *hash /* digest_len */, uint64_t *value, uint8_t blinding[32]);
 
 /* Tree introspection for parity dumps: level 0 = root .. height = leaves; nodes of a level are in tree
  * order with the two children of a parent adjacent. */
@@ -226,7 +231,7 @@ DAPOL_API uint64_t dapol_tree_num_nodes(const dapol_tree *tree);
 DAPOL_API uint64_t dapol_tree_num_padding(const dapol_tree *tree);
 DAPOL_API uint64_t dapol_tree_level_size(const dapol_tree *tree, int level);
 DAPOL_API int dapol_tree_level_copy(const dapol_tree *tree, int level, uint64_t *idx, uint64_t *values, uint8_t *blindings,
-                          uint8_t *coms, uint8_t *hashes, uint8_t *is_padding); /* any pointer may be NULL */
+                          uint8_t *coms, uint8_t *hashes /* n*digest_len */, uint8_t *is_padding); /* any pointer may be NULL */
 /* id -> TreeIndex map of Dapol::new (id_to_idx_map, mod.rs:80,389): leaf index of the i-th input liability */
 DAPOL_API int dapol_tree_leaf_index_of(const dapol_tree *tree, uint64_t input_pos, uint64_t *leaf_idx);
 /* ... and by the internal id itself: Dapol::generate_proof_for_id / generate_proof_batch_for_ids (mod.rs:148-165) =
@@ -242,8 +247,8 @@ DAPOL_API int dapol_tree_index_of_batch(const dapol_tree *tree, uint64_t k, cons
 /* smtree get_merkle_path_ref_batch for one leaf (src/dapol/mod.rs:173-184): the K x height siblings,
  * leaf level first, with their secret (value, blinding) and public (com, hash) parts. */
 DAPOL_API int dapol_tree_paths(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t *values /* k*h */,
-                     uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*32 */,
-                     uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*32 or NULL */);
+                     uint8_t *blindings /* k*h*32 */, uint8_t *coms /* k*h*32 */, uint8_t *hashes /* k*h*digest_len */,
+                     uint8_t *leaf_coms /* k*32 or NULL */, uint8_t *leaf_hashes /* k*digest_len or NULL */);
 
 /* ---- persistence (the reference keeps the tree in memory only and leaves "write the proofs to a local
  * file" as a TODO, src/dapol/mod.rs:250).  dapol_tree_save writes the whole node store of a built tree (every level: index,
@@ -267,15 +272,16 @@ DAPOL_API int dapol_prove_to_file(const dapol_tree *tree, uint64_t k, const uint
  * k leaves run as a few large GPU batches (one per aggregate size, one of singles).  DAPOL_ERR_NOT_FOUND if a leaf index
  * is not a leaf of the tree (reference: None), DAPOL_ERR_BAD_ARG if aggregation_factor > height (reference: panic),
  * DAPOL_ERR_BUFFER (with *proof_size set) if cap < k * size. */
-DAPOL_API uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy);
+DAPOL_API uint64_t dapol_inclusion_proof_size(int height, uint64_t aggregation_factor, int policy);  /* 32-byte digests */
+DAPOL_API uint64_t dapol_inclusion_proof_size_d(int height, uint64_t aggregation_factor, int policy, int hash_id); /* sibling = com || hash: 32 + digest_len */
 DAPOL_API int dapol_prove_batch(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
                                 const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size);
 /* DapolProof::deserialize + verify (src/proof/mod.rs:41-47,76-95) for k proofs against one root: proof i is
  * proofs[offsets[i] .. offsets[i+1]), leaf i = DapolProofNode{leaf_coms[i], leaf_hashes[i]}.  ok[i] = 1 iff the Merkle
  * path folds to the root (DapolProofNode::merge, src/proof/node.rs:56-69) and R::verify accepts the siblings'
  * commitments (padding.rs:168-197 / splitting.rs:180-211).  Malformed bytes are a reject, never an error. */
-DAPOL_API int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
-                                 const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*32 */, const uint8_t *proofs,
+DAPOL_API int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t *root_hash /* digest_len */,
+                                 const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*digest_len */, const uint8_t *proofs,
                                  const uint64_t *offsets /* k+1 */, uint8_t *ok /* k */);
 
 /* ---- batch proofs: ONE DapolProof for several leaves.
@@ -289,13 +295,14 @@ DAPOL_API int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64
  * slice panic), if the indexes are not increasing, or if the tree is a shard with a top tree attached; DAPOL_ERR_NOT_FOUND if
  * an index is not a leaf (reference: None).  dapol_batch_proof_size: size of that proof (0 = bad arguments). */
 DAPOL_API uint64_t dapol_batch_proof_size(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy);
+DAPOL_API uint64_t dapol_batch_proof_size_d(int height, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy, int hash_id);
 DAPOL_API int dapol_generate_proof_batch(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, uint64_t aggregation_factor, int policy,
                                          const uint8_t seed[32], uint8_t *out, uint64_t cap, uint64_t *proof_size);
 /* DapolProof::deserialize + verify_batch(&root, &leaves) (src/proof/mod.rs:49-54,76-95): *ok = 1 iff the k leaves (in index
  * order) and the proof's siblings fold to the root (MerkleProof::verify_batch by level-synchronous DapolProofNode::merge on the
  * device) and R::verify accepts the siblings' commitments.  Malformed bytes or a wrong number of leaves are a reject. */
-DAPOL_API int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t root_hash[32],
-                                       const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*32 */, const uint8_t *proof,
+DAPOL_API int dapol_proof_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint64_t k, const uint8_t root_com[32], const uint8_t *root_hash /* digest_len */,
+                                       const uint8_t *leaf_coms /* k*32 */, const uint8_t *leaf_hashes /* k*digest_len */, const uint8_t *proof,
                                        uint64_t proof_len, uint8_t *ok);
 
 /* ---- range proofs: src/range/mod.rs:48-119 generate_/verify_{single,aggregated}_range_proof in batches.

@@ -27,7 +27,10 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
-enum { HASH_BLAKE3 = 0, HASH_BLAKE2S = 1 };
+enum { HASH_BLAKE3 = 0, HASH_BLAKE2S = 1, HASH_BLAKE2B = 2 };
+/* digest length of D: 32, or 64 for blake2::Blake2b (src/tests.rs:104-105: the 64-byte-digest half of the reference's test matrix,
+ * reachable through new_blank + build only, since Dapol::new insists on 32 bytes, mod.rs:101-103) */
+#define DLEN(hash_id) ((hash_id) == HASH_BLAKE2B ? 64 : 32)
 enum { ERR_OK = 0, ERR_TREE_HEIGHT_TOO_BIG = 1, ERR_SPARSITY_TOO_SMALL = 2, ERR_INVALID_DIGEST_SIZE = 3,
        ERR_DUPLICATED_INTERNAL_ID = 4, ERR_FAILED_TO_MAP_INDEX = 5, ERR_BAD_ARG = 16, ERR_NOT_FOUND = 17, ERR_BUFFER = 18 };
 
@@ -71,12 +74,13 @@ EXPORT void dor_init(void) {
     g_init = 1;
 }
 
-static int hash_buf(int hash_id, const uint8_t *in, size_t len, uint8_t out[32]) {
+static int hash_buf(int hash_id, const uint8_t *in, size_t len, uint8_t *out /* DLEN(hash_id) bytes */) {
     if (hash_id == HASH_BLAKE3) return blake3_hash(in, len, out);
     if (hash_id == HASH_BLAKE2S) return blake2s_hash(in, len, out);
+    if (hash_id == HASH_BLAKE2B) return blake2b_hash(in, len, out);
     return -1;
 }
-EXPORT int dor_hash(int hash_id, const uint8_t *in, size_t len, uint8_t out[32]) { return hash_buf(hash_id, in, len, out); }
+EXPORT int dor_hash(int hash_id, const uint8_t *in, size_t len, uint8_t *out) { return hash_buf(hash_id, in, len, out); }
 
 /* PedersenGens::commit via 2-base Straus, as dalek's constant-time multiscalar_mul does */
 static void commit_ge(ge *out, uint64_t v, const sc *r) {
@@ -167,6 +171,7 @@ static void set_free(u64set *s) { free(s->slot); free(s->used); }
 EXPORT int dor_derive_leaves(int hash_id, uint64_t n, const uint8_t *iid_blob, const uint64_t *iid_off,
                              const uint8_t *eid_blob, const uint64_t *eid_off, const uint8_t *audit_seed, uint64_t seed_len,
                              int height, uint64_t *out_idx, uint8_t *out_blind, uint64_t *err_pos) {
+    if (DLEN(hash_id) != 32) return ERR_INVALID_DIGEST_SIZE; /* mod.rs:101-103 */
     if (height > 64) return ERR_TREE_HEIGHT_TOO_BIG;
     if (height < 64 && ((uint64_t)1 << height) < n * 2) return ERR_SPARSITY_TOO_SMALL;
     if (height == 0 && n) return ERR_BAD_ARG;
@@ -232,7 +237,7 @@ typedef struct {
     uint64_t idx, v;
     uint8_t r[32];    /* blinding bytes as the reference holds them (leaf: from_bits, maybe unreduced) */
     uint8_t comc[32]; /* compress(com) */
-    uint8_t hash[32];
+    uint8_t hash[64]; /* DLEN(hash_id) bytes used */
     uint8_t is_pad;
     ge ext;
 } node;
@@ -252,9 +257,10 @@ static void node_new(int hash_id, node *nd, uint64_t idx, uint64_t v, const uint
     node_finish(hash_id, nd);
 }
 static void node_merge(int hash_id, node *p, const node *l, const node *r) { /* node.rs:64-80 */
-    uint8_t buf[128];
-    memcpy(buf, l->comc, 32); memcpy(buf + 32, r->comc, 32); memcpy(buf + 64, l->hash, 32); memcpy(buf + 96, r->hash, 32);
-    hash_buf(hash_id, buf, 128, p->hash);
+    uint8_t buf[192];
+    const int dl = DLEN(hash_id);
+    memcpy(buf, l->comc, 32); memcpy(buf + 32, r->comc, 32); memcpy(buf + 64, l->hash, dl); memcpy(buf + 64 + dl, r->hash, dl);
+    hash_buf(hash_id, buf, 64 + 2 * dl, p->hash);
     p->idx = l->idx >> 1; p->v = l->v + r->v; p->is_pad = 0;
     sc a, b; sc_frombytes_reduce(&a, l->r); sc_frombytes_reduce(&b, r->r); sc_add(&a, &a, &b); sc_tobytes(p->r, &a);
     ge_add(&p->ext, &l->ext, &r->ext);
@@ -343,7 +349,7 @@ static int tree_build_mode(int hash_id, int height, uint64_t n, const uint64_t *
 #pragma omp parallel for schedule(dynamic, 16)
     for (uint64_t i = 0; i < n; i++) {
         node_new(hash_id, &cur[i], idx_sorted[i], values[i], blindings + 32 * i, 0);
-        if (g_leaf_hash_override) memcpy(cur[i].hash, g_leaf_hash_override + 32 * i, 32);
+        if (g_leaf_hash_override) memcpy(cur[i].hash, g_leaf_hash_override + DLEN(hash_id) * i, DLEN(hash_id));
     }
     for (int h = height; h >= 1; h--) {
         uint64_t np = 0;
@@ -397,7 +403,7 @@ EXPORT void dor_tree_level_copy(const dor_tree *t, int h, uint64_t *idx, uint64_
         if (v) v[i] = nd->v;
         if (r) memcpy(r + 32 * i, nd->r, 32);
         if (comc) memcpy(comc + 32 * i, nd->comc, 32);
-        if (hash) memcpy(hash + 32 * i, nd->hash, 32);
+        if (hash) memcpy(hash + DLEN(t->hash_id) * i, nd->hash, DLEN(t->hash_id));
         if (is_pad) is_pad[i] = nd->is_pad;
     }
 }
@@ -424,14 +430,14 @@ EXPORT int dor_tree_path(const dor_tree *t, uint64_t leaf_idx, uint64_t *v, uint
     int rc = tree_path(t, leaf_idx, sib, NULL);
     if (rc) return rc;
     for (int k = 0; k < t->height; k++) {
-        v[k] = sib[k]->v; memcpy(r + 32 * k, sib[k]->r, 32); memcpy(comc + 32 * k, sib[k]->comc, 32); memcpy(hash + 32 * k, sib[k]->hash, 32);
+        v[k] = sib[k]->v; memcpy(r + 32 * k, sib[k]->r, 32); memcpy(comc + 32 * k, sib[k]->comc, 32); memcpy(hash + DLEN(t->hash_id) * k, sib[k]->hash, DLEN(t->hash_id));
     }
     return ERR_OK;
 }
-EXPORT int dor_tree_get_node(const dor_tree *t, int h, uint64_t idx, uint64_t *v, uint8_t r[32], uint8_t comc[32], uint8_t hash[32], uint8_t *is_pad) {
+EXPORT int dor_tree_get_node(const dor_tree *t, int h, uint64_t idx, uint64_t *v, uint8_t r[32], uint8_t comc[32], uint8_t *hash, uint8_t *is_pad) {
     const node *nd = tree_find(t, h, idx);
     if (!nd) return ERR_NOT_FOUND;
-    *v = nd->v; memcpy(r, nd->r, 32); memcpy(comc, nd->comc, 32); memcpy(hash, nd->hash, 32); *is_pad = nd->is_pad;
+    *v = nd->v; memcpy(r, nd->r, 32); memcpy(comc, nd->comc, 32); memcpy(hash, nd->hash, DLEN(t->hash_id)); *is_pad = nd->is_pad;
     return ERR_OK;
 }
 
@@ -713,17 +719,26 @@ EXPORT uint64_t dor_inclusion_proof_size(int height, uint64_t agg, int policy) {
     sz += 2 + 8 + ((uint64_t)height + 7) / 8 + 8 + 64 * (uint64_t)height;
     return sz;
 }
+/* the same for a digest of dlen bytes: a sibling is com (32) || hash (dlen), src/proof/node.rs:74-79 */
+EXPORT uint64_t dor_inclusion_proof_size_d(int height, uint64_t agg, int policy, int dlen) {
+    uint64_t sz = dor_inclusion_proof_size(height, agg, policy);
+    return sz ? sz + (uint64_t)(dlen - 32) * (uint64_t)height : 0;
+}
 /* ChaCha20 key of the prover's nonce streams of one tree (RNG contract, include/dapol_b200.h): BLAKE3(label || seed || root
  * commitment || root hash || le64 policy || le64 aggregation factor || le64 height) -- the seed bound to the tree (its root
  * commits to every witness), the policy and the factor, so a re-used seed never re-uses a nonce with another witness. */
+static void prover_nonce_key_d(const uint8_t seed[32], const uint8_t root_com[32], const uint8_t *root_hash, int dl, int policy, uint64_t agg,
+                               int height, uint8_t key[32]) {
+    static const char label[] = "dapol-b200 prover nonce key v1";
+    uint8_t buf[30 + 64 + 64 + 24];
+    uint64_t w[3] = {(uint64_t)policy, agg, (uint64_t)height};
+    memcpy(buf, label, 30); memcpy(buf + 30, seed, 32); memcpy(buf + 62, root_com, 32); memcpy(buf + 94, root_hash, dl);
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 8; k++) buf[94 + dl + 8 * i + k] = (uint8_t)(w[i] >> (8 * k));
+    hash_buf(0, buf, 94 + dl + 24, key);
+}
 EXPORT void dor_prover_nonce_key(const uint8_t seed[32], const uint8_t root_com[32], const uint8_t root_hash[32], int policy, uint64_t agg,
                                  int height, uint8_t key[32]) {
-    static const char label[] = "dapol-b200 prover nonce key v1";
-    uint8_t buf[30 + 96 + 24];
-    uint64_t w[3] = {(uint64_t)policy, agg, (uint64_t)height};
-    memcpy(buf, label, 30); memcpy(buf + 30, seed, 32); memcpy(buf + 62, root_com, 32); memcpy(buf + 94, root_hash, 32);
-    for (int i = 0; i < 3; i++) for (int k = 0; k < 8; k++) buf[126 + 8 * i + k] = (uint8_t)(w[i] >> (8 * k));
-    hash_buf(0, buf, sizeof buf, key);
+    prover_nonce_key_d(seed, root_com, root_hash, 32, policy, agg, height, key);
 }
 /* Dapol::generate_proof (mod.rs:167-190) + DapolProof::serialize (proof/mod.rs:68-73).
  * RNG contract: range proof #q of this DapolProof (aggregated first, then singles) draws from
@@ -733,13 +748,14 @@ EXPORT int dor_prove_inclusion(const dor_tree *t, uint64_t leaf_idx, uint64_t ag
     const node *sib[64];
     int rc = tree_path(t, leaf_idx, sib, NULL);
     if (rc) return rc;
-    uint64_t H = (uint64_t)t->height, need = dor_inclusion_proof_size(t->height, agg, policy);
+    const int dl = DLEN(t->hash_id);
+    uint64_t H = (uint64_t)t->height, need = dor_inclusion_proof_size_d(t->height, agg, policy, dl);
     if (!need) return ERR_BAD_ARG;
     if (cap < need) return ERR_BUFFER;
     agg_group g[64]; int ng; uint64_t sf;
     policy_plan(H, agg, policy, g, &ng, &sf);
     uint8_t key[32];
-    dor_prover_nonce_key(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, policy, agg, t->height, key);
+    prover_nonce_key_d(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, DLEN(t->hash_id), policy, agg, t->height, key);
     seed = key;
     uint8_t *o = out; uint64_t q = 0, plen;
     if (policy == POLICY_SPLITTING) { put_be(o, (uint64_t)ng, 2); o += 2; }
@@ -765,13 +781,15 @@ EXPORT int dor_prove_inclusion(const dor_tree *t, uint64_t leaf_idx, uint64_t ag
     uint64_t nb = (H + 7) / 8;
     if (nb) { put_be(o, H == 64 ? leaf_idx : leaf_idx << (8 * nb - H), (int)nb); o += nb; }
     put_be(o, H, 8); o += 8;
-    for (uint64_t k = 0; k < H; k++) { memcpy(o, sib[k]->comc, 32); memcpy(o + 32, sib[k]->hash, 32); o += 64; }
+    for (uint64_t k = 0; k < H; k++) { memcpy(o, sib[k]->comc, 32); memcpy(o + 32, sib[k]->hash, dl); o += 32 + dl; }
     *out_len = (uint64_t)(o - out);
     return ERR_OK;
 }
 /* DapolProof::deserialize + verify (proof/mod.rs:41-47,76-95); 1 = accept */
 EXPORT int dor_verify_inclusion(int hash_id, int policy, const uint8_t *p, uint64_t len, const uint8_t root_com[32],
-                                const uint8_t root_hash[32], const uint8_t leaf_com[32], const uint8_t leaf_hash[32]) {
+                                const uint8_t *root_hash, const uint8_t leaf_com[32], const uint8_t *leaf_hash) {
+    const int dl = DLEN(hash_id);
+    const uint64_t ss = 32 + (uint64_t)dl; /* bytes of one sibling */
     uint64_t pos = 0, nagg = 1;
     const uint8_t *aggp[64]; uint64_t aggl[64];
 #define NEED(k) do { if (len - pos < (uint64_t)(k)) return 0; } while (0)
@@ -792,22 +810,22 @@ EXPORT int dor_verify_inclusion(int hash_id, int policy, const uint8_t *p, uint6
     if (nb && H != 64) idx >>= (8 * nb - H);
     pos += nb;
     uint64_t nsib = get_be(p + pos, 8); pos += 8;
-    if (nsib != H || (len - pos) / 64 < nsib) return 0;
+    if (nsib != H || (len - pos) / ss < nsib) return 0;
     const uint8_t *sib = p + pos;
     /* MerkleProof::verify: fold upward with DapolProofNode::merge (proof/node.rs:56-69) */
-    ge cur, s; uint8_t curc[32], curh[32], buf[128];
+    ge cur, s; uint8_t curc[32], curh[64], buf[192];
     if (!ge_decompress(&cur, leaf_com)) return 0;
-    memcpy(curc, leaf_com, 32); memcpy(curh, leaf_hash, 32);
+    memcpy(curc, leaf_com, 32); memcpy(curh, leaf_hash, dl);
     for (uint64_t k = 0; k < H; k++) {
-        const uint8_t *sc_ = sib + 64 * k, *sh = sc_ + 32;
+        const uint8_t *sc_ = sib + ss * k, *sh = sc_ + 32;
         if (!ge_decompress(&s, sc_)) return 0;
         int cur_is_right = (int)((idx >> k) & 1);
         memcpy(buf, cur_is_right ? sc_ : curc, 32); memcpy(buf + 32, cur_is_right ? curc : sc_, 32);
-        memcpy(buf + 64, cur_is_right ? sh : curh, 32); memcpy(buf + 96, cur_is_right ? curh : sh, 32);
-        hash_buf(hash_id, buf, 128, curh);
+        memcpy(buf + 64, cur_is_right ? sh : curh, dl); memcpy(buf + 64 + dl, cur_is_right ? curh : sh, dl);
+        hash_buf(hash_id, buf, 64 + 2 * dl, curh);
         ge_add(&cur, &cur, &s); ge_compress(curc, &cur);
     }
-    if (memcmp(curc, root_com, 32) || memcmp(curh, root_hash, 32)) return 0;
+    if (memcmp(curc, root_com, 32) || memcmp(curh, root_hash, dl)) return 0;
     /* R::verify on the siblings' commitments (padding.rs:168-197 / splitting.rs:180-211) */
     if (nind > nsib) return 0;
     uint64_t n_agg_coms = nsib - nind;
@@ -815,14 +833,14 @@ EXPORT int dor_verify_inclusion(int hash_id, int policy, const uint8_t *p, uint6
     if (policy == POLICY_PADDING) {
         uint64_t m = next_pow2(n_agg_coms);
         uint8_t bbl[32]; ge_compress(bbl, &GE_BBL);
-        for (uint64_t k = 0; k < m; k++) memcpy(coms + 32 * k, k < n_agg_coms ? sib + 64 * k : bbl, 32);
+        for (uint64_t k = 0; k < m; k++) memcpy(coms + 32 * k, k < n_agg_coms ? sib + ss * k : bbl, 32);
         if (!dor_rp_verify(64, (int)m, aggp[0], aggl[0], coms)) return 0;
     } else {
         uint64_t base = next_pow2(n_agg_coms), at = 0, i = 0;
         while (at < n_agg_coms) {
             if (n_agg_coms & base) {
                 if (i >= nagg) return 0;
-                for (uint64_t k = 0; k < base; k++) memcpy(coms + 32 * k, sib + 64 * (at + k), 32);
+                for (uint64_t k = 0; k < base; k++) memcpy(coms + 32 * k, sib + ss * (at + k), 32);
                 if (!dor_rp_verify(64, (int)base, aggp[i], aggl[i], coms)) return 0;
                 i++; at += base;
             }
@@ -830,7 +848,7 @@ EXPORT int dor_verify_inclusion(int hash_id, int policy, const uint8_t *p, uint6
         }
     }
     for (uint64_t k = 0; k < nind; k++)
-        if (!dor_rp_verify(64, 1, ind + 672 * k, 672, sib + 64 * (n_agg_coms + k))) return 0;
+        if (!dor_rp_verify(64, 1, ind + 672 * k, 672, sib + ss * (n_agg_coms + k))) return 0;
     return 1;
 }
 
@@ -884,10 +902,15 @@ EXPORT uint64_t dor_batch_proof_size(int height, uint64_t k, const uint64_t *idx
     if (!rs) return 0;
     return rs + 2 + 8 + k * (((uint64_t)height + 7) / 8) + 8 + 64 * nsib;
 }
+EXPORT uint64_t dor_batch_proof_size_d(int height, uint64_t k, const uint64_t *idx, uint64_t agg, int policy, int dlen) {
+    uint64_t sz = dor_batch_proof_size(height, k, idx, agg, policy);
+    return sz ? sz + (uint64_t)(dlen - 32) * batch_sibling_plan(height, k, idx, NULL) : 0;
+}
 EXPORT int dor_prove_inclusion_batch(const dor_tree *t, uint64_t k, const uint64_t *idx, uint64_t agg, int policy, const uint8_t seed[32],
                                      uint8_t *out, uint64_t cap, uint64_t *out_len) {
     if (k == 1) return dor_prove_inclusion(t, idx[0], agg, policy, seed, out, cap, out_len);
-    uint64_t need = dor_batch_proof_size(t->height, k, idx, agg, policy);
+    const int dl = DLEN(t->hash_id);
+    uint64_t need = dor_batch_proof_size_d(t->height, k, idx, agg, policy, dl);
     if (!need) return ERR_BAD_ARG;
     if (cap < need) return ERR_BUFFER;
     for (uint64_t i = 0; i < k; i++) { const node *lf = tree_find(t, t->height, idx[i]); if (!lf || lf->is_pad) return ERR_NOT_FOUND; }
@@ -897,7 +920,7 @@ EXPORT int dor_prove_inclusion_batch(const dor_tree *t, uint64_t k, const uint64
     batch_sibling_plan(t->height, k, idx, plan);
     for (uint64_t i = 0; i < nsib; i++) sib[i] = tree_find(t, plan[i].h, plan[i].idx);
     uint8_t key[32];
-    dor_prover_nonce_key(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, policy, agg, t->height, key);
+    prover_nonce_key_d(seed, t->lv[0].nodes[0].comc, t->lv[0].nodes[0].hash, DLEN(t->hash_id), policy, agg, t->height, key);
     batch_nonce_key(key, k, idx);
     agg_group g[64]; int ng; uint64_t sf, q = 0, plen; int rc = 0;
     policy_plan(nsib, agg, policy, g, &ng, &sf);
@@ -919,15 +942,17 @@ EXPORT int dor_prove_inclusion_batch(const dor_tree *t, uint64_t k, const uint64
     put_be(o, H, 2); o += 2; put_be(o, k, 8); o += 8;
     for (uint64_t i = 0; i < k; i++) if (nb) { put_be(o, H == 64 ? idx[i] : idx[i] << (8 * nb - H), (int)nb); o += nb; }
     put_be(o, nsib, 8); o += 8;
-    for (uint64_t j = 0; j < nsib; j++) { memcpy(o, sib[j]->comc, 32); memcpy(o + 32, sib[j]->hash, 32); o += 64; }
+    for (uint64_t j = 0; j < nsib; j++) { memcpy(o, sib[j]->comc, 32); memcpy(o + 32, sib[j]->hash, dl); o += 32 + dl; }
     *out_len = (uint64_t)(o - out);
     free(plan); free(sib);
     return rc;
 }
-typedef struct { uint64_t idx; ge p; uint8_t c[32], h[32]; } pnode;
+typedef struct { uint64_t idx; ge p; uint8_t c[32], h[64]; } pnode;
 /* DapolProof::deserialize + verify_batch(root, leaves) (proof/mod.rs:49-54,76-95); leaves in index order; 1 = accept */
-EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p, uint64_t len, const uint8_t root_com[32], const uint8_t root_hash[32],
+EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p, uint64_t len, const uint8_t root_com[32], const uint8_t *root_hash,
                                       uint64_t k, const uint8_t *leaf_coms, const uint8_t *leaf_hashes) {
+    const int dl = DLEN(hash_id);
+    const uint64_t ss = 32 + (uint64_t)dl;
     uint64_t pos = 0, nagg = 1;
     const uint8_t *aggp[64]; uint64_t aggl[64];
 #define NEEDB(n) do { if (len - pos < (uint64_t)(n)) return 0; } while (0)
@@ -951,7 +976,7 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
     for (uint64_t i = 1; i < k; i++) if (idx[i] <= idx[i - 1]) ok = 0;
     uint64_t nsib = 0;
     if (ok && len - pos >= 8) { nsib = get_be(p + pos, 8); pos += 8; } else ok = 0;
-    if (ok && ((len - pos) / 64 < nsib || nsib != batch_sibling_plan((int)H, k, idx, NULL) || nind > nsib)) ok = 0;
+    if (ok && ((len - pos) / ss < nsib || nsib != batch_sibling_plan((int)H, k, idx, NULL) || nind > nsib)) ok = 0;
     if (!ok) { free(idx); return 0; }
     const uint8_t *sib = p + pos;
     sib_ref *plan = malloc(sizeof(sib_ref) * (nsib + 1));
@@ -959,7 +984,7 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
     pnode *cur = malloc(sizeof(pnode) * k), *nxt = malloc(sizeof(pnode) * k);
     uint64_t n = k, used = 0;
     for (uint64_t i = 0; i < k && ok; i++) {
-        cur[i].idx = idx[i]; memcpy(cur[i].c, leaf_coms + 32 * i, 32); memcpy(cur[i].h, leaf_hashes + 32 * i, 32);
+        cur[i].idx = idx[i]; memcpy(cur[i].c, leaf_coms + 32 * i, 32); memcpy(cur[i].h, leaf_hashes + (uint64_t)dl * i, dl);
         ok = ge_decompress(&cur[i].p, cur[i].c);
     }
     /* siblings are consumed in plan order: all of a level (left to right) before the next level up */
@@ -973,15 +998,15 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
             if (i + 1 < n && cur[i + 1].idx == (cur[i].idx ^ 1)) { other = cur[i + 1]; step = 2; }
             else {
                 if (at >= used + lvl_cnt || plan[at].idx != (cur[i].idx ^ 1)) { ok = 0; break; }
-                other.idx = plan[at].idx; memcpy(other.c, sib + 64 * at, 32); memcpy(other.h, sib + 64 * at + 32, 32);
+                other.idx = plan[at].idx; memcpy(other.c, sib + ss * at, 32); memcpy(other.h, sib + ss * at + 32, dl);
                 ok = ge_decompress(&other.p, other.c); at++;
                 if (!ok) break;
             }
             if (cur[i].idx & 1) { l = &other; r = &cur[i]; } else { l = &cur[i]; r = &other; }
-            uint8_t buf[128];
-            memcpy(buf, l->c, 32); memcpy(buf + 32, r->c, 32); memcpy(buf + 64, l->h, 32); memcpy(buf + 96, r->h, 32);
+            uint8_t buf[192];
+            memcpy(buf, l->c, 32); memcpy(buf + 32, r->c, 32); memcpy(buf + 64, l->h, dl); memcpy(buf + 64 + dl, r->h, dl);
             nxt[m].idx = cur[i].idx >> 1;
-            hash_buf(hash_id, buf, 128, nxt[m].h);
+            hash_buf(hash_id, buf, 64 + 2 * dl, nxt[m].h);
             ge_add(&nxt[m].p, &l->p, &r->p); ge_compress(nxt[m].c, &nxt[m].p);
             m++; i += step;
         }
@@ -989,7 +1014,7 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
         used += lvl_cnt;
         pnode *t_ = cur; cur = nxt; nxt = t_; n = m;
     }
-    if (ok && (n != 1 || memcmp(cur[0].c, root_com, 32) || memcmp(cur[0].h, root_hash, 32))) ok = 0;
+    if (ok && (n != 1 || memcmp(cur[0].c, root_com, 32) || memcmp(cur[0].h, root_hash, dl))) ok = 0;
     free(cur); free(nxt); free(plan); free(idx);
     if (!ok) return 0;
     /* R::verify on the siblings' commitments, in proof order (padding.rs:168-197 / splitting.rs:180-211) */
@@ -999,14 +1024,14 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
     if (policy == POLICY_PADDING) {
         uint64_t m = next_pow2(n_agg_coms);
         uint8_t bbl[32]; ge_compress(bbl, &GE_BBL);
-        for (uint64_t j = 0; j < m; j++) memcpy(coms + 32 * j, j < n_agg_coms ? sib + 64 * j : bbl, 32);
+        for (uint64_t j = 0; j < m; j++) memcpy(coms + 32 * j, j < n_agg_coms ? sib + ss * j : bbl, 32);
         if (nagg != 1 || !dor_rp_verify(64, (int)m, aggp[0], aggl[0], coms)) return 0;
     } else {
         uint64_t base = next_pow2(n_agg_coms), at = 0, i = 0;
         while (at < n_agg_coms) {
             if (n_agg_coms & base) {
                 if (i >= nagg) return 0;
-                for (uint64_t j = 0; j < base; j++) memcpy(coms + 32 * j, sib + 64 * (at + j), 32);
+                for (uint64_t j = 0; j < base; j++) memcpy(coms + 32 * j, sib + ss * (at + j), 32);
                 if (!dor_rp_verify(64, (int)base, aggp[i], aggl[i], coms)) return 0;
                 i++; at += base;
             }
@@ -1014,7 +1039,7 @@ EXPORT int dor_verify_inclusion_batch(int hash_id, int policy, const uint8_t *p,
         }
     }
     for (uint64_t j = 0; j < nind; j++)
-        if (!dor_rp_verify(64, 1, ind + 672 * j, 672, sib + 64 * (n_agg_coms + j))) return 0;
+        if (!dor_rp_verify(64, 1, ind + 672 * j, 672, sib + ss * (n_agg_coms + j))) return 0;
     return 1;
 #undef NEEDB
 }

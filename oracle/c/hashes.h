@@ -124,6 +124,49 @@ static inline int blake2s_hash(const uint8_t *in, size_t len, uint8_t out[32]) {
     return 0;
 }
 
+/* ---------------------------------------------------------------- BLAKE2b-512 (blake2::Blake2b, src/tests.rs:104-105: 64-byte digests) */
+static const uint64_t B2B_IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                                   0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+static inline uint64_t b2b_rotr(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+#define B2B_G(a, b, c, d, x, y)                      \
+    do {                                             \
+        a = a + b + (x); d = b2b_rotr(d ^ a, 32);    \
+        c = c + d;       b = b2b_rotr(b ^ c, 24);    \
+        a = a + b + (y); d = b2b_rotr(d ^ a, 16);    \
+        c = c + d;       b = b2b_rotr(b ^ c, 63);    \
+    } while (0)
+static inline void blake2b_compress(uint64_t h[8], const uint8_t block[128], uint64_t t, int last) {
+    uint64_t m[16], v[16];
+    memcpy(m, block, 128);
+    for (int i = 0; i < 8; i++) { v[i] = h[i]; v[i + 8] = B2B_IV[i]; }
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+    for (int r = 0; r < 12; r++) {
+        const uint8_t *s = B2S_SIGMA[r % 10];
+        B2B_G(v[0], v[4], v[8], v[12], m[s[0]], m[s[1]]);
+        B2B_G(v[1], v[5], v[9], v[13], m[s[2]], m[s[3]]);
+        B2B_G(v[2], v[6], v[10], v[14], m[s[4]], m[s[5]]);
+        B2B_G(v[3], v[7], v[11], v[15], m[s[6]], m[s[7]]);
+        B2B_G(v[0], v[5], v[10], v[15], m[s[8]], m[s[9]]);
+        B2B_G(v[1], v[6], v[11], v[12], m[s[10]], m[s[11]]);
+        B2B_G(v[2], v[7], v[8], v[13], m[s[12]], m[s[13]]);
+        B2B_G(v[3], v[4], v[9], v[14], m[s[14]], m[s[15]]);
+    }
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+static inline int blake2b_hash(const uint8_t *in, size_t len, uint8_t out[64]) {
+    uint64_t h[8];
+    memcpy(h, B2B_IV, 64);
+    h[0] ^= 0x01010040ULL;
+    size_t off = 0;
+    while (len - off > 128) { blake2b_compress(h, in + off, off + 128, 0); off += 128; }
+    uint8_t block[128] = {0};
+    memcpy(block, in + off, len - off);
+    blake2b_compress(h, block, len, 1);
+    memcpy(out, h, 64);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- Keccak-f[1600] */
 static const uint64_t KECCAK_RC[24] = {
     0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808AULL, 0x8000000080008000ULL, 0x000000000000808BULL,

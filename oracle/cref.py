@@ -51,8 +51,13 @@ def _np(a, dtype):
     return a, a.ctypes.data_as(C.c_void_p)
 
 
+def dlen(hash_id: int) -> int:
+    """Digest length of D: 32 (blake3, Blake2s) or 64 (Blake2b, src/tests.rs:104-105)."""
+    return 64 if hash_id == 2 else 32
+
+
 def hash(hash_id: int, data: bytes) -> bytes:
-    out = (C.c_uint8 * 32)()
+    out = (C.c_uint8 * dlen(hash_id))()
     rc = lib().dor_hash(hash_id, _b(data) if data else None, C.c_size_t(len(data)), out)
     assert rc == 0
     return bytes(out)
@@ -176,7 +181,7 @@ class Tree:
     def level(self, h):
         n = lib().dor_tree_level_size(self.h, h)
         idx = np.zeros(n, np.uint64); v = np.zeros(n, np.uint64)
-        r = np.zeros((n, 32), np.uint8); comc = np.zeros((n, 32), np.uint8); hs = np.zeros((n, 32), np.uint8)
+        r = np.zeros((n, 32), np.uint8); comc = np.zeros((n, 32), np.uint8); hs = np.zeros((n, dlen(self.hash_id)), np.uint8)
         pad = np.zeros(n, np.uint8)
         lib().dor_tree_level_copy(self.h, h, *[a.ctypes.data_as(C.c_void_p) for a in (idx, v, r, comc, hs, pad)])
         return dict(idx=idx, v=v, r=r, comc=comc, hash=hs, is_pad=pad)
@@ -191,7 +196,7 @@ class Tree:
 
     def path(self, leaf_idx):
         H = self.height
-        v = np.zeros(H, np.uint64); r = np.zeros((H, 32), np.uint8); c = np.zeros((H, 32), np.uint8); hs = np.zeros((H, 32), np.uint8)
+        v = np.zeros(H, np.uint64); r = np.zeros((H, 32), np.uint8); c = np.zeros((H, 32), np.uint8); hs = np.zeros((H, dlen(self.hash_id)), np.uint8)
         rc = lib().dor_tree_path(self.h, C.c_uint64(leaf_idx), *[a.ctypes.data_as(C.c_void_p) for a in (v, r, c, hs)])
         if rc:
             return None
@@ -199,14 +204,15 @@ class Tree:
 
     def get_node(self, h, idx):
         v = C.c_uint64(); pad = C.c_uint8()
-        r = (C.c_uint8 * 32)(); c = (C.c_uint8 * 32)(); hs = (C.c_uint8 * 32)()
+        r = (C.c_uint8 * 32)(); c = (C.c_uint8 * 32)(); hs = (C.c_uint8 * dlen(self.hash_id))()
         rc = lib().dor_tree_get_node(self.h, h, C.c_uint64(idx), C.byref(v), r, c, hs, C.byref(pad))
         if rc:
             return None
         return dict(v=v.value, r=bytes(r), comc=bytes(c), hash=bytes(hs), is_pad=pad.value)
 
     def prove_inclusion(self, leaf_idx, agg, policy, seed: bytes):
-        cap = lib().dor_inclusion_proof_size(self.height, C.c_uint64(agg), policy)
+        lib().dor_inclusion_proof_size_d.restype = C.c_uint64
+        cap = lib().dor_inclusion_proof_size_d(self.height, C.c_uint64(agg), policy, dlen(self.hash_id))
         if cap == 0:
             return None
         out = (C.c_uint8 * cap)()
@@ -245,9 +251,9 @@ def tree_with_leaf_hashes(hash_id, height, idx_sorted, values, blindings, leaf_h
 def prove_inclusion_batch(tree: "Tree", leaf_idxs, agg, policy, seed: bytes):
     """Dapol::generate_proof_batch (mod.rs:172-190): ONE DapolProof for several leaves (strictly increasing indexes)."""
     L = lib()
-    L.dor_batch_proof_size.restype = C.c_uint64
+    L.dor_batch_proof_size_d.restype = C.c_uint64
     ia, iap = _np(leaf_idxs, np.uint64)
-    cap = L.dor_batch_proof_size(tree.height, C.c_uint64(ia.size), iap, C.c_uint64(agg), policy)
+    cap = L.dor_batch_proof_size_d(tree.height, C.c_uint64(ia.size), iap, C.c_uint64(agg), policy, dlen(tree.hash_id))
     if cap == 0:
         return None
     out = (C.c_uint8 * cap)()

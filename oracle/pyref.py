@@ -266,6 +266,7 @@ def rng_scalar(seed: bytes, k: int, stream: int = 0) -> int:
 # --------------------------------------------------------------------------------------
 HASH_BLAKE3 = 0
 HASH_BLAKE2S = 1
+HASH_BLAKE2B = 2
 
 
 def digest(hash_id: int, *parts: bytes) -> bytes:
@@ -274,7 +275,13 @@ def digest(hash_id: int, *parts: bytes) -> bytes:
         return _blake3.blake3(data).digest()
     if hash_id == HASH_BLAKE2S:
         return hashlib.blake2s(data).digest()
+    if hash_id == HASH_BLAKE2B:  # blake2::Blake2b, 64-byte digests (src/tests.rs:104-105; new_blank + build only)
+        return hashlib.blake2b(data).digest()
     raise ValueError("hash id")
+
+
+def dlen(hash_id: int) -> int:
+    return 64 if hash_id == HASH_BLAKE2B else 32
 
 
 # --------------------------------------------------------------------------------------
@@ -985,7 +992,7 @@ def verify_inclusion(hash_id, proof: bytes, policy: int, root, leaf) -> bool:
     if r is None:
         return False
     aggregated, individual, begin = r
-    mk = merkle_deserialize(proof, begin)
+    mk = merkle_deserialize(proof, begin, dlen(hash_id))
     if mk is None:
         return False
     height, idx, sibs, end = mk
@@ -1060,8 +1067,9 @@ def prove_inclusion_batch(tree: Tree, leaf_idxs, agg: int, policy: int, seed: by
     return policy_serialize(aggregated, individual, policy) + merkle_serialize_batch(tree.height, leaf_idxs, [(s.comc, s.hash) for s in sibs])
 
 
-def verify_inclusion_batch(hash_id, proof: bytes, policy: int, root, leaves, dlen=32) -> bool:
+def verify_inclusion_batch(hash_id, proof: bytes, policy: int, root, leaves) -> bool:
     """DapolProof::deserialize + verify_batch(root, leaves); root / leaves = (comc, hash), leaves in index order."""
+    dlen = 64 if hash_id == HASH_BLAKE2B else 32
     r = policy_deserialize(proof, policy)
     if r is None:
         return False

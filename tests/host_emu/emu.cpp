@@ -136,7 +136,7 @@ EX void emu_commit(int w, uint64_t v, const uint8_t r[32], uint8_t out[32]) {
 // ---- serial tree build through the kernel bodies (mirrors the CUDA host orchestration)
 struct EmuTree {
     int height; std::vector<uint64_t> level_off, level_n;
-    std::vector<uint64_t> idx, v; std::vector<uint32_t> r, comc, hash, ext; std::vector<uint8_t> is_pad;
+    std::vector<uint64_t> idx, v; std::vector<uint32_t> r, comc, hash, ext, hash_hi; std::vector<uint8_t> is_pad;
     uint64_t n_pads;
 };
 static int g_positional = 0;  // padding mode of the next emulated builds (dapol_ctx_set_padding_mode)
@@ -168,6 +168,8 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     t->idx.assign(T, 0); t->v.assign(T, 0); t->r.assign(8 * T, 0); t->comc.assign(8 * T, 0); t->hash.assign(8 * T, 0);
     t->ext.assign(32 * T, 0); t->is_pad.assign(T, 0);
     NodeStore ns{t->idx.data(), t->v.data(), t->r.data(), t->comc.data(), t->hash.data(), t->ext.data(), t->is_pad.data()};
+    const bool b2b = hash_id == DAPOL_HASH_BLAKE2B;  // 64-byte digests: the orchestration of tree_build_dev / dapol_launch_merges
+    if (b2b) { t->hash_hi.assign(8 * T, 0); ns.hash_hi = t->hash_hi.data(); }
     std::vector<uint64_t> pad_dest(total_pads + 1), pad_rng(total_pads + 1);
     std::vector<std::vector<uint64_t>> real(height + 1);
     std::vector<std::vector<uint32_t>> pos(height + 1);
@@ -196,10 +198,15 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     std::vector<uint32_t> bw(8 * n); b2w(bw.data(), blind, 8 * n);
     constexpr int BT = 3;  // units per emulated thread (exercises full and partial batches)
     auto threads = [](uint64_t units) { return (units + BT - 1) / BT; };
-    if (height == 0) { uint32_t p0 = 0; leaf_batch_body<W, BT>(0, 1, 1, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0]; return t; }
+    if (height == 0) {
+        uint32_t p0 = 0; leaf_batch_body<W, BT>(0, 1, 1, ns, 0, &p0, hash_id, values, bw.data(), tb.data(), tbbl.data()); t->idx[0] = leaf_idx[0];
+        if (b2b) leafpad_hash_b2b_body(0, ns, 0);
+        return t;
+    }
     for (uint64_t i = 0, st = threads(n); i < st; i++)
         leaf_batch_body<W, BT>(i, st, n, ns, t->level_off[height], pos[height].data(), hash_id, values, bw.data(), tb.data(), tbbl.data());
     for (uint64_t g = 0, st = threads(total_pads); g < st; g++) pad_batch_body<W, BT>(g, st, total_pads, ns, pad_dest.data(), hash_id, seed, pad_rng.data(), tbbl.data(), ps);
+    if (b2b) for (uint64_t g = 0; g < T; g++) leafpad_hash_b2b_body(g, ns, t->level_off[height]);
     // merges: sums per level, one compress pass over all internal nodes, hashes per level (as tree_build_dev)
     for (int h = height; h >= 1; h--)
         for (uint64_t j = 0; j < nparents[h]; j++)
@@ -214,8 +221,10 @@ EX EmuTree *emu_tree_build(int hash_id, int height, uint64_t n, const uint64_t *
     im.start[height] = n_int;
     for (uint64_t j = 0, st = threads(n_int); j < st; j++) compress_internal_body<BT>(j, st, n_int, ns, im);
     for (int h = height; h >= 1; h--)
-        for (uint64_t j = 0; j < nparents[h]; j++)
-            merge_hash_body(j, ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);
+        for (uint64_t j = 0; j < nparents[h]; j++) {
+            if (b2b) merge_hash_b2b_body(j, ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data());
+            else merge_hash_body(j, ns, t->level_off[h], t->level_off[h - 1], h - 1 == 0 ? nullptr : pos[h - 1].data(), hash_id);
+        }
     return t;
 }
 // leaf derivation through the kernel bodies, with the sort/fix-point orchestration mirrored serially
@@ -256,7 +265,9 @@ EX uint64_t emu_tree_num_pads(EmuTree *t) { return t->n_pads; }
 EX void emu_tree_level_copy(EmuTree *t, int h, uint64_t *idx, uint64_t *v, uint8_t *r, uint8_t *comc, uint8_t *hash, uint8_t *is_pad) {
     uint64_t o = t->level_off[h], n = t->level_n[h];
     memcpy(idx, &t->idx[o], 8 * n); memcpy(v, &t->v[o], 8 * n);
-    memcpy(r, &t->r[8 * o], 32 * n); memcpy(comc, &t->comc[8 * o], 32 * n); memcpy(hash, &t->hash[8 * o], 32 * n);
+    memcpy(r, &t->r[8 * o], 32 * n); memcpy(comc, &t->comc[8 * o], 32 * n);
+    if (t->hash_hi.empty()) memcpy(hash, &t->hash[8 * o], 32 * n);
+    else for (uint64_t i = 0; i < n; i++) { memcpy(hash + 64 * i, &t->hash[8 * (o + i)], 32); memcpy(hash + 64 * i + 32, &t->hash_hi[8 * (o + i)], 32); }
     memcpy(is_pad, &t->is_pad[o], n);
 }
 EX void emu_tree_free(EmuTree *t) { delete t; }

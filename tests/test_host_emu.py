@@ -148,7 +148,8 @@ def test_hashes(E, pyref):
 
 
 @pytest.mark.parametrize("positional", [False, True])
-@pytest.mark.parametrize("hid,H,n", [(0, 6, 9), (1, 4, 4), (0, 10, 200), (0, 16, 64), (0, 3, 4), (0, 1, 1), (0, 1, 2), (0, 5, 1), (0, 40, 20), (0, 64, 6)])
+@pytest.mark.parametrize("hid,H,n", [(0, 6, 9), (1, 4, 4), (0, 10, 200), (0, 16, 64), (0, 3, 4), (0, 1, 1), (0, 1, 2), (0, 5, 1), (0, 40, 20), (0, 64, 6),
+                                     (2, 6, 9), (2, 10, 100), (2, 1, 1), (2, 0, 1), (2, 33, 12)])  # hid 2: Blake2b, 64-byte digests (N2)
 def test_tree_bodies_vs_oracle(E, cref, hid, H, n, positional):
     """positional: padding blindings keyed by (level, index) instead of the creation-order stream."""
     rnd = random.Random(100 + H + n)
@@ -166,7 +167,7 @@ def test_tree_bodies_vs_oracle(E, cref, hid, H, n, positional):
         Lc = T.level(h); m = E.emu_tree_level_size(t, h)
         assert m == len(Lc["idx"])
         i2 = np.zeros(m, np.uint64); v2 = np.zeros(m, np.uint64); r2 = np.zeros((m, 32), np.uint8); c2 = np.zeros((m, 32), np.uint8)
-        h2 = np.zeros((m, 32), np.uint8); p2 = np.zeros(m, np.uint8)
+        h2 = np.zeros((m, 64 if hid == 2 else 32), np.uint8); p2 = np.zeros(m, np.uint8)
         E.emu_tree_level_copy(C.c_void_p(t), h, *[a.ctypes.data_as(C.c_void_p) for a in (i2, v2, r2, c2, h2, p2)])
         assert (i2 == Lc["idx"]).all() and (v2 == Lc["v"]).all() and (c2 == Lc["comc"]).all() and (h2 == Lc["hash"]).all() and (p2 == Lc["is_pad"]).all()
         assert [int.from_bytes(x.tobytes(), "little") % L for x in r2] == [int.from_bytes(x.tobytes(), "little") % L for x in Lc["r"]]

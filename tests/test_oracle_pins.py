@@ -88,6 +88,7 @@ def test_hashes(cref):
         d = bytes(rnd.randrange(256) for _ in range(n))
         assert cref.hash(0, d) == blake3.blake3(d).digest()
         assert cref.hash(1, d) == hashlib.blake2s(d).digest()
+        assert cref.hash(2, d) == hashlib.blake2b(d).digest()  # 64-byte digests (src/tests.rs:104-105)
 
 
 def test_scalar_arith(pyref, cref):
@@ -265,3 +266,53 @@ def test_id_salt_leaf_hash_pinned_to_hashlib(cref):
             audit = D(b"seed" + ids[i])
             salt = D(audit + b"salt_seed" + eids[i])
             assert got[i].tobytes() == D(b"leaf" + eids[i] + salt)
+
+
+def test_blake2b_tree_and_proofs_c_vs_bigint(pyref, cref):
+    """D = blake2::Blake2b, 64-byte digests (src/tests.rs:104-105; SURVEY 8(f) N2): reachable through new_blank + build only
+    (Dapol::new insists on 32 bytes, mod.rs:101-103).  The two restatements agree on every node, on single and batch proof bytes
+    (siblings are 32 + 64 bytes on the wire, proof/node.rs:74-79) and on the verdicts; D is pinned to hashlib.blake2b."""
+    H, n, hid = 5, 7, 2
+    rnd = random.Random(64)
+    idx = np.array(sorted(rnd.sample(range(1 << H), n)), np.uint64)
+    vals = np.array([rnd.randrange(1 << 32) for _ in range(n)], np.uint64)
+    rs = [rnd.randrange(pyref.L) for _ in range(n)]
+    bl = np.array([list(r.to_bytes(32, "little")) for r in rs], np.uint8)
+    T = cref.Tree(hid, H, idx, vals, bl, PAD_SEED)
+    pt = pyref.build_tree(hid, H, [(int(i), pyref.node_new(hid, int(v), r)) for i, v, r in zip(idx, vals, rs)], PAD_SEED)
+    for h in range(H + 1):
+        Lv = T.level(h)
+        assert Lv["hash"].shape[1] == 64 and len(Lv["idx"]) == len(pt.levels[h])
+        for k, i in enumerate(Lv["idx"]):
+            nd = pt.levels[h][int(i)]
+            assert nd.comc == Lv["comc"][k].tobytes() and nd.hash == Lv["hash"][k].tobytes() and nd.v == int(Lv["v"][k])
+    lf0 = T.get_node(H, int(idx[0]))
+    assert lf0["hash"] == hashlib.blake2b(lf0["comc"]).digest()                                # DapolNode::new: D(compress(com)), node.rs:33-36
+    seed = bytes(range(32))
+    rt = T.root()
+    assert len(rt["hash"]) == 64
+    leaf = int(idx[2]); lf = T.get_node(H, leaf)
+    for policy, agg in ((0, 3), (1, 5), (0, 0)):
+        pc = T.prove_inclusion(leaf, agg, policy, seed)
+        assert pc is not None
+        if agg == 3:
+            assert pc == pyref.prove_inclusion(pt, leaf, agg, policy, seed)
+            assert pyref.verify_inclusion(hid, pc, policy, (rt["comc"], rt["hash"]), (lf["comc"], lf["hash"]))
+        assert cref.verify_inclusion(hid, policy, pc, rt["comc"], rt["hash"], lf["comc"], lf["hash"])
+        assert not cref.verify_inclusion(0, policy, pc, rt["comc"], rt["hash"][:32], lf["comc"], lf["hash"][:32])  # wrong D: framing differs
+        for pos in (40, len(pc) - 5, len(pc) - 40, len(pc) - 100):
+            bb = bytearray(pc); bb[pos] ^= 4
+            assert not cref.verify_inclusion(hid, policy, bytes(bb), rt["comc"], rt["hash"], lf["comc"], lf["hash"])
+    picks = [int(x) for x in idx[[0, 3, 4]]]
+    leaves = [T.get_node(H, x) for x in picks]
+    lc, lh = [l["comc"] for l in leaves], [l["hash"] for l in leaves]
+    pb = cref.prove_inclusion_batch(T, picks, 2, 1, seed)
+    assert pb == pyref.prove_inclusion_batch(pt, picks, 2, 1, seed)
+    assert cref.verify_inclusion_batch(hid, 1, pb, rt["comc"], rt["hash"], lc, lh)
+    assert pyref.verify_inclusion_batch(hid, pb, 1, (rt["comc"], rt["hash"]), list(zip(lc, lh)))
+    assert not cref.verify_inclusion_batch(hid, 1, pb, rt["comc"], rt["hash"], lc[::-1], lh[::-1])
+    bb = bytearray(pb); bb[-33] ^= 1                                                            # upper half of the last sibling's hash
+    assert not cref.verify_inclusion_batch(hid, 1, bytes(bb), rt["comc"], rt["hash"], lc, lh)
+    # Dapol::new rejects a 64-byte digest (mod.rs:101-103)
+    ib, io = cref.pack_ids([b"a"]); eb, eo = cref.pack_ids([b"b"])
+    assert cref.derive_leaves(hid, ib, io, eb, eo, b"seed", 8)[0] == 3
