@@ -42,6 +42,7 @@ def lib():
     L.dapol_tree_destroy.argtypes = [vp]
     L.dapol_tree_build_from_nodes.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
     L.dapol_tree_build_from_nodes_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
+    L.dapol_tree_update.argtypes = [vp, u64, vp, vp, vp, vp, u64, C.POINTER(vp)]
     L.dapol_tree_build_from_liabilities.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp, u64, vp, u64,
                                                     C.POINTER(vp), C.POINTER(u64)]
     L.dapol_leaves_derive_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]

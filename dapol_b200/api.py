@@ -271,6 +271,23 @@ class Dapol:
         self._t = h
         return self
 
+    def update(self, leaf_idx, values, blindings, pad_seed: bytes, pad_base: int = 0):
+        """Dapol::update(&idx, node, &secret) (mod.rs:210-213) for one leaf or a batch (strictly increasing indexes): the tree now
+        holds the old leaves plus these, a leaf at an existing index being replaced.  On a blank Dapol this is build()."""
+        idx = np.atleast_1d(np.ascontiguousarray(leaf_idx, np.uint64))
+        val = np.atleast_1d(np.ascontiguousarray(values, np.uint64))
+        bl = np.ascontiguousarray(blindings, np.uint8).reshape(-1, 32)
+        if not (len(idx) == len(val) == len(bl)):
+            raise DapolError(16)
+        if self._t is None:
+            return self.build(idx, val, bl, pad_seed, pad_base)
+        h = C.c_void_p()
+        seed = (C.c_uint8 * 32).from_buffer_copy(pad_seed)
+        _check(_ffi.lib().dapol_tree_update(self._t, len(idx), _p(idx), _p(val), _p(bl), seed, pad_base, C.byref(h)))
+        self._free()
+        self._t = h
+        return self
+
     def build_dev(self, n, d_leaf_idx: int, d_values: int, d_blindings: int, pad_seed: bytes, pad_base: int = 0):
         """Same as build() with the inputs already in device memory (raw device pointers)."""
         self._free()

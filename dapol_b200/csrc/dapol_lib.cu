@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "dapol_internal.h"
 #include "tree_kernels.cuh"
@@ -729,6 +730,100 @@ extern "C" int dapol_tree_build_from_nodes(dapol_ctx *ctx, int hash_id, int heig
     cudaMemcpyAsync(d_bl, blindings, n * 32, cudaMemcpyHostToDevice, ctx->stream);
     int rc = tree_build_dev(ctx, hash_id, height, n, d_idx, d_val, d_bl, pad_seed, pad_base, out);
     dfree(mem, ctx->stream);
+    return rc;
+}
+
+// ---- Dapol::update (src/dapol/mod.rs:210-213 -> smtree SparseMerkleTree::update), batched: the leaves of `t` with k
+// leaves inserted (or replaced where the index is already a leaf).  Both lists are sorted, so the union is a merge by rank:
+// binary searches + one scan of the "replaces an old leaf" flags; then the level-synchronous build runs over the merged leaves.
+__global__ void k_update_find(uint64_t k, const uint64_t *new_idx, const uint64_t *old_lvl_idx, uint64_t n_lvl, const uint8_t *old_is_pad,
+                              int height, uint64_t *found, int *bad) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const uint64_t x = new_idx[i];
+    if ((height < 64 && (x >> height)) || (i && new_idx[i - 1] >= x)) *bad = 1;  // out of the tree / not strictly increasing
+    int64_t slot = find_leaf_slot(old_lvl_idx, n_lvl, x);
+    found[i] = (slot >= 0 && !old_is_pad[slot]) ? 1 : 0;
+}
+DAPOL_HD_INLINE uint64_t lower_bound_u64(const uint64_t *a, uint64_t n, uint64_t x) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (a[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// old real leaf j (slot pos[j] of level H) -> rank j + #{new < idx} - #{replaced old before it}; dropped if a new leaf has its index
+__global__ void k_update_place_old(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, uint64_t k, const uint64_t *new_idx,
+                                   const uint64_t *found_prefix, uint64_t *o_idx, uint64_t *o_v, uint32_t *o_r) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t g = level_off + pos[j], x = ns.idx[g];
+    const uint64_t lb = lower_bound_u64(new_idx, k, x);
+    if (lb < k && new_idx[lb] == x) return;  // replaced
+    const uint64_t dst = j + lb - found_prefix[lb];
+    uint32_t w[8];
+    o_idx[dst] = x; o_v[dst] = ns.v[g];
+    load8(w, ns.r + 8 * g); store8(o_r + 8 * dst, w);
+}
+// new leaf i -> rank i + #{old real leaves < idx} - #{replaced old before it}
+__global__ void k_update_place_new(uint64_t k, const uint64_t *new_idx, const uint64_t *new_v, const uint32_t *new_r, const uint64_t *old_sorted_idx,
+                                   uint64_t n, const uint64_t *found_prefix, uint64_t *o_idx, uint64_t *o_v, uint32_t *o_r) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const uint64_t x = new_idx[i];
+    const uint64_t dst = i + lower_bound_u64(old_sorted_idx, n, x) - found_prefix[i];
+    uint32_t w[8];
+    o_idx[dst] = x; o_v[dst] = new_v[i];
+    load8(w, new_r + 8 * i); store8(o_r + 8 * dst, w);
+}
+__global__ void k_gather_real_idx(uint64_t n, NodeStore ns, uint64_t level_off, const uint32_t *pos, uint64_t *out) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = ns.idx[level_off + pos[j]];
+}
+extern "C" int dapol_tree_update(const dapol_tree *t, uint64_t k, const uint64_t *leaf_idx, const uint64_t *values, const uint8_t *blindings,
+                                 const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
+    if (!t || !k || !leaf_idx || !values || !blindings || !pad_seed || !out) return DAPOL_ERR_BAD_ARG;
+    *out = nullptr;
+    if (t->top || t->height == 0 || t->n_leaves + k >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;  // a shard is updated through a rebuild of its slice
+    dapol_ctx *ctx = t->ctx;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int H = t->height;
+    const uint64_t n = t->n_leaves, cap = n + k;
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)(k + 1), st);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = 2 * Arena::need(k, 8) + Arena::need(k, 32) + 2 * Arena::need(k + 1, 8) + Arena::need(n, 8) + 2 * Arena::need(cap, 8) + Arena::need(cap, 32) +
+              Arena::need(scan_bytes, 1) + 256;
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    uint64_t *n_idx = ar.take<uint64_t>(k), *n_v = ar.take<uint64_t>(k);
+    uint32_t *n_r = ar.take<uint32_t>(8 * k);
+    uint64_t *found = ar.take<uint64_t>(k + 1), *prefix = ar.take<uint64_t>(k + 1), *old_idx = ar.take<uint64_t>(n);
+    uint64_t *o_idx = ar.take<uint64_t>(cap), *o_v = ar.take<uint64_t>(cap);
+    uint32_t *o_r = ar.take<uint32_t>(8 * cap);
+    uint8_t *scan_tmp = ar.take<uint8_t>(scan_bytes);
+    int *d_bad = ar.take<int>(1), bad = 0;
+    uint64_t replaced = 0;
+    int rc = DAPOL_OK;
+    cudaMemsetAsync(d_bad, 0, 4, st);
+    cudaMemsetAsync(found, 0, (k + 1) * 8, st);
+    cudaMemcpyAsync(n_idx, leaf_idx, k * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(n_v, values, k * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(n_r, blindings, k * 32, cudaMemcpyHostToDevice, st);
+    const uint64_t loff = t->level_off[H];
+    k_update_find<<<grid_for(k, 128), 128, 0, st>>>(k, n_idx, t->ns.idx + loff, t->level_n[H], t->ns.is_pad + loff, H, found, d_bad);
+    cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, found, prefix, (int)(k + 1), st);
+    k_gather_real_idx<<<grid_for(n, 256), 256, 0, st>>>(n, t->ns, loff, t->pos[H], old_idx);
+    k_update_place_old<<<grid_for(n, 256), 256, 0, st>>>(n, t->ns, loff, t->pos[H], k, n_idx, prefix, o_idx, o_v, o_r);
+    k_update_place_new<<<grid_for(k, 128), 128, 0, st>>>(k, n_idx, n_v, n_r, old_idx, n, prefix, o_idx, o_v, o_r);
+    ctx->launches += 5;
+    cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&replaced, prefix + k, 8, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { dfree(mem, st); CUDA_TRY(cudaGetLastError()); return DAPOL_ERR_CUDA; }
+    if (bad) rc = DAPOL_ERR_BAD_ARG;
+    if (rc == DAPOL_OK)
+        rc = tree_build_dev(ctx, t->hash_id, H, cap - replaced, o_idx, o_v, reinterpret_cast<const uint8_t *>(o_r), pad_seed, pad_base, out, nullptr, nullptr, nullptr);
+    dfree(mem, st);
     return rc;
 }
 

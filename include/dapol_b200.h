@@ -119,6 +119,19 @@ DAPOL_API int dapol_tree_build_from_nodes_dev(dapol_ctx *ctx, int hash_id, int h
                                     const uint64_t *d_values, const uint8_t *d_blindings, const uint8_t pad_seed[32],
                                     uint64_t pad_base, dapol_tree **out);
 
+/* Dapol::update(&idx, node, &secret)   (src/dapol/mod.rs:210-213 -> smtree SparseMerkleTree::update), for a batch:
+ * *out = the tree over the leaves of `tree` with the k given leaves inserted, a leaf whose index is already in the tree being
+ * replaced (leaf_idx strictly increasing; host buffers).  `tree` itself is not modified (handles are immutable) -- destroy it
+ * when the new one replaces it.  The union of the two sorted leaf lists is formed on the device and the level-synchronous build
+ * runs over it, so one call costs a build (26 ms at 2^20 leaves) whatever k is: batch the updates.  The result is the tree
+ * dapol_tree_build_from_nodes gives for the merged leaves with the same pad_seed / pad_base -- in the positional padding mode
+ * that makes update and build agree bit for bit; in the stream mode pass a pad_base past the blocks already drawn (num_padding),
+ * so that no padding blinding is used twice (the reference draws fresh thread_rng() values either way, and its own test compares
+ * the two roots by value only, src/tests.rs:47, src/dapol/node.rs:115-120).  Trees built from liabilities lose their id -> index
+ * map (the new leaves have no ids).  DAPOL_ERR_BAD_ARG for a shard with a top tree attached or a height-0 tree. */
+DAPOL_API int dapol_tree_update(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, const uint64_t *values,
+                                const uint8_t *blindings /* k*32 */, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out);
+
 /* Dapol::new(liabilities, options)   (src/dapol/mod.rs:100-128): argument checks, build_leaf_nodes
  * (mod.rs:323-399: audit_id / index_seed / shuffle_index / blind_seed), sort, build.
  * Ids are concatenated in a blob with n+1 offsets.  On DUPLICATED_INTERNAL_ID / FAILED_TO_MAP_INDEX
