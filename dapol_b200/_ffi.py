@@ -91,6 +91,9 @@ def lib():
     L.dapol_rangeproof_prove_batch_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, vp, vp, vp, vp, vp]
     L.dapol_rangeproof_verify_batch.argtypes = [vp, C.c_int, C.c_int, u64, vp, u64, vp, vp]
     L.dapol_rangeproof_verify_batch_dev.argtypes = [vp, C.c_int, C.c_int, u64, vp, u64, vp, vp]
+    L.dapol_ctx_set_verify_mode.argtypes = [vp, u64, C.c_int, vp]
+    L.dapol_ctx_verify_fallbacks.argtypes = [vp]
+    L.dapol_ctx_verify_fallbacks.restype = u64
     L.dapol_ctx_set_rangeproof_window.argtypes = [vp, C.c_int]
     L.dapol_rangeproof_last_times.argtypes = [vp, vp]
     L.dapol_rangeproof_last_kernel_times.argtypes = [vp, vp]

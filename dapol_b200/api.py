@@ -114,6 +114,16 @@ class Context:
     def rangeproof_table_bytes(self) -> int:
         return _ffi.lib().dapol_ctx_rangeproof_table_bytes(self._h)
 
+    def set_verify_mode(self, group: int = 0, window_bits: int = 0, weight_seed: bytes | None = None):
+        """group <= 1: every proof verified on its own (Straus).  group = G: G proofs per random-linear-combination check with the
+        bucket method (Pippenger); failed groups are re-verified per proof, so the verdicts are the same (include/dapol_b200.h)."""
+        sd = (C.c_uint8 * 32).from_buffer_copy(weight_seed) if weight_seed is not None else None
+        _check(_ffi.lib().dapol_ctx_set_verify_mode(self._h, group, window_bits, sd))
+
+    @property
+    def verify_fallbacks(self) -> int:
+        return _ffi.lib().dapol_ctx_verify_fallbacks(self._h)
+
     def set_rangeproof_window(self, window: int):
         _check(_ffi.lib().dapol_ctx_set_rangeproof_window(self._h, window))
 

@@ -62,6 +62,12 @@ struct dapol_ctx {
     // last range-proof batch: [0] total, [1] MSM passes, [2] other passes, [3] table build, and the MSM passes split per
     // kernel class: [4] k_rp_p10 (L / R of the table rounds), [5] k_rp_p3 (A, S), [6] hybrid rounds (pm, pv, pf), [7] verifier (v1, v2)
     float rp_last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // verifier mode (dapol_ctx_set_verify_mode): 0 / 1 = every proof on its own (Straus); G > 1 = groups of G proofs checked by one
+    // random linear combination with the bucket method, failed groups re-verified per proof
+    int rp_verify_group = 0, rp_verify_window = 0;
+    bool rp_verify_seeded = false;
+    uint32_t rp_verify_seed[8] = {};
+    uint64_t rp_verify_redone = 0;  // proofs re-verified one by one so far (their group's combination failed)
 };
 
 struct dapol_tree {

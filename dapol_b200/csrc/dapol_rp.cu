@@ -3,8 +3,9 @@
 // Replaces /root/reference/src/range/mod.rs:48-119 (generate_/verify_{single,aggregated}_range_proof).
 #include <algorithm>
 #include <cstring>
+#include <random>
 #include <vector>
-#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 #include "dapol_internal.h"
 #include "rp_kernels.cuh"
 
@@ -548,6 +549,171 @@ int dapol_rp_prove_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint6
     tm.publish(ctx->rp_last_ms);
     return bad ? DAPOL_ERR_BAD_ARG : DAPOL_OK;
 }
+// ------------------------------------------------------------------------------------------------ batched verifier (bucket method)
+// kernels over the bodies of rp_kernels.cuh ("batched verification"): weights, terms, buckets, bucket fold, fixed part, verdicts
+__global__ void k_rpb_weights(RpBatch b, RpbPlan pl) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rpb_weight_body(pl, p);
+}
+__global__ void __launch_bounds__(64) k_rpb_terms(RpBatch b, RpbPlan pl) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nv = (uint64_t)rp_nvar(b.lg, b.m);
+    if (t < b.K * nv) rpb_terms_body(b, pl, t / nv, (int)(t % nv));
+}
+__global__ void __launch_bounds__(128) k_rpb_buckets(RpbPlan pl, uint64_t n_buckets, uint64_t n_terms) {
+    uint64_t bk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bk < n_buckets) rpb_bucket_body(pl, bk, n_terms);
+}
+__global__ void __launch_bounds__(128) k_rpb_chunks(RpbPlan pl, uint64_t n_chunks) {
+    uint64_t ch = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < n_chunks) rpb_chunk_body(pl, ch);
+}
+__global__ void __launch_bounds__(64) k_rpb_windows(RpbPlan pl, uint64_t n_gw) {
+    uint64_t gw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gw < n_gw) rpb_window_body(pl, gw);
+}
+__global__ void __launch_bounds__(128) k_rpb_combine(RpBatch b, RpbPlan pl) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = 2ull * b.N + 2;
+    if (t < pl.groups * per) rpb_combine_body(b, pl, t / per, (uint32_t)(t % per));
+}
+template <int W, bool INL>
+__global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rpb_fixed(RpBatch b, RpbPlan pl) {
+    __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
+    ge acc;
+    rpb_fixed_partial<W, INL>(acc, b, pl, blockIdx.x, threadIdx.x, blockDim.x);
+    block_reduce_ge(acc, sh);
+    if (threadIdx.x == 0) rp_store_ext(pl.gfix + (uint64_t)blockIdx.x * 32, acc);
+}
+__global__ void __launch_bounds__(32) k_rpb_groups(RpBatch b, RpbPlan pl) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < pl.groups) rpb_group_body(b, pl, g);
+}
+__global__ void k_rpb_group_ok(uint64_t K, int G, const int *gok, uint8_t *ok) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < K) ok[p] = gok[p / (uint64_t)G] ? 1 : 0;
+}
+// proofs and commitments of the listed groups, packed back to back (the re-verification input of the failed groups)
+__global__ void k_rpb_gather(uint64_t n, const uint32_t *src_p, const uint32_t *src_c, const uint64_t *which, uint32_t pw, uint32_t cw, uint32_t *dst_p, uint32_t *dst_c) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (pw + cw)) return;
+    const uint64_t i = t / (pw + cw), k = t % (pw + cw), p = which[i];
+    if (k < pw) dst_p[i * pw + k] = src_p[p * pw + k]; else dst_c[i * cw + (k - pw)] = src_c[p * cw + (k - pw)];
+}
+__global__ void k_rpb_scatter(uint64_t n, const uint64_t *which, const uint8_t *src, uint8_t *ok) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ok[which[i]] = src[i];
+}
+// window of the bucket method for groups of M points: about 16 .. 32 points per bucket on average keeps a thread per bucket busy
+// while the fold of the 2^(c-1) buckets per window stays a small share
+static int rpb_window_for(uint64_t M) {
+    int lgm = 0;
+    while ((2ull << lgm) <= M) lgm++;
+    int c = lgm - 3;
+    return c < 3 ? 3 : (c > 16 ? 16 : c);
+}
+int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);
+// one chunk: V0 + expansions as the per-proof verifier, then the groups' combined checks; groups that fail are re-verified
+// proof by proof (Straus path) so that d_ok holds the per-proof verdicts
+template <int W>
+static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok) {
+    cudaStream_t st = ctx->stream;
+    const uint64_t K = b.K, N = b.N, nv = (uint64_t)rp_nvar(b.lg, b.m);
+    RpbPlan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.G = (int)std::min<uint64_t>((uint64_t)ctx->rp_verify_group, K);
+    pl.groups = (K + pl.G - 1) / pl.G;
+    pl.c = ctx->rp_verify_window ? ctx->rp_verify_window : rpb_window_for((uint64_t)pl.G * nv);
+    pl.NW = 253 / pl.c + 1;
+    const uint64_t nb = 1ull << (pl.c - 1);
+    pl.L = (int)std::min<uint64_t>(32, nb);
+    const uint64_t n_terms = K * nv * pl.NW, n_buckets = pl.groups * pl.NW * nb, n_chunks = n_buckets / pl.L, n_gw = pl.groups * pl.NW;
+    if (n_terms >= (1ull << 31) || n_buckets >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
+    {   // weights: fresh secret randomness per call (the reference's verifier draws its batching weight from thread_rng)
+        std::random_device rd;
+        for (int i = 0; i < 8; i++) pl.wseed[i] = ctx->rp_verify_seeded ? ctx->rp_verify_seed[i] : (uint32_t)rd();
+    }
+    size_t sort_bytes = 0;
+    int key_bits = 1;
+    while ((1ull << key_bits) <= n_buckets) key_bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (int)n_terms, 0, key_bits, st);
+    uint8_t *mem = nullptr;
+    Arena ar;
+    ar.size = Arena::need(K, 32) + Arena::need(K * nv, 128) + 4 * Arena::need(n_terms, 4) + Arena::need(n_buckets, 128) + 2 * Arena::need(n_chunks, 128) +
+              Arena::need(n_gw, 128) + Arena::need(pl.groups * (2 * N + 2), 32) + Arena::need(pl.groups, 128) + Arena::need(pl.groups, 4) +
+              Arena::need(sort_bytes, 1);
+    CUDA_TRY(dmalloc(&mem, ar.size, st));
+    ar.base = mem;
+    pl.rho = ar.take<uint32_t>(K * 8);
+    pl.cached = ar.take<uint32_t>(K * nv * 32);
+    pl.keys_in = ar.take<uint32_t>(n_terms); pl.keys = ar.take<uint32_t>(n_terms);
+    pl.vals_in = ar.take<uint32_t>(n_terms); pl.vals = ar.take<uint32_t>(n_terms);
+    pl.bucket = ar.take<uint32_t>(n_buckets * 32);
+    pl.chunk_run = ar.take<uint32_t>(n_chunks * 32); pl.chunk_tot = ar.take<uint32_t>(n_chunks * 32);
+    pl.window = ar.take<uint32_t>(n_gw * 32);
+    pl.gsc = ar.take<uint32_t>(pl.groups * (2 * N + 2) * 8);
+    pl.gfix = ar.take<uint32_t>(pl.groups * 32);
+    pl.gok = ar.take<int>(pl.groups);
+    uint8_t *sort_tmp = ar.take<uint8_t>(sort_bytes);
+    tm.begin(1);
+    k_rp_v0<<<grid_for(K, 64), 64, 0, st>>>(b);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.svec, 2);
+    k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
+    k_rpb_weights<<<grid_for(K, 128), 128, 0, st>>>(b, pl);
+    tm.end();
+    tm.begin(TM_VER);
+    k_rpb_terms<<<grid_for(K * nv, 64), 64, 0, st>>>(b, pl);
+    cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, pl.keys_in, pl.keys, pl.vals_in, pl.vals, (int)n_terms, 0, key_bits, st);
+    k_rpb_buckets<<<grid_for(n_buckets, 128), 128, 0, st>>>(pl, n_buckets, n_terms);
+    k_rpb_chunks<<<grid_for(n_chunks, 128), 128, 0, st>>>(pl, n_chunks);
+    k_rpb_windows<<<grid_for(n_gw, 64), 64, 0, st>>>(pl, n_gw);
+    k_rpb_combine<<<grid_for(pl.groups * (2 * N + 2), 128), 128, 0, st>>>(b, pl);
+    if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rpb_fixed<W, true><<<(unsigned)pl.groups, msm_threads(2 * N), 0, st>>>(b, pl);
+    else k_rpb_fixed<W, false><<<(unsigned)pl.groups, msm_threads(2 * N), 0, st>>>(b, pl);
+    k_rpb_groups<<<grid_for(pl.groups, 32), 32, 0, st>>>(b, pl);
+    k_rpb_group_ok<<<grid_for(K, 128), 128, 0, st>>>(K, pl.G, pl.gok, d_ok);
+    tm.end();
+    ctx->launches += 15;  // 12 kernels + the radix sort's passes (counted as 3)
+    std::vector<int> gok(pl.groups);
+    cudaError_t ce = cudaMemcpyAsync(gok.data(), pl.gok, pl.groups * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    dfree(mem, st);
+    CUDA_TRY(ce);
+    // failed groups: per-proof verdicts from the Straus path
+    std::vector<uint64_t> redo;
+    for (uint64_t g = 0; g < pl.groups; g++)
+        if (!gok[g]) for (uint64_t p = g * pl.G; p < std::min<uint64_t>(K, (g + 1) * pl.G); p++) redo.push_back(p);
+    ctx->rp_verify_redone += redo.size();
+    if (redo.empty()) return DAPOL_OK;
+    const uint64_t nr = redo.size();
+    const uint32_t pw = b.plen / 4, cw = (uint32_t)b.m * 8;
+    Arena a2;
+    a2.size = Arena::need(nr, 8) + Arena::need(nr, b.plen) + Arena::need(nr * b.m, 32) + Arena::need(nr, 1);
+    CUDA_TRY(dmalloc(&mem, a2.size, st));
+    a2.base = mem;
+    uint64_t *d_which = a2.take<uint64_t>(nr);
+    uint32_t *r_p = a2.take<uint32_t>(nr * pw), *r_c = a2.take<uint32_t>(nr * cw);
+    uint8_t *r_ok = a2.take<uint8_t>(nr);
+    cudaMemcpyAsync(d_which, redo.data(), nr * 8, cudaMemcpyHostToDevice, st);
+    k_rpb_gather<<<grid_for(nr * (pw + cw), 256), 256, 0, st>>>(nr, reinterpret_cast<const uint32_t *>(d_proofs), reinterpret_cast<const uint32_t *>(d_coms), d_which, pw, cw, r_p, r_c);
+    const int saved = ctx->rp_verify_group;
+    ctx->rp_verify_group = 0;
+    float keep[8];
+    memcpy(keep, ctx->rp_last_ms, sizeof keep);
+    int rc = dapol_rp_verify_dev(ctx, b.nbits, b.m, nr, reinterpret_cast<const uint8_t *>(r_p), reinterpret_cast<const uint8_t *>(r_c), r_ok);
+    ctx->rp_verify_group = saved;
+    memcpy(ctx->rp_last_ms, keep, sizeof keep);
+    if (rc == DAPOL_OK) {
+        k_rpb_scatter<<<grid_for(nr, 128), 128, 0, st>>>(nr, d_which, r_ok, d_ok);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = DAPOL_ERR_CUDA;
+    }
+    ctx->launches += 2;
+    dfree(mem, st);
+    return rc;
+}
+
 // Device-resident batch verify.  d_proofs [K][plen], d_coms [K][m][32], d_ok [K] out (1 accept, 0 reject).
 int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint8_t *d_proofs, const uint8_t *d_coms, uint8_t *d_ok);
 __global__ void k_status_to_ok(uint64_t K, const int *status, uint8_t *ok) {
@@ -574,15 +740,19 @@ int dapol_rp_verify_dev(dapol_ctx *ctx, int nbits, int m, uint64_t K, const uint
         RpBatch &b = pl.b;
         b.proof_in = reinterpret_cast<const uint32_t *>(d_proofs + first * plen);
         b.coms = reinterpret_cast<const uint32_t *>(d_coms) + first * m * 8;
+        const bool batched = ctx->rp_verify_group > 1 && kc > 1;
         switch (ctx->rp_W) {
-#define W_CASE(w) case w: rc = rp_verify_chunk<w>(ctx, b, tm); break;
+#define W_CASE(w) case w: rc = batched ? rp_verify_chunk_batched<w>(ctx, b, tm, d_proofs + first * plen, d_coms + first * m * 32, d_ok + first) \
+                                       : rp_verify_chunk<w>(ctx, b, tm); break;
             RP_W_CASES(W_CASE)
 #undef W_CASE
             default: rc = DAPOL_ERR_BAD_ARG;
         }
         if (rc) { dfree(pl.mem, st); return rc; }
-        k_status_to_ok<<<grid_for(kc, 128), 128, 0, st>>>(kc, b.status, d_ok + first);
-        ctx->launches++;
+        if (!batched) {
+            k_status_to_ok<<<grid_for(kc, 128), 128, 0, st>>>(kc, b.status, d_ok + first);
+            ctx->launches++;
+        }
         dfree(pl.mem, st);
     }
     cudaEventRecord(e1, st);
@@ -671,6 +841,15 @@ extern "C" int dapol_rangeproof_last_kernel_times(const dapol_ctx *ctx, float ms
     memcpy(ms, ctx->rp_last_ms, sizeof(float) * 8);
     return DAPOL_OK;
 }
+extern "C" int dapol_ctx_set_verify_mode(dapol_ctx *ctx, uint64_t group, int window_bits, const uint8_t *weight_seed) {
+    if (!ctx || group > (1u << 20) || window_bits < 0 || (window_bits && (window_bits < 3 || window_bits > 16))) return DAPOL_ERR_BAD_ARG;
+    ctx->rp_verify_group = (int)group;
+    ctx->rp_verify_window = window_bits;
+    ctx->rp_verify_seeded = weight_seed != nullptr;
+    if (weight_seed) memcpy(ctx->rp_verify_seed, weight_seed, 32);
+    return DAPOL_OK;
+}
+extern "C" uint64_t dapol_ctx_verify_fallbacks(const dapol_ctx *ctx) { return ctx ? ctx->rp_verify_redone : 0; }
 extern "C" int dapol_ctx_set_rangeproof_table_budget(dapol_ctx *ctx, uint64_t bytes) {
     if (!ctx) return DAPOL_ERR_BAD_ARG;
     ctx->rp_budget = bytes;

@@ -992,3 +992,195 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
         ge_add(acc, acc, q);
     }
 }
+
+// ================================================================================================ batched verification (bucket method)
+// A batch of proofs is accepted as a whole when ONE random linear combination of their verification equations holds:
+//   sum_p rho_p * (equation of proof p) == identity,     rho_p = secret random weights, one per proof
+// (bulletproofs' own batching idea, verify_multiple_with_rng's weight c, carried across proofs).  The generators are shared,
+// so their scalars add up mod l and the fixed-base part costs ONE table multi-scalar multiplication per GROUP of proofs instead
+// of one per proof; the variable points (A, S, T_1, T_2, L_k, R_k, V_j of every proof: G * nv of them) form one large
+// variable-base MSM, which is where the BUCKET METHOD (Pippenger) pays: each point is added once per c-bit window into the
+// bucket of its signed digit -- 253 / c additions per point, no doublings -- and the buckets of a window are folded by
+// running sums.  A group that fails is re-verified proof by proof with the Straus path above, so the verdicts are exactly
+// those of the per-proof verifier (a bad proof passes a group with probability 2^-252).
+struct RpbPlan {
+    int G;                 // proofs per group
+    int c, NW;             // window bits, windows = 253 / c + 1 (signed digits |d| <= 2^(c-1))
+    int L;                 // buckets per chunk of the bucket fold (power of two)
+    uint64_t groups;       // ceil(K / G)
+    uint32_t wseed[8];     // ChaCha20 key of the weights
+    uint32_t *rho;         // [K][8]
+    uint32_t *cached;      // [K * nv][32] variable points in cached form (Y+X, Y-X, 2Z, 2dT)
+    uint32_t *keys_in, *keys;    // [K * nv * NW] bucket id of every (point, window) term (zero digit: the id past the last bucket), unsorted / sorted
+    uint32_t *vals_in, *vals;    // [K * nv * NW] (point index << 1) | sign
+    uint32_t *bucket;      // [groups * NW * 2^(c-1)][32] bucket sums (extended)
+    uint32_t *chunk_run, *chunk_tot;  // [groups * NW * nchunks][32]
+    uint32_t *window;      // [groups * NW][32]
+    uint32_t *gsc;         // [groups][2N + 2][8] combined scalars of G_i, H_i, B, B_blinding
+    uint32_t *gfix;        // [groups][32] fixed-base part of the group's combination (extended)
+    int *gok;              // [groups] 1 = the group's combination is the identity and every proof passed the format checks
+};
+DAPOL_HD_INLINE uint64_t rpb_buckets_per_window(const RpbPlan &pl) { return 1ull << (pl.c - 1); }
+// weight of proof p: draw p of ChaCha20(wseed); never zero in practice (probability 2^-252; a zero weight only weakens the check)
+DAPOL_HD_INLINE void rpb_weight_body(const RpbPlan &pl, uint64_t p) {
+    uint32_t ks[16];
+    chacha20_block(ks, pl.wseed, p, 0x70697070656e6765ull);
+    sc r;
+    sc_from_wide(r, ks);
+    rp_st(pl.rho + p * 8, r);
+}
+// VB1 (thread per variable point (p, q)): decompress, weight the scalar, emit one (bucket, point) term per window
+DAPOL_HD_INLINE void rpb_terms_body(const RpBatch &b, const RpbPlan &pl, uint64_t p, int q) {
+    const int lg = b.lg, m = b.m, nv = rp_nvar(lg, m);
+    const uint64_t pt = p * nv + q;
+    const uint32_t *src;
+    if (q < 4) src = b.proof_in + p * (b.plen / 4) + 8 * q;
+    else if (q < 4 + 2 * lg) src = b.proof_in + p * (b.plen / 4) + 56 + 8 * (q - 4);
+    else src = b.coms + (p * m + (q - 4 - 2 * lg)) * 8;
+    uint32_t w[8];
+    load8(w, src);
+    ge P;
+    int good = ge_decompress(P, w);
+    if (!good) { b.status[p] = 0; ge_identity(P); }  // RangeProof::verify -> Err for a point that does not decompress
+    ge_cached cp;
+    ge_to_cached(cp, P);
+    rp_store_cached(pl.cached + pt * 32, cp);
+    sc s, rho;
+    rp_ld(s, b.varsc + pt * 8); rp_ld(rho, pl.rho + p * 8);
+    sc_mul(s, s, rho);
+    const uint64_t nb = rpb_buckets_per_window(pl), g = p / (uint64_t)pl.G;
+    const uint32_t none = (uint32_t)(pl.groups * (uint64_t)pl.NW * nb);
+    uint32_t carry = 0;
+    const uint32_t c = (uint32_t)pl.c;
+#pragma unroll 1
+    for (int k = 0; k < pl.NW; k++) {
+        uint32_t bit = (uint32_t)k * c, wi = bit >> 5, sh = bit & 31, raw = 0;
+        if (wi < 8) {
+            raw = s.v[wi] >> sh;
+            if (sh + c > 32 && wi + 1 < 8) raw |= s.v[wi + 1] << (32 - sh);
+        }
+        raw = (raw & ((1u << c) - 1u)) + carry;
+        carry = raw > (1u << (c - 1)) ? 1u : 0u;
+        int32_t d = (int32_t)raw - (int32_t)(carry << c);
+        uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d);
+        const uint64_t e = pt * (uint64_t)pl.NW + k;
+        pl.keys_in[e] = (mag && good) ? (uint32_t)((g * pl.NW + k) * nb + (mag - 1)) : none;
+        pl.vals_in[e] = ((uint32_t)pt << 1) | neg;
+    }
+}
+// VB2 (thread per bucket): sum of the points whose digit in this window selects the bucket -- a run of the sorted terms
+DAPOL_HD_INLINE void rpb_bucket_body(const RpbPlan &pl, uint64_t bk, uint64_t n_terms) {
+    uint64_t lo = 0, hi = n_terms;
+    const uint32_t want = (uint32_t)bk;
+    while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (pl.keys[mid] < want) lo = mid + 1; else hi = mid; }
+    ge acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (uint64_t j = lo; j < n_terms && pl.keys[j] == want; j++) {
+        const uint32_t v = pl.vals[j];
+        ge_cached cp;
+        rp_load_cached(cp, pl.cached + (uint64_t)(v >> 1) * 32);
+        ge_cadd(acc, acc, cp, (int)(v & 1u));
+    }
+    rp_store_ext(pl.bucket + bk * 32, acc);
+}
+// VB3 (thread per chunk of L buckets of one window): run = sum S_b, tot = sum (i + 1) S_(b0 + i), by running sums from the top
+DAPOL_HD_INLINE void rpb_chunk_body(const RpbPlan &pl, uint64_t ch) {
+    const uint64_t b0 = ch * (uint64_t)pl.L;
+    ge run, tot, s;
+    ge_identity(run); ge_identity(tot);
+#pragma unroll 1
+    for (int i = pl.L - 1; i >= 0; i--) {
+        rp_load_ext(s, pl.bucket + (b0 + i) * 32);
+        ge_add(run, run, s);
+        ge_add(tot, tot, run);
+    }
+    rp_store_ext(pl.chunk_run + ch * 32, run);
+    rp_store_ext(pl.chunk_tot + ch * 32, tot);
+}
+// VB4 (thread per (group, window)): sum_b (b + 1) S_b = sum_ch tot_ch + L * sum_(ch >= 1) (run_ch + run_(ch+1) + ...)
+DAPOL_HD_INLINE void rpb_window_body(const RpbPlan &pl, uint64_t gw) {
+    const uint64_t nch = rpb_buckets_per_window(pl) / (uint64_t)pl.L;
+    ge suf, hi, lo, s;
+    ge_identity(suf); ge_identity(hi); ge_identity(lo);
+#pragma unroll 1
+    for (int64_t ch = (int64_t)nch - 1; ch >= 0; ch--) {
+        rp_load_ext(s, pl.chunk_tot + (gw * nch + ch) * 32);
+        ge_add(lo, lo, s);
+        if (ch >= 1) {
+            rp_load_ext(s, pl.chunk_run + (gw * nch + ch) * 32);
+            ge_add(suf, suf, s);
+            ge_add(hi, hi, suf);
+        }
+    }
+    for (int L = pl.L; L > 1; L >>= 1) ge_dbl(hi, hi);
+    ge_add(lo, lo, hi);
+    rp_store_ext(pl.window + gw * 32, lo);
+}
+// VB5 (thread per group): Horner over the windows, plus the fixed-base part; the group passes iff the sum is the identity
+// and no proof of the group failed a format / decompression check
+DAPOL_HD_INLINE void rpb_group_body(const RpBatch &b, const RpbPlan &pl, uint64_t g) {
+    ge acc, s;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int w = pl.NW - 1; w >= 0; w--) {
+        if (w != pl.NW - 1)
+            for (int i = 0; i < pl.c; i++) ge_dbl(acc, acc);
+        rp_load_ext(s, pl.window + (g * pl.NW + w) * 32);
+        ge_add(acc, acc, s);
+    }
+    rp_load_ext(s, pl.gfix + g * 32);
+    ge_add(acc, acc, s);
+    int ok = ge_is_identity(acc);
+    const uint64_t p0 = g * (uint64_t)pl.G, p1 = p0 + pl.G < b.K ? p0 + pl.G : b.K;
+    for (uint64_t p = p0; p < p1; p++) ok &= b.status[p] != 0;
+    pl.gok[g] = ok;
+}
+// VBc (thread per (group, t)): weighted sum over the group's proofs of the scalar of generator t --
+// t < N: G_t; t < 2N: H_(t-N); 2N: B; 2N + 1: B_blinding (the per-proof scalars are those of rp_v2_partial)
+DAPOL_HD_INLINE void rpb_combine_body(const RpBatch &b, const RpbPlan &pl, uint64_t g, uint32_t t) {
+    const uint32_t N = (uint32_t)b.N;
+    const uint64_t p0 = g * (uint64_t)pl.G, p1 = p0 + pl.G < b.K ? p0 + pl.G : b.K;
+    sc sum;
+    sc_set_u64(sum, 0);
+#pragma unroll 1
+    for (uint64_t p = p0; p < p1; p++) {
+        sc s, c, rho;
+        if (t < N) {
+            sc mz, a;
+            rp_ld(mz, rp_ch(b, p, CH_MZ)); rp_ld(a, rp_ch(b, p, CH_A));
+            rp_ld(s, b.svec + (p * N + t) * 8);
+            sc_mul(s, a, s); sc_sub(s, mz, s);
+        } else if (t < 2 * N) {
+            const uint32_t I = t - N;
+            sc z, bb;
+            rp_ld(z, rp_ch(b, p, CH_Z)); rp_ld(bb, rp_ch(b, p, CH_B));
+            rp_ld(s, b.svec + (p * N + (N - 1 - I)) * 8);
+            sc_mul(s, bb, s);
+            rp_zz2(c, b, p, I);
+            sc_sub(s, c, s);
+            rp_ld(c, b.ypow + (p * N + I) * 8);
+            sc_mul(s, s, c);
+            sc_add(s, z, s);
+        } else rp_ld(s, rp_ch(b, p, t == 2 * N ? CH_SB : CH_SBBL));
+        rp_ld(rho, pl.rho + p * 8);
+        sc_mul(s, s, rho);
+        sc_add(sum, sum, s);
+    }
+    rp_st(pl.gsc + (g * (2 * N + 2) + t) * 8, sum);
+}
+// VBf (CTA per group, partial sums): the group's fixed-base part from the generator tables
+template <int W, bool INL = false>
+DAPOL_HD_INLINE void rpb_fixed_partial(ge &acc, const RpBatch &b, const RpbPlan &pl, uint64_t g, uint32_t tid, uint32_t T) {
+    ge_identity(acc);
+    const uint32_t N = (uint32_t)b.N;
+#pragma unroll 1
+    for (uint32_t t = tid; t < 2 * N + 2; t += T) {
+        sc s;
+        rp_ld(s, pl.gsc + (g * (2 * N + 2) + t) * 8);
+        if (t < N) rp_fixed_mul_acc<W, INL>(acc, b.tabG, rp_gen_of(b, t), s);
+        else if (t < 2 * N) rp_fixed_mul_acc<W, INL>(acc, b.tabH, rp_gen_of(b, t - N), s);
+        else if (t == 2 * N) rp_fixed_mul_acc<W, INL>(acc, b.tabB, 0, s);
+        else rp_fixed_mul_acc<W, INL>(acc, b.tabBbl, 0, s);
+    }
+}

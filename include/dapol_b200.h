@@ -338,6 +338,19 @@ DAPOL_API int dapol_rangeproof_prove_batch_dev(dapol_ctx *ctx, int nbits, int m,
                                                const uint8_t seed[32], const uint64_t *d_streams, const uint64_t *d_base_blocks, uint8_t *d_proofs);
 DAPOL_API int dapol_rangeproof_verify_batch_dev(dapol_ctx *ctx, int nbits, int m, uint64_t k, const uint8_t *d_proofs, uint64_t proof_len,
                                                 const uint8_t *d_commitments, uint8_t *d_ok);
+/* How the verifier entry points of this context (dapol_rangeproof_verify_batch[_dev], dapol_verify_batch, dapol_proof_verify_batch)
+ * check a batch.  group <= 1 (default): every proof on its own, its 17 .. 102 variable points by Straus' interleaving -- what
+ * RangeProof::verify_multiple does per proof (src/range/mod.rs:83-119).  group = G > 1: the proofs are taken G at a time and each
+ * group is checked by ONE random linear combination of its G verification equations (secret 253-bit weights, fresh per call
+ * from the OS; weight_seed != NULL fixes the 32-byte ChaCha20 key instead, for reproducible tests): the shared generators cost
+ * one table MSM per group, and the G * nv variable points are summed by the BUCKET METHOD (Pippenger: window_bits-bit signed
+ * digits, one addition per point and window into its bucket, buckets folded by running sums; window_bits = 0 picks
+ * log2(G * nv) - 3).  A group whose combination is not the identity, or that holds a malformed proof, is re-verified proof by
+ * proof, so ok[] is exactly the per-proof verdict either way (a bad proof slips through a group with probability 2^-252).
+ * Large groups pay when (almost) all proofs are valid -- an auditor checking its own output, C3 / the north-star run; with
+ * many bad proofs keep G small or 0.  dapol_ctx_verify_fallbacks: proofs re-verified one by one so far. */
+DAPOL_API int dapol_ctx_set_verify_mode(dapol_ctx *ctx, uint64_t group, int window_bits, const uint8_t *weight_seed /* 32 bytes or NULL */);
+DAPOL_API uint64_t dapol_ctx_verify_fallbacks(const dapol_ctx *ctx);
 /* window (8, 12, 13, 14, 15 or 16 bits) of the generator tables; drops tables already built.  0 (the default) = the widest
  * window whose tables fit 70 % of the free HBM, at most 128 GB (16 bits up to m = 8 ... 15 bits at m = 32, 14 at m = 64);
  * if the allocation fails after all, the next narrower window is tried. */

@@ -230,3 +230,50 @@ EX void emu_rp_verify(int nbits, int m, uint64_t K, const uint8_t *proofs, const
         ok[p] = (uint8_t)(b.status[p] && ge_is_identity(sum));
     }
 }
+
+// Batched verifier (bucket method, "batched verification" in rp_kernels.cuh) in the order rp_verify_chunk_batched runs it:
+// V0 + expansions, weights, terms, a stable sort of the terms by bucket id, buckets, chunk fold, windows, combined scalars,
+// fixed part with T emulated threads per group, group verdicts.  gok[g] = verdict of group g.
+#include <algorithm>
+#include <numeric>
+EX void emu_rp_verify_batched(int nbits, int m, uint64_t K, const uint8_t *proofs, const uint8_t *coms, int T, int G, int cbits, const uint8_t wseed[32],
+                              int *gok) {
+    RpBatch b;
+    Bufs u;
+    setup(b, u, nbits, m, K);
+    b.proof_in = reinterpret_cast<const uint32_t *>(proofs);
+    b.coms = reinterpret_cast<const uint32_t *>(coms);
+    const uint64_t nv = (uint64_t)rp_nvar(b.lg, m), N = (uint64_t)b.N;
+    for (uint64_t p = 0; p < K; p++) rp_v0_body(b, p);
+    expand(b, b.svec, 2);
+    expand(b, b.ypow, 1);
+    RpbPlan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.G = G; pl.groups = (K + G - 1) / G; pl.c = cbits; pl.NW = 253 / cbits + 1;
+    const uint64_t nb = 1ull << (cbits - 1);
+    pl.L = (int)std::min<uint64_t>(4, nb);  // small chunks so that several chunks per window are exercised
+    const uint64_t n_terms = K * nv * pl.NW, n_buckets = pl.groups * pl.NW * nb, n_chunks = n_buckets / pl.L, n_gw = pl.groups * pl.NW;
+    memcpy(pl.wseed, wseed, 32);
+    std::vector<uint32_t> rho(K * 8), cached(K * nv * 32), keys_in(n_terms), keys(n_terms), vals_in(n_terms), vals(n_terms), bucket(n_buckets * 32),
+        crun(n_chunks * 32), ctot(n_chunks * 32), window(n_gw * 32), gsc(pl.groups * (2 * N + 2) * 8), gfix(pl.groups * 32);
+    pl.rho = rho.data(); pl.cached = cached.data(); pl.keys_in = keys_in.data(); pl.keys = keys.data(); pl.vals_in = vals_in.data(); pl.vals = vals.data();
+    pl.bucket = bucket.data(); pl.chunk_run = crun.data(); pl.chunk_tot = ctot.data(); pl.window = window.data(); pl.gsc = gsc.data(); pl.gfix = gfix.data();
+    pl.gok = gok;
+    for (uint64_t p = 0; p < K; p++) rpb_weight_body(pl, p);
+    for (uint64_t p = 0; p < K; p++) for (uint64_t q = 0; q < nv; q++) rpb_terms_body(b, pl, p, (int)q);
+    std::vector<uint64_t> order(n_terms);
+    std::iota(order.begin(), order.end(), 0ull);
+    std::stable_sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return keys_in[x] < keys_in[y]; });
+    for (uint64_t j = 0; j < n_terms; j++) { keys[j] = keys_in[order[j]]; vals[j] = vals_in[order[j]]; }
+    for (uint64_t bk = 0; bk < n_buckets; bk++) rpb_bucket_body(pl, bk, n_terms);
+    for (uint64_t ch = 0; ch < n_chunks; ch++) rpb_chunk_body(pl, ch);
+    for (uint64_t gw = 0; gw < n_gw; gw++) rpb_window_body(pl, gw);
+    for (uint64_t g = 0; g < pl.groups; g++) for (uint32_t t = 0; t < 2 * N + 2; t++) rpb_combine_body(b, pl, g, t);
+    for (uint64_t g = 0; g < pl.groups; g++) {
+        ge sum, part;
+        ge_identity(sum);
+        for (int t = 0; t < T; t++) { rpb_fixed_partial<W>(part, b, pl, g, (uint32_t)t, (uint32_t)T); ge_add(sum, sum, part); }
+        rp_store_ext(pl.gfix + g * 32, sum);
+    }
+    for (uint64_t g = 0; g < pl.groups; g++) rpb_group_body(b, pl, g);
+}

@@ -109,3 +109,49 @@ def test_bad_shapes(ctx):
         ctx.rangeproof_prove_batch(64, np.zeros((1, 3), np.uint64), np.zeros((1, 3, 32), np.uint8), SEED, [0], [0])  # m not a power of two
     with pytest.raises(DapolError):
         ctx.rangeproof_prove_batch(24, np.zeros((1, 1), np.uint64), np.zeros((1, 1, 32), np.uint8), SEED, [0], [0])  # bulletproofs: n in {8,16,32,64}
+
+
+@pytest.mark.parametrize("nbits,m,k,G,cbits", [(64, 1, 300, 64, 0), (64, 1, 257, 1000, 0), (64, 1, 64, 7, 4), (32, 2, 40, 16, 0), (64, 16, 12, 4, 6), (8, 1, 33, 33, 9)])
+def test_batched_verifier_same_verdicts(ctx, cref, nbits, m, k, G, cbits):
+    """dapol_ctx_set_verify_mode(G): groups of G proofs checked by one random linear combination with the bucket method (Pippenger).
+    All-valid batches pass without a single per-proof re-verification; with bad proofs (every malformed-input class) the verdicts
+    are those of the per-proof verifier and of the oracle, and only the groups that hold a bad proof are re-verified."""
+    rnd = random.Random(nbits + 31 * m + k)
+    vals, bl, streams, bases = _batch(rnd, nbits, m, k)
+    proofs = ctx.rangeproof_prove_batch(nbits, vals, bl, SEED, streams, bases)
+    coms = _coms(cref, vals, bl)
+    try:
+        ctx.set_verify_mode(G, cbits)
+        f0 = ctx.verify_fallbacks
+        assert ctx.rangeproof_verify_batch(nbits, m, proofs, coms).all()
+        assert ctx.verify_fallbacks == f0
+        ctx.set_verify_mode(G, cbits, bytes(range(32)))  # fixed weights: the same verdicts
+        assert ctx.rangeproof_verify_batch(nbits, m, proofs, coms).all()
+        bad = sorted(rnd.sample(range(k), max(2, k // 30)))
+        plen = proofs.shape[1]
+        for n_, i in enumerate(bad):
+            kind = n_ % 5
+            if kind == 0:
+                proofs[i, rnd.randrange(plen)] ^= 1 << rnd.randrange(8)
+            elif kind == 1:
+                coms[i, 0] = coms[(i + 1) % k, 0]
+            elif kind == 2:
+                proofs[i, 128:160] = np.frombuffer((L + 3).to_bytes(32, "little"), np.uint8)
+            elif kind == 3:
+                proofs[i, 32:64] = 0
+            else:
+                proofs[i, 224:256] = np.frombuffer((2 ** 255 - 19 + 2).to_bytes(32, "little"), np.uint8)
+        ctx.set_verify_mode(G, cbits)
+        f0 = ctx.verify_fallbacks
+        got = ctx.rangeproof_verify_batch(nbits, m, proofs, coms)
+        redone = ctx.verify_fallbacks - f0
+        ctx.set_verify_mode(0)
+        per_proof = ctx.rangeproof_verify_batch(nbits, m, proofs, coms)
+        assert (got == per_proof).all()
+        assert not got[bad].any() and got.sum() == k - len(bad)
+        groups = {i // min(G, k) for i in bad}
+        assert redone == sum(min(min(G, k), k - g * min(G, k)) for g in groups)
+        for i in bad[:3] + [j for j in range(k) if j not in bad][:2]:
+            assert bool(got[i]) == cref.rp_verify(proofs[i].tobytes(), [c.tobytes() for c in coms[i]], nbits)
+    finally:
+        ctx.set_verify_mode(0)

@@ -67,6 +67,17 @@ def emu_verify(E, nbits, m, proofs, coms, T=3):
     return res
 
 
+def emu_verify_batched(E, nbits, m, proofs, coms, G, cbits, T=3, wseed=SEED):
+    """Group verdicts of the batched verifier (one random linear combination per G proofs, bucket method with cbits-bit windows)."""
+    K = len(proofs)
+    pr = np.frombuffer(b"".join(proofs), np.uint8).copy()
+    cm = np.frombuffer(b"".join(b"".join(c) for c in coms), np.uint8).copy()
+    gok = np.zeros((K + G - 1) // G, np.int32)
+    E.emu_rp_verify_batched(nbits, m, C.c_uint64(K), pr.ctypes.data_as(C.c_void_p), cm.ctypes.data_as(C.c_void_p), T, G, cbits, B(wseed),
+                            gok.ctypes.data_as(C.c_void_p))
+    return [bool(x) for x in gok]
+
+
 def test_generators_and_tables(E, cref):
     out = (C.c_uint8 * 32)()
     for is_h, party, i in [(0, 0, 0), (0, 0, 1), (1, 0, 0), (0, 1, 0), (1, 1, 63), (0, 3, 17), (1, 2, 40)]:
@@ -138,3 +149,31 @@ def test_out_of_range_value_rejected(E, cref):
     assert emu_verify(E, 8, 1, [pf], [[cref.commit(256, bl)]]) == [False]
     pf = emu_prove(E, 8, [[300]], [[bl]], [0], [0])[0]  # bits of 300 & 0xff are proven, the commitment holds 300
     assert emu_verify(E, 8, 1, [pf], [[cref.commit(300, bl)]]) == [cref.rp_verify(pf, [cref.commit(300, bl)], 8)] == [False]
+
+
+@pytest.mark.parametrize("nbits,m,G,cbits", [(8, 1, 3, 3), (8, 2, 4, 5), (16, 1, 2, 7), (64, 1, 5, 4)])
+def test_batched_verifier_group_verdicts(E, cref, nbits, m, G, cbits):
+    """Batched verification by the bucket method (Pippenger; dapol_ctx_set_verify_mode): a group's random linear combination is the
+    identity iff every proof of the group verifies on its own (the per-proof verifier and the oracle), for any grouping / window /
+    weights; one bad proof fails exactly its group."""
+    rnd = random.Random(nbits + 7 * m + G)
+    K = 2 * G + 1  # two full groups and a partial one
+    cases = [_case(rnd, nbits, m) for _ in range(K)]
+    proofs = emu_prove(E, nbits, [c[0] for c in cases], [c[1] for c in cases], list(range(K)), [0] * K, 2)
+    coms = [[cref.commit(v, (int.from_bytes(b, "little") % L).to_bytes(32, "little")) for v, b in zip(vals, bls)] for vals, bls in cases]
+    assert emu_verify_batched(E, nbits, m, proofs, coms, G, cbits) == [True, True, True]
+    assert emu_verify_batched(E, nbits, m, proofs, coms, K, cbits + 1, wseed=bytes(range(32))) == [True]          # one group of everything
+    for victim, how in ((1, "bit"), (G, "com"), (2 * G, "scalar"), (G + 1, "point")):
+        bad, badc = list(proofs), [list(c) for c in coms]
+        if how == "bit":
+            bb = bytearray(bad[victim]); bb[70] ^= 4; bad[victim] = bytes(bb)                                      # T_1 changed
+        elif how == "com":
+            badc[victim][0] = cref.commit(cases[victim][0][0] + 1, (int.from_bytes(cases[victim][1][0], "little") % L).to_bytes(32, "little"))
+        elif how == "scalar":
+            bb = bytearray(bad[victim]); bb[128:160] = (L + 5).to_bytes(32, "little"); bad[victim] = bytes(bb)    # non-canonical t_x
+        else:
+            bb = bytearray(bad[victim]); bb[0:32] = (2).to_bytes(32, "little"); bad[victim] = bytes(bb)           # A does not decompress
+        per_proof = emu_verify(E, nbits, m, bad, badc, 2)
+        assert per_proof == [i != victim for i in range(K)] == [cref.rp_verify(p, c, nbits) for p, c in zip(bad, badc)]
+        want = [all(per_proof[g * G:(g + 1) * G]) for g in range((K + G - 1) // G)]
+        assert emu_verify_batched(E, nbits, m, bad, badc, G, cbits) == want
