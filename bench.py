@@ -212,6 +212,20 @@ def rangeproof_leg(ctx, L, dev, world, dist, args, imad_peak):
         torch.cuda.synchronize()
         t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], device=dev)
         all_ok = bool(d_ok.all().item())
+        # head-to-head of the verifier's variable-base MSM: per-proof Straus (above) vs groups of G proofs checked by one random
+        # linear combination with the bucket method (Pippenger; dapol_ctx_set_verify_mode).  Same proofs, all valid.
+        batched = []
+        for G in [g for g in (16, 256, 4096, K) if g <= K]:
+            ctx.set_verify_mode(G)
+            f0 = ctx.verify_fallbacks
+            verify_dev()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); verify_dev(); e1.record()
+            torch.cuda.synchronize()
+            batched.append({"group": G, "verify_per_s": world * K / e0.elapsed_time(e1) * 1e3, "all_verified": bool(d_ok.all().item()),
+                            "fallbacks": int(ctx.verify_fallbacks - f0), "kernel_class_ms": ctx.rangeproof_last_kernel_times()})
+        ctx.set_verify_mode(0)
         # end to end: host buffers in, proofs / verdicts out
         h_proofs = np.zeros((K, size), np.uint8); h_ok = np.zeros(K, np.uint8)
         t0 = time.perf_counter()
@@ -240,6 +254,7 @@ def rangeproof_leg(ctx, L, dev, world, dist, args, imad_peak):
                             "e2e_prove_per_s": world * K / pe * 1e3, "e2e_verify_per_s": world * K / ve * 1e3,
                             "e2e_prove_plus_verify_per_s": world * K / (pe + ve) * 1e3,
                             "all_verified": all_ok and bool(h_ok.all()), "proof_bytes": int(size),
+                            "verify_batched_bucket_method": batched,
                             "roofline": {"bound": "imad", "kernel": "k_rp_p10 (L/R MSMs of the inner-product rounds over the generator tables)",
                                          "achieved": achieved, "peak": imad_peak, "unit": "GMAC32/s",
                                          "frac": achieved / imad_peak if achieved and imad_peak else None,

@@ -10,7 +10,13 @@
 struct ge {  // extended coordinates, x = X/Z, y = Y/Z, T = XY/Z
     fe X, Y, Z, T;
 };
-struct ge_niels {  // affine precomputed: (y+x, y-x, 2d*x*y) -- 96 bytes
+// DAPOL_NIELS_PAD (experiment, profiles/r02_variants.txt): table entries in 128-byte slots, so that an entry never straddles two
+// 128-byte lines (a 96-byte entry at a 96-byte stride does, two times out of three)
+struct
+#ifdef DAPOL_NIELS_PAD
+    alignas(128)
+#endif
+    ge_niels {  // affine precomputed: (y+x, y-x, 2d*x*y) -- 96 bytes
     fe ypx, ymx, t2d;
 };
 struct ge_cached {  // projective precomputed: (Y+X, Y-X, 2Z, 2d*T) -- 128 bytes

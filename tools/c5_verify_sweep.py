@@ -1,7 +1,9 @@
 """BASELINE.json configs[4]: batch range-proof verification sweep (1k - 1M proofs, 32- and 64-bit ranges) on one GPU, with the
 host CPU (oracle port, all threads) timed beside it on a bounded sample.  1 % of the proofs are corrupted; the GPU verdicts
 must be exactly "corrupted <=> rejected", and a sample of them is cross-checked against the oracle verifier (reject parity).
-Prints one JSON line per (nbits, K).   python tools/c5_verify_sweep.py [max_log2=20] [--gpus handled by torchrun: each rank = K proofs]"""
+Prints one JSON line per (nbits, K, group).   python tools/c5_verify_sweep.py [max_log2=20] [groups=0] [--gpus handled by torchrun: each rank = K proofs]
+groups: comma list of dapol_ctx_set_verify_mode group sizes (0 = every proof on its own by Straus; G > 1 = bucket-method groups with
+per-proof fallback) -- the head-to-head of the two verifiers on a batch with 1 % bad proofs."""
 import concurrent.futures as cf
 import hashlib
 import json
@@ -21,6 +23,7 @@ SEED = hashlib.sha256(b"dapol-b200").digest()
 
 def main():
     max_log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    groups = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
@@ -56,8 +59,10 @@ def main():
         rows = torch.nonzero(bad_t).squeeze(1)
         pv[rows, byte[rows]] ^= 1 << 3
         d_ok = torch.empty(Kmax, dtype=torch.uint8, device=dev)
-        for lg in range(10, max_log2 + 1, 2):
+        for lg, G in [(lg, G) for lg in range(10, max_log2 + 1, 2) for G in groups]:
             K = 1 << lg
+            ctx.set_verify_mode(G)
+            f0 = ctx.verify_fallbacks
             L.dapol_rangeproof_verify_batch_dev(ctx._h, nbits, 1, K, d_proofs.data_ptr(), size, tc.data_ptr(), d_ok.data_ptr())  # warm-up
             torch.cuda.synchronize()
             if world > 1:
@@ -76,8 +81,9 @@ def main():
                 dist.all_reduce(e, op=dist.ReduceOp.MIN)
                 exact = bool(e.item())
             line = {"config": "C5 batch range-proof verification", "nbits": nbits, "m": 1, "proofs_per_gpu": K, "n_gpus": world, "verify_ms": ms,
-                    "verifies_per_s": world * K / ms * 1e3, "corrupted": int(bad[:K].sum()), "verdicts_exact": exact}
-            if lg == 10 and rank == 0:  # CPU leg + reject parity on the first 1024 proofs
+                    "verifies_per_s": world * K / ms * 1e3, "corrupted": int(bad[:K].sum()), "verdicts_exact": exact,
+                    "verify_group": G, "reverified_per_call": int(ctx.verify_fallbacks - f0) // 2}
+            if lg == 10 and rank == 0 and G == groups[0]:  # CPU leg + reject parity on the first 1024 proofs
                 hp = pv[:1024].cpu().numpy(); hc = coms[:1024]
                 t0 = time.perf_counter()
                 with cf.ThreadPoolExecutor(cores) as ex:
