@@ -574,8 +574,17 @@ __global__ void __launch_bounds__(64) k_rpb_windows(RpbPlan pl, uint64_t n_gw) {
 }
 __global__ void __launch_bounds__(128) k_rpb_combine(RpBatch b, RpbPlan pl) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = 2ull * b.N + 2, parts = rpb_parts(pl);
+    if (t < pl.groups * parts * per) rpb_combine_body(b, pl, t / (parts * per), (t / per) % parts, (uint32_t)(t % per));
+}
+__global__ void __launch_bounds__(128) k_rpb_combine_sum(RpBatch b, RpbPlan pl) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t per = 2ull * b.N + 2;
-    if (t < pl.groups * per) rpb_combine_body(b, pl, t / per, (uint32_t)(t % per));
+    if (t < pl.groups * per) rpb_combine_sum_body(b, pl, t / per, (uint32_t)(t % per));
+}
+__global__ void k_rpb_status(RpBatch b, RpbPlan pl) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < b.K) rpb_status_body(b, pl, p);
 }
 template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rpb_fixed(RpBatch b, RpbPlan pl) {
@@ -623,10 +632,13 @@ static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, c
     memset(&pl, 0, sizeof pl);
     pl.G = (int)std::min<uint64_t>((uint64_t)ctx->rp_verify_group, K);
     pl.groups = (K + pl.G - 1) / pl.G;
-    pl.c = ctx->rp_verify_window ? ctx->rp_verify_window : rpb_window_for((uint64_t)pl.G * nv);
-    pl.NW = 253 / pl.c + 1;
+    rpb_set_windows(pl, ctx->rp_verify_window ? ctx->rp_verify_window : rpb_window_for((uint64_t)pl.G * nv));
     const uint64_t nb = 1ull << (pl.c - 1);
-    pl.L = (int)std::min<uint64_t>(32, nb);
+    pl.L = 1;  // chunks of about sqrt(2 nb) buckets: the chunk pass (2 L additions) and the per-window pass (3 nb / L) stay short chains
+    while ((uint64_t)pl.L * pl.L < 2 * nb) pl.L <<= 1;
+    pl.L = (int)std::min<uint64_t>(pl.L, nb);
+    pl.P = 16;
+    const uint64_t parts = rpb_parts(pl);
     const uint64_t n_terms = K * nv * pl.NW, n_buckets = pl.groups * pl.NW * nb, n_chunks = n_buckets / pl.L, n_gw = pl.groups * pl.NW;
     if (n_terms >= (1ull << 31) || n_buckets >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
     {   // weights: fresh secret randomness per call (the reference's verifier draws its batching weight from thread_rng)
@@ -641,8 +653,8 @@ static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, c
     uint8_t *mem = nullptr;
     Arena ar;
     ar.size = Arena::need(K, 32) + Arena::need(K * nv, 128) + 4 * Arena::need(n_terms, 4) + Arena::need(n_buckets, 128) + 2 * Arena::need(n_chunks, 128) +
-              Arena::need(n_gw, 128) + Arena::need(pl.groups * (2 * N + 2), 32) + Arena::need(pl.groups, 128) + Arena::need(pl.groups, 4) +
-              Arena::need(sort_bytes, 1);
+              Arena::need(n_gw, 128) + Arena::need(pl.groups * (2 * N + 2), 32) + Arena::need(pl.groups * parts * (2 * N + 2), 32) +
+              Arena::need(pl.groups, 128) + 2 * Arena::need(pl.groups, 4) + Arena::need(sort_bytes, 1);
     CUDA_TRY(dmalloc(&mem, ar.size, st));
     ar.base = mem;
     pl.rho = ar.take<uint32_t>(K * 8);
@@ -653,6 +665,8 @@ static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, c
     pl.chunk_run = ar.take<uint32_t>(n_chunks * 32); pl.chunk_tot = ar.take<uint32_t>(n_chunks * 32);
     pl.window = ar.take<uint32_t>(n_gw * 32);
     pl.gsc = ar.take<uint32_t>(pl.groups * (2 * N + 2) * 8);
+    pl.gpart = ar.take<uint32_t>(pl.groups * parts * (2 * N + 2) * 8);
+    pl.gbad = ar.take<int>(pl.groups);
     pl.gfix = ar.take<uint32_t>(pl.groups * 32);
     pl.gok = ar.take<int>(pl.groups);
     uint8_t *sort_tmp = ar.take<uint8_t>(sort_bytes);
@@ -661,6 +675,7 @@ static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, c
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.svec, 2);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     k_rpb_weights<<<grid_for(K, 128), 128, 0, st>>>(b, pl);
+    cudaMemsetAsync(pl.gbad, 0, pl.groups * 4, st);
     tm.end();
     tm.begin(TM_VER);
     k_rpb_terms<<<grid_for(K * nv, 64), 64, 0, st>>>(b, pl);
@@ -668,13 +683,15 @@ static int rp_verify_chunk_batched(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm, c
     k_rpb_buckets<<<grid_for(n_buckets, 128), 128, 0, st>>>(pl, n_buckets, n_terms);
     k_rpb_chunks<<<grid_for(n_chunks, 128), 128, 0, st>>>(pl, n_chunks);
     k_rpb_windows<<<grid_for(n_gw, 64), 64, 0, st>>>(pl, n_gw);
-    k_rpb_combine<<<grid_for(pl.groups * (2 * N + 2), 128), 128, 0, st>>>(b, pl);
+    k_rpb_combine<<<grid_for(pl.groups * parts * (2 * N + 2), 128), 128, 0, st>>>(b, pl);
+    k_rpb_combine_sum<<<grid_for(pl.groups * (2 * N + 2), 128), 128, 0, st>>>(b, pl);
+    k_rpb_status<<<grid_for(K, 128), 128, 0, st>>>(b, pl);
     if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rpb_fixed<W, true><<<(unsigned)pl.groups, msm_threads(2 * N), 0, st>>>(b, pl);
     else k_rpb_fixed<W, false><<<(unsigned)pl.groups, msm_threads(2 * N), 0, st>>>(b, pl);
     k_rpb_groups<<<grid_for(pl.groups, 32), 32, 0, st>>>(b, pl);
     k_rpb_group_ok<<<grid_for(K, 128), 128, 0, st>>>(K, pl.G, pl.gok, d_ok);
     tm.end();
-    ctx->launches += 15;  // 12 kernels + the radix sort's passes (counted as 3)
+    ctx->launches += 17;  // 14 kernels + the radix sort's passes (counted as 3)
     std::vector<int> gok(pl.groups);
     cudaError_t ce = cudaMemcpyAsync(gok.data(), pl.gok, pl.groups * 4, cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);

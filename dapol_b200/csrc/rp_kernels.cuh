@@ -1005,8 +1005,13 @@ DAPOL_HD_INLINE void rp_v2_partial(ge &acc, const RpBatch &b, uint64_t p, uint32
 // those of the per-proof verifier (a bad proof passes a group with probability 2^-252).
 struct RpbPlan {
     int G;                 // proofs per group
-    int c, NW;             // window bits, windows = 253 / c + 1 (signed digits |d| <= 2^(c-1))
+    // Windows: NW = ceil(254 / c) of them cover the 253 bits of a scalar.  Windows 0 .. NW-2 carry SIGNED digits |d| <= 2^(c-1); the
+    // top window is unsigned and c - 1 bits wide, so there is no carry out of it and its digits spread over half of its buckets
+    // instead of piling into one or two (a narrow top window would put every point of the group into the same bucket -- one thread
+    // adding G * nv points).  The slack bits NW c - 1 - 253 come off the lowest windows, one bit each.
+    int c, NW, slack;
     int L;                 // buckets per chunk of the bucket fold (power of two)
+    int P;                 // proofs per partial sum of the combined scalars
     uint64_t groups;       // ceil(K / G)
     uint32_t wseed[8];     // ChaCha20 key of the weights
     uint32_t *rho;         // [K][8]
@@ -1016,11 +1021,16 @@ struct RpbPlan {
     uint32_t *bucket;      // [groups * NW * 2^(c-1)][32] bucket sums (extended)
     uint32_t *chunk_run, *chunk_tot;  // [groups * NW * nchunks][32]
     uint32_t *window;      // [groups * NW][32]
+    uint32_t *gpart;       // [groups][ceil(G / P)][2N + 2][8] partial sums of the combined scalars
     uint32_t *gsc;         // [groups][2N + 2][8] combined scalars of G_i, H_i, B, B_blinding
     uint32_t *gfix;        // [groups][32] fixed-base part of the group's combination (extended)
+    int *gbad;             // [groups] set when a proof of the group failed a format / decompression check
     int *gok;              // [groups] 1 = the group's combination is the identity and every proof passed the format checks
 };
 DAPOL_HD_INLINE uint64_t rpb_buckets_per_window(const RpbPlan &pl) { return 1ull << (pl.c - 1); }
+DAPOL_HD_INLINE void rpb_set_windows(RpbPlan &pl, int c) { pl.c = c; pl.NW = (254 + c - 1) / c; pl.slack = pl.NW * c - 1 - 253; }
+DAPOL_HD_INLINE uint32_t rpb_window_bits(const RpbPlan &pl, int k) { return (uint32_t)(k == pl.NW - 1 || k < pl.slack ? pl.c - 1 : pl.c); }
+DAPOL_HD_INLINE uint32_t rpb_window_offset(const RpbPlan &pl, int k) { return (uint32_t)(k * pl.c - (k < pl.slack ? k : pl.slack)); }
 // weight of proof p: draw p of ChaCha20(wseed); never zero in practice (probability 2^-252; a zero weight only weakens the check)
 DAPOL_HD_INLINE void rpb_weight_body(const RpbPlan &pl, uint64_t p) {
     uint32_t ks[16];
@@ -1051,16 +1061,16 @@ DAPOL_HD_INLINE void rpb_terms_body(const RpBatch &b, const RpbPlan &pl, uint64_
     const uint64_t nb = rpb_buckets_per_window(pl), g = p / (uint64_t)pl.G;
     const uint32_t none = (uint32_t)(pl.groups * (uint64_t)pl.NW * nb);
     uint32_t carry = 0;
-    const uint32_t c = (uint32_t)pl.c;
 #pragma unroll 1
     for (int k = 0; k < pl.NW; k++) {
-        uint32_t bit = (uint32_t)k * c, wi = bit >> 5, sh = bit & 31, raw = 0;
+        const uint32_t c = rpb_window_bits(pl, k);
+        uint32_t bit = rpb_window_offset(pl, k), wi = bit >> 5, sh = bit & 31, raw = 0;
         if (wi < 8) {
             raw = s.v[wi] >> sh;
             if (sh + c > 32 && wi + 1 < 8) raw |= s.v[wi + 1] << (32 - sh);
         }
         raw = (raw & ((1u << c) - 1u)) + carry;
-        carry = raw > (1u << (c - 1)) ? 1u : 0u;
+        carry = (k != pl.NW - 1 && raw > (1u << (c - 1))) ? 1u : 0u;  // the top window keeps its value: at most 2^(c-1) with the carry in
         int32_t d = (int32_t)raw - (int32_t)(carry << c);
         uint32_t neg = d < 0, mag = (uint32_t)(neg ? -d : d);
         const uint64_t e = pt * (uint64_t)pl.NW + k;
@@ -1125,22 +1135,26 @@ DAPOL_HD_INLINE void rpb_group_body(const RpBatch &b, const RpbPlan &pl, uint64_
 #pragma unroll 1
     for (int w = pl.NW - 1; w >= 0; w--) {
         if (w != pl.NW - 1)
-            for (int i = 0; i < pl.c; i++) ge_dbl(acc, acc);
+            for (uint32_t i = 0; i < rpb_window_bits(pl, w); i++) ge_dbl(acc, acc);
         rp_load_ext(s, pl.window + (g * pl.NW + w) * 32);
         ge_add(acc, acc, s);
     }
     rp_load_ext(s, pl.gfix + g * 32);
     ge_add(acc, acc, s);
-    int ok = ge_is_identity(acc);
-    const uint64_t p0 = g * (uint64_t)pl.G, p1 = p0 + pl.G < b.K ? p0 + pl.G : b.K;
-    for (uint64_t p = p0; p < p1; p++) ok &= b.status[p] != 0;
-    pl.gok[g] = ok;
+    pl.gok[g] = ge_is_identity(acc) && !pl.gbad[g];
 }
-// VBc (thread per (group, t)): weighted sum over the group's proofs of the scalar of generator t --
-// t < N: G_t; t < 2N: H_(t-N); 2N: B; 2N + 1: B_blinding (the per-proof scalars are those of rp_v2_partial)
-DAPOL_HD_INLINE void rpb_combine_body(const RpBatch &b, const RpbPlan &pl, uint64_t g, uint32_t t) {
+// (thread per proof) a proof that failed a format / decompression check fails its group
+DAPOL_HD_INLINE void rpb_status_body(const RpBatch &b, const RpbPlan &pl, uint64_t p) {
+    if (!b.status[p]) pl.gbad[p / (uint64_t)pl.G] = 1;
+}
+// VBc (thread per (group, part, t)): weighted sum over P proofs of the group of the scalar of generator t --
+// t < N: G_t; t < 2N: H_(t-N); 2N: B; 2N + 1: B_blinding (the per-proof scalars are those of rp_v2_partial); then (thread per
+// (group, t)) the sum of the parts
+DAPOL_HD_INLINE uint64_t rpb_parts(const RpbPlan &pl) { return ((uint64_t)pl.G + pl.P - 1) / pl.P; }
+DAPOL_HD_INLINE void rpb_combine_body(const RpBatch &b, const RpbPlan &pl, uint64_t g, uint64_t part, uint32_t t) {
     const uint32_t N = (uint32_t)b.N;
-    const uint64_t p0 = g * (uint64_t)pl.G, p1 = p0 + pl.G < b.K ? p0 + pl.G : b.K;
+    const uint64_t gend = g * (uint64_t)pl.G + pl.G < b.K ? g * (uint64_t)pl.G + pl.G : b.K;
+    const uint64_t p0 = g * (uint64_t)pl.G + part * pl.P, p1 = p0 + pl.P < gend ? p0 + pl.P : gend;
     sc sum;
     sc_set_u64(sum, 0);
 #pragma unroll 1
@@ -1167,7 +1181,18 @@ DAPOL_HD_INLINE void rpb_combine_body(const RpBatch &b, const RpbPlan &pl, uint6
         sc_mul(s, s, rho);
         sc_add(sum, sum, s);
     }
-    rp_st(pl.gsc + (g * (2 * N + 2) + t) * 8, sum);
+    rp_st(pl.gpart + ((g * rpb_parts(pl) + part) * (2 * N + 2) + t) * 8, sum);
+}
+DAPOL_HD_INLINE void rpb_combine_sum_body(const RpBatch &b, const RpbPlan &pl, uint64_t g, uint32_t t) {
+    const uint64_t per = 2ull * b.N + 2, parts = rpb_parts(pl);
+    sc sum, s;
+    sc_set_u64(sum, 0);
+#pragma unroll 1
+    for (uint64_t q = 0; q < parts; q++) {
+        rp_ld(s, pl.gpart + ((g * parts + q) * per + t) * 8);
+        sc_add(sum, sum, s);
+    }
+    rp_st(pl.gsc + (g * per + t) * 8, sum);
 }
 // VBf (CTA per group, partial sums): the group's fixed-base part from the generator tables
 template <int W, bool INL = false>

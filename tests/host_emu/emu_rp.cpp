@@ -249,13 +249,17 @@ EX void emu_rp_verify_batched(int nbits, int m, uint64_t K, const uint8_t *proof
     expand(b, b.ypow, 1);
     RpbPlan pl;
     memset(&pl, 0, sizeof pl);
-    pl.G = G; pl.groups = (K + G - 1) / G; pl.c = cbits; pl.NW = 253 / cbits + 1;
+    pl.G = G; pl.groups = (K + G - 1) / G; pl.P = 2;
+    rpb_set_windows(pl, cbits);
     const uint64_t nb = 1ull << (cbits - 1);
     pl.L = (int)std::min<uint64_t>(4, nb);  // small chunks so that several chunks per window are exercised
     const uint64_t n_terms = K * nv * pl.NW, n_buckets = pl.groups * pl.NW * nb, n_chunks = n_buckets / pl.L, n_gw = pl.groups * pl.NW;
     memcpy(pl.wseed, wseed, 32);
     std::vector<uint32_t> rho(K * 8), cached(K * nv * 32), keys_in(n_terms), keys(n_terms), vals_in(n_terms), vals(n_terms), bucket(n_buckets * 32),
-        crun(n_chunks * 32), ctot(n_chunks * 32), window(n_gw * 32), gsc(pl.groups * (2 * N + 2) * 8), gfix(pl.groups * 32);
+        crun(n_chunks * 32), ctot(n_chunks * 32), window(n_gw * 32), gsc(pl.groups * (2 * N + 2) * 8), gfix(pl.groups * 32),
+        gpart(pl.groups * rpb_parts(pl) * (2 * N + 2) * 8);
+    std::vector<int> gbad(pl.groups, 0);
+    pl.gpart = gpart.data(); pl.gbad = gbad.data();
     pl.rho = rho.data(); pl.cached = cached.data(); pl.keys_in = keys_in.data(); pl.keys = keys.data(); pl.vals_in = vals_in.data(); pl.vals = vals.data();
     pl.bucket = bucket.data(); pl.chunk_run = crun.data(); pl.chunk_tot = ctot.data(); pl.window = window.data(); pl.gsc = gsc.data(); pl.gfix = gfix.data();
     pl.gok = gok;
@@ -268,7 +272,10 @@ EX void emu_rp_verify_batched(int nbits, int m, uint64_t K, const uint8_t *proof
     for (uint64_t bk = 0; bk < n_buckets; bk++) rpb_bucket_body(pl, bk, n_terms);
     for (uint64_t ch = 0; ch < n_chunks; ch++) rpb_chunk_body(pl, ch);
     for (uint64_t gw = 0; gw < n_gw; gw++) rpb_window_body(pl, gw);
-    for (uint64_t g = 0; g < pl.groups; g++) for (uint32_t t = 0; t < 2 * N + 2; t++) rpb_combine_body(b, pl, g, t);
+    for (uint64_t g = 0; g < pl.groups; g++)
+        for (uint64_t part = 0; part < rpb_parts(pl); part++) for (uint32_t t = 0; t < 2 * N + 2; t++) rpb_combine_body(b, pl, g, part, t);
+    for (uint64_t g = 0; g < pl.groups; g++) for (uint32_t t = 0; t < 2 * N + 2; t++) rpb_combine_sum_body(b, pl, g, t);
+    for (uint64_t p = 0; p < K; p++) rpb_status_body(b, pl, p);
     for (uint64_t g = 0; g < pl.groups; g++) {
         ge sum, part;
         ge_identity(sum);

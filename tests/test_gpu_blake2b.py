@@ -29,7 +29,10 @@ def ctx():
 def _trees(ctx, cref, n, H, seed, agg=1, policy=0):
     from dapol_b200 import Dapol
     rnd = random.Random(seed)
-    idx = np.array(sorted(rnd.sample(range(1 << H), n)) if H else [0], np.uint64)
+    pick = set()
+    while len(pick) < n:
+        pick.add(rnd.randrange(1 << H) if H else 0)
+    idx = np.array(sorted(pick), np.uint64)
     vals = np.array([rnd.randrange(1 << 32) for _ in range(n)], np.uint64)
     bl = np.frombuffer(rnd.randbytes(32 * n), np.uint8).copy().reshape(n, 32)
     bl[:, 31] &= 0x7F
