@@ -200,15 +200,20 @@ __global__ void __launch_bounds__(128) k_rp_p2(RpBatch b) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < b.K * b.N) rp_p2_body(b, t / b.N, (uint32_t)(t % b.N));
 }
+// result of CTA (proof x, which y, split z): the point itself, or one of gridDim.z partial sums
+__device__ __forceinline__ void store_msm_point(const RpBatch &b, const ge &acc) {
+    if (gridDim.z == 1) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
+    else rp_store_ext(b.parts + (((uint64_t)blockIdx.x * 2 + blockIdx.y) * RP_SPLIT_MAX + blockIdx.z) * 32, acc);
+}
 // MSM kernels (CTA per proof).  INL: 128-thread CTAs of the large shapes run the mixed additions with inlined products; the
 // single-warp CTAs of the small shapes share the called multiplication (see ge25519.cuh, ge_madd_inl).
 template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rp_p3(RpBatch b) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
-    rp_p3_partial<W, INL>(acc, b, blockIdx.x, blockIdx.y, threadIdx.x, blockDim.x);
+    rp_p3_partial<W, INL>(acc, b, blockIdx.x, blockIdx.y, blockIdx.z * blockDim.x + threadIdx.x, gridDim.z * blockDim.x);
     block_reduce_ge(acc, sh);
-    if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
+    if (threadIdx.x == 0) store_msm_point(b, acc);
 }
 __global__ void __launch_bounds__(64) k_rp_p4(RpBatch b) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,9 +260,14 @@ template <int W, bool INL>
 __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_MINB) k_rp_p10(RpBatch b, int rnd) {
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
-    rp_p10_partial<W, INL>(acc, b, blockIdx.x, rnd, blockIdx.y, threadIdx.x, blockDim.x);
+    rp_p10_partial<W, INL>(acc, b, blockIdx.x, rnd, blockIdx.y, blockIdx.z * blockDim.x + threadIdx.x, gridDim.z * blockDim.x);
     block_reduce_ge(acc, sh);
-    if (threadIdx.x == 0) rp_store_point(b, blockIdx.x, blockIdx.y, acc);
+    if (threadIdx.x == 0) store_msm_point(b, acc);
+}
+// small batches: the S partial sums of a split MSM (grid z) -> the point of (proof, L | R)
+__global__ void __launch_bounds__(32) k_rp_sum_parts(RpBatch b, uint32_t S) {
+    uint64_t pw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pw < 2 * b.K) rp_sum_parts_body(b, pw, S);
 }
 __global__ void __launch_bounds__(64) k_rp_p11(RpBatch b, int rnd) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -336,6 +346,14 @@ static size_t rp_per_proof_bytes(int N, int m, int lg, bool verify) {
     if (verify) s += (size_t)rp_nvar(lg, m) * (128 + 32 + 8 * 128);  // partial points, scalars, cached multiples
     return s;
 }
+#define RP_SPLIT_MAX_K 64  // batches up to this many proofs split their MSMs over several CTAs
+// CTAs per (proof, L | R) MSM of `terms` terms on T threads: enough CTAs to cover the SMs twice, at least ~2 terms per thread
+static unsigned msm_split(uint64_t K, uint64_t terms, unsigned T) {
+    if (K > RP_SPLIT_MAX_K) return 1;
+    uint64_t s = (2 * 148 + 2 * K - 1) / (2 * K);
+    s = std::min<uint64_t>(s, std::max<uint64_t>(1, terms / (2ull * T)));
+    return (unsigned)std::min<uint64_t>(s, RP_SPLIT_MAX);
+}
 struct RpPlan {
     RpBatch b;
     uint8_t *mem = nullptr;
@@ -351,7 +369,8 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
     Arena ar;
     ar.size = Arena::need(K, sizeof(merlin)) + 3 * Arena::need(K * m, 32) + Arena::need(K * CH_COUNT, 32) + Arena::need(K * 3 * 32, 32) +
               4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * nv, 128) +
-              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : Arena::need(K * 2 * RP_FOLD_N, 128));
+              Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : Arena::need(K * 2 * RP_FOLD_N, 128)) +
+              (!verify && K <= RP_SPLIT_MAX_K ? Arena::need(K * 2 * RP_SPLIT_MAX, 128) : 0);
     CUDA_TRY(dmalloc(&pl.mem, ar.size, ctx->stream));
     ar.base = pl.mem;
     b.tr = ar.take<merlin>(K);
@@ -375,6 +394,7 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
         for (int i = 0; i < 2; i++) { b.cu[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); b.cui[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); }
         b.pts = ar.take<uint32_t>(K * 2 * 32);
         b.gfold = ar.take<uint32_t>(K * 2 * RP_FOLD_N * 32);
+        if (K <= RP_SPLIT_MAX_K) b.parts = ar.take<uint32_t>(K * 2 * RP_SPLIT_MAX * 32);
         b.proof = ar.take<uint32_t>(K * b.plen / 4);
     }
     b.status = ar.take<int>(K);
@@ -442,8 +462,10 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     tm.end();
     tm.begin(TM_P3);
-    if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
-    else k_rp_p3<W, false><<<dim3((unsigned)K, 2), TS, 0, st>>>(b);
+    const unsigned S3 = b.parts ? msm_split(K, N, TS) : 1, S10 = b.parts ? msm_split(K, N, T) : 1;
+    if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
+    else k_rp_p3<W, false><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
+    if (S3 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S3); ctx->launches++; }
     tm.end();
     tm.begin(1);
     k_rp_p4<<<grid_for(K, 64), 64, 0, st>>>(b);
@@ -455,7 +477,10 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     tm.end();
     ctx->launches += 10;
-    const int sw = rp_switch_round(b.N, b.lg);  // first round over folded generators (large aggregates), else lg + 1
+    // first round over folded generators (large aggregates), else lg + 1.  Small batches stay on the generator tables: the
+    // variable-base chains of the folded rounds (252 doublings each) are latency a handful of proofs cannot hide, while a table
+    // round split over the whole GPU is a few additions per thread -- same L_k, R_k, so the same bytes.
+    const int sw = S10 > 1 ? b.lg + 1 : rp_switch_round(b.N, b.lg);
     for (int rnd = 1; rnd <= b.lg; rnd++) {
         uint32_t h = (uint32_t)(N >> rnd), cnt = std::max<uint32_t>(h, 1u << (rnd - 1));
         tm.begin(1);
@@ -464,8 +489,9 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         tm.begin(rnd >= sw ? TM_HYB : TM_P10);
         if (rnd == sw) { k_rp_pm<W><<<grid_for(K * 2 * RP_FOLD_N, 64), 64, 0, st>>>(b, sw); ctx->launches++; }
         if (rnd >= sw) k_rp_pv<W><<<grid_for(K * 4 * h, 128), 128, 0, st>>>(b, rnd);
-        else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
-        else k_rp_p10<W, false><<<dim3((unsigned)K, 2), T, 0, st>>>(b, rnd);
+        else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
+        else k_rp_p10<W, false><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
+        if (rnd < sw && S10 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S10); ctx->launches++; }
         tm.end();
         tm.begin(1);
         k_rp_p11<<<grid_for(K, 64), 64, 0, st>>>(b, rnd);

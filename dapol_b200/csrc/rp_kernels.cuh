@@ -358,6 +358,7 @@ struct RpBatch {
     uint32_t *svec;             // [K][N][8]   verifier s vector
     uint32_t *cu[2], *cui[2];   // [K][N/2][8] coefficient tables, ping-pong
     uint32_t *pts;              // [K][2][32]  extended points out of the MSM passes
+    uint32_t *parts;            // [K][2][RP_SPLIT_MAX][32] small batches: partial sums of an MSM split over several CTAs (else nullptr)
     uint32_t *gfold;            // [K][2][RP_FOLD_N][32] folded generators G^(k), H^(k) of the variable-base rounds (extended)
     uint32_t *varpts;           // [K][nvar][32] verifier: partial sums of s_q * P_q (the first vgroups entries are used)
     uint32_t *varsc;            // [K][nvar][8]  verifier: scalars of the variable points
@@ -471,6 +472,17 @@ DAPOL_HD_INLINE void rp_p3_partial(ge &acc, const RpBatch &b, uint64_t p, int wh
         rp_ld(s, rp_ch(b, p, CH_SBL));
         rp_fixed_mul_spread<W>(acc, b.tabBbl, 0, s, tid, T);
     }
+}
+// Small batches (a single proof is the reference's own benchmark, benches/dapol.rs:59-141): one CTA per (proof, L | R) leaves
+// most of the GPU idle, so an MSM is split over S CTAs -- the strided term loops take (tid, T) over all S * blockDim threads --
+// and the S partial sums are added by rp_sum_parts_body (thread per (proof, L | R)).
+#define RP_SPLIT_MAX 32
+DAPOL_HD_INLINE void rp_sum_parts_body(const RpBatch &b, uint64_t pw, uint32_t S) {
+    ge acc, q;
+    rp_load_ext(acc, b.parts + (pw * RP_SPLIT_MAX) * 32);
+#pragma unroll 1
+    for (uint32_t z = 1; z < S; z++) { rp_load_ext(q, b.parts + (pw * RP_SPLIT_MAX + z) * 32); ge_add(acc, acc, q); }
+    rp_store_ext(b.pts + pw * 32, acc);
 }
 // write the sum point of an MSM pass
 DAPOL_HD_INLINE void rp_store_point(const RpBatch &b, uint64_t p, int which, const ge &pt) { rp_store_ext(b.pts + (p * 2 + which) * 32, pt); }

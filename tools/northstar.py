@@ -5,6 +5,8 @@ to a per-rank file and verified against the gathered root -- each rank handles t
 communication after the tree build.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/northstar.py
       [users_log2=24] [height=40] [policy=0] [chunk=4096] [limit_per_rank=0] [oracle_sample_per_rank=8]
+VERIFY_GROUP=G in the environment: the verifier checks G proofs per random linear combination with the bucket method
+(dapol_ctx_set_verify_mode; 0 / unset = every proof on its own).
 Checks: rank 0's subtree root equals the ORACLE's root of shard 0 (tests/golden/full_size_golden.json, when the config is the
 golden's); every proof verifies on the GPU; a tampered proof is rejected; a sample of proofs per rank is verified by the CPU
 oracle's DapolProof::verify restatement.  Timing: wall clock between barrier + synchronize pairs, max over ranks."""
@@ -42,6 +44,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    verify_group = int(os.environ.get("VERIFY_GROUP", "0"))
+    ctx.set_verify_mode(verify_group)
     L = _ffi.lib()
     comm, engine = Comm(), CudaEngine(ctx)
     native = NativeComm(ctx, comm, "nccl")
@@ -155,7 +159,7 @@ def main():
             "prove_s_max_rank": mx[0].item(), "write_s_max_rank": mx[6].item(), "verify_s_max_rank": mx[1].item(), "prove_write_verify_wall_s": mx[2].item(),
             "prove_per_s": done / mx[0].item(), "verify_per_s": done / mx[1].item(), "proofs_per_s_wall": done / mx[2].item(),
             "total_wall_s_build_plus_proofs": build_s + mx[2].item(),
-            "rangeproof_window": params["rangeproof_window"], "comb_window": params["comb_window"], "chunk": chunk,
+            "verify_group": verify_group, "verify_fallbacks_rank0": int(ctx.verify_fallbacks), "rangeproof_window": params["rangeproof_window"], "comb_window": params["comb_window"], "chunk": chunk,
             "rank0_chunk_s_prove_write_verify": chunk_times,
             "timing": "wall clock between barrier + synchronize pairs, max over ranks; host buffers (proofs D2H after prove, written, H2D for verify)"}), flush=True)
     tree.close(); native.close(); ctx.close()
