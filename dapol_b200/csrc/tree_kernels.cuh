@@ -183,6 +183,11 @@ DAPOL_HD_INLINE void leaf_batch_body(uint64_t t, uint64_t stride, uint64_t n, co
     }
 }
 
+// mixed additions of the padding comb with inlined products (experiment, profiles/r02_variants.txt): the loop of 10 additions per
+// node is where k_pad spends 70 % of its time, and every called product costs 24 register moves on the multiply pipe
+#ifndef DAPOL_PAD_COMB_INL
+#define DAPOL_PAD_COMB_INL false
+#endif
 // ChaCha stream of the padding node with creation ordinal g.  Stream mode: always 0.  Positional mode: the
 // node's level inside the whole tree; ordinals run level H first, so level h owns [start[h], start[h - 1]).
 struct PadStreams {
@@ -218,7 +223,7 @@ DAPOL_HD_INLINE void pad_batch_body(uint64_t t, uint64_t stride, uint64_t n, con
         sc_signed_digits<W, NWR>(d, rh.v, 8);
         ge acc;
         ge_identity(acc);
-        ge_comb_accumulate<W, NWR, true>(acc, tab_bbl, d);
+        ge_comb_accumulate<W, NWR, true, DAPOL_PAD_COMB_INL>(acc, tab_bbl, d);
         uint64_t dest = pad_dest[g];
         ns.v[dest] = 0;
         store8(ns.r + 8 * dest, r.v);
