@@ -81,6 +81,7 @@ struct dapol_tree {
     uint32_t **d_pos = nullptr;   // device copy of the pointer table
     uint64_t *d_level_off = nullptr;
     uint64_t *leaf_index_of = nullptr;  // device [n]: leaf idx of the i-th input liability (from_liabilities only)
+    bool custom_leaf_hashes = false;  // leaf hashes are the id / salt ones (DAPOL_LEAF_HASH_ID_SALT), not D(compress(com))
     uint64_t index_map_first = 0, index_map_n = 0;  // sharded build: the map covers input positions [first, first + n) (0: all n_leaves)
     // lookup by internal id (Dapol::generate_proof_for_id, mod.rs:148-165): audit ids of the mapped liabilities, the audit seed, and
     // -- built on the first lookup -- the ids' 64-bit prefixes sorted with the input position of each

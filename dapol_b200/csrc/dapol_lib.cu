@@ -782,7 +782,8 @@ extern "C" int dapol_tree_update(const dapol_tree *t, uint64_t k, const uint64_t
                                  const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out) {
     if (!t || !k || !leaf_idx || !values || !blindings || !pad_seed || !out) return DAPOL_ERR_BAD_ARG;
     *out = nullptr;
-    if (t->top || t->height == 0 || t->n_leaves + k >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;  // a shard is updated through a rebuild of its slice
+    // a shard is updated through a rebuild of its slice; id / salt leaf hashes cannot be recomputed from (value, blinding)
+    if (t->top || t->custom_leaf_hashes || t->height == 0 || t->n_leaves + k >= (1ull << 31)) return DAPOL_ERR_BAD_ARG;
     dapol_ctx *ctx = t->ctx;
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -955,6 +956,7 @@ static int liabilities_build_dev(dapol_ctx *ctx, int hash_id, int height, uint64
     dfree(mem, st);
     if (rc != DAPOL_OK) { dfree(cand, st); dfree(audit, st); return rc; }
     (*out)->leaf_index_of = cand;
+    (*out)->custom_leaf_hashes = leaf_hashes != nullptr;
     (*out)->audit_ids = audit;
     (*out)->audit_seed.assign(audit_seed, audit_seed + seed_len);
 #undef TRY_L
@@ -1139,7 +1141,7 @@ struct TreeFileHeader {  // little-endian, 64 bytes
     char magic[8];
     uint32_t version;
     int32_t hash_id, height;
-    uint32_t flags;  // bit 0: id -> leaf-index map present
+    uint32_t flags;  // bit 0: id -> leaf-index map present; bit 1: the leaves carry id / salt hashes
     uint64_t n_leaves, T, n_pads, pos_words;
     uint64_t reserved;
 };
@@ -1225,7 +1227,7 @@ extern "C" int dapol_tree_save(const dapol_tree *t, const char *path) {
     TreeFileHeader h = {};
     memcpy(h.magic, TREE_MAGIC, 8);
     const bool save_map = t->leaf_index_of && t->index_map_n == 0;  // a shard's local slice of the map is not saved
-    h.version = 1; h.hash_id = t->hash_id; h.height = H; h.flags = save_map ? 1u : 0u;
+    h.version = 1; h.hash_id = t->hash_id; h.height = H; h.flags = (save_map ? 1u : 0u) | (t->custom_leaf_hashes ? 2u : 0u);
     h.n_leaves = t->n_leaves; h.T = T; h.n_pads = t->n_pads; h.pos_words = pos_words_of(t->n_real, H, nullptr);
     int rc = DAPOL_OK;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1;
@@ -1262,6 +1264,7 @@ extern "C" int dapol_tree_load(dapol_ctx *ctx, const char *path, dapol_tree **ou
     const int H = h.height;
     dapol_tree *t = new dapol_tree();
     t->ctx = ctx; t->hash_id = h.hash_id; t->height = H; t->n_leaves = h.n_leaves; t->T = h.T; t->n_pads = h.n_pads;
+    t->custom_leaf_hashes = (h.flags & 2u) != 0;
     t->level_off.assign(H + 1, 0); t->level_n.assign(H + 1, 0); t->n_real.assign(H + 1, 0); t->npads.assign(H + 1, 0);
     t->pos.assign(H + 1, nullptr);
     int rc = DAPOL_OK;

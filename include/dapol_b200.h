@@ -128,7 +128,8 @@ DAPOL_API int dapol_tree_build_from_nodes_dev(dapol_ctx *ctx, int hash_id, int h
  * that makes update and build agree bit for bit; in the stream mode pass a pad_base past the blocks already drawn (num_padding),
  * so that no padding blinding is used twice (the reference draws fresh thread_rng() values either way, and its own test compares
  * the two roots by value only, src/tests.rs:47, src/dapol/node.rs:115-120).  Trees built from liabilities lose their id -> index
- * map (the new leaves have no ids).  DAPOL_ERR_BAD_ARG for a shard with a top tree attached or a height-0 tree. */
+ * map (the new leaves have no ids).  DAPOL_ERR_BAD_ARG for a shard with a top tree attached, a height-0 tree, or a tree whose leaves
+ * carry id / salt hashes (DAPOL_LEAF_HASH_ID_SALT: they cannot be recomputed from value and blinding). */
 DAPOL_API int dapol_tree_update(const dapol_tree *tree, uint64_t k, const uint64_t *leaf_idx, const uint64_t *values,
                                 const uint8_t *blindings /* k*32 */, const uint8_t pad_seed[32], uint64_t pad_base, dapol_tree **out);
 

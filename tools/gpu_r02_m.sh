@@ -1,0 +1,33 @@
+#!/bin/bash
+# Round 2, GPU call M (one GPU): final state -- smoke, the WHOLE GPU parity suite, bench N=1 (all legs), the CPU arm, ncu launch list of the
+# bench command, ncu --set full of the bucket-method kernels, window sweep of the group verifier.
+mkdir -p gpurun_out
+P=gpurun_out/r02m
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > ${P}_gpu.txt; nproc >> ${P}_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee ${P}_smoke.txt
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -12 | tee ${P}_pytest_gpu.txt
+timeout 1200 python bench.py > ${P}_bench_n1.json 2> ${P}_bench_n1.err; tail -3 ${P}_bench_n1.err
+timeout 600 python bench.py --impl reference --steps 2 > ${P}_bench_reference_arm.json 2> ${P}_bench_reference_arm.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file ${P}_launches.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --rp-singles 0 --rp-aggregates 0 > ${P}_ncu_bench.log 2>&1
+timeout 600 python tools/verify_probe.py 64x1x16384 256,256:8,256:10,256:11,1024,1024:10,1024:12,4096:11,4096:13,64,64:6,64:8 > ${P}_verify_probe_m1.json 2> ${P}_verify_probe_m1.err
+timeout 600 python tools/verify_probe.py 64x32x2048 256,256:10,256:12,64,64:9,2048:13 > ${P}_verify_probe_m32.json 2> ${P}_verify_probe_m32.err
+cat ${P}_verify_probe_m1.json ${P}_verify_probe_m32.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches_verify.csv \
+  python tools/verify_probe.py 64x1x16384 256 > ${P}_ncu_verify.log 2>&1
+for k in k_rpb_buckets k_rpb_terms; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -o ${P}_$k -f \
+    python tools/verify_probe.py 64x1x16384 256 > ${P}_ncu_$k.log 2>&1
+  ncu -i ${P}_$k.ncu-rep --page raw --csv > ${P}_${k}_raw.csv 2>/dev/null
+done
+rm -f gpurun_out/*.ncu-rep
+python - <<PY
+import json
+d = json.loads([l for l in open("${P}_bench_n1.json") if l.startswith("{")][-1])
+print(round(d["value"]/1e6,2), d["phase_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["gpu_launches"], d["clocks"], d.get("gpu_root_matches"))
+print(json.dumps(d.get("c1")))
+rp = d["range_proofs"]
+for k in ("n64_m1", "n64_m32"):
+    print(k, round(rp[k]["prove_per_s"]), round(rp[k]["verify_per_s"]), rp[k]["roofline"]["frac"], [(b["group"], round(b["verify_per_s"])) for b in rp[k]["verify_batched_bucket_method"]])
+print(d.get("cpu_baseline"))
+PY
