@@ -218,21 +218,7 @@ __global__ void k_resolve_collisions(uint64_t n, const uint64_t *sorted_cand, co
 // so that a leaf's hash binds the user's id and a per-user salt instead of being computable from the commitment alone.
 __global__ void k_leaf_id_hashes(uint64_t n, int hash_id, const uint32_t *audit, const uint8_t *eid_blob, const uint64_t *eid_off, uint32_t *out, int *too_long) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t tag_s[9] = {'s', 'a', 'l', 't', '_', 's', 'e', 'e', 'd'}, tag_l[4] = {'l', 'e', 'a', 'f'};
-    const uint8_t *eid = eid_blob + eid_off[i];
-    const uint32_t elen = (uint32_t)(eid_off[i + 1] - eid_off[i]);
-    dapol_hasher hs;
-    uint32_t a[8], salt[8], h[8];
-    load8(a, audit + 8 * i);
-    hasher_init(hs, hash_id);
-    hasher_update_words(hs, a, 8); hasher_update(hs, tag_s, 9); hasher_update(hs, eid, elen);
-    int rc = hasher_final(hs, salt);
-    hasher_init(hs, hash_id);
-    hasher_update(hs, tag_l, 4); hasher_update(hs, eid, elen); hasher_update_words(hs, salt, 8);
-    rc |= hasher_final(hs, h);
-    if (rc) *too_long = 1;
-    store8(out + 8 * i, h);
+    if (i < n && leaf_id_hash_body(i, hash_id, audit, eid_blob, eid_off, out)) *too_long = 1;
 }
 __global__ void k_gather_hashes(uint64_t n, const uint32_t *who, const uint32_t *src, uint32_t *dst) {
     uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

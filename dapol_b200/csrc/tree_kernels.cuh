@@ -130,6 +130,29 @@ DAPOL_HD_INLINE int rehash_body(uint64_t u, int hash_id, int height, uint32_t *c
     return 1;
 }
 
+// Opt-in leaf hash of the DAPOL+ paper (NOT the reference's bytes, which hash the commitment only, node.rs:33-36):
+//   salt = D(audit_id || "salt_seed" || external_id),  leaf hash = D("leaf" || external_id || salt).
+// Keep this a function: with the two tag arrays declared directly inside the __global__ kernel, nvcc 12.9 (sm_100a, -O3) produced
+// wrong digests for every input while the very same statements inside a device function are right (tools/dbg/idsalt8.cu runs
+// both shapes side by side on the device; found when tests/test_gpu_ids.py went red without a source change in this path).
+DAPOL_HD_INLINE int leaf_id_hash_body(uint64_t i, int hash_id, const uint32_t *audit, const uint8_t *eid_blob, const uint64_t *eid_off, uint32_t *out) {
+    const uint8_t tag_s[9] = {'s', 'a', 'l', 't', '_', 's', 'e', 'e', 'd'};
+    const uint8_t tag_l[4] = {'l', 'e', 'a', 'f'};
+    const uint8_t *eid = eid_blob + eid_off[i];
+    const uint32_t elen = (uint32_t)(eid_off[i + 1] - eid_off[i]);
+    dapol_hasher hs;
+    uint32_t a[8], salt[8], h[8];
+    load8(a, audit + 8 * i);
+    hasher_init(hs, hash_id);
+    hasher_update_words(hs, a, 8); hasher_update(hs, tag_s, 9); hasher_update(hs, eid, elen);
+    int rc = hasher_final(hs, salt);
+    hasher_init(hs, hash_id);
+    hasher_update(hs, tag_l, 4); hasher_update(hs, eid, elen); hasher_update_words(hs, salt, 8);
+    rc |= hasher_final(hs, h);
+    store8(out + 8 * i, h);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Node passes.  Every commitment is carried as its HALF point Q (com = 2Q) in ns.ext: scalars are halved mod l
 // before the comb and parents are Q_L + Q_R, so that compress(com) is the batched double-and-compress of

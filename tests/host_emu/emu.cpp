@@ -271,3 +271,15 @@ EX void emu_tree_level_copy(EmuTree *t, int h, uint64_t *idx, uint64_t *v, uint8
     memcpy(is_pad, &t->is_pad[o], n);
 }
 EX void emu_tree_free(EmuTree *t) { delete t; }
+
+// id / salt leaf hashes (opt-in mode) through the kernel body: audit ids as derive_body leaves them
+EX int emu_leaf_id_hashes(int hash_id, uint64_t n, const uint8_t *iid_blob, const uint64_t *iid_off, const uint8_t *eid_blob, const uint64_t *eid_off,
+                          const uint8_t *seed, uint32_t seed_len, int height, uint8_t *out) {
+    std::vector<uint32_t> audit(8 * n), cur(8 * n), blind(8 * n), h(8 * n);
+    std::vector<uint64_t> cand(n);
+    int rc = 0;
+    for (uint64_t i = 0; i < n; i++) rc |= derive_body(i, hash_id, iid_blob, iid_off, eid_blob, eid_off, seed, seed_len, height, audit.data(), cur.data(), cand.data(), blind.data());
+    for (uint64_t i = 0; i < n; i++) rc |= leaf_id_hash_body(i, hash_id, audit.data(), eid_blob, eid_off, h.data());
+    w2b(out, h.data(), 8 * n);
+    return rc;
+}

@@ -234,3 +234,18 @@ def test_leaf_derivation_bodies_vs_oracle(E, cref, hid, H, n, dup):
             assert list(idx1) == [7, 12, 2, 4]
     else:
         assert err0 == err1.value == 57
+
+
+def test_id_salt_leaf_hash_body(E, cref):
+    """Opt-in id / salt leaf hash (DAPOL_LEAF_HASH_ID_SALT): the kernel body against the C oracle (itself pinned to hashlib / blake3 in
+    tests/test_oracle_pins.py), ids and external ids of every length class incl. empty and longer than one BLAKE3 chunk."""
+    rnd = random.Random(31)
+    ids = [b"user-%d" % i for i in range(40)]
+    eids = [rnd.randbytes(rnd.choice([0, 1, 4, 33, 64, 119, 1024, 1200, 2500])) for _ in range(40)]
+    ib, io = cref.pack_ids(ids); eb, eo = cref.pack_ids(eids)
+    for hid in (0, 1):
+        want = cref.leaf_id_hashes(hid, ib, io, eb, eo, b"id-salt")
+        out = np.zeros((40, 32), np.uint8)
+        rc = E.emu_leaf_id_hashes(hid, C.c_uint64(40), ib.ctypes.data_as(C.c_void_p), io.ctypes.data_as(C.c_void_p), eb.ctypes.data_as(C.c_void_p),
+                                  eo.ctypes.data_as(C.c_void_p), B(b"id-salt"), 7, 10, out.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and (out == want).all()
