@@ -201,68 +201,77 @@ extern "C" int dapol_prove_batch(const dapol_tree *t, uint64_t k, const uint64_t
 
 // ------------------------------------------------------------------------------------------------ verify
 // MerkleProof::verify: fold upward from the leaf with DapolProofNode::merge (src/proof/node.rs:56-69):
-// hash = D(C_l || C_r || H_l || H_r), com = com_l + com_r.  One thread per proof; sibs = [H][com 32 || hash 32].
-__global__ void __launch_bounds__(64) k_merkle_fold(uint64_t k, int hash_id, const uint8_t *blob, const uint64_t *sib_off, const uint32_t *heights,
-                                                    const uint64_t *idx, const uint32_t *leaf_c, const uint32_t *leaf_h, const uint32_t *root,
-                                                    uint8_t *ok) {
+// hash = D(C_l || C_r || H_l || H_r), com = com_l + com_r; sibs = [H][com 32 || hash Dlen].
+// The expensive steps run side by side (a thread per proof would run 2 H inverse square roots one after the other -- 3.8 ms for
+// ONE height-16 proof -- and leave the GPU idle on small batches): every point of a proof is decompressed by its
+// own thread, the running commitment of level lv = leaf + sib_0 + .. + sib_(lv-1) is summed and compressed by its own thread, and
+// only the hash chain (H short hashes) stays sequential.  pts: [k][hmax + 1][32] (0 = leaf, j + 1 = sibling j); comc: [k][hmax + 1][8].
+__global__ void __launch_bounds__(64) k_merkle_decompress(uint64_t k, uint32_t hmax, uint32_t ss, const uint8_t *blob, const uint64_t *sib_off, const uint32_t *heights,
+                                                          const uint32_t *leaf_c, uint32_t *pts, uint8_t *ok) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * (hmax + 1)) return;
+    const uint64_t p = t / (hmax + 1);
+    const uint32_t j = (uint32_t)(t % (hmax + 1));
+    if (!ok[p] || j > heights[p]) return;
+    uint32_t w[8];
+    if (j == 0) load8(w, leaf_c + 8 * p);
+    else {
+        const uint8_t *a = blob + sib_off[p] + (uint64_t)ss * (j - 1);  // the blob is byte-aligned only
+        for (int i = 0; i < 8; i++) w[i] = (uint32_t)a[4 * i] | ((uint32_t)a[4 * i + 1] << 8) | ((uint32_t)a[4 * i + 2] << 16) | ((uint32_t)a[4 * i + 3] << 24);
+    }
+    ge q;
+    if (!ge_decompress(q, w)) { ok[p] = 0; return; }
+    rp_store_ext(pts + (p * (hmax + 1) + j) * 32, q);
+}
+__global__ void __launch_bounds__(64) k_merkle_prefix(uint64_t k, uint32_t hmax, const uint32_t *heights, const uint32_t *pts, uint32_t *comc, const uint8_t *ok) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * (hmax + 1)) return;
+    const uint64_t p = t / (hmax + 1);
+    const uint32_t lv = (uint32_t)(t % (hmax + 1));
+    if (!ok[p] || lv == 0 || lv > heights[p]) return;
+    ge acc, q;
+    rp_load_ext(acc, pts + (p * (hmax + 1)) * 32);
+#pragma unroll 1
+    for (uint32_t j = 1; j <= lv; j++) { rp_load_ext(q, pts + (p * (hmax + 1) + j) * 32); ge_add(acc, acc, q); }
+    uint32_t c[8];
+    ge_compress(c, acc);
+    store8(comc + (p * (hmax + 1) + lv) * 8, c);
+}
+__global__ void __launch_bounds__(64) k_merkle_hash_chain(uint64_t k, uint32_t hmax, int hash_id, uint32_t ss, const uint8_t *blob, const uint64_t *sib_off,
+                                                          const uint32_t *heights, const uint64_t *idx, const uint32_t *leaf_c, const uint32_t *leaf_h,
+                                                          const uint32_t *comc, const uint32_t *root, uint8_t *ok) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= k || !ok[p]) return;
-    if (hash_id == DAPOL_HASH_BLAKE2B) {  // 64-byte digests: leaf_h = [k][16], root = com (8) | hash (16), siblings of 96 bytes
-        uint32_t curc[8], curl[8], curu[8], sc_[8], sl[8], su[8];
-        load8(curc, leaf_c + 8 * p); load8(curl, leaf_h + 16 * p); load8(curu, leaf_h + 16 * p + 8);
-        ge cur, s;
-        int good = ge_decompress(cur, curc);
-        const uint8_t *sib = blob + sib_off[p];
-        const uint32_t H = heights[p];
-        const uint64_t x = idx[p];
-#pragma unroll 1
-        for (uint32_t lv = 0; lv < H && good; lv++) {
-            for (int i = 0; i < 8; i++) {
-                const uint8_t *a = sib + 96 * lv + 4 * i;
-                sc_[i] = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);
-                sl[i] = (uint32_t)a[32] | ((uint32_t)a[33] << 8) | ((uint32_t)a[34] << 16) | ((uint32_t)a[35] << 24);
-                su[i] = (uint32_t)a[64] | ((uint32_t)a[65] << 8) | ((uint32_t)a[66] << 16) | ((uint32_t)a[67] << 24);
-            }
-            good &= ge_decompress(s, sc_);
-            uint32_t lo[8], hi[8];
-            if ((x >> lv) & 1) dapol_b2b_hash192(lo, hi, sc_, curc, sl, su, curl, curu);
-            else dapol_b2b_hash192(lo, hi, curc, sc_, curl, curu, sl, su);
-#pragma unroll
-            for (int i = 0; i < 8; i++) { curl[i] = lo[i]; curu[i] = hi[i]; }
-            ge_add(cur, cur, s);
-            ge_compress(curc, cur);
-        }
-        uint32_t d = 0;
-        for (int i = 0; i < 8; i++) d |= (curc[i] ^ root[i]) | (curl[i] ^ root[8 + i]) | (curu[i] ^ root[16 + i]);
-        ok[p] = (uint8_t)(good && d == 0);
-        return;
-    }
-    uint32_t curc[8], curh[8], sc_[8], sh[8];
-    load8(curc, leaf_c + 8 * p); load8(curh, leaf_h + 8 * p);
-    ge cur, s;
-    int good = ge_decompress(cur, curc);
+    const bool wide = hash_id == DAPOL_HASH_BLAKE2B;  // 64-byte digests: leaf_h = [k][16], root = com (8) | hash (16)
+    const int hw = wide ? 16 : 8;
+    uint32_t curc[8], curl[8], curu[8], sc_[8], sl[8], su[8];
+    load8(curc, leaf_c + 8 * p); load8(curl, leaf_h + (uint64_t)hw * p);
+    if (wide) load8(curu, leaf_h + 16 * p + 8);
     const uint8_t *sib = blob + sib_off[p];
     const uint32_t H = heights[p];
     const uint64_t x = idx[p];
 #pragma unroll 1
-    for (uint32_t lv = 0; lv < H && good; lv++) {
-        for (int i = 0; i < 8; i++) {  // the blob is byte-aligned only
-            const uint8_t *a = sib + 64 * lv + 4 * i;
-            sc_[i] = (uint32_t)a[0] | ((uint32_t)a[1] << 8) | ((uint32_t)a[2] << 16) | ((uint32_t)a[3] << 24);
-            sh[i] = (uint32_t)a[32] | ((uint32_t)a[33] << 8) | ((uint32_t)a[34] << 16) | ((uint32_t)a[35] << 24);
+    for (uint32_t lv = 0; lv < H; lv++) {
+        const uint8_t *a = sib + (uint64_t)ss * lv;
+        for (int i = 0; i < 8; i++) {
+            sc_[i] = (uint32_t)a[4 * i] | ((uint32_t)a[4 * i + 1] << 8) | ((uint32_t)a[4 * i + 2] << 16) | ((uint32_t)a[4 * i + 3] << 24);
+            sl[i] = (uint32_t)a[32 + 4 * i] | ((uint32_t)a[33 + 4 * i] << 8) | ((uint32_t)a[34 + 4 * i] << 16) | ((uint32_t)a[35 + 4 * i] << 24);
+            if (wide) su[i] = (uint32_t)a[64 + 4 * i] | ((uint32_t)a[65 + 4 * i] << 8) | ((uint32_t)a[66 + 4 * i] << 16) | ((uint32_t)a[67 + 4 * i] << 24);
         }
-        good &= ge_decompress(s, sc_);
-        uint32_t hh[8];
-        if ((x >> lv) & 1) dapol_hash128(hash_id, hh, sc_, curc, sh, curh);
-        else dapol_hash128(hash_id, hh, curc, sc_, curh, sh);
+        uint32_t lo[8], hi[8];
+        const bool right = (x >> lv) & 1;  // the running node is the right child
+        if (wide) {
+            if (right) dapol_b2b_hash192(lo, hi, sc_, curc, sl, su, curl, curu); else dapol_b2b_hash192(lo, hi, curc, sc_, curl, curu, sl, su);
+        } else {
+            if (right) dapol_hash128(hash_id, lo, sc_, curc, sl, curl); else dapol_hash128(hash_id, lo, curc, sc_, curl, sl);
+        }
 #pragma unroll
-        for (int i = 0; i < 8; i++) curh[i] = hh[i];
-        ge_add(cur, cur, s);
-        ge_compress(curc, cur);
+        for (int i = 0; i < 8; i++) { curl[i] = lo[i]; if (wide) curu[i] = hi[i]; }
+        load8(curc, comc + (p * (hmax + 1) + lv + 1) * 8);
     }
     uint32_t d = 0;
-    for (int i = 0; i < 8; i++) d |= (curc[i] ^ root[i]) | (curh[i] ^ root[8 + i]);
-    ok[p] = (uint8_t)(good && d == 0);
+    for (int i = 0; i < 8; i++) d |= (curc[i] ^ root[i]) | (curl[i] ^ root[8 + i]) | (wide ? (curu[i] ^ root[16 + i]) : 0u);
+    ok[p] = (uint8_t)(d == 0);
 }
 
 struct ParsedProof {
@@ -359,8 +368,24 @@ extern "C" int dapol_verify_batch(dapol_ctx *ctx, int hash_id, int policy, uint6
     cudaMemcpyAsync(d_root, root_com, 32, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_root + 8, root_hash, dl, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_ok, ok, k, cudaMemcpyHostToDevice, st);
-    k_merkle_fold<<<grid_for(k, 64), 64, 0, st>>>(k, hash_id, d_blob, d_sib, d_H, d_idx, d_lc, d_lh, d_root, d_ok);
-    ctx->launches++;
+    uint32_t hmax = 0;
+    for (uint64_t p = 0; p < k; p++) if (pp[p].ok) hmax = std::max(hmax, h_H[p]);
+    {   // Merkle fold in slices of at most 2^20 (proof, level) items = 160 MB of scratch
+        const uint64_t per = hmax + 1, slice = std::max<uint64_t>(1, (1ull << 20) / per), items = std::min(k, slice) * per;
+        const int hw = hash_id == DAPOL_HASH_BLAKE2B ? 16 : 8;
+        uint8_t *fold_mem = nullptr;
+        if (dmalloc(&fold_mem, Arena::need(items, 128) + Arena::need(items, 32), st) != cudaSuccess) { dfree(mem, st); CUDA_TRY(cudaGetLastError()); return DAPOL_ERR_CUDA; }
+        uint32_t *pts = reinterpret_cast<uint32_t *>(fold_mem), *comc = reinterpret_cast<uint32_t *>(fold_mem + Arena::need(items, 128));
+        for (uint64_t p0 = 0; p0 < k; p0 += slice) {
+            const uint64_t kc = std::min(slice, k - p0), it = kc * per;
+            k_merkle_decompress<<<grid_for(it, 64), 64, 0, st>>>(kc, hmax, (uint32_t)ss, d_blob, d_sib + p0, d_H + p0, d_lc + 8 * p0, pts, d_ok + p0);
+            k_merkle_prefix<<<grid_for(it, 64), 64, 0, st>>>(kc, hmax, d_H + p0, pts, comc, d_ok + p0);
+            k_merkle_hash_chain<<<grid_for(kc, 64), 64, 0, st>>>(kc, hmax, hash_id, (uint32_t)ss, d_blob, d_sib + p0, d_H + p0, d_idx + p0, d_lc + 8 * p0,
+                                                                 d_lh + (uint64_t)hw * p0, comc, d_root, d_ok + p0);
+            ctx->launches += 3;
+        }
+        dfree(fold_mem, st);
+    }
     cudaMemcpyAsync(ok, d_ok, k, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { dfree(mem, st); CUDA_TRY(cudaGetLastError()); return DAPOL_ERR_CUDA; }
     dfree(mem, st);
