@@ -67,7 +67,8 @@ struct dapol_ctx {
     int rp_verify_group = 0, rp_verify_window = 0;
     bool rp_verify_seeded = false;
     uint32_t rp_verify_seed[8] = {};
-    uint64_t rp_verify_redone = 0;  // proofs re-verified one by one so far (their group's combination failed)
+    uint64_t rp_verify_redone = 0;
+    int rp_pack_lanes = 8;  // lanes per MSM of the packed prover kernels for small shapes in large batches (0: a warp per MSM); DAPOL_RP_PACK_LANES  // proofs re-verified one by one so far (their group's combination failed)
 };
 
 struct dapol_tree {

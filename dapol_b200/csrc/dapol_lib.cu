@@ -424,6 +424,10 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
     dapol_ctx *ctx = new dapol_ctx();
     ctx->device = device;
     ctx->W = comb_window;
+    if (const char *e = getenv("DAPOL_RP_PACK_LANES")) {  // tuning experiments: 0 (a warp per MSM), 4, 8, 16
+        int v = atoi(e);
+        if (v == 0 || v == 4 || v == 8 || v == 16) ctx->rp_pack_lanes = v;
+    }
     if (comb_window == 0) {
         // the wide window keeps 9.5 GB of tables in HBM (11 additions per blinding instead of 17); a device that is short
         // of memory (or shared with other contexts) stays with the L2-resident 27 MB tables

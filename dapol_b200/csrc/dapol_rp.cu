@@ -264,10 +264,46 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_M
     block_reduce_ge(acc, sh);
     if (threadIdx.x == 0) store_msm_point(b, acc);
 }
+// compressed form of the two points of every proof (thread per (proof, point)), read by the transcript passes
+__global__ void __launch_bounds__(64) k_rp_compress_pts(RpBatch b) {
+    uint64_t pw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pw < 2 * b.K) rp_compress_point_body(b, pw);
+}
 // small batches: the S partial sums of a split MSM (grid z) -> the point of (proof, L | R)
 __global__ void __launch_bounds__(32) k_rp_sum_parts(RpBatch b, uint32_t S) {
     uint64_t pw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pw < 2 * b.K) rp_sum_parts_body(b, pw, S);
+}
+// Small shapes in large batches (N <= 128: a warp per MSM spends a fifth of its time in the 5-step shuffle reduction of 32 partial
+// points that are only 2 .. 4 terms each): g = 8 lanes per (proof, L | R), four MSMs per warp, 8 .. 16 terms per lane and a
+// 3-step segmented reduction.  Same partial-sum bodies, other (tid, T).
+__device__ __forceinline__ void segmented_reduce_ge(ge &acc, uint32_t g) {
+#pragma unroll 1
+    for (uint32_t d = g >> 1; d > 0; d >>= 1) {
+        ge o;
+        shfl_down_ge(o, acc, (int)d);
+        ge_add(acc, acc, o);
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(RP_MSM_MAX_T, RP_MSM_MINB) k_rp_p3g(RpBatch b, uint32_t g) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t pw = idx / g;
+    ge acc;
+    if (pw < 2 * b.K) rp_p3_partial<W, false>(acc, b, pw >> 1, (int)(pw & 1), (uint32_t)(idx % g), g);
+    else ge_identity(acc);
+    segmented_reduce_ge(acc, g);
+    if (pw < 2 * b.K && idx % g == 0) rp_store_point(b, pw >> 1, (int)(pw & 1), acc);
+}
+template <int W>
+__global__ void __launch_bounds__(RP_MSM_MAX_T, RP_MSM_MINB) k_rp_p10g(RpBatch b, int rnd, uint32_t g) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t pw = idx / g;
+    ge acc;
+    if (pw < 2 * b.K) rp_p10_partial<W, false>(acc, b, pw >> 1, rnd, (int)(pw & 1), (uint32_t)(idx % g), g);
+    else ge_identity(acc);
+    segmented_reduce_ge(acc, g);
+    if (pw < 2 * b.K && idx % g == 0) rp_store_point(b, pw >> 1, (int)(pw & 1), acc);
 }
 __global__ void __launch_bounds__(64) k_rp_p11(RpBatch b, int rnd) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,9 +355,22 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_M
     __shared__ uint32_t sh[RP_REDUCE_SH_WORDS];
     ge acc;
     uint64_t p = blockIdx.x;
-    rp_v2_partial<W, INL>(acc, b, p, threadIdx.x, blockDim.x);
+    rp_v2_partial<W, INL>(acc, b, p, blockIdx.z * blockDim.x + threadIdx.x, gridDim.z * blockDim.x);
     block_reduce_ge(acc, sh);
-    if (threadIdx.x == 0) b.status[p] = b.status[p] && ge_is_identity(acc);
+    if (threadIdx.x == 0) {
+        if (gridDim.z == 1) b.status[p] = b.status[p] && ge_is_identity(acc);
+        else rp_store_ext(b.parts + ((p * 2) * RP_SPLIT_MAX + blockIdx.z) * 32, acc);  // small batches: one of gridDim.z partial sums
+    }
+}
+// small batches: the verification equation's sum was split over S CTAs; add the parts and test the identity
+__global__ void __launch_bounds__(32) k_rp_v2_finish(RpBatch b, uint32_t S) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= b.K) return;
+    ge acc, q;
+    rp_load_ext(acc, b.parts + (p * 2 * RP_SPLIT_MAX) * 32);
+#pragma unroll 1
+    for (uint32_t z = 1; z < S; z++) { rp_load_ext(q, b.parts + (p * 2 * RP_SPLIT_MAX + z) * 32); ge_add(acc, acc, q); }
+    b.status[p] = b.status[p] && ge_is_identity(acc);
 }
 
 // ------------------------------------------------------------------------------------------------ host orchestration
@@ -368,9 +417,9 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
     const uint64_t N = b.N;
     Arena ar;
     ar.size = Arena::need(K, sizeof(merlin)) + 3 * Arena::need(K * m, 32) + Arena::need(K * CH_COUNT, 32) + Arena::need(K * 3 * 32, 32) +
-              4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * nv, 128) +
+              4 * Arena::need(K * N, 32) + 4 * Arena::need(K * (N / 2 + 1), 32) + Arena::need(K * 2, 128) + Arena::need(K * 2, 32) + Arena::need(K * nv, 128) +
               Arena::need(K * nv, 32) + Arena::need(K, b.plen) + Arena::need(K, 4) + (verify ? Arena::need(K * nv * 8, 128) : Arena::need(K * 2 * RP_FOLD_N, 128)) +
-              (!verify && K <= RP_SPLIT_MAX_K ? Arena::need(K * 2 * RP_SPLIT_MAX, 128) : 0);
+              (K <= RP_SPLIT_MAX_K ? Arena::need(K * 2 * RP_SPLIT_MAX, 128) : 0);
     CUDA_TRY(dmalloc(&pl.mem, ar.size, ctx->stream));
     ar.base = pl.mem;
     b.tr = ar.take<merlin>(K);
@@ -389,10 +438,12 @@ static int rp_plan(dapol_ctx *ctx, RpPlan &pl, int nbits, int m, uint64_t K, boo
         while (g < nv && K * g < 65536) g <<= 1;
         while (g * RP_V1_PMAX < nv) g <<= 1;
         b.vgroups = g < nv ? g : nv;
+        if (K <= RP_SPLIT_MAX_K) b.parts = ar.take<uint32_t>(K * 2 * RP_SPLIT_MAX * 32);
     } else {
         b.vecA = ar.take<uint32_t>(K * N * 8); b.vecB = ar.take<uint32_t>(K * N * 8);
         for (int i = 0; i < 2; i++) { b.cu[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); b.cui[i] = ar.take<uint32_t>(K * (N / 2 + 1) * 8); }
         b.pts = ar.take<uint32_t>(K * 2 * 32);
+        b.ptc = ar.take<uint32_t>(K * 2 * 8);
         b.gfold = ar.take<uint32_t>(K * 2 * RP_FOLD_N * 32);
         if (K <= RP_SPLIT_MAX_K) b.parts = ar.take<uint32_t>(K * 2 * RP_SPLIT_MAX * 32);
         b.proof = ar.take<uint32_t>(K * b.plen / 4);
@@ -463,20 +514,25 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     tm.end();
     tm.begin(TM_P3);
     const unsigned S3 = b.parts ? msm_split(K, N, TS) : 1, S10 = b.parts ? msm_split(K, N, T) : 1;
-    if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
+    // lanes per MSM of the packed kernels: small shapes whose batch fills the GPU several times over even at 8 lanes per MSM
+    const unsigned GP = (N <= 128 && K * 16 >= 8ull * 148 * 2048 / 8 && ctx->rp_pack_lanes) ? (unsigned)ctx->rp_pack_lanes : 0;
+    if (GP) k_rp_p3g<W><<<grid_for(2 * K * GP, RP_MSM_MAX_T), RP_MSM_MAX_T, 0, st>>>(b, GP);
+    else if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
     else k_rp_p3<W, false><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
     if (S3 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S3); ctx->launches++; }
+    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
     tm.end();
     tm.begin(1);
     k_rp_p4<<<grid_for(K, 64), 64, 0, st>>>(b);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 0);
     k_rp_p5<<<(unsigned)K, T, 0, st>>>(b);
     k_rp_p6<W><<<grid_for(2 * K, 64), 64, 0, st>>>(b);
+    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
     k_rp_p7<<<grid_for(K, 64), 64, 0, st>>>(b);
     k_rp_p8<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
     tm.end();
-    ctx->launches += 10;
+    ctx->launches += 12;
     // first round over folded generators (large aggregates), else lg + 1.  Small batches stay on the generator tables: the
     // variable-base chains of the folded rounds (252 doublings each) are latency a handful of proofs cannot hide, while a table
     // round split over the whole GPU is a few additions per thread -- same L_k, R_k, so the same bytes.
@@ -489,15 +545,17 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         tm.begin(rnd >= sw ? TM_HYB : TM_P10);
         if (rnd == sw) { k_rp_pm<W><<<grid_for(K * 2 * RP_FOLD_N, 64), 64, 0, st>>>(b, sw); ctx->launches++; }
         if (rnd >= sw) k_rp_pv<W><<<grid_for(K * 4 * h, 128), 128, 0, st>>>(b, rnd);
+        else if (GP) k_rp_p10g<W><<<grid_for(2 * K * GP, RP_MSM_MAX_T), RP_MSM_MAX_T, 0, st>>>(b, rnd, GP);
         else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
         else k_rp_p10<W, false><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
         if (rnd < sw && S10 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S10); ctx->launches++; }
+        k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
         tm.end();
         tm.begin(1);
         k_rp_p11<<<grid_for(K, 64), 64, 0, st>>>(b, rnd);
         k_rp_p12<<<grid_for(K * cnt, 128), 128, 0, st>>>(b, rnd, cnt);
         tm.end();
-        ctx->launches += 4;
+        ctx->launches += 5;
         if (rnd >= sw && rnd < b.lg) {
             tm.begin(TM_HYB);
             k_rp_pf<<<grid_for(K * 2 * h, 64), 64, 0, st>>>(b, rnd);
@@ -520,8 +578,10 @@ static int rp_verify_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     tm.end();
     tm.begin(TM_VER);
     k_rp_v1<<<grid_for(K * b.vgroups, 64), 64, 0, st>>>(b);
-    if (msm_threads(2 * N) >= RP_INL_MIN_T) k_rp_v2<W, true><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
-    else k_rp_v2<W, false><<<(unsigned)K, msm_threads(2 * N), 0, st>>>(b);
+    const unsigned TV = msm_threads(2 * N), SV = b.parts ? msm_split(K, 2 * N, TV) : 1;
+    if (TV >= RP_INL_MIN_T) k_rp_v2<W, true><<<dim3((unsigned)K, 1, SV), TV, 0, st>>>(b);
+    else k_rp_v2<W, false><<<dim3((unsigned)K, 1, SV), TV, 0, st>>>(b);
+    if (SV > 1) { k_rp_v2_finish<<<grid_for(K, 32), 32, 0, st>>>(b, SV); ctx->launches++; }
     tm.end();
     ctx->launches += 5;
     CUDA_TRY(cudaGetLastError());

@@ -358,6 +358,7 @@ struct RpBatch {
     uint32_t *svec;             // [K][N][8]   verifier s vector
     uint32_t *cu[2], *cui[2];   // [K][N/2][8] coefficient tables, ping-pong
     uint32_t *pts;              // [K][2][32]  extended points out of the MSM passes
+    uint32_t *ptc;              // [K][2][8]   the same points compressed (rp_compress_point_body: a thread per (proof, point))
     uint32_t *parts;            // [K][2][RP_SPLIT_MAX][32] small batches: partial sums of an MSM split over several CTAs (else nullptr)
     uint32_t *gfold;            // [K][2][RP_FOLD_N][32] folded generators G^(k), H^(k) of the variable-base rounds (extended)
     uint32_t *varpts;           // [K][nvar][32] verifier: partial sums of s_q * P_q (the first vgroups entries are used)
@@ -487,15 +488,23 @@ DAPOL_HD_INLINE void rp_sum_parts_body(const RpBatch &b, uint64_t pw, uint32_t S
 // write the sum point of an MSM pass
 DAPOL_HD_INLINE void rp_store_point(const RpBatch &b, uint64_t p, int which, const ge &pt) { rp_store_ext(b.pts + (p * 2 + which) * 32, pt); }
 
-// P4 (thread per proof): compress A, S; transcript V.., A, S -> y, z; z powers; doubling multipliers of y
+// (thread per (proof, which)) compress the point of an MSM pass: the two points of a proof side by side instead of one after
+// the other inside the thread-per-proof transcript passes (an inverse square root each: a third of a single proof's latency)
+DAPOL_HD_INLINE void rp_compress_point_body(const RpBatch &b, uint64_t pw) {
+    ge pt;
+    uint32_t cc[8];
+    rp_load_ext(pt, b.pts + pw * 32);
+    ge_compress(cc, pt);
+    store8(b.ptc + pw * 8, cc);
+}
+// P4 (thread per proof): A, S compressed -> proof; transcript V.., A, S -> y, z; z powers; doubling multipliers of y
 DAPOL_HD_INLINE void rp_p4_body(const RpBatch &b, uint64_t p) {
     merlin tr = b.tr[p];
     for (int j = 0; j < b.m; j++) tr_append_words(tr, "V", 1, b.Vc + (p * b.m + j) * 8, 32);
-    ge pt;
     uint32_t cc[8];
     uint32_t *out = b.proof + p * (b.plen / 4);
-    rp_load_ext(pt, b.pts + (p * 2 + 0) * 32); ge_compress(cc, pt); store8(out, cc); tr_append_words(tr, "A", 1, cc, 32);
-    rp_load_ext(pt, b.pts + (p * 2 + 1) * 32); ge_compress(cc, pt); store8(out + 8, cc); tr_append_words(tr, "S", 1, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 0) * 8); store8(out, cc); tr_append_words(tr, "A", 1, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 1) * 8); store8(out + 8, cc); tr_append_words(tr, "S", 1, cc, 32);
     sc y, z, zz, t;
     tr_challenge_scalar(tr, "y", 1, y);
     tr_challenge_scalar(tr, "z", 1, z);
@@ -569,11 +578,10 @@ DAPOL_HD_INLINE void rp_p6_body(const RpBatch &b, uint64_t p, int which) {
 // multipliers; coefficient tables start at 1
 DAPOL_HD_INLINE void rp_p7_body(const RpBatch &b, uint64_t p) {
     merlin tr = b.tr[p];
-    ge pt;
     uint32_t cc[8];
     uint32_t *out = b.proof + p * (b.plen / 4);
-    rp_load_ext(pt, b.pts + (p * 2 + 0) * 32); ge_compress(cc, pt); store8(out + 16, cc); tr_append_words(tr, "T_1", 3, cc, 32);
-    rp_load_ext(pt, b.pts + (p * 2 + 1) * 32); ge_compress(cc, pt); store8(out + 24, cc); tr_append_words(tr, "T_2", 3, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 0) * 8); store8(out + 16, cc); tr_append_words(tr, "T_1", 3, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 1) * 8); store8(out + 24, cc); tr_append_words(tr, "T_2", 3, cc, 32);
     sc x, xx, w, t, u, tx, txb, eb;
     tr_challenge_scalar(tr, "x", 1, x);
     if (sc_iszero(x)) b.status[p] = DAPOL_RP_ERR_CHALLENGE;
@@ -685,11 +693,10 @@ DAPOL_HD_INLINE void rp_p10_partial(ge &acc, const RpBatch &b, uint64_t p, int r
 // P11 (thread per proof): L, R -> u, u^-1
 DAPOL_HD_INLINE void rp_p11_body(const RpBatch &b, uint64_t p, int rnd) {
     merlin tr = b.tr[p];
-    ge pt;
     uint32_t cc[8];
     uint32_t *out = b.proof + p * (b.plen / 4) + 56 + 16 * (rnd - 1);
-    rp_load_ext(pt, b.pts + (p * 2 + 0) * 32); ge_compress(cc, pt); store8(out, cc); tr_append_words(tr, "L", 1, cc, 32);
-    rp_load_ext(pt, b.pts + (p * 2 + 1) * 32); ge_compress(cc, pt); store8(out + 8, cc); tr_append_words(tr, "R", 1, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 0) * 8); store8(out, cc); tr_append_words(tr, "L", 1, cc, 32);
+    load8(cc, b.ptc + (p * 2 + 1) * 8); store8(out + 8, cc); tr_append_words(tr, "R", 1, cc, 32);
     sc u, ui;
     tr_challenge_scalar(tr, "u", 1, u);
     sc_invert(ui, u);

@@ -82,7 +82,7 @@ EX void emu_merlin_test(const uint8_t *label, uint32_t llen, const uint8_t *mlab
 
 struct Bufs {
     std::vector<merlin> tr;
-    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, varpts, varsc, vartab, gfold, proof;
+    std::vector<uint32_t> Vc, blr, chal, zpow, mult, vecA, vecB, ypow, svec, cu0, cu1, cui0, cui1, pts, ptc, varpts, varsc, vartab, gfold, proof;
     std::vector<int> status;
 };
 static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
@@ -97,12 +97,12 @@ static void setup(RpBatch &b, Bufs &u, int nbits, int m, uint64_t K) {
     u.tr.resize(K); u.Vc.resize(K * m * 8); u.blr.resize(K * m * 8); u.chal.resize(K * CH_COUNT * 8); u.zpow.resize(K * m * 8);
     u.mult.resize(K * 3 * 32 * 8); u.vecA.resize(K * N * 8); u.vecB.resize(K * N * 8); u.ypow.resize(K * N * 8); u.svec.resize(K * N * 8);
     u.cu0.resize(K * N / 2 * 8); u.cu1.resize(K * N / 2 * 8); u.cui0.resize(K * N / 2 * 8); u.cui1.resize(K * N / 2 * 8);
-    u.pts.resize(K * 2 * 32); u.gfold.resize(K * 2 * RP_FOLD_N * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.vartab.resize(K * nv * 8 * 32); u.proof.resize(K * b.plen / 4);
+    u.pts.resize(K * 2 * 32); u.ptc.resize(K * 2 * 8); u.gfold.resize(K * 2 * RP_FOLD_N * 32); u.varpts.resize(K * nv * 32); u.varsc.resize(K * nv * 8); u.vartab.resize(K * nv * 8 * 32); u.proof.resize(K * b.plen / 4);
     u.status.resize(K);
     b.tr = u.tr.data(); b.Vc = u.Vc.data(); b.blr = u.blr.data(); b.chal = u.chal.data(); b.zpow = u.zpow.data(); b.mult = u.mult.data();
     b.vecA = u.vecA.data(); b.vecB = u.vecB.data(); b.ypow = u.ypow.data(); b.svec = u.svec.data();
     b.cu[0] = u.cu0.data(); b.cu[1] = u.cu1.data(); b.cui[0] = u.cui0.data(); b.cui[1] = u.cui1.data();
-    b.pts = u.pts.data(); b.gfold = u.gfold.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.vartab = u.vartab.data(); b.proof = u.proof.data(); b.status = u.status.data();
+    b.pts = u.pts.data(); b.ptc = u.ptc.data(); b.gfold = u.gfold.data(); b.varpts = u.varpts.data(); b.varsc = u.varsc.data(); b.vartab = u.vartab.data(); b.proof = u.proof.data(); b.status = u.status.data();
     uint64_t per = (uint64_t)NW * HALF;
     b.tabG = g_tab.tab.data();
     b.tabH = b.tabG + 64ull * g_tab.mcap * per;
@@ -159,6 +159,8 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
             }
     };
     msm([&](ge &acc, uint64_t p, int which, uint32_t t) { rp_p3_partial<W>(acc, b, p, which, t, (uint32_t)T); });
+    auto compress_pts = [&]() { for (uint64_t pw = 0; pw < 2 * K; pw++) rp_compress_point_body(b, pw); };
+    compress_pts();
     for (uint64_t p = 0; p < K; p++) rp_p4_body(b, p);
     expand(b, b.ypow, 0);
     for (uint64_t p = 0; p < K; p++) {
@@ -168,6 +170,7 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
         rp_st(rp_ch(b, p, CH_T0), t0); rp_st(rp_ch(b, p, CH_T1), t1); rp_st(rp_ch(b, p, CH_T2), t2);
     }
     for (uint64_t p = 0; p < K; p++) for (int which = 0; which < 2; which++) rp_p6_body<W>(b, p, which);
+    compress_pts();
     for (uint64_t p = 0; p < K; p++) rp_p7_body(b, p);
     for (uint64_t p = 0; p < K; p++) for (uint32_t k = 0; k < N; k++) rp_p8_body(b, p, k);
     expand(b, b.ypow, 1);
@@ -193,6 +196,7 @@ EX int emu_rp_prove(int nbits, int m, uint64_t K, const uint64_t *values, const 
         } else {
             msm([&](ge &acc, uint64_t p, int which, uint32_t t) { rp_p10_partial<W>(acc, b, p, rnd, which, t, (uint32_t)T); });
         }
+        compress_pts();
         for (uint64_t p = 0; p < K; p++) rp_p11_body(b, p, rnd);
         // a thread reads a[i], a[h+i] and writes a[i]; table growth reads cur, writes nxt: any order is fine
         for (uint64_t p = 0; p < K; p++) for (uint32_t i = 0; i < cnt; i++) rp_p12_body(b, p, rnd, i);
