@@ -68,6 +68,8 @@ struct dapol_ctx {
     bool rp_verify_seeded = false;
     uint32_t rp_verify_seed[8] = {};
     uint64_t rp_verify_redone = 0;
+    int rp_pack_min_k = 8192;  // ... from this many proofs per batch on (DAPOL_RP_PACK_MIN_K)
+    int rp_pack_max_n = 32;    // ... for shapes of at most this many generators per vector (DAPOL_RP_PACK_MAX_N)
     int rp_pack_lanes = 8;  // lanes per MSM of the packed prover kernels for small shapes in large batches (0: a warp per MSM); DAPOL_RP_PACK_LANES  // proofs re-verified one by one so far (their group's combination failed)
 };
 

@@ -428,6 +428,8 @@ extern "C" int dapol_ctx_create(int device, int comb_window, dapol_ctx **out) {
         int v = atoi(e);
         if (v == 0 || v == 4 || v == 8 || v == 16) ctx->rp_pack_lanes = v;
     }
+    if (const char *e = getenv("DAPOL_RP_PACK_MIN_K")) { int v = atoi(e); if (v >= 1) ctx->rp_pack_min_k = v; }
+    if (const char *e = getenv("DAPOL_RP_PACK_MAX_N")) { int v = atoi(e); if (v >= 8 && v <= 128) ctx->rp_pack_max_n = v; }
     if (comb_window == 0) {
         // the wide window keeps 9.5 GB of tables in HBM (11 additions per blinding instead of 17); a device that is short
         // of memory (or shared with other contexts) stays with the L2-resident 27 MB tables

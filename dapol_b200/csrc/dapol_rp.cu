@@ -2,6 +2,7 @@
 // window tables they run on, and the C-ABI entry points (include/dapol_b200.h).  Per-thread bodies: rp_kernels.cuh.
 // Replaces /root/reference/src/range/mod.rs:48-119 (generate_/verify_{single,aggregated}_range_proof).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
@@ -265,8 +266,12 @@ __global__ void __launch_bounds__(RP_MSM_MAX_T, INL ? RP_MSM_MINB_INL : RP_MSM_M
     if (threadIdx.x == 0) store_msm_point(b, acc);
 }
 // compressed form of the two points of every proof (thread per (proof, point)), read by the transcript passes
-__global__ void __launch_bounds__(64) k_rp_compress_pts(RpBatch b) {
+__global__ void __launch_bounds__(64) k_rp_compress_pts(RpBatch b, int per_proof) {
     uint64_t pw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (per_proof) {  // A/B knob (DAPOL_RP_COMPRESS_SEQ): both points of a proof by one thread, as the transcript passes used to do
+        if (pw < b.K) { rp_compress_point_body(b, 2 * pw); rp_compress_point_body(b, 2 * pw + 1); }
+        return;
+    }
     if (pw < 2 * b.K) rp_compress_point_body(b, pw);
 }
 // small batches: the S partial sums of a split MSM (grid z) -> the point of (proof, L | R)
@@ -274,9 +279,9 @@ __global__ void __launch_bounds__(32) k_rp_sum_parts(RpBatch b, uint32_t S) {
     uint64_t pw = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (pw < 2 * b.K) rp_sum_parts_body(b, pw, S);
 }
-// Small shapes in large batches (N <= 128: a warp per MSM spends a fifth of its time in the 5-step shuffle reduction of 32 partial
-// points that are only 2 .. 4 terms each): g = 8 lanes per (proof, L | R), four MSMs per warp, 8 .. 16 terms per lane and a
-// 3-step segmented reduction.  Same partial-sum bodies, other (tid, T).
+// The smallest shapes in large batches (N <= 32: a warp per MSM gives every lane ONE term and then runs a 5-step shuffle reduction
+// of 32 partial points): g = 8 lanes per (proof, L | R), four MSMs per warp, 4 terms per lane and a 3-step segmented reduction.
+// Same partial-sum bodies, other (tid, T).
 __device__ __forceinline__ void segmented_reduce_ge(ge &acc, uint32_t g) {
 #pragma unroll 1
     for (uint32_t d = g >> 1; d > 0; d >>= 1) {
@@ -502,6 +507,7 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     cudaStream_t st = ctx->stream;
     const uint64_t K = b.K, N = b.N;
     const unsigned T = msm_threads(N), TS = msm_threads(2 * N);
+    static const int cseq = getenv("DAPOL_RP_COMPRESS_SEQ") ? atoi(getenv("DAPOL_RP_COMPRESS_SEQ")) : 0;
     tm.begin(1);
     k_rp_p0<<<grid_for(K, 64), 64, 0, st>>>(b);
     switch (ctx->W) {
@@ -513,21 +519,23 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
     k_rp_p2<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     tm.end();
     tm.begin(TM_P3);
-    const unsigned S3 = b.parts ? msm_split(K, N, TS) : 1, S10 = b.parts ? msm_split(K, N, T) : 1;
-    // lanes per MSM of the packed kernels: small shapes whose batch fills the GPU several times over even at 8 lanes per MSM
-    const unsigned GP = (N <= 128 && K * 16 >= 8ull * 148 * 2048 / 8 && ctx->rp_pack_lanes) ? (unsigned)ctx->rp_pack_lanes : 0;
+    // lanes per MSM of the packed kernels: shapes of at most 32 generators per vector in batches that fill the GPU several times over
+    // even at 8 lanes per MSM.  Measured (profiles/r02_variants.txt 9): n = 32, m = 1: MSM passes 40.4 -> 23.7 ms per 32768 proofs;
+    // N = 64 and 128 gain nothing (26.1 vs 26.3 ms, 54.3 vs 56.9 ms) and keep a warp per MSM.
+    const unsigned GP = (N <= (uint64_t)ctx->rp_pack_max_n && K >= (uint64_t)ctx->rp_pack_min_k && ctx->rp_pack_lanes) ? (unsigned)ctx->rp_pack_lanes : 0;
+    const unsigned S3 = (b.parts && !GP) ? msm_split(K, N, TS) : 1, S10 = (b.parts && !GP) ? msm_split(K, N, T) : 1;
     if (GP) k_rp_p3g<W><<<grid_for(2 * K * GP, RP_MSM_MAX_T), RP_MSM_MAX_T, 0, st>>>(b, GP);
     else if (TS >= RP_INL_MIN_T) k_rp_p3<W, true><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
     else k_rp_p3<W, false><<<dim3((unsigned)K, 2, S3), TS, 0, st>>>(b);
     if (S3 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S3); ctx->launches++; }
-    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
+    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b, cseq);
     tm.end();
     tm.begin(1);
     k_rp_p4<<<grid_for(K, 64), 64, 0, st>>>(b);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 0);
     k_rp_p5<<<(unsigned)K, T, 0, st>>>(b);
     k_rp_p6<W><<<grid_for(2 * K, 64), 64, 0, st>>>(b);
-    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
+    k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b, cseq);
     k_rp_p7<<<grid_for(K, 64), 64, 0, st>>>(b);
     k_rp_p8<<<grid_for(K * N, 128), 128, 0, st>>>(b);
     k_rp_expand<<<(unsigned)K, 256, 0, st>>>(b, b.ypow, 1);
@@ -549,7 +557,7 @@ static int rp_prove_chunk(dapol_ctx *ctx, RpBatch &b, PhaseTimer &tm) {
         else if (T >= RP_INL_MIN_T) k_rp_p10<W, true><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
         else k_rp_p10<W, false><<<dim3((unsigned)K, 2, S10), T, 0, st>>>(b, rnd);
         if (rnd < sw && S10 > 1) { k_rp_sum_parts<<<grid_for(2 * K, 32), 32, 0, st>>>(b, S10); ctx->launches++; }
-        k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b);
+        k_rp_compress_pts<<<grid_for(2 * K, 64), 64, 0, st>>>(b, cseq);
         tm.end();
         tm.begin(1);
         k_rp_p11<<<grid_for(K, 64), 64, 0, st>>>(b, rnd);

@@ -155,3 +155,26 @@ def test_batched_verifier_same_verdicts(ctx, cref, nbits, m, k, G, cbits):
             assert bool(got[i]) == cref.rp_verify(proofs[i].tobytes(), [c.tobytes() for c in coms[i]], nbits)
     finally:
         ctx.set_verify_mode(0)
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16])
+def test_packed_small_shape_kernels_same_bytes(cref, lanes, monkeypatch):
+    """Small shapes in large batches run 4 / 8 / 16 lanes per MSM (k_rp_p3g / k_rp_p10g) instead of a warp per MSM: forced here on small
+    batches (DAPOL_RP_PACK_MIN_K = 1), the proofs are byte for byte the oracle's and verify."""
+    from dapol_b200 import Context
+    monkeypatch.setenv("DAPOL_RP_PACK_MIN_K", "1")
+    monkeypatch.setenv("DAPOL_RP_PACK_MAX_N", "128")
+    monkeypatch.setenv("DAPOL_RP_PACK_LANES", str(lanes))
+    c = Context(0, 15)
+    c.set_rangeproof_window(12)
+    try:
+        for nbits, m, k in [(64, 1, 70), (64, 2, 9), (32, 4, 5), (8, 1, 33), (16, 8, 3)]:
+            rnd = random.Random(nbits * 3 + m + lanes)
+            vals, bl, streams, bases = _batch(rnd, nbits, m, k)
+            proofs = c.rangeproof_prove_batch(nbits, vals, bl, SEED, streams, bases)
+            for i in range(min(k, 12)):
+                want = cref.rp_prove([int(x) for x in vals[i]], [b.tobytes() for b in bl[i]], SEED, int(streams[i]), int(bases[i]), nbits)
+                assert proofs[i].tobytes() == want, (nbits, m, i)
+            assert c.rangeproof_verify_batch(nbits, m, proofs, _coms(cref, vals, bl)).all()
+    finally:
+        c.close()
