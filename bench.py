@@ -363,7 +363,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--users-log2", type=int, default=20, help="users per GPU (weak scaling)")
     ap.add_argument("--height", type=int, default=32, help="tree height at 1 GPU; N GPUs build ONE tree of height + log2(N)")
-    ap.add_argument("--comb-window", type=int, default=0)
+    ap.add_argument("--comb-window", type=int, default=26, help="window of the tree's fixed-base tables: 26 bits = 32 GB of HBM tables, 10 windows per "
+                    "blinding (measured 25.0 vs 26.0 ms per build against the library default 24 = 8.9 GB, profiles/r02_variants.txt 11); 0 = library default")
     ap.add_argument("--cpu-sample-log2", type=int, default=17)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -497,13 +498,30 @@ def main():
     h2d = int(iid.nbytes + io.nbytes + eid.nbytes + eo.nbytes + vals.nbytes)
     d2h = 104 + 65 * 8 + 32 * 4  # root record + level histogram + collision-round counters (approx. 4 rounds)
 
+    # The tree context (up to 33 GB of comb tables) is released before the range-proof leg, which runs on a context of its own with the
+    # L2-resident comb tables, so that the generator tables get their full HBM budget (110 GB at m = 32).
+    params = ctx.params()
+    spot = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cb, (sn, sH, sroot) = cpu_baseline_leg(args)
+        # the same sample through the GPU path must give the oracle's root (parity spot check, untimed)
+        t = Dapol.new(ctx, 0, synth_liabilities(sn), AUDIT_SEED, sH, sH, PAD_SEED)
+        cb["gpu_root_matches"] = bool(t.root_raw().com == sroot)
+        t.close()
+        spot = cb
+    used_native = native is not None
+    if native is not None:
+        native.close()
+        native = None
+    ctx.close()
+    ctx = Context(local, 15)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     rp = rangeproof_leg(ctx, L, dev, world, dist, args, imad_peak) if (args.rp_singles or args.rp_aggregates) else None
 
     if rank == 0:
         internal = (nodes - 1) // 2  # every internal node has exactly two children
         leaves_here = nodes - pads - internal
         med = {kk: statistics.median(v) for kk, v in phase_ms.items()}
-        params = ctx.params()
         MAC32_LEAF_EXEC, MAC32_PAD_EXEC, MAC32_MERGE_EXEC = executed_mac32(params["comb_window"], params["node_batch"])
         achieved = pads * MAC32_PAD_EXEC / (med["padding"] * 1e-3) / 1e9  # GMAC32/s
         build_exec = leaves_here * MAC32_LEAF_EXEC + pads * MAC32_PAD_EXEC + internal * MAC32_MERGE_EXEC
@@ -526,7 +544,7 @@ def main():
                        "parallelism": ((f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs, one dapol_sharded_build call per rank "
                                         f"(library-owned NCCL communicator): all-to-all of 96 B per local user (duplicate check + index claims), "
                                         f"losers-only re-claim rounds, all-gather of padding counts and of {world} subtree roots (232 B)")
-                                       if native else (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs (staged C-ABI calls, "
+                                       if used_native else (f"one tree sharded by {k}-bit leaf-index prefix over {world} GPUs (staged C-ABI calls, "
                                                        f"torch.distributed): all-gather of user records (112 B/user) + all-gather of {world} subtree roots"))
                        if world > 1 else "single GPU",
                        "l2": "per-step working set (node store + half points ~%.1f GB) >> 126 MB L2; no reuse across steps" % (nodes * 232 / 1e9)},
@@ -552,13 +570,7 @@ def main():
         if rp is not None:
             line["range_proofs"] = rp
         if not args.no_cpu_baseline and world == 1:
-            cb, (sn, sH, sroot) = cpu_baseline_leg(args)
-            line["cpu_baseline"] = cb
-            # the same sample through the GPU path must give the oracle's root (parity spot check, untimed)
-            s = synth_liabilities(sn)
-            t = Dapol.new(ctx, 0, s, AUDIT_SEED, sH, sH, PAD_SEED)
-            line["cpu_baseline"]["gpu_root_matches"] = bool(t.root_raw().com == sroot)
-            t.close()
+            line["cpu_baseline"] = spot
             # the timed full-size build against the oracle's root of the same workload (tests/golden/full_size_golden.json,
             # produced once on the CPU by tests/golden/gen_golden_full.py: the oracle needs minutes for this tree)
             try:

@@ -39,7 +39,7 @@ static inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)(
 #define DAPOL_WIDE_COMB_MIN_FREE_GB 48
 #endif
 #ifndef DAPOL_W_CASES
-#define DAPOL_W_CASES(X) X(4) X(8) X(12) X(15) X(16) X(20) X(22) X(24)
+#define DAPOL_W_CASES(X) X(4) X(8) X(12) X(15) X(16) X(20) X(22) X(24) X(26)
 #endif
 
 struct dapol_ctx {

@@ -77,8 +77,9 @@ typedef struct dapol_tree dapol_tree;
 /* Context = one CUDA device + its stream + the precomputed generator tables
  * (PedersenGens::default(), src/dapol/node.rs:31; BulletproofGens::new, src/range/mod.rs:50,66 --
  * the reference re-derives them on every call, here once).  comb_window = window of the fixed-base tables of B/2 and
- * B_blinding (4, 8, 12, 15, 16: L2-resident; 20, 22, 24: up to 9.5 GB in HBM, fewer additions per commitment); 0 picks 24 when
- * at least 48 GB of device memory are free and the tables can be allocated, else 15.  Every window gives the same bytes. */
+ * B_blinding (4, 8, 12, 15, 16: L2-resident; 20, 22, 24: up to 9.5 GB in HBM, fewer additions per commitment; 26: 32.8 GB, one
+ * addition fewer again -- for a device dedicated to tree building); 0 picks 24 when at least 48 GB of device memory are free
+ * and the tables can be allocated, else 15.  Every window gives the same bytes. */
 DAPOL_API int dapol_ctx_create(int device, int comb_window, dapol_ctx **out);
 DAPOL_API void dapol_ctx_destroy(dapol_ctx *ctx);  /* destroy the context's trees first: a tree holds a pointer to its context */
 /* Run this context's kernels and copies on a caller-owned CUDA stream (cudaStream_t), e.g. the framework's

@@ -75,7 +75,7 @@ def test_tree_every_node_vs_oracle(ctx, cref, hash_id, H, n, stride):
     gpu.close()
 
 
-@pytest.mark.parametrize("W", [4, 8, 12, 15, 16, 20, 22, 24])
+@pytest.mark.parametrize("W", [4, 8, 12, 15, 16, 20, 22, 24, 26])
 def test_every_comb_window_gives_the_same_tree(cref, W):
     """The comb window of the fixed-base tables is a speed knob only: every instantiated width gives the oracle's tree."""
     from dapol_b200 import Context, Dapol
