@@ -54,3 +54,46 @@ def test_proof_sizes_match_the_oracle_layout():
                 merkle = len(pyref.merkle_serialize(H, 0, [(bytes(32), bytes(32))] * H))
                 assert L.dapol_inclusion_proof_size(H, agg, policy) == rng + merkle, (H, agg, policy)
         assert L.dapol_inclusion_proof_size(H, H + 1, 0) == 0  # the reference panics (slice out of bounds)
+
+
+def test_batch_and_digest_aware_sizes_match_the_oracle():
+    """Host-only: the sibling plan of a batch proof (Dapol::generate_proof_batch, mod.rs:172-190: a sibling is carried only if it is not
+    itself on the way up from the batch) and the digest-aware wire sizes (a sibling is com || hash of Dlen bytes, proof/node.rs:74-79)
+    of the library's C++ against both oracle restatements, for random batches incl. adjacent leaves, one leaf and a whole level."""
+    import random
+
+    import numpy as np
+
+    from oracle import cref, pyref
+    L = _ffi.lib()
+    O = cref.lib()
+    O.dor_batch_proof_size_d.restype = ctypes.c_uint64
+    O.dor_inclusion_proof_size_d.restype = ctypes.c_uint64
+    assert [L.dapol_digest_len(h) for h in (0, 1, 2, 3, -1)] == [32, 32, 64, 0, 0]
+    rnd = random.Random(11)
+    for H in (1, 3, 8, 10, 20, 40, 64):
+        for hash_id, dl in ((0, 32), (2, 64)):
+            for agg, policy in ((0, 0), (1, 1), (H, 0), (H // 2, 1)):
+                want = O.dor_inclusion_proof_size_d(H, ctypes.c_uint64(agg), policy, dl)
+                assert L.dapol_inclusion_proof_size_d(H, agg, policy, hash_id) == want > 0
+                assert want == L.dapol_inclusion_proof_size(H, agg, policy) + (dl - 32) * H
+        assert L.dapol_inclusion_proof_size_d(H, 1, 0, 7) == 0  # unknown digest
+        for k in (1, 2, 3, 10, min(64, 1 << H)):
+            k = min(k, 1 << min(H, 20))
+            picks = set()
+            while len(picks) < k:
+                picks.add(rnd.randrange(1 << H) if rnd.random() < 0.5 or not picks else min((1 << H) - 1, max(picks) ^ 1))
+            idx = np.array(sorted(picks), np.uint64)
+            plan = pyref.batch_sibling_plan(H, [int(x) for x in idx])
+            for agg, policy in ((0, 0), (1, 1), (len(plan), 0), (len(plan) // 2, 1)):
+                for hash_id, dl in ((0, 32), (2, 64)):
+                    got = L.dapol_batch_proof_size_d(H, len(idx), idx.ctypes.data_as(ctypes.c_void_p), agg, policy, hash_id)
+                    want = O.dor_batch_proof_size_d(H, ctypes.c_uint64(len(idx)), idx.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(agg), policy, dl)
+                    assert got == want, (H, k, agg, policy, hash_id)
+                    if len(idx) > 1:  # the Merkle part alone (framing + one (32 + Dlen)-byte entry per planned sibling) is smaller than the whole
+                        nb = (H + 7) // 8
+                        assert got == 0 or (got - (2 + 8 + len(idx) * nb + 8 + (32 + dl) * len(plan))) > 0
+            assert L.dapol_batch_proof_size_d(H, len(idx), idx.ctypes.data_as(ctypes.c_void_p), len(plan) + 1, 0, 0) == 0 or len(idx) == 1  # slice out of bounds in the reference
+        if H >= 3:
+            bad = np.array([5, 2], np.uint64)  # not increasing: smtree rejects
+            assert L.dapol_batch_proof_size_d(H, 2, bad.ctypes.data_as(ctypes.c_void_p), 0, 0, 0) == 0
