@@ -97,3 +97,22 @@ def test_batch_and_digest_aware_sizes_match_the_oracle():
         if H >= 3:
             bad = np.array([5, 2], np.uint64)  # not increasing: smtree rejects
             assert L.dapol_batch_proof_size_d(H, 2, bad.ctypes.data_as(ctypes.c_void_p), 0, 0, 0) == 0
+
+
+def test_python_mirror_covers_the_reference_surface():
+    """The host-side mirror exposes what the crate's root re-exports (src/lib.rs:1-14) and the methods the hot path uses:
+    Dapol::{new, new_blank, build, update, root, root_raw, generate_proof[_for_id], generate_proof_batch[_for_ids]} (src/dapol/mod.rs:100-213),
+    DapolNode::{get_value, get_blinding} (node.rs:48-56), DapolProofNode::{get_com, get_hash} (proof/node.rs:30-49),
+    DapolProof::{serialize, deserialize, verify, verify_batch} (proof/mod.rs:41-84), both policies, the three digests."""
+    import dapol_b200 as d
+    for name in ("Dapol", "DapolNode", "DapolProof", "DapolProofNode", "DapolError", "Context", "ShardedDapol", "POLICY_PADDING", "POLICY_SPLITTING",
+                 "HASH_BLAKE3", "HASH_BLAKE2S", "HASH_BLAKE2B"):
+        assert hasattr(d, name), name
+    for m in ("new", "new_blank", "build", "update", "root", "root_raw", "generate_proof", "generate_proof_for_id", "generate_proof_batch",
+              "generate_proof_batch_for_ids", "leaf_index_of", "save", "load"):
+        assert callable(getattr(d.Dapol, m)), m
+    for m in ("serialize", "deserialize", "verify", "verify_batch", "verify_many"):
+        assert callable(getattr(d.DapolProof, m)), m
+    n = d.DapolNode(5, bytes(32), bytes(32), bytes(64))
+    assert (n.get_value(), n.get_blinding(), n.get_proof_node().serialize()) == (5, bytes(32), bytes(96))  # com || hash (proof/node.rs:74-79), 64-byte digest
+    assert (d.POLICY_PADDING, d.POLICY_SPLITTING, d.HASH_BLAKE3, d.HASH_BLAKE2S, d.HASH_BLAKE2B) == (0, 1, 0, 1, 2)
