@@ -41,8 +41,29 @@ def tree_fixture(name, hash_id, H, liabilities, audit_seed, proofs_for=(), agg=N
     return fx
 
 
+def node_tree_fixture(name, hash_id, H, leaf_idx, values, blind, proofs_for=(), batches=()):
+    """Dapol::new_blank + build from ready nodes (mod.rs:196-208) -- the only way to a 64-byte digest (Blake2b, src/tests.rs:104-105) --
+    with single proofs and batch proofs (generate_proof_batch, mod.rs:172-190)."""
+    t = o.build_tree(hash_id, H, [(i, o.node_new(hash_id, v, r)) for i, v, r in zip(leaf_idx, values, blind)], PAD_SEED)
+    levels = [[{"idx": i, "v": t.levels[h][i].v, "com": t.levels[h][i].comc.hex(), "hash": t.levels[h][i].hash.hex(), "pad": int(i in t.is_pad[h])}
+               for i in sorted(t.levels[h])] for h in range(H + 1)]
+    fx = {"name": name, "hash_id": hash_id, "height": H, "leaf_idx": list(leaf_idx), "values": list(values), "blindings": [o.sc_bytes(r).hex() for r in blind],
+          "pad_seed": PAD_SEED.hex(), "levels": levels, "proofs": [], "batch_proofs": []}
+    root = (t.root.comc, t.root.hash)
+    for leaf, policy, agg in proofs_for:
+        p = o.prove_inclusion(t, leaf, agg, policy, PROVE_SEED)
+        node = t.levels[H][leaf]
+        assert o.verify_inclusion(hash_id, p, policy, root, (node.comc, node.hash))
+        fx["proofs"].append({"leaf_idx": leaf, "policy": policy, "aggregation_factor": agg, "seed": PROVE_SEED.hex(), "bytes": p.hex()})
+    for leaves, policy, agg in batches:
+        p = o.prove_inclusion_batch(t, list(leaves), agg, policy, PROVE_SEED)
+        assert o.verify_inclusion_batch(hash_id, p, policy, root, [(t.levels[H][x].comc, t.levels[H][x].hash) for x in leaves])
+        fx["batch_proofs"].append({"leaf_idxs": list(leaves), "policy": policy, "aggregation_factor": agg, "seed": PROVE_SEED.hex(), "bytes": p.hex()})
+    return fx
+
+
 def main():
-    out = {"generator": "tests/golden/gen_golden.py (oracle/pyref.py)", "trees": [], "range_proofs": []}
+    out = {"generator": "tests/golden/gen_golden.py (oracle/pyref.py)", "trees": [], "range_proofs": [], "node_trees": []}
     kat = [(b"a", b"w", 3), (b"b", b"x", 5), (b"c", b"y", 7), (b"d", b"z", 11)]
     out["trees"].append(tree_fixture("reference KAT src/dapol/tests.rs:17-84 (Blake2s, H=4)", 1, 4, kat, b"test",
                                      proofs_for=[(0, 0), (1, 1)], agg=2))
@@ -57,6 +78,13 @@ def main():
         out["range_proofs"].append({"nbits": nbits, "m": m, "values": values, "blindings": [o.sc_bytes(r).hex() for r in blind],
                                     "seed": PROVE_SEED.hex(), "stream": 3, "base_block": 5, "commitments": [c.hex() for c in coms],
                                     "proof": proof.hex()})
+    idx = [1, 4, 5, 11, 18, 19, 30]
+    vals = [(i * 2654435761) & 0xFFFFFFFF for i in range(1, 8)]
+    blind = [int.from_bytes(hashlib.sha256(b"node-blind-%d" % j).digest(), "little") % o.L for j in range(7)]
+    out["node_trees"].append(node_tree_fixture("7 nodes, Blake2b 64-byte digests, H=5", o.HASH_BLAKE2B, 5, idx, vals, blind,
+                                               proofs_for=[(11, 1, 1)], batches=[((4, 5, 18), 1, 1)]))
+    out["node_trees"].append(node_tree_fixture("7 nodes, blake3, H=5, batch proof", o.HASH_BLAKE3, 5, idx, vals, blind,
+                                               batches=[((1, 19, 30), 0, 0)]))
     json.dump(out, open(os.path.join(HERE, "dapol_golden.json"), "w"), indent=1)
     print("wrote", os.path.join(HERE, "dapol_golden.json"))
 
