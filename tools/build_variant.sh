@@ -6,6 +6,7 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; tu=$2; shift 2
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+# variants are throw-away measurement builds: -split-compile for speed (not reproducible, see build.sh)
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -split-compile 0 -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xptxas -v"
 $NVCC $FLAGS "$@" -c -o build/var_$name.o dapol_b200/csrc/$tu.cu > build/var_$name.log 2>&1
 objs=""
